@@ -1,0 +1,70 @@
+"""ctypes loader for libicgvins_b200.so (the C ABI declared in include/icgvins_b200.h).
+
+There is no CPU fallback: if the library is missing this raises, and every create() call fails without a B200.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicgvins_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int32)
+vp = C.c_void_p
+
+_lib = None
+
+
+class IcgError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IcgError(f"{LIB_PATH} not built: run `python -m ic_gvins_b200.build` (there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().icg_last_error().decode("utf-8", "replace")
+        raise IcgError(f"{what} failed with code {rc}: {msg}")
+
+
+def _declare(L: C.CDLL) -> None:
+    L.icg_last_error.restype = C.c_char_p
+    L.icg_version.restype = C.c_int
+    L.icg_launch_count.restype = C.c_uint64
+    L.icg_launch_count_reset.restype = None
+    # ---- KLT
+    L.icg_klt_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.icg_klt_destroy.argtypes = [vp]
+    L.icg_klt_destroy.restype = None
+    L.icg_klt_calc_optical_flow_pyr_lk.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                   C.c_double, C.c_int]
+    L.icg_klt_track_fb.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int]
+    L.icg_klt_upload.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.icg_klt_upload_level0.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.icg_klt_slot_level0.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.icg_klt_slot_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.icg_klt_build_pyramids.argtypes = [vp, C.c_int, C.c_int]
+    L.icg_klt_track_batch_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
+    L.icg_klt_sync.argtypes = [vp]
+    L.icg_klt_download_level.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
+
+
+# every symbol include/icgvins_b200.h declares (checked by tests/test_abi.py against the header text)
+EXPORTS = [
+    "icg_last_error", "icg_version", "icg_launch_count", "icg_launch_count_reset",
+    "icg_klt_create", "icg_klt_destroy", "icg_klt_calc_optical_flow_pyr_lk", "icg_klt_track_fb", "icg_klt_upload",
+    "icg_klt_upload_level0", "icg_klt_slot_level0", "icg_klt_slot_level", "icg_klt_build_pyramids",
+    "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
+]

@@ -1,0 +1,770 @@
+// klt.cu -- Path A: pyramid build + pyramidal Lucas-Kanade tracker for sm_100a.
+//
+// Replaces cv::calcOpticalFlowPyrLK as called from IG/tracking/tracking.cc:385,390,487,493 (OpenCV is an
+// un-vendored dependency of the reference; the arithmetic restated here is specified in SURVEY.md Appendix A.1-A.3
+// and pinned by oracle/klt_ref.c + tests/golden/klt_golden.npz).
+//
+// Design (B200-first, not a translation of OpenCV's row-parallel CPU code):
+//   * pyramids live in HBM as [slot][row][pitch] u8 planes per level; one 3-D TMA descriptor per level.
+//   * one warp tracks one point through all levels (forward, then backward): the 21x21 template
+//     (I, Ix, Iy) lives in registers (14 px / lane), the 32x32 search window of the second image is staged
+//     into shared memory by TMA (cp.async.bulk.tensor.3d, mbarrier completion) and re-centred only when the
+//     track leaves it; Scharr derivatives are computed in-kernel from the staged template window
+//     (no derivative image ever touches HBM); the 2x2 normal equations are reduced with REDUX (exact integer).
+//   * compile with -fmad=false: the float sequence of the reference library must not be contracted.
+#include <math.h>
+#include <string.h>
+
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace icg {
+
+constexpr int KLT_WIN     = 21;
+constexpr int KLT_LEVELS  = 4;  // maxLevel 3 (IG/tracking/tracking.h:113)
+constexpr int KLT_BOX     = 32; // TMA box edge (bytes / rows)
+constexpr int KLT_MARGIN  = 5;  // search window slack on each side: 32 - 22 = 10
+constexpr int KLT_WPB     = 4;  // warps per block
+constexpr int KLT_PXL     = 14; // template pixels per lane: ceil(441 / 32)
+
+struct KltLevel {
+    const uint8_t *base;
+    int W, H, pitch;
+    size_t slot_stride;
+};
+
+struct KltMaps {
+    CUtensorMap m[KLT_LEVELS];
+};
+
+struct KltArgs {
+    KltLevel lv[KLT_LEVELS];
+    int n_total;
+    int n_levels;  // maxLevel + 1
+    int max_iter;
+    int mode;      // 0 forward only, 1 forward+backward+gates
+    int use_initial_flow;
+    int check_final;  // level-0 epilogue status check (OpenCV does it only when err is requested)
+    double eps2;
+    double min_eig_thr;
+    float img_w, img_h;  // level-0 size for the border gate
+    const int32_t *slots;
+    const float2 *prev_xy;
+    const float2 *init_xy;
+    float2 *fwd_xy;
+    float2 *bwd_xy;
+    uint8_t *status;
+    float *err;
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ pyrDown
+// cv::pyrDown: dst(y,x) = (sum_{i,j} k_i k_j src(2y+i, 2x+j) + 128) >> 8, k = [1 4 6 4 1], reflect-101.
+// One block produces a 64x16 output tile: stage the (2*64+4) x (2*16+4) input tile in smem (coalesced rows),
+// horizontal pass into int16 smem, vertical pass to the output.
+constexpr int PD_TW = 64, PD_TH = 16;
+__global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict__ src, int sW, int sH, int spitch, size_t s_slot,
+                                                       uint8_t *__restrict__ dst, int dW, int dH, int dpitch, size_t d_slot,
+                                                       int first_slot) {
+    __shared__ uint8_t tile[2 * PD_TH + 4][2 * PD_TW + 4 + 4];
+    __shared__ uint16_t hsum[2 * PD_TH + 4][PD_TW];
+    const int slot = first_slot + blockIdx.z;
+    src += (size_t) slot * s_slot;
+    dst += (size_t) slot * d_slot;
+    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
+    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
+    const int tid = threadIdx.x;
+    constexpr int IW = 2 * PD_TW + 4, IH = 2 * PD_TH + 4;
+    for (int i = tid; i < IW * IH; i += 256) {
+        int r = i / IW, c = i - r * IW;
+        int y = reflect101(iy0 + r, sH), x = reflect101(ix0 + c, sW);
+        tile[r][c] = src[(size_t) y * spitch + x];
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * PD_TW; i += 256) {
+        int r = i / PD_TW, c = i - r * PD_TW;
+        const uint8_t *t = &tile[r][2 * c];
+        hsum[r][c] = (uint16_t) (t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
+    }
+    __syncthreads();
+    for (int i = tid; i < PD_TH * PD_TW; i += 256) {
+        int r = i / PD_TW, c = i - r * PD_TW;
+        int x = ox + c, y = oy + r;
+        if (x < dW && y < dH) {
+            int s = hsum[2 * r][c] + 4 * hsum[2 * r + 1][c] + 6 * hsum[2 * r + 2][c] + 4 * hsum[2 * r + 3][c] + hsum[2 * r + 4][c];
+            dst[(size_t) y * dpitch + x] = (uint8_t) ((s + 128) >> 8);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LK tracker
+struct WarpSmem {
+    uint8_t *iw;    // 32x32 template window (rows 0..23 used), origin (ipx-1, ipy-1)
+    uint8_t *jw;    // 32x32 search window
+    int *dv;        // 22x22 packed (Ix | Iy << 16)
+    uint64_t *bar;  // mbarrier
+    uint32_t phase;
+};
+
+__device__ __forceinline__ void window_fixup(uint8_t *w, int x0, int y0, int rows, const KltLevel &L, int slot, int lane) {
+    // TMA zero-fills outside the tensor; OpenCV's pyramid is reflect-101 padded: patch the out-of-image bytes.
+    if (x0 >= 0 && y0 >= 0 && x0 + KLT_BOX <= L.W && y0 + rows <= L.H) return;
+    const uint8_t *img = L.base + (size_t) slot * L.slot_stride;
+    for (int i = lane; i < KLT_BOX * rows; i += 32) {
+        int x = x0 + (i & 31), y = y0 + (i >> 5);
+        if (x < 0 || x >= L.W || y < 0 || y >= L.H) w[i] = img[(size_t) reflect101(y, L.H) * L.pitch + reflect101(x, L.W)];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11) {
+    iw00 = __float2int_rn((1.f - a) * (1.f - b) * 16384.f);
+    iw01 = __float2int_rn(a * (1.f - b) * 16384.f);
+    iw10 = __float2int_rn((1.f - a) * b * 16384.f);
+    iw11 = 16384 - iw00 - iw01 - iw10;
+}
+
+__device__ __forceinline__ long long warp_sum_exact(int v) {
+    // exact 64-bit sum of 32 int32 values with two REDUX instructions
+    int lo = v & 0xFFFF, hi = v >> 16;
+    int slo = __reduce_add_sync(0xffffffffu, lo);
+    int shi = __reduce_add_sync(0xffffffffu, hi);
+    return (long long) shi * 65536ll + (long long) slo;
+}
+
+// Track one point from image slot sI to image slot sJ through all levels.  All lanes hold identical scalars.
+__device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArgs &A, WarpSmem &S, int lane, int sI, int sJ,
+                                               float2 prev, float2 init, bool check_final, float2 &out, int &status,
+                                               float *err_out) {
+    // lane's template pixels: idx = lane + 32k -> (x, y) in the 21x21 window
+    int joff[KLT_PXL];
+#pragma unroll
+    for (int k = 0; k < KLT_PXL; k++) {
+        int idx = lane + 32 * k;
+        int y = (idx * 3121) >> 16, x = idx - 21 * y;
+        joff[k] = (idx < KLT_WIN * KLT_WIN) ? (y * KLT_BOX + x) : 0;  // dead slots (k = 13, lane >= 25) carry I = G = 0
+    }
+    const float half = 10.f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    status = 1;
+    float err_val = 0.f;
+    float2 nextPt = make_float2(0.f, 0.f);
+    const int maxLevel = A.n_levels - 1;
+
+    for (int level = maxLevel; level >= 0; level--) {
+        const KltLevel &L = A.lv[level];
+        const float scale = (float) (1. / (1 << level));
+        float px = prev.x * scale, py = prev.y * scale;
+        if (level == maxLevel) {
+            if (A.use_initial_flow) {
+                nextPt.x = init.x * scale;
+                nextPt.y = init.y * scale;
+            } else {
+                nextPt.x = px;
+                nextPt.y = py;
+            }
+        } else {
+            nextPt.x = nextPt.x * 2.f;
+            nextPt.y = nextPt.y * 2.f;
+        }
+        px -= half;
+        py -= half;
+        const int ipx = __float2int_rd(px), ipy = __float2int_rd(py);
+        if (ipx < -KLT_WIN || ipx >= L.W || ipy < -KLT_WIN || ipy >= L.H) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        float nx = nextPt.x - half, ny = nextPt.y - half;
+        int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+        const bool j_ok = !(inx < -KLT_WIN || inx >= L.W || iny < -KLT_WIN || iny >= L.H);
+        int jx0 = inx - KLT_MARGIN, jy0 = iny - KLT_MARGIN;
+
+        // ---- stage template window (+ first search window) with TMA
+        __syncwarp();
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(S.bar, j_ok ? 2 * KLT_BOX * KLT_BOX : KLT_BOX * KLT_BOX);
+            tma_load_3d(S.iw, &maps.m[level], ipx - 1, ipy - 1, sI, S.bar);
+            if (j_ok) tma_load_3d(S.jw, &maps.m[level], jx0, jy0, sJ, S.bar);
+        }
+        mbar_wait(S.bar, S.phase);
+        S.phase ^= 1;
+        window_fixup(S.iw, ipx - 1, ipy - 1, 24, L, sI, lane);
+        if (j_ok) window_fixup(S.jw, jx0, jy0, KLT_BOX, L, sJ, lane);
+
+        // ---- Scharr derivatives on the 22x22 tap grid (zero outside the image: OpenCV pads derivI with zeros)
+        for (int i = lane; i < 22 * 22; i += 32) {
+            int dy = i / 22, dx = i - dy * 22;
+            const uint8_t *r0 = S.iw + dy * KLT_BOX + dx;
+            const uint8_t *r1 = r0 + KLT_BOX, *r2 = r1 + KLT_BOX;
+            int t0m = 3 * (r0[0] + r2[0]) + 10 * r1[0];
+            int t0p = 3 * (r0[2] + r2[2]) + 10 * r1[2];
+            int t1m = r2[0] - r0[0], t1c = r2[1] - r0[1], t1p = r2[2] - r0[2];
+            int gx = t0p - t0m, gy = 3 * (t1m + t1p) + 10 * t1c;
+            int X = ipx + dx, Y = ipy + dy;
+            if (X < 0 || X >= L.W || Y < 0 || Y >= L.H) gx = gy = 0;
+            S.dv[i] = (gx & 0xFFFF) | (gy << 16);
+        }
+        __syncwarp();
+
+        // ---- template patch + structure tensor
+        float a = px - (float) ipx, b = py - (float) ipy;
+        int iw00, iw01, iw10, iw11;
+        bilinear_weights(a, b, iw00, iw01, iw10, iw11);
+        int Ireg[KLT_PXL], Greg[KLT_PXL];
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+        for (int k = 0; k < KLT_PXL; k++) {
+            if (lane + 32 * k < KLT_WIN * KLT_WIN) {
+                int idx = lane + 32 * k;
+                int y = (idx * 3121) >> 16, x = idx - 21 * y;
+                const uint8_t *s = S.iw + (y + 1) * KLT_BOX + x + 1;
+                int ival = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOX] * iw10 + s[KLT_BOX + 1] * iw11 + (1 << 8)) >> 9;
+                const int *d = S.dv + y * 22 + x;
+                int d00 = d[0], d01 = d[1], d10 = d[22], d11 = d[23];
+                int ixv = ((short) d00 * iw00 + (short) d01 * iw01 + (short) d10 * iw10 + (short) d11 * iw11 + (1 << 13)) >> 14;
+                int iyv = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
+                Ireg[k] = ival;
+                Greg[k] = (ixv & 0xFFFF) | (iyv << 16);
+                sA11 += ixv * ixv;
+                sA12 += ixv * iyv;
+                sA22 += iyv * iyv;
+            } else {
+                Ireg[k] = 0;
+                Greg[k] = 0;
+            }
+        }
+        // per-lane partials fit int32 (14 * 4080^2 < 2^28); the warp total needs 64 bits
+        const float A11 = (float) warp_sum_exact(sA11) * FLT_SCALE;
+        const float A12 = (float) warp_sum_exact(sA12) * FLT_SCALE;
+        const float A22 = (float) warp_sum_exact(sA22) * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float) (2 * KLT_WIN * KLT_WIN);
+        if ((double) minEig < A.min_eig_thr || D < 1.192092896e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = 1.f / D;
+
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < A.max_iter; j++) {
+            inx = __float2int_rd(nx);
+            iny = __float2int_rd(ny);
+            if (inx < -KLT_WIN || inx >= L.W || iny < -KLT_WIN || iny >= L.H) {
+                if (level == 0) status = 0;
+                break;
+            }
+            int ox = inx - jx0, oy = iny - jy0;
+            if (ox < 0 || ox > KLT_BOX - 22 || oy < 0 || oy > KLT_BOX - 22) {
+                // the track left the staged window: re-centre it
+                jx0 = inx - KLT_MARGIN;
+                jy0 = iny - KLT_MARGIN;
+                __syncwarp();
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(S.bar, KLT_BOX * KLT_BOX);
+                    tma_load_3d(S.jw, &maps.m[level], jx0, jy0, sJ, S.bar);
+                }
+                mbar_wait(S.bar, S.phase);
+                S.phase ^= 1;
+                window_fixup(S.jw, jx0, jy0, KLT_BOX, L, sJ, lane);
+                ox = oy = KLT_MARGIN;
+            }
+            a = nx - (float) inx;
+            b = ny - (float) iny;
+            bilinear_weights(a, b, iw00, iw01, iw10, iw11);
+            const uint8_t *jb = S.jw + oy * KLT_BOX + ox;
+            int sb1 = 0, sb2 = 0;
+#pragma unroll
+            for (int k = 0; k < KLT_PXL; k++) {
+                const uint8_t *s = jb + joff[k];
+                int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOX] * iw10 + s[KLT_BOX + 1] * iw11 + (1 << 8)) >> 9;
+                int diff = v - Ireg[k];
+                sb1 += diff * (int) (short) Greg[k];
+                sb2 += diff * (Greg[k] >> 16);
+            }
+            const float b1 = (float) warp_sum_exact(sb1) * FLT_SCALE;
+            const float b2 = (float) warp_sum_exact(sb2) * FLT_SCALE;
+            const float dx = (A12 * b2 - A22 * b1) * D;
+            const float dy = (A12 * b1 - A11 * b2) * D;
+            nx += dx;
+            ny += dy;
+            nextPt.x = nx + half;
+            nextPt.y = ny + half;
+            if ((double) dx * (double) dx + (double) dy * (double) dy <= A.eps2) break;
+            if (j > 0 && fabs((double) (dx + pdx)) < 0.01 && fabs((double) (dy + pdy)) < 0.01) {
+                nextPt.x -= dx * 0.5f;
+                nextPt.y -= dy * 0.5f;
+                break;
+            }
+            pdx = dx;
+            pdy = dy;
+        }
+
+        if (level == 0 && status && check_final) {
+            // lkpyramid.cpp level-0 epilogue: the final window origin must still be inside [-win, cols) x [-win, rows)
+            float fx = nextPt.x - half, fy = nextPt.y - half;
+            int fix = __float2int_rd(fx), fiy = __float2int_rd(fy);
+            if (fix < -KLT_WIN || fix >= L.W || fiy < -KLT_WIN || fiy >= L.H) {
+                status = 0;
+            } else if (err_out != nullptr) {
+                int ox = fix - jx0, oy = fiy - jy0;
+                if (ox < 0 || ox > KLT_BOX - 22 || oy < 0 || oy > KLT_BOX - 22) {
+                    jx0 = fix - KLT_MARGIN;
+                    jy0 = fiy - KLT_MARGIN;
+                    __syncwarp();
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(S.bar, KLT_BOX * KLT_BOX);
+                        tma_load_3d(S.jw, &maps.m[level], jx0, jy0, sJ, S.bar);
+                    }
+                    mbar_wait(S.bar, S.phase);
+                    S.phase ^= 1;
+                    window_fixup(S.jw, jx0, jy0, KLT_BOX, L, sJ, lane);
+                    ox = oy = KLT_MARGIN;
+                }
+                a = fx - (float) fix;
+                b = fy - (float) fiy;
+                bilinear_weights(a, b, iw00, iw01, iw10, iw11);
+                const uint8_t *jb = S.jw + oy * KLT_BOX + ox;
+                int se = 0;
+#pragma unroll
+                for (int k = 0; k < KLT_PXL; k++) {
+                    if (lane + 32 * k < KLT_WIN * KLT_WIN) {
+                        const uint8_t *s = jb + joff[k];
+                        int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOX] * iw10 + s[KLT_BOX + 1] * iw11 + (1 << 8)) >> 9;
+                        se += abs(v - Ireg[k]);
+                    }
+                }
+                err_val = (float) warp_sum_exact(se) * 1.f / (float) (32 * KLT_WIN * KLT_WIN);
+            }
+        }
+    }
+    out = nextPt;
+    if (err_out != nullptr) *err_out = status ? err_val : 0.f;
+}
+
+__global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid_constant__ KltMaps maps, const KltArgs A) {
+    __shared__ __align__(128) uint8_t s_win[KLT_WPB][2][KLT_BOX * KLT_BOX];
+    __shared__ int s_dv[KLT_WPB][22 * 22];
+    __shared__ __align__(8) uint64_t s_bar[KLT_WPB];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int task = blockIdx.x * KLT_WPB + warp;
+    if (lane == 0) {
+        mbar_init(&s_bar[warp], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (task >= A.n_total) return;
+
+    WarpSmem S;
+    S.iw    = s_win[warp][0];
+    S.jw    = s_win[warp][1];
+    S.dv    = s_dv[warp];
+    S.bar   = &s_bar[warp];
+    S.phase = 0;
+
+    const int sP = A.slots[2 * task], sN = A.slots[2 * task + 1];
+    const float2 prev = A.prev_xy[task];
+    const float2 init = A.init_xy[task];
+
+    // direction 0: forward (prev slot -> next slot); direction 1 (mode 1 only): backward with
+    // prevPts = forward result and initial flow = the original points (IG/tracking/tracking.cc:390-393).
+    float2 fwd = make_float2(0.f, 0.f), bwd = make_float2(0.f, 0.f);
+    int st = 0, st2 = 0;
+    float err_v = 0.f;
+    const int ndir = A.mode == 0 ? 1 : 2;
+#pragma unroll 1
+    for (int dir = 0; dir < ndir; dir++) {
+        float2 o;
+        int s;
+        lk_track_point(maps, A, S, lane, dir == 0 ? sP : sN, dir == 0 ? sN : sP, dir == 0 ? prev : fwd, dir == 0 ? init : prev,
+                       dir == 0 ? (A.check_final != 0) : true, o, s, (dir == 0 && A.err) ? &err_v : nullptr);
+        if (dir == 0) {
+            fwd = o;
+            st  = s;
+        } else {
+            bwd = o;
+            st2 = s;
+        }
+    }
+    if (lane != 0) return;
+    if (A.mode == 0) {
+        A.fwd_xy[task] = fwd;
+        A.status[task] = (uint8_t) st;
+        if (A.err) A.err[task] = err_v;
+        return;
+    }
+    // gates (tracking.cc:396-403): isOnBorder (tracking.cc:847-849, double compare) and ptsDistance (841-845)
+    bool on_border = (double) fwd.x < 5.0 || (double) fwd.y < 5.0 || (double) fwd.x > ((double) A.img_w - 5.0) ||
+                     (double) fwd.y > ((double) A.img_h - 5.0);
+    double ddx = (double) (bwd.x - prev.x), ddy = (double) (bwd.y - prev.y);
+    double dist = sqrt(ddx * ddx + ddy * ddy);
+    A.fwd_xy[task] = fwd;
+    if (A.bwd_xy) A.bwd_xy[task] = bwd;
+    A.status[task] = (uint8_t) ((st && st2 && !on_border && dist < 0.5) ? 1 : 0);
+}
+
+}  // namespace icg
+
+// ======================================================================================================= C ABI
+using namespace icg;
+
+struct icg_klt {
+    int W, H, n_slots, max_pts, device;
+    cudaStream_t stream;
+    bool own_stream;
+    KltLevel lv[KLT_LEVELS];
+    uint8_t *planes[KLT_LEVELS];
+    KltMaps maps;
+    // device scratch for the host-pointer API
+    int32_t *d_slots;
+    float *d_prev, *d_init, *d_fwd, *d_bwd, *d_err;
+    uint8_t *d_status;
+    // pinned staging
+    uint8_t *h_stage;
+    size_t h_stage_bytes;
+    // content-addressed cache for the host-pointer API: hash -> slot
+    std::vector<uint64_t> slot_hash;
+    std::vector<uint64_t> slot_age;
+    uint64_t age;
+};
+
+static uint64_t hash_image(const uint8_t *p, int W, int H, int stride) {
+    // 64-bit multiply-fold hash over the full image (a false cache hit would be a correctness bug)
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ ((uint64_t) W << 32) ^ (uint64_t) H;
+    for (int y = 0; y < H; y++) {
+        const uint8_t *r = p + (size_t) y * stride;
+        int x = 0;
+        for (; x + 8 <= W; x += 8) {
+            uint64_t v;
+            memcpy(&v, r + x, 8);
+            h = (h ^ v) * 0xFF51AFD7ED558CCDull;
+            h ^= h >> 29;
+        }
+        for (; x < W; x++) {
+            h = (h ^ r[x]) * 0xC4CEB9FE1A85EC53ull;
+            h ^= h >> 31;
+        }
+    }
+    return h ? h : 1;
+}
+
+extern "C" {
+
+int icg_klt_create(icg_klt **out, int width, int height, int n_slots, int max_points, int device, void *stream) {
+    if (!out || width < 32 || height < 32 || n_slots < 2 || max_points < 1) {
+        set_error("icg_klt_create: bad arguments");
+        return ICG_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        set_error("icg_klt_create: no CUDA device (this library has no CPU fallback)");
+        return ICG_ENODEVICE;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("icg_klt_create: device %d out of range (%d devices)", device, ndev);
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ICG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("icg_klt_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+        return ICG_ENODEVICE;
+    }
+    icg_klt *h = new icg_klt();
+    h->W = width;
+    h->H = height;
+    h->n_slots = n_slots;
+    h->max_pts = max_points;
+    h->device = device;
+    h->own_stream = (stream == nullptr);
+    if (stream)
+        h->stream = (cudaStream_t) stream;
+    else
+        ICG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    int w = width, hh = height;
+    for (int l = 0; l < KLT_LEVELS; l++) {
+        if (l > 0) {
+            w = (w + 1) / 2;
+            hh = (hh + 1) / 2;
+        }
+        int pitch = (w + 15) & ~15;
+        size_t slot_stride = (size_t) pitch * hh;
+        ICG_CUDA(cudaMalloc(&h->planes[l], slot_stride * n_slots));
+        ICG_CUDA(cudaMemsetAsync(h->planes[l], 0, slot_stride * n_slots, h->stream));
+        h->lv[l] = KltLevel{h->planes[l], w, hh, pitch, slot_stride};
+        int rc = encode_tensor_map_u8_3d(&h->maps.m[l], h->planes[l], (uint64_t) w, (uint64_t) hh, (uint64_t) n_slots, (uint64_t) pitch,
+                                         (uint64_t) slot_stride, KLT_BOX, KLT_BOX, 1);
+        if (rc != ICG_OK) return rc;
+    }
+    ICG_CUDA(cudaMalloc(&h->d_slots, sizeof(int32_t) * 2 * max_points));
+    ICG_CUDA(cudaMalloc(&h->d_prev, sizeof(float) * 2 * max_points));
+    ICG_CUDA(cudaMalloc(&h->d_init, sizeof(float) * 2 * max_points));
+    ICG_CUDA(cudaMalloc(&h->d_fwd, sizeof(float) * 2 * max_points));
+    ICG_CUDA(cudaMalloc(&h->d_bwd, sizeof(float) * 2 * max_points));
+    ICG_CUDA(cudaMalloc(&h->d_err, sizeof(float) * max_points));
+    ICG_CUDA(cudaMalloc(&h->d_status, max_points));
+    h->h_stage_bytes = (size_t) max_points * (2 * 4 + 8 * 4 + 4 + 1) + 64;
+    ICG_CUDA(cudaMallocHost(&h->h_stage, h->h_stage_bytes));
+    h->slot_hash.assign(n_slots, 0);
+    h->slot_age.assign(n_slots, 0);
+    h->age = 0;
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return ICG_OK;
+}
+
+void icg_klt_destroy(icg_klt *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int l = 0; l < KLT_LEVELS; l++) cudaFree(h->planes[l]);
+    cudaFree(h->d_slots);
+    cudaFree(h->d_prev);
+    cudaFree(h->d_init);
+    cudaFree(h->d_fwd);
+    cudaFree(h->d_bwd);
+    cudaFree(h->d_err);
+    cudaFree(h->d_status);
+    cudaFreeHost(h->h_stage);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int icg_klt_slot_level(icg_klt *h, int slot, int level, void **dev_ptr, int *pitch, int *w, int *hgt) {
+    if (!h || slot < 0 || slot >= h->n_slots || level < 0 || level >= KLT_LEVELS) {
+        set_error("icg_klt_slot_level: bad arguments");
+        return ICG_EINVAL;
+    }
+    if (dev_ptr) *dev_ptr = h->planes[level] + (size_t) slot * h->lv[level].slot_stride;
+    if (pitch) *pitch = h->lv[level].pitch;
+    if (w) *w = h->lv[level].W;
+    if (hgt) *hgt = h->lv[level].H;
+    return ICG_OK;
+}
+
+int icg_klt_slot_level0(icg_klt *h, int slot, void **dev_ptr, int *pitch) { return icg_klt_slot_level(h, slot, 0, dev_ptr, pitch, nullptr, nullptr); }
+
+int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
+    if (!h || first_slot < 0 || count < 1 || first_slot + count > h->n_slots) {
+        set_error("icg_klt_build_pyramids: bad slot range");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    for (int l = 1; l < KLT_LEVELS; l++) {
+        const KltLevel &s = h->lv[l - 1], &d = h->lv[l];
+        dim3 grid((d.W + PD_TW - 1) / PD_TW, (d.H + PD_TH - 1) / PD_TH, count);
+        pyr_down_kernel<<<grid, 256, 0, h->stream>>>(s.base, s.W, s.H, s.pitch, s.slot_stride, h->planes[l], d.W, d.H, d.pitch,
+                                                     d.slot_stride, first_slot);
+        ICG_CHECK_LAUNCH();
+        count_launch();
+    }
+    return ICG_OK;
+}
+
+int icg_klt_upload_level0(icg_klt *h, int slot, const uint8_t *host_img, int stride) {
+    if (!h || !host_img || slot < 0 || slot >= h->n_slots || stride < h->W) {
+        set_error("icg_klt_upload: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    ICG_CUDA(cudaMemcpy2DAsync(h->planes[0] + (size_t) slot * h->lv[0].slot_stride, h->lv[0].pitch, host_img, stride, h->W, h->H,
+                               cudaMemcpyHostToDevice, h->stream));
+    h->slot_hash[slot] = 0;
+    return ICG_OK;
+}
+
+int icg_klt_upload(icg_klt *h, int slot, const uint8_t *host_img, int stride) {
+    int rc = icg_klt_upload_level0(h, slot, host_img, stride);
+    if (rc != ICG_OK) return rc;
+    return icg_klt_build_pyramids(h, slot, 1);
+}
+
+int icg_klt_download_level(icg_klt *h, int slot, int level, uint8_t *host_img, int stride) {
+    if (!h || !host_img || slot < 0 || slot >= h->n_slots || level < 0 || level >= KLT_LEVELS || stride < h->lv[level].W) {
+        set_error("icg_klt_download_level: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    const KltLevel &L = h->lv[level];
+    ICG_CUDA(cudaMemcpy2DAsync(host_img, stride, h->planes[level] + (size_t) slot * L.slot_stride, L.pitch, L.W, L.H,
+                               cudaMemcpyDeviceToHost, h->stream));
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    return ICG_OK;
+}
+
+static int launch_track(icg_klt *h, int n_total, const int32_t *d_slots, const float *d_prev, const float *d_init, float *d_fwd,
+                        float *d_bwd, uint8_t *d_status, float *d_err, int mode, int n_levels, int max_iter, double eps, int flags,
+                        int check_final) {
+    KltArgs A;
+    for (int l = 0; l < KLT_LEVELS; l++) A.lv[l] = h->lv[l];
+    A.n_total = n_total;
+    A.n_levels = n_levels;
+    if (max_iter < 0) max_iter = 0;
+    if (max_iter > 100) max_iter = 100;
+    if (eps < 0) eps = 0;
+    if (eps > 10) eps = 10;
+    A.max_iter = max_iter;
+    A.mode = mode;
+    A.use_initial_flow = (flags & ICG_OPTFLOW_USE_INITIAL_FLOW) ? 1 : 0;
+    A.check_final = check_final;
+    A.eps2 = eps * eps;
+    A.min_eig_thr = 1e-4;
+    A.img_w = (float) h->W;
+    A.img_h = (float) h->H;
+    A.slots = d_slots;
+    A.prev_xy = (const float2 *) d_prev;
+    A.init_xy = (const float2 *) d_init;
+    A.fwd_xy = (float2 *) d_fwd;
+    A.bwd_xy = (float2 *) d_bwd;
+    A.status = d_status;
+    A.err = d_err;
+    int grid = (n_total + KLT_WPB - 1) / KLT_WPB;
+    klt_track_kernel<<<grid, KLT_WPB * 32, 0, h->stream>>>(h->maps, A);
+    ICG_CHECK_LAUNCH();
+    count_launch();
+    return ICG_OK;
+}
+
+int icg_klt_track_batch_dev(icg_klt *h, int n_total, const int32_t *dev_slots, const float *dev_prev_xy, const float *dev_init_xy,
+                            float *dev_fwd_xy, float *dev_bwd_xy, uint8_t *dev_status, int mode) {
+    if (!h || n_total < 0 || !dev_slots || !dev_prev_xy || !dev_init_xy || !dev_fwd_xy || !dev_status || (mode != 0 && mode != 1)) {
+        set_error("icg_klt_track_batch_dev: bad arguments");
+        return ICG_EINVAL;
+    }
+    if (n_total == 0) return ICG_OK;
+    ICG_CUDA(cudaSetDevice(h->device));
+    // reference parameters (IG/tracking/tracking.cc:385-393): maxLevel 3, (COUNT+EPS, 30, 0.01), USE_INITIAL_FLOW, err requested
+    return launch_track(h, n_total, dev_slots, dev_prev_xy, dev_init_xy, dev_fwd_xy, dev_bwd_xy, dev_status, nullptr, mode, KLT_LEVELS,
+                        30, 0.01, ICG_OPTFLOW_USE_INITIAL_FLOW, 1);
+}
+
+int icg_klt_sync(icg_klt *h) {
+    if (!h) return ICG_EINVAL;
+    ICG_CUDA(cudaSetDevice(h->device));
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    return ICG_OK;
+}
+
+// find (or create) the slot holding this host image; never evicts `keep`
+static int slot_for_image(icg_klt *h, const uint8_t *img, int stride, int keep, int *slot_out) {
+    uint64_t hv = hash_image(img, h->W, h->H, stride);
+    h->age++;
+    int victim = -1;
+    uint64_t oldest = ~0ull;
+    for (int s = 0; s < h->n_slots; s++) {
+        if (h->slot_hash[s] == hv) {
+            h->slot_age[s] = h->age;
+            *slot_out = s;
+            return ICG_OK;
+        }
+        if (s != keep && h->slot_age[s] < oldest) {
+            oldest = h->slot_age[s];
+            victim = s;
+        }
+    }
+    int rc = icg_klt_upload(h, victim, img, stride);
+    if (rc != ICG_OK) return rc;
+    h->slot_hash[victim] = hv;
+    h->slot_age[victim] = h->age;
+    *slot_out = victim;
+    return ICG_OK;
+}
+
+static int host_track(icg_klt *h, const uint8_t *prev, const uint8_t *next, int stride, const float *prev_xy, float *next_xy,
+                      float *back_xy, uint8_t *status, float *err, int n, int mode, int n_levels, int max_iter, double eps, int flags) {
+    if (!h || !prev || !next || !prev_xy || !next_xy || !status || n < 0 || stride < h->W) {
+        set_error("klt host call: bad arguments");
+        return ICG_EINVAL;
+    }
+    if (n > h->max_pts) {
+        set_error("klt host call: n=%d exceeds max_points=%d of the handle", n, h->max_pts);
+        return ICG_EINVAL;
+    }
+    if (n == 0) return ICG_OK;
+    ICG_CUDA(cudaSetDevice(h->device));
+    int sp, sn;
+    int rc = slot_for_image(h, prev, stride, -1, &sp);
+    if (rc != ICG_OK) return rc;
+    rc = slot_for_image(h, next, stride, sp, &sn);
+    if (rc != ICG_OK) return rc;
+    // pack inputs into the pinned stage: [slots int2*n][prev float2*n][init float2*n]
+    int32_t *hs = (int32_t *) h->h_stage;
+    float *hp = (float *) (hs + 2 * n);
+    float *hi = hp + 2 * n;
+    for (int k = 0; k < n; k++) {
+        hs[2 * k] = sp;
+        hs[2 * k + 1] = sn;
+    }
+    memcpy(hp, prev_xy, sizeof(float) * 2 * n);
+    if (flags & ICG_OPTFLOW_USE_INITIAL_FLOW)
+        memcpy(hi, next_xy, sizeof(float) * 2 * n);
+    else
+        memcpy(hi, prev_xy, sizeof(float) * 2 * n);
+    ICG_CUDA(cudaMemcpyAsync(h->d_slots, hs, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    ICG_CUDA(cudaMemcpyAsync(h->d_prev, hp, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    ICG_CUDA(cudaMemcpyAsync(h->d_init, hi, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, h->stream));
+    rc = launch_track(h, n, h->d_slots, h->d_prev, h->d_init, h->d_fwd, h->d_bwd, h->d_status, (err && mode == 0) ? h->d_err : nullptr, mode,
+                      n_levels, max_iter, eps, flags, (mode == 1 || err != nullptr) ? 1 : 0);
+    if (rc != ICG_OK) return rc;
+    float *of = (float *) h->h_stage;
+    float *ob = of + 2 * n;
+    float *oe = ob + 2 * n;
+    uint8_t *os = (uint8_t *) (oe + n);
+    ICG_CUDA(cudaMemcpyAsync(of, h->d_fwd, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (mode == 1) ICG_CUDA(cudaMemcpyAsync(ob, h->d_bwd, sizeof(float) * 2 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (err && mode == 0) ICG_CUDA(cudaMemcpyAsync(oe, h->d_err, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    ICG_CUDA(cudaMemcpyAsync(os, h->d_status, n, cudaMemcpyDeviceToHost, h->stream));
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(next_xy, of, sizeof(float) * 2 * n);
+    if (mode == 1 && back_xy) memcpy(back_xy, ob, sizeof(float) * 2 * n);
+    if (err) {
+        if (mode == 0)
+            memcpy(err, oe, sizeof(float) * n);
+        else
+            memset(err, 0, sizeof(float) * n);
+    }
+    memcpy(status, os, n);
+    return ICG_OK;
+}
+
+int icg_klt_calc_optical_flow_pyr_lk(icg_klt *h, const uint8_t *prev, const uint8_t *next, int stride, const float *prev_xy,
+                                     float *next_xy, uint8_t *status, float *err, int n, int win, int max_level, int max_iter,
+                                     double eps, int flags) {
+    if (win != KLT_WIN || max_level < 0 || max_level > KLT_LEVELS - 1) {
+        set_error("calcOpticalFlowPyrLK: only winSize 21 and maxLevel 0..3 are built (got win=%d maxLevel=%d)", win, max_level);
+        return ICG_EUNSUPPORTED;
+    }
+    if (!h) return ICG_EINVAL;
+    // cv::buildOpticalFlowPyramid stops at the first level that is not larger than the window
+    int n_levels = 1;
+    for (int l = 1; l <= max_level; l++) {
+        if (h->lv[l].W <= KLT_WIN || h->lv[l].H <= KLT_WIN) break;
+        n_levels++;
+    }
+    return host_track(h, prev, next, stride, prev_xy, next_xy, nullptr, status, err, n, 0, n_levels, max_iter, eps, flags);
+}
+
+int icg_klt_track_fb(icg_klt *h, const uint8_t *prev, const uint8_t *next, int stride, const float *prev_xy, float *next_xy,
+                     float *back_xy, uint8_t *status, int n) {
+    if (!h) return ICG_EINVAL;
+    int n_levels = 1;
+    for (int l = 1; l < KLT_LEVELS; l++) {
+        if (h->lv[l].W <= KLT_WIN || h->lv[l].H <= KLT_WIN) break;
+        n_levels++;
+    }
+    return host_track(h, prev, next, stride, prev_xy, next_xy, back_xy, status, nullptr, n, 1, n_levels, 30, 0.01,
+                      ICG_OPTFLOW_USE_INITIAL_FLOW);
+}
+
+}  // extern "C"
