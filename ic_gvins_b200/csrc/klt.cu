@@ -24,8 +24,12 @@ namespace icg {
 
 constexpr int KLT_WIN     = 21;
 constexpr int KLT_LEVELS  = 4;  // maxLevel 3 (IG/tracking/tracking.h:113)
-constexpr int KLT_BOX     = 32; // TMA box edge (bytes / rows)
-constexpr int KLT_MARGIN  = 5;  // search window slack on each side: 32 - 22 = 10
+constexpr int KLT_BOXW    = 48; // TMA box width in bytes: the innermost TMA coordinate must be 16-byte aligned
+                                // (measured: UTMALDG raises "illegal instruction" otherwise), so windows start at
+                                // x & ~15 and over-fetch: 15 + 24 <= 48
+constexpr int KLT_BOXH_J  = 32; // search-window rows (22 needed + 10 slack)
+constexpr int KLT_BOXH_I  = 24; // template-window rows (21 + 1 bilinear + 2 Scharr)
+constexpr int KLT_MARGIN  = 5;  // search window slack kept on the low side when (re-)centring
 constexpr int KLT_WPB     = 4;  // warps per block
 constexpr int KLT_PXL     = 14; // template pixels per lane: ceil(441 / 32)
 
@@ -36,7 +40,8 @@ struct KltLevel {
 };
 
 struct KltMaps {
-    CUtensorMap m[KLT_LEVELS];
+    CUtensorMap mj[KLT_LEVELS];  // box 48 x 32 x 1 (search window)
+    CUtensorMap mi[KLT_LEVELS];  // box 48 x 24 x 1 (template window)
 };
 
 struct KltArgs {
@@ -106,8 +111,8 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
 
 // ------------------------------------------------------------------------------------------------ LK tracker
 struct WarpSmem {
-    uint8_t *iw;    // 32x32 template window (rows 0..23 used), origin (ipx-1, ipy-1)
-    uint8_t *jw;    // 32x32 search window
+    uint8_t *iw;    // 48x24 template window, origin ((ipx-1) & ~15, ipy-1)
+    uint8_t *jw;    // 48x32 search window, origin (jx0 (16-aligned), jy0)
     int *dv;        // 22x22 packed (Ix | Iy << 16)
     uint64_t *bar;  // mbarrier
     uint32_t phase;
@@ -115,10 +120,11 @@ struct WarpSmem {
 
 __device__ __forceinline__ void window_fixup(uint8_t *w, int x0, int y0, int rows, const KltLevel &L, int slot, int lane) {
     // TMA zero-fills outside the tensor; OpenCV's pyramid is reflect-101 padded: patch the out-of-image bytes.
-    if (x0 >= 0 && y0 >= 0 && x0 + KLT_BOX <= L.W && y0 + rows <= L.H) return;
+    if (x0 >= 0 && y0 >= 0 && x0 + KLT_BOXW <= L.W && y0 + rows <= L.H) return;
     const uint8_t *img = L.base + (size_t) slot * L.slot_stride;
-    for (int i = lane; i < KLT_BOX * rows; i += 32) {
-        int x = x0 + (i & 31), y = y0 + (i >> 5);
+    for (int i = lane; i < KLT_BOXW * rows; i += 32) {
+        int r = i / KLT_BOXW, c = i - r * KLT_BOXW;
+        int x = x0 + c, y = y0 + r;
         if (x < 0 || x >= L.W || y < 0 || y >= L.H) w[i] = img[(size_t) reflect101(y, L.H) * L.pitch + reflect101(x, L.W)];
     }
     __syncwarp();
@@ -149,7 +155,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
     for (int k = 0; k < KLT_PXL; k++) {
         int idx = lane + 32 * k;
         int y = (idx * 3121) >> 16, x = idx - 21 * y;
-        joff[k] = (idx < KLT_WIN * KLT_WIN) ? (y * KLT_BOX + x) : 0;  // dead slots (k = 13, lane >= 25) carry I = G = 0
+        joff[k] = (idx < KLT_WIN * KLT_WIN) ? (y * KLT_BOXW + x) : 0;  // dead slots (k = 13, lane >= 25) carry I = G = 0
     }
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
@@ -184,26 +190,28 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         float nx = nextPt.x - half, ny = nextPt.y - half;
         int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
         const bool j_ok = !(inx < -KLT_WIN || inx >= L.W || iny < -KLT_WIN || iny >= L.H);
-        int jx0 = inx - KLT_MARGIN, jy0 = iny - KLT_MARGIN;
+        int jx0 = (inx - KLT_MARGIN) & ~15, jy0 = iny - KLT_MARGIN;
+        const int ix0 = (ipx - 1) & ~15;   // 16-byte aligned TMA x origin of the template window
+        const int oxI = ipx - 1 - ix0;     // 0..15
 
         // ---- stage template window (+ first search window) with TMA
         __syncwarp();
         if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(S.bar, j_ok ? 2 * KLT_BOX * KLT_BOX : KLT_BOX * KLT_BOX);
-            tma_load_3d(S.iw, &maps.m[level], ipx - 1, ipy - 1, sI, S.bar);
-            if (j_ok) tma_load_3d(S.jw, &maps.m[level], jx0, jy0, sJ, S.bar);
+            mbar_expect_tx(S.bar, KLT_BOXW * KLT_BOXH_I + (j_ok ? KLT_BOXW * KLT_BOXH_J : 0));
+            tma_load_3d(S.iw, &maps.mi[level], ix0, ipy - 1, sI, S.bar);
+            if (j_ok) tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar);
         }
         mbar_wait(S.bar, S.phase);
         S.phase ^= 1;
-        window_fixup(S.iw, ipx - 1, ipy - 1, 24, L, sI, lane);
-        if (j_ok) window_fixup(S.jw, jx0, jy0, KLT_BOX, L, sJ, lane);
+        window_fixup(S.iw, ix0, ipy - 1, KLT_BOXH_I, L, sI, lane);
+        if (j_ok) window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
 
         // ---- Scharr derivatives on the 22x22 tap grid (zero outside the image: OpenCV pads derivI with zeros)
         for (int i = lane; i < 22 * 22; i += 32) {
             int dy = i / 22, dx = i - dy * 22;
-            const uint8_t *r0 = S.iw + dy * KLT_BOX + dx;
-            const uint8_t *r1 = r0 + KLT_BOX, *r2 = r1 + KLT_BOX;
+            const uint8_t *r0 = S.iw + dy * KLT_BOXW + dx + oxI;
+            const uint8_t *r1 = r0 + KLT_BOXW, *r2 = r1 + KLT_BOXW;
             int t0m = 3 * (r0[0] + r2[0]) + 10 * r1[0];
             int t0p = 3 * (r0[2] + r2[2]) + 10 * r1[2];
             int t1m = r2[0] - r0[0], t1c = r2[1] - r0[1], t1p = r2[2] - r0[2];
@@ -225,8 +233,8 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             if (lane + 32 * k < KLT_WIN * KLT_WIN) {
                 int idx = lane + 32 * k;
                 int y = (idx * 3121) >> 16, x = idx - 21 * y;
-                const uint8_t *s = S.iw + (y + 1) * KLT_BOX + x + 1;
-                int ival = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOX] * iw10 + s[KLT_BOX + 1] * iw11 + (1 << 8)) >> 9;
+                const uint8_t *s = S.iw + (y + 1) * KLT_BOXW + x + 1 + oxI;
+                int ival = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
                 const int *d = S.dv + y * 22 + x;
                 int d00 = d[0], d01 = d[1], d10 = d[22], d11 = d[23];
                 int ixv = ((short) d00 * iw00 + (short) d01 * iw01 + (short) d10 * iw10 + (short) d11 * iw11 + (1 << 13)) >> 14;
@@ -262,30 +270,31 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 break;
             }
             int ox = inx - jx0, oy = iny - jy0;
-            if (ox < 0 || ox > KLT_BOX - 22 || oy < 0 || oy > KLT_BOX - 22) {
+            if (ox < 0 || ox > KLT_BOXW - 22 || oy < 0 || oy > KLT_BOXH_J - 22) {
                 // the track left the staged window: re-centre it
-                jx0 = inx - KLT_MARGIN;
+                jx0 = (inx - KLT_MARGIN) & ~15;
                 jy0 = iny - KLT_MARGIN;
                 __syncwarp();
                 if (lane == 0) {
                     fence_proxy_async();
-                    mbar_expect_tx(S.bar, KLT_BOX * KLT_BOX);
-                    tma_load_3d(S.jw, &maps.m[level], jx0, jy0, sJ, S.bar);
+                    mbar_expect_tx(S.bar, KLT_BOXW * KLT_BOXH_J);
+                    tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar);
                 }
                 mbar_wait(S.bar, S.phase);
                 S.phase ^= 1;
-                window_fixup(S.jw, jx0, jy0, KLT_BOX, L, sJ, lane);
-                ox = oy = KLT_MARGIN;
+                window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
+                ox = inx - jx0;
+                oy = KLT_MARGIN;
             }
             a = nx - (float) inx;
             b = ny - (float) iny;
             bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-            const uint8_t *jb = S.jw + oy * KLT_BOX + ox;
+            const uint8_t *jb = S.jw + oy * KLT_BOXW + ox;
             int sb1 = 0, sb2 = 0;
 #pragma unroll
             for (int k = 0; k < KLT_PXL; k++) {
                 const uint8_t *s = jb + joff[k];
-                int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOX] * iw10 + s[KLT_BOX + 1] * iw11 + (1 << 8)) >> 9;
+                int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
                 int diff = v - Ireg[k];
                 sb1 += diff * (int) (short) Greg[k];
                 sb2 += diff * (Greg[k] >> 16);
@@ -316,30 +325,31 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 status = 0;
             } else if (err_out != nullptr) {
                 int ox = fix - jx0, oy = fiy - jy0;
-                if (ox < 0 || ox > KLT_BOX - 22 || oy < 0 || oy > KLT_BOX - 22) {
-                    jx0 = fix - KLT_MARGIN;
+                if (ox < 0 || ox > KLT_BOXW - 22 || oy < 0 || oy > KLT_BOXH_J - 22) {
+                    jx0 = (fix - KLT_MARGIN) & ~15;
                     jy0 = fiy - KLT_MARGIN;
                     __syncwarp();
                     if (lane == 0) {
                         fence_proxy_async();
-                        mbar_expect_tx(S.bar, KLT_BOX * KLT_BOX);
-                        tma_load_3d(S.jw, &maps.m[level], jx0, jy0, sJ, S.bar);
+                        mbar_expect_tx(S.bar, KLT_BOXW * KLT_BOXH_J);
+                        tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar);
                     }
                     mbar_wait(S.bar, S.phase);
                     S.phase ^= 1;
-                    window_fixup(S.jw, jx0, jy0, KLT_BOX, L, sJ, lane);
-                    ox = oy = KLT_MARGIN;
+                    window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
+                    ox = fix - jx0;
+                    oy = KLT_MARGIN;
                 }
                 a = fx - (float) fix;
                 b = fy - (float) fiy;
                 bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-                const uint8_t *jb = S.jw + oy * KLT_BOX + ox;
+                const uint8_t *jb = S.jw + oy * KLT_BOXW + ox;
                 int se = 0;
 #pragma unroll
                 for (int k = 0; k < KLT_PXL; k++) {
                     if (lane + 32 * k < KLT_WIN * KLT_WIN) {
                         const uint8_t *s = jb + joff[k];
-                        int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOX] * iw10 + s[KLT_BOX + 1] * iw11 + (1 << 8)) >> 9;
+                        int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
                         se += abs(v - Ireg[k]);
                     }
                 }
@@ -352,7 +362,8 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
 }
 
 __global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid_constant__ KltMaps maps, const KltArgs A) {
-    __shared__ __align__(128) uint8_t s_win[KLT_WPB][2][KLT_BOX * KLT_BOX];
+    __shared__ __align__(128) uint8_t s_iw[KLT_WPB][KLT_BOXW * KLT_BOXH_I];
+    __shared__ __align__(128) uint8_t s_jw[KLT_WPB][KLT_BOXW * KLT_BOXH_J];
     __shared__ int s_dv[KLT_WPB][22 * 22];
     __shared__ __align__(8) uint64_t s_bar[KLT_WPB];
 
@@ -366,8 +377,8 @@ __global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid
     if (task >= A.n_total) return;
 
     WarpSmem S;
-    S.iw    = s_win[warp][0];
-    S.jw    = s_win[warp][1];
+    S.iw    = s_iw[warp];
+    S.jw    = s_jw[warp];
     S.dv    = s_dv[warp];
     S.bar   = &s_bar[warp];
     S.phase = 0;
@@ -503,8 +514,11 @@ int icg_klt_create(icg_klt **out, int width, int height, int n_slots, int max_po
         ICG_CUDA(cudaMalloc(&h->planes[l], slot_stride * n_slots));
         ICG_CUDA(cudaMemsetAsync(h->planes[l], 0, slot_stride * n_slots, h->stream));
         h->lv[l] = KltLevel{h->planes[l], w, hh, pitch, slot_stride};
-        int rc = encode_tensor_map_u8_3d(&h->maps.m[l], h->planes[l], (uint64_t) w, (uint64_t) hh, (uint64_t) n_slots, (uint64_t) pitch,
-                                         (uint64_t) slot_stride, KLT_BOX, KLT_BOX, 1);
+        int rc = encode_tensor_map_u8_3d(&h->maps.mj[l], h->planes[l], (uint64_t) w, (uint64_t) hh, (uint64_t) n_slots, (uint64_t) pitch,
+                                         (uint64_t) slot_stride, KLT_BOXW, KLT_BOXH_J, 1);
+        if (rc != ICG_OK) return rc;
+        rc = encode_tensor_map_u8_3d(&h->maps.mi[l], h->planes[l], (uint64_t) w, (uint64_t) hh, (uint64_t) n_slots, (uint64_t) pitch,
+                                     (uint64_t) slot_stride, KLT_BOXW, KLT_BOXH_I, 1);
         if (rc != ICG_OK) return rc;
     }
     ICG_CUDA(cudaMalloc(&h->d_slots, sizeof(int32_t) * 2 * max_points));
