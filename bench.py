@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the IC-GVINS hot paths on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank / GPU)
+    python bench.py --impl reference ...                     (the reference's CPU path: cv2 LK + the BA oracle port)
+
+A "step" = one frame of every one of B independent 1280x560 synthetic streams resident on this GPU:
+pyramid build (levels 1..3) of the B new frames + fused forward/backward KLT of 300 points per stream
+(+ one 10-KF / 300-landmark window solve per frame once `--ba` is on).  value = frames/s over all ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NPTS = 1280, 560, 300
+NFRAMES = 6           # distinct frames per stream (ping-pong sequence 0..5..0)
+KLT_BYTES_PER_FRAME_TRACK = 2 * 952_000 + 58 * NPTS                     # tracker kernel only (both pyramids + point I/O)
+KLT_BYTES_PER_FRAME_TOTAL = int(W * H * (1 + 5 / 16 + 21 / 64 + 2 * 85 / 64) + 58 * NPTS)  # 3 097 400
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=64, help="independent streams (frames in flight) per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-ba", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- synthetic stream
+def make_stream(seed: int):
+    from datagen import synth_klt as synth
+    st = synth.KltStream(W, H, NPTS, seed)
+    frames = [st.frame(t) for t in range(NFRAMES)]
+    pts = [st.points(t) for t in range(NFRAMES)]
+    return frames, pts
+
+
+def frame_sequence(n_steps: int):
+    """ping-pong frame indices so that consecutive entries are always adjacent frames of the stream"""
+    period = list(range(NFRAMES)) + list(range(NFRAMES - 2, 0, -1))
+    return [period[i % len(period)] for i in range(n_steps + 1)]
+
+
+def pair_points(pts, fa, fb, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    prev = pts[fa].astype(np.float32)
+    init = (pts[fb] + rng.normal(0.0, 1.0, size=pts[fb].shape)).astype(np.float32)
+    return prev, init
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_klt_frames_per_sec(frames, pts, seconds: float, threads: int):
+    """The reference front end on host cores: cv2 (the OpenCV the reference links) called as tracking.cc:385-403 does.
+    Falls back to the C oracle port when cv2 is not importable.  Returns (frames/s, kind, cores, sample)."""
+    seq = frame_sequence(1000)
+    try:
+        import cv2
+        cv2.setNumThreads(threads)
+        crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+
+        def one(fa, fb, k):
+            prev, init = pair_points(pts, fa, fb, 99 + k)
+            fwd, st, _ = cv2.calcOpticalFlowPyrLK(frames[fa], frames[fb], prev.reshape(-1, 1, 2), init.reshape(-1, 1, 2).copy(),
+                                                  winSize=(21, 21), maxLevel=3, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+            bwd, st2, _ = cv2.calcOpticalFlowPyrLK(frames[fb], frames[fa], fwd, prev.reshape(-1, 1, 2).copy(), winSize=(21, 21),
+                                                   maxLevel=3, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+            return int(st.sum())
+        kind, cores = "reference", cv2.getNumThreads()
+        label = f"cv2 {cv2.__version__} calcOpticalFlowPyrLK fwd+bwd"
+    except Exception:
+        import ctypes as C
+        import oracle
+        from tests import oracle_api as oa
+        olib = C.CDLL(oracle.build())
+        oa.declare(olib)
+
+        def one(fa, fb, k):
+            prev, init = pair_points(pts, fa, fb, 99 + k)
+            return int(oa.track_fb(olib, frames[fa], frames[fb], prev, init)[2].sum())
+        kind, cores, label = "port", 1, "oracle/klt_ref.c fwd+bwd"
+    one(seq[0], seq[1], 0)
+    t0 = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < seconds:
+        one(seq[k % 10], seq[k % 10 + 1], k)
+        k += 1
+    dt = time.perf_counter() - t0
+    return k / dt, kind, cores, f"{k} frames of one stream in {dt:.1f}s: {label}, 300 pts, 1280x560"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames, pts = make_stream(1234)
+    threads = os.cpu_count() or 1
+    per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, per_step, threads)
+        info = (kind, cores, sample)
+        if i >= args.warmup:
+            vals.append(fps)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "frames/sec (KLT+BA) 1280x560 300-feat 10-KF window", "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT)", "data": "synthetic",
+            "config": {"workload": "cfg2: synthetic 1280x560 stream, 300 feats, 4-level pyramid KLT fwd+bwd (BA not yet in the step)",
+                       "streams_per_gpu": 1},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": info[1], "kind": info[0], "sample": info[2]},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from ic_gvins_b200 import lib
+    from ic_gvins_b200.klt import KltTracker
+
+    B = args.streams
+    stream = torch.cuda.Stream(device=dev)
+    frames, pts = make_stream(1234 + rank)
+    n_slots = NFRAMES * B
+    trk = KltTracker(W, H, n_slots=n_slots, max_points=B * NPTS, device=local_rank, stream=stream.cuda_stream)
+
+    # pinned host frames (one copy per frame index; every stream uploads its own device copy)
+    h_frames = [torch.from_numpy(f.copy()).pin_memory() for f in frames]
+    # level-0 planes resident in HBM: slot = f * B + b
+    for f in range(NFRAMES):
+        for b in range(B):
+            trk.upload_ptr(f * B + b, h_frames[f].data_ptr(), W, build=False)
+    trk.sync()
+
+    total = args.warmup + args.steps
+    seq = frame_sequence(total + 1)
+    # per-step point sets (host, pinned) and device buffers
+    n_total = B * NPTS
+    h_prev = torch.empty((total, n_total, 2), dtype=torch.float32).pin_memory()
+    h_init = torch.empty((total, n_total, 2), dtype=torch.float32).pin_memory()
+    h_slots = torch.empty((total, n_total, 2), dtype=torch.int32).pin_memory()
+    for s in range(total):
+        fa, fb = seq[s], seq[s + 1]
+        for b in range(B):
+            p, i = pair_points(pts, fa, fb, 1000 * s + b)
+            h_prev[s, b * NPTS:(b + 1) * NPTS] = torch.from_numpy(p)
+            h_init[s, b * NPTS:(b + 1) * NPTS] = torch.from_numpy(i)
+            h_slots[s, b * NPTS:(b + 1) * NPTS, 0] = fa * B + b
+            h_slots[s, b * NPTS:(b + 1) * NPTS, 1] = fb * B + b
+    d_prev = h_prev.to(dev)
+    d_init = h_init.to(dev)
+    d_slots = h_slots.to(dev)
+    d_fwd = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
+    d_bwd = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
+    d_st = torch.empty((n_total,), dtype=torch.uint8, device=dev)
+    h_fwd = torch.empty((n_total, 2), dtype=torch.float32).pin_memory()
+    h_st = torch.empty((n_total,), dtype=torch.uint8).pin_memory()
+    # e2e staging buffers on the device for per-step point uploads
+    e_prev = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
+    e_init = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
+    e_slots = torch.empty((n_total, 2), dtype=torch.int32, device=dev)
+
+    def step_resident(s):
+        fb = seq[s + 1]
+        trk.build_pyramids(fb * B, B)
+        trk.track_batch_dev(n_total, d_slots[s].data_ptr(), d_prev[s].data_ptr(), d_init[s].data_ptr(), d_fwd.data_ptr(),
+                            d_bwd.data_ptr(), d_st.data_ptr(), 1)
+
+    def step_e2e(s):
+        fb = seq[s + 1]
+        for b in range(B):  # H2D of this step's B new frames from pinned host memory
+            trk.upload_ptr(fb * B + b, h_frames[fb].data_ptr(), W, build=False)
+        e_prev.copy_(h_prev[s], non_blocking=True)
+        e_init.copy_(h_init[s], non_blocking=True)
+        e_slots.copy_(h_slots[s], non_blocking=True)
+        trk.build_pyramids(fb * B, B)
+        trk.track_batch_dev(n_total, e_slots.data_ptr(), e_prev.data_ptr(), e_init.data_ptr(), d_fwd.data_ptr(), d_bwd.data_ptr(),
+                            d_st.data_ptr(), 1)
+        h_fwd.copy_(d_fwd, non_blocking=True)
+        h_st.copy_(d_st, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, per_kernel=False):
+        with torch.cuda.stream(stream):
+            for s in range(args.warmup):
+                step_fn(s)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kev = []
+            ev0.record(stream)
+            for s in range(args.warmup, total):
+                if per_kernel:
+                    fb = seq[s + 1]
+                    trk.build_pyramids(fb * B, B)
+                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    trk.track_batch_dev(n_total, d_slots[s].data_ptr(), d_prev[s].data_ptr(), d_init[s].data_ptr(), d_fwd.data_ptr(),
+                                        d_bwd.data_ptr(), d_st.data_ptr(), 1)
+                    b_.record(stream)
+                    kev.append((a, b_))
+                else:
+                    step_fn(s)
+            ev1.record(stream)
+            barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        kms = [a.elapsed_time(b_) for a, b_ in kev]
+        return ms, kms
+
+    lib().icg_launch_count_reset()
+    with ClockSampler(local_rank) as clk:
+        ms_res, _ = timed(step_resident)
+        launches = int(lib().icg_launch_count())
+        ms_e2e, _ = timed(step_e2e)
+        _, kms = timed(step_resident, per_kernel=True)
+    clocks = clk.summary()
+    good = int(d_st.sum().item())
+
+    frames_per_step = B * world
+    value = frames_per_step * args.steps / (ms_res / 1e3)
+    e2e = frames_per_step * args.steps / (ms_e2e / 1e3)
+    k_ms = float(np.mean(kms))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = B * KLT_BYTES_PER_FRAME_TRACK / (k_ms / 1e3) / 1e9
+    line = {
+        "metric": "frames/sec (KLT+BA) 1280x560 300-feat 10-KF window", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT)", "data": "synthetic",
+        "config": {"workload": "cfg5-style throughput mode, KLT leg (cfg2 x B): B independent synthetic 1280x560 streams per GPU, per frame: "
+                               "pyramid levels 1..3 + fused fwd+bwd 21x21 LK of 300 pts (BA solve per frame not yet in the step)",
+                   "streams_per_gpu": B, "points_per_frame": NPTS, "l2": f"inputs larger than L2: {B * 2 * 1.127:.0f} MB of pyramids touched per step"},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24), "d2h_bytes_per_step": B * NPTS * 9},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "klt_track_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": B * KLT_BYTES_PER_FRAME_TRACK},
+        "tracked_fraction": good / float(n_total),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, args.cpu_seconds, os.cpu_count() or 1)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+    if rank == 0:
+        print(json.dumps(line))
+    trk.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,6 +1,6 @@
 """Synthetic inputs for the IC-GVINS hot paths.  numpy only (cv2 optional for CLAHE).
 
-TEST/BENCH INFRASTRUCTURE: seeds are fixed so that the oracle, the golden vectors and the CUDA path all see
+Input generators only (no algorithm under test lives here): seeds are fixed so that the oracle, the golden vectors and the CUDA path all see
 byte-identical inputs.  Nothing here is on the product path.
 """
 from __future__ import annotations

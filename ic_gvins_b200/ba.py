@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's window-solve seam (IG/ic_gvins.cc:1130-1239): `WindowSolver` plays the role of
+`ceres::Problem` + `ceres::Solver::Solve`, `gvins_optimization()` restates the two-pass protocol of
+GVINS::gvinsOptimization (solve N/4 -> chi-square culling -> solve N - N/4).  All arithmetic runs in libicgvins_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib, vp
+
+IMU_BLOB = 480
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+bp = C.POINTER(C.c_uint8)
+
+
+class BaProblem(C.Structure):
+    """ctypes image of `icg_ba_problem` (include/icgvins_b200.h)."""
+    _fields_ = [
+        ("K", C.c_int32), ("L", C.c_int32), ("F", C.c_int32),
+        ("pose", dp), ("mix", dp), ("ext", dp), ("invdepth", dp),
+        ("ext_const", C.c_int32), ("td_const", C.c_int32),
+        ("f_lm", ip), ("f_ref", ip), ("f_obs", ip), ("f_const", dp), ("f_active", bp),
+        ("reproj_std", C.c_double), ("reproj_huber", C.c_int32),
+        ("n_imu", C.c_int32), ("imu_blob", dp), ("has_imu_error", C.c_int32),
+        ("has_pose_prior", C.c_int32), ("pose_prior", dp), ("pose_prior_std", dp),
+        ("has_mix_prior", C.c_int32), ("mix_prior", dp), ("mix_prior_std", dp),
+        ("n_gnss", C.c_int32), ("gnss_node", ip), ("gnss_blh", dp), ("gnss_std", dp), ("lever", C.c_double * 3),
+        ("gnss_huber", C.c_int32),
+        ("marg_r", C.c_int32), ("marg_nblocks", C.c_int32), ("marg_block_type", ip), ("marg_block_node", ip),
+        ("marg_x0", dp), ("marg_J0", dp), ("marg_e0", dp),
+    ]
+
+
+class BaSummary(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("num_successful_steps", C.c_int32), ("termination", C.c_int32), ("reserved", C.c_int32),
+                ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double)]
+
+
+_ARR = dict(pose=np.float64, mix=np.float64, ext=np.float64, invdepth=np.float64, f_lm=np.int32, f_ref=np.int32, f_obs=np.int32,
+            f_const=np.float64, f_active=np.uint8, imu_blob=np.float64, pose_prior=np.float64, pose_prior_std=np.float64,
+            mix_prior=np.float64, mix_prior_std=np.float64, gnss_node=np.int32, gnss_blh=np.float64, gnss_std=np.float64,
+            marg_block_type=np.int32, marg_block_node=np.int32, marg_x0=np.float64, marg_J0=np.float64, marg_e0=np.float64)
+_SCAL = ["K", "L", "F", "ext_const", "td_const", "reproj_std", "reproj_huber", "n_imu", "has_imu_error", "has_pose_prior",
+         "has_mix_prior", "n_gnss", "gnss_huber", "marg_r", "marg_nblocks"]
+
+
+def to_struct(prob: dict) -> BaProblem:
+    """Build the C struct over the dict's numpy arrays IN PLACE (arrays are made contiguous inside the dict so that the
+    solve's in/out parameter updates are visible to the caller)."""
+    s = BaProblem()
+    for k, dt in _ARR.items():
+        a = np.ascontiguousarray(prob[k], dtype=dt)
+        prob[k] = a
+        ptr_t = dp if dt == np.float64 else ip if dt == np.int32 else bp
+        setattr(s, k, a.ctypes.data_as(ptr_t) if a.size else ptr_t())
+    for k in _SCAL:
+        setattr(s, k, prob[k])
+    for i in range(3):
+        s.lever[i] = float(prob["lever"][i])
+    return s
+
+
+def imu_preintegrate(state16, iewn, gravity, noise5, imu):
+    """B3 host-side propagation in the product library (PreintegrationEarth::integrationProcess, preintegration_earth.cc:205-303)."""
+    imu = np.ascontiguousarray(imu, np.float64)
+    n = imu.shape[0]
+    blob = np.zeros(IMU_BLOB)
+    end = np.zeros(10)
+    st, iw, g, nz = (np.ascontiguousarray(x, np.float64) for x in (state16, iewn, gravity, noise5))
+    check(lib().icg_imu_preintegrate(vp(st.ctypes.data), vp(iw.ctypes.data), vp(g.ctypes.data), vp(nz.ctypes.data), vp(imu.ctypes.data),
+                                     n, vp(blob.ctypes.data), vp(end.ctypes.data)), "icg_imu_preintegrate")
+    return blob, end
+
+
+class WindowSolver:
+    """Batched sliding-window solver handle (one per optimization thread / GPU)."""
+
+    def __init__(self, max_windows=1, max_K=10, max_L=300, max_F=2700, max_gnss=16, max_marg_r=160, device=0, stream=None):
+        self._h = vp()
+        check(lib().icg_ba_create(C.byref(self._h), max_windows, max_K, max_L, max_F, max_gnss, max_marg_r, device,
+                                  vp(stream) if stream else None), "icg_ba_create")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().icg_ba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, problems, max_num_iterations: int):
+        """ceres::Solver::Solve on a list of problem dicts (updated in place).  Returns a list of summaries."""
+        if isinstance(problems, dict):
+            problems = [problems]
+        n = len(problems)
+        arr = (BaProblem * n)(*[to_struct(p) for p in problems])
+        summ = (BaSummary * n)()
+        check(lib().icg_ba_solve(self._h, n, arr, max_num_iterations, summ), "icg_ba_solve")
+        return [dict(iterations=s.iterations, num_successful_steps=s.num_successful_steps, termination=s.termination,
+                     initial_cost=s.initial_cost, final_cost=s.final_cost, final_radius=s.final_radius) for s in summ]
+
+    def solve_structs(self, arr, n, max_num_iterations, summ):
+        check(lib().icg_ba_solve(self._h, n, arr, max_num_iterations, summ), "icg_ba_solve")
+
+    # -- device-resident stages
+    def upload(self, problems):
+        n = len(problems)
+        self._keep = (BaProblem * n)(*[to_struct(p) for p in problems])
+        self._n = n
+        check(lib().icg_ba_upload(self._h, n, self._keep), "icg_ba_upload")
+
+    def run(self, max_num_iterations: int, restart: bool = False):
+        check(lib().icg_ba_run(self._h, max_num_iterations, 1 if restart else 0), "icg_ba_run")
+
+    def download(self, write_back: bool = True):
+        summ = (BaSummary * self._n)()
+        check(lib().icg_ba_download(self._h, self._n, self._keep if write_back else None, summ), "icg_ba_download")
+        return [dict(iterations=s.iterations, num_successful_steps=s.num_successful_steps, termination=s.termination,
+                     initial_cost=s.initial_cost, final_cost=s.final_cost, final_radius=s.final_radius) for s in summ]
+
+    def sync(self):
+        check(lib().icg_ba_sync(self._h), "icg_ba_sync")
+
+    def residual_costs(self, prob):
+        s = to_struct(prob)
+        rc = np.zeros(prob["F"])
+        gc = np.zeros(prob["n_gnss"])
+        check(lib().icg_ba_residual_costs(self._h, C.byref(s), vp(rc.ctypes.data), vp(gc.ctypes.data) if gc.size else None),
+              "icg_ba_residual_costs")
+        return rc, gc
+
+    def gvins_optimization(self, prob, num_iterations=20):
+        """GVINS::gvinsOptimization (IG/ic_gvins.cc:1130-1239): pass 1 (N/4 iterations, Huber on GNSS + reprojection),
+        GNSS chi2 re-weighting (:1241-1267), reprojection chi2 removal (:1269-1297), pass 2 (N - N/4, GNSS without loss)."""
+        first = num_iterations // 4
+        second = num_iterations - first
+        prob["gnss_huber"] = 1
+        s1 = self.solve(prob, first)[0]
+        rc, gc = self.residual_costs(prob)
+        gnss_std = prob["gnss_std"].reshape(-1, 3)
+        n_gnss_out = 0
+        for g in range(prob["n_gnss"]):
+            chi2 = 2.0 * gc[g]
+            if chi2 > 7.815:
+                gnss_std[g] *= np.sqrt(chi2 / 7.815)
+                n_gnss_out += 1
+        prob["gnss_std"] = gnss_std.reshape(-1)
+        act = prob["f_active"]
+        out = (2.0 * rc > 5.991) & (act != 0)
+        act[out] = 0
+        prob["gnss_huber"] = 0
+        s2 = self.solve(prob, second)[0]
+        return dict(pass1=s1, pass2=s2, reproj_removed=int(out.sum()), gnss_reweighted=n_gnss_out)
+
+    # -- single-factor Evaluate (Ceres CostFunction contract), computed on the device
+    def reproj_evaluate(self, pose0, pose1, ext, invdepth, td, const14, std, want_jac=True):
+        a = [np.ascontiguousarray(x, np.float64) for x in (pose0, pose1, ext, np.atleast_1d(invdepth), np.atleast_1d(td), const14)]
+        r = np.zeros(2)
+        Js = [np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 1)), np.zeros((2, 1))]
+        jp = (vp * 5)(*[vp(j.ctypes.data) for j in Js])
+        check(lib().icg_ba_reproj_evaluate(self._h, *[vp(x.ctypes.data) for x in a], float(std), vp(r.ctypes.data),
+                                           jp if want_jac else None), "icg_ba_reproj_evaluate")
+        return r, Js
+
+    def imu_evaluate(self, blob, pose0, mix0, pose1, mix1, want_jac=True):
+        a = [np.ascontiguousarray(x, np.float64) for x in (blob, pose0, mix0, pose1, mix1)]
+        r = np.zeros(15)
+        Js = [np.zeros((15, 7)), np.zeros((15, 9)), np.zeros((15, 7)), np.zeros((15, 9))]
+        jp = (vp * 4)(*[vp(j.ctypes.data) for j in Js])
+        check(lib().icg_ba_imu_evaluate(self._h, *[vp(x.ctypes.data) for x in a], vp(r.ctypes.data), jp if want_jac else None),
+              "icg_ba_imu_evaluate")
+        return r, Js

@@ -99,6 +99,106 @@ int icg_klt_track_batch_dev(icg_klt *h, int n_total, const int32_t *dev_slots, c
                             int mode);
 int icg_klt_sync(icg_klt *h);
 
+/* ===================================================================================================== *
+ *  Path B: sliding-window factor-graph solve
+ * ===================================================================================================== */
+/*
+ * One window problem == what GVINS::gvinsOptimization hands to Ceres (IG/ic_gvins.cc:1130-1239, 1697-1909):
+ *   parameter blocks  statedatalist_[k].pose[7] = (p, q_xyzw), .mix[9] = (v, bg, ba)      (IG/preintegration/integration_state.h:53-66)
+ *                     extrinsic_[8] = (t_bc, q_bc xyzw, td)                                 (IG/ic_gvins.cc:1736-1756)
+ *                     invdepthlist_ values, one per landmark                                (IG/ic_gvins.cc:1727)
+ *   residual blocks   ReprojectionFactor(pose_ref, pose_obs, extrinsic, invdepth, td) + HuberLoss(1.0)   (:1826-1831)
+ *                     PreintegrationFactor(pose_k, mix_k, pose_k+1, mix_k+1)                              (:1870-1872)
+ *                     ImuErrorFactor(mix_last), ImuPosePriorFactor(pose_0), ImuMixPriorFactor(mix_0)       (:1877-1887)
+ *                     GnssFactor(pose_node) + HuberLoss(1.0) in the first pass                             (:1896-1903)
+ *                     MarginalizationFactor(remained blocks)                                               (:1158-1161)
+ * All arrays are caller-owned host memory; pose/mix/ext/invdepth are updated in place by the solve
+ * (as Ceres mutates the reference's parameter arrays in place).
+ */
+#define ICG_IMU_BLOB_DOUBLES 480
+/* IMU preintegration blob (doubles): [0] delta_time, [1..3] delta p, [4..6] delta v, [7..10] delta q (x,y,z,w),
+ * [11..13] bg, [14..16] ba (linearisation biases), [17..19] gravity, [20..22] iewn,
+ * [23] S0 = sum_i dt_i, [24..26] S1 = sum_i dt_i * pn_i   (the two moments of pn_ that
+ *      PreintegrationEarth::evaluate's position-compensation loop needs, IG/preintegration/preintegration_earth.cc:55-59),
+ * [27..251] jacobian_ 15x15 row-major, [252..476] covariance_ 15x15 row-major, [477..479] reserved. */
+typedef struct icg_ba_problem {
+    int32_t K, L, F;
+    double *pose;     /* K*7 in/out */
+    double *mix;      /* K*9 in/out */
+    double *ext;      /* 8   in/out */
+    double *invdepth; /* L   in/out */
+    int32_t ext_const, td_const; /* SetParameterBlockConstant (IG/ic_gvins.cc:1750,1758) */
+    const int32_t *f_lm, *f_ref, *f_obs; /* F each: landmark, reference node, observing node */
+    const double *f_const;               /* F*14: pts0[3] pts1[3] vel0[3] vel1[3] td0 td1 */
+    const uint8_t *f_active;             /* F, or NULL == all active (RemoveResidualBlock, IG/ic_gvins.cc:1291) */
+    double reproj_std;
+    int32_t reproj_huber;
+    int32_t n_imu;
+    const double *imu_blob; /* n_imu * ICG_IMU_BLOB_DOUBLES; factor k joins node k and k+1 */
+    int32_t has_imu_error;
+    int32_t has_pose_prior;
+    const double *pose_prior, *pose_prior_std; /* 7, 6 */
+    int32_t has_mix_prior;
+    const double *mix_prior, *mix_prior_std; /* 9, 9 */
+    int32_t n_gnss;
+    const int32_t *gnss_node;
+    const double *gnss_blh, *gnss_std; /* n_gnss*3 each */
+    double lever[3];
+    int32_t gnss_huber;
+    int32_t marg_r, marg_nblocks;                    /* 0 == no prior */
+    const int32_t *marg_block_type, *marg_block_node; /* type 0 pose(node) 1 mix(node) 2 extrinsic 3 td */
+    const double *marg_x0, *marg_J0, *marg_e0;        /* concatenated x0 (global sizes), J0 row-major r x r, e0 */
+} icg_ba_problem;
+
+typedef struct icg_ba_summary {
+    int32_t iterations;           /* LM iterations executed */
+    int32_t num_successful_steps; /* ceres::Solver::Summary::num_successful_steps (IG/ic_gvins.cc:1186) */
+    int32_t termination;          /* 0 NO_CONVERGENCE (max iterations), 1 CONVERGENCE, 2 FAILURE */
+    int32_t reserved;
+    double initial_cost, final_cost, final_radius;
+} icg_ba_summary;
+
+/* B3 (host side, as in the reference: fusion thread, IG/ic_gvins.cc:917-919): IMU preintegration propagation
+ * PreintegrationEarth::resetState/integrationProcess/updateJacobianAndCovariance (IG/preintegration/preintegration_earth.cc:205-338).
+ * state16 = p[3] q_xyzw[4] v[3] bg[3] ba[3] at the interval start; noise5 = gyr_arw, acc_vrw, gyr_bias_std, acc_bias_std, corr_time;
+ * imu = n rows of (dt, dtheta[3], dvel[3]), row 0 being the sample at the interval start.  Writes the factor blob and the
+ * mechanised end state (p, q_xyzw, v).  Sequential recurrence; runs on the calling host thread. */
+int icg_imu_preintegrate(const double *state16, const double *iewn3, const double *gravity3, const double *noise5, const double *imu,
+                         int n, double *blob_out, double *end_state10);
+
+typedef struct icg_ba icg_ba;
+/*
+ * Solver for batches of up to max_windows windows of at most max_K nodes / max_L landmarks / max_F reprojection
+ * factors each (throughput mode: one window per independent stream).  stream may be NULL.
+ */
+int icg_ba_create(icg_ba **h, int max_windows, int max_K, int max_L, int max_F, int max_gnss, int max_marg_r, int device,
+                  void *stream);
+void icg_ba_destroy(icg_ba *h);
+/*
+ * Drop-in for `ceres::Solver::Solve(options, &problem, &summary)` with LEVENBERG_MARQUARDT + DENSE_SCHUR
+ * (IG/ic_gvins.cc:1143-1146, 1183, 1217) on n_windows independent problems at once.  Parameters are updated in place.
+ */
+int icg_ba_solve(icg_ba *h, int n_windows, const icg_ba_problem *problems, int max_num_iterations, icg_ba_summary *summaries);
+/* The three stages of icg_ba_solve, exposed for device-resident operation (throughput mode / benchmarking):
+ *   upload   : pack + H2D of n problems (what AddParameterBlock / AddResidualBlock build, IG/ic_gvins.cc:1697-1909)
+ *   run      : enqueue max_num_iterations LM iterations, asynchronously on the handle's stream; restart != 0 first restores
+ *              the parameters that were uploaded (re-solve the same problems)
+ *   download : D2H of the parameters into the problems' arrays (problems may be NULL) + summaries; synchronises. */
+int icg_ba_upload(icg_ba *h, int n_windows, const icg_ba_problem *problems);
+int icg_ba_run(icg_ba *h, int max_num_iterations, int restart);
+int icg_ba_download(icg_ba *h, int n_windows, const icg_ba_problem *problems, icg_ba_summary *summaries);
+int icg_ba_sync(icg_ba *h);
+/* Problem::EvaluateResidualBlock(id, false, &cost, NULL, NULL) for every reprojection / GNSS block
+ * (the two chi-square passes, IG/ic_gvins.cc:1251,1278): cost = 0.5 |r|^2 without the loss function. */
+int icg_ba_residual_costs(icg_ba *h, const icg_ba_problem *problem, double *reproj_cost /* F */, double *gnss_cost /* n_gnss */);
+/* Single-factor evaluation with the Ceres CostFunction::Evaluate contract (IG/factors/reprojection_factor.h:55):
+ * residuals[2]; jacobians row-major 2x7, 2x7, 2x7, 2x1, 2x1 (any may be NULL).  Computed on the device. */
+int icg_ba_reproj_evaluate(icg_ba *h, const double *pose0, const double *pose1, const double *ext, const double *invdepth,
+                           const double *td, const double *f_const14, double std, double *residuals, double **jacobians);
+/* PreintegrationFactor::Evaluate (IG/preintegration/preintegration_factor.h:45): residuals[15], jacobians 15x7,15x9,15x7,15x9 */
+int icg_ba_imu_evaluate(icg_ba *h, const double *imu_blob, const double *pose0, const double *mix0, const double *pose1,
+                        const double *mix1, double *residuals, double **jacobians);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ Writes tests/golden/klt_golden.npz.  Calls cv2 exactly as the reference does
 (ic_gvins/ic_gvins/tracking/tracking.cc:385-403): forward LK with USE_INITIAL_FLOW, backward LK,
 win 21x21, maxLevel 3, (COUNT+EPS, 30, 0.01).
 
-Large images are not stored: they are re-rendered from oracle/synth.py (numpy PCG64, deterministic) and
+Large images are not stored: they are re-rendered from datagen/synth_klt.py (numpy PCG64, deterministic) and
 guarded by a CRC32 stored beside the outputs.  Small cases store their images.
 """
 import os
@@ -18,7 +18,7 @@ import cv2
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
-from oracle import synth  # noqa: E402
+from datagen import synth_klt as synth  # noqa: E402
 
 CRIT = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
 

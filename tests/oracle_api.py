@@ -52,3 +52,73 @@ def track_fb(lib, a, b, p, init):
     st = np.zeros(n, np.uint8)
     lib.icgo_track_fb(_p(a), _p(b), W, H, W, _p(p), _p(q), _p(back), _p(st), n, 21, 3, 30, 0.01, 0.5, 5.0)
     return q, back, st
+
+
+# ------------------------------------------------------------------------------------------------ BA oracle
+def declare_ba(lib):
+    from ic_gvins_b200.ba import BaProblem, BaSummary
+    lib.icgo_ba_solve.argtypes = [C.POINTER(BaProblem), vp, vp, C.c_int, C.c_int, C.POINTER(BaSummary)]
+    lib.icgo_ba_residual_costs.argtypes = [C.POINTER(BaProblem), vp, vp]
+    lib.icgo_preintegrate.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp, vp]
+    lib.icgo_reproj_eval.argtypes = [vp, vp, vp, vp, vp, vp, C.c_double, vp, vp]
+    lib.icgo_imu_eval.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.icgo_gnss_eval.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.icgo_pose_prior_eval.argtypes = [vp, vp, vp, vp, vp]
+    lib.icgo_pose_plus.argtypes = [vp, vp, vp]
+    lib.icgo_pose_plus.restype = None
+
+
+def preintegrate(lib, state16, iewn, gravity, noise5, imu):
+    imu = np.ascontiguousarray(imu, np.float64)
+    n = imu.shape[0]
+    blob = np.zeros(480)
+    pn = np.zeros((n - 1, 4))
+    end = np.zeros(10)
+    a = [np.ascontiguousarray(x, np.float64) for x in (state16, iewn, gravity, noise5)]
+    lib.icgo_preintegrate(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(imu), n, _p(blob), _p(pn), _p(end))
+    return blob, pn, end
+
+
+def ba_solve(lib, prob, max_iter, num_threads=1):
+    from ic_gvins_b200.ba import BaSummary, to_struct
+    s = to_struct(prob)
+    pn = np.ascontiguousarray(prob["pn"], np.float64)
+    off = np.ascontiguousarray(prob["pn_off"], np.int32)
+    summ = BaSummary()
+    lib.icgo_ba_solve(C.byref(s), _p(pn), _p(off), max_iter, num_threads, C.byref(summ))
+    return dict(iterations=summ.iterations, num_successful_steps=summ.num_successful_steps, termination=summ.termination,
+                initial_cost=summ.initial_cost, final_cost=summ.final_cost, final_radius=summ.final_radius)
+
+
+def ba_residual_costs(lib, prob):
+    from ic_gvins_b200.ba import to_struct
+    s = to_struct(prob)
+    rc = np.zeros(prob["F"])
+    gc = np.zeros(prob["n_gnss"])
+    lib.icgo_ba_residual_costs(C.byref(s), _p(rc), _p(gc))
+    return rc, gc
+
+
+def reproj_eval(lib, pose0, pose1, ext, rho, td, c14, std, want_jac=True):
+    a = [np.ascontiguousarray(x, np.float64) for x in (pose0, pose1, ext, np.atleast_1d(rho), np.atleast_1d(td), c14)]
+    r = np.zeros(2)
+    Js = [np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 7)), np.zeros((2, 1)), np.zeros((2, 1))]
+    jp = (vp * 5)(*[vp(j.ctypes.data) for j in Js])
+    lib.icgo_reproj_eval(*[_p(x) for x in a], float(std), _p(r), jp if want_jac else None)
+    return r, Js
+
+
+def imu_eval(lib, blob, pn, pose0, mix0, pose1, mix1, want_jac=True):
+    a = [np.ascontiguousarray(x, np.float64) for x in (blob, pn, pose0, mix0, pose1, mix1)]
+    r = np.zeros(15)
+    Js = [np.zeros((15, 7)), np.zeros((15, 9)), np.zeros((15, 7)), np.zeros((15, 9))]
+    jp = (vp * 4)(*[vp(j.ctypes.data) for j in Js])
+    lib.icgo_imu_eval(_p(a[0]), _p(a[1]), a[1].size // 4, _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]), _p(r), jp if want_jac else None)
+    return r, Js
+
+
+def pose_plus(lib, x, d):
+    x = np.ascontiguousarray(x, np.float64); d = np.ascontiguousarray(d, np.float64)
+    out = np.zeros(7)
+    lib.icgo_pose_plus(_p(x), _p(d), _p(out))
+    return out

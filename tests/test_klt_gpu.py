@@ -7,7 +7,7 @@ import zlib
 import numpy as np
 import pytest
 
-from oracle import synth
+from datagen import synth_klt as synth
 from tests import oracle_api as oa
 from tests.test_oracle_klt import SMALL, assert_px
 

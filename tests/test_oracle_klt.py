@@ -8,7 +8,7 @@ import zlib
 import numpy as np
 import pytest
 
-from oracle import synth
+from datagen import synth_klt as synth
 from tests import oracle_api as oa
 
 SMALL = ["small_plain", "small_noisy", "small_flat", "small_edge", "odd_size"]
