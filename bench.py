@@ -24,6 +24,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H, NPTS = 1280, 560, 300
+WORKLOAD = ("cfg5-style throughput mode (cfg2 + cfg3 per frame): B independent synthetic 1280x560 streams per GPU; per frame: pyramid levels 1..3 + "
+            "fused fwd+bwd 21x21 LK of 300 pts, and one 10-KF / 300-landmark window solve (reprojection + IMU-preintegration + GNSS "
+            "factors, gvinsOptimization protocol 5 + chi2 culling + 15 LM iterations; every frame treated as a keyframe)")
+WORKLOAD_KLT = "cfg2 x B: B independent synthetic 1280x560 streams per GPU, pyramid + fused fwd+bwd LK of 300 pts (KLT only, --no-ba)"
 NFRAMES = 6           # distinct frames per stream (ping-pong sequence 0..5..0)
 KLT_BYTES_PER_FRAME_TRACK = 2 * 952_000 + 58 * NPTS                     # tracker kernel only (both pyramids + point I/O)
 KLT_BYTES_PER_FRAME_TOTAL = int(W * H * (1 + 5 / 16 + 21 / 64 + 2 * 85 / 64) + 58 * NPTS)  # 3 097 400
@@ -141,6 +145,47 @@ def cpu_klt_frames_per_sec(frames, pts, seconds: float, threads: int):
     return k / dt, kind, cores, f"{k} frames of one stream in {dt:.1f}s: {label}, 300 pts, 1280x560"
 
 
+def make_windows(n, preintegrate, seed0=2024):
+    from datagen import synth_ba
+    return [synth_ba.make_window(preintegrate, K=10, L=300, seed=seed0 + b)[0] for b in range(n)]
+
+
+def cpu_ba_solves_per_sec(seconds: float, threads: int = 4):
+    """The reference's window solve on host cores.  Ceres is not installed (and cannot be: no network), so this is the
+    oracle PORT of GVINS::gvinsOptimization (5 + chi2 culling + 15 LM iterations, DENSE_SCHUR) with num_threads = 4
+    as the reference configures Ceres (IG/ic_gvins.cc:1146).  Returns (solves/s, sample)."""
+    import copy
+    import ctypes as C
+    import oracle
+    from tests import oracle_api as oa
+    olib = C.CDLL(oracle.build())
+    oa.declare(olib)
+    oa.declare_ba(olib)
+    probs = make_windows(2, lambda *a: oa.preintegrate(olib, *a))
+
+    def one(p):
+        p = copy.deepcopy(p)
+        p["gnss_huber"] = 1
+        oa.ba_solve(olib, p, 5, threads)
+        rc, gc = oa.ba_residual_costs(olib, p)
+        std = p["gnss_std"].reshape(-1, 3)
+        for g in range(p["n_gnss"]):
+            if 2 * gc[g] > 7.815:
+                std[g] *= np.sqrt(2 * gc[g] / 7.815)
+        p["gnss_std"] = std.reshape(-1)
+        p["f_active"][2 * rc > 5.991] = 0
+        p["gnss_huber"] = 0
+        oa.ba_solve(olib, p, 15, threads)
+    one(probs[0])
+    t0 = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < seconds:
+        one(probs[k % 2])
+        k += 1
+    dt = time.perf_counter() - t0
+    return k / dt, f"{k} window solves in {dt:.1f}s: oracle port of gvinsOptimization (K=10, L=300, 5+15 LM its), {threads} threads"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -151,7 +196,12 @@ def run_reference(args):
     vals = []
     info = None
     for i in range(args.warmup + args.steps):
-        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, per_step, threads)
+        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, per_step * (0.5 if not args.no_ba else 1.0), threads)
+        if not args.no_ba:
+            sps, bsample = cpu_ba_solves_per_sec(per_step * 0.5)
+            fps = 1.0 / (1.0 / fps + 1.0 / sps)  # one window solve per frame (conservative: every frame a keyframe)
+            sample = sample + " + " + bsample
+            kind = "reference(cv2 KLT) + port(BA oracle)"
         info = (kind, cores, sample)
         if i >= args.warmup:
             vals.append(fps)
@@ -159,8 +209,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "frames/sec (KLT+BA) 1280x560 300-feat 10-KF window", "value": v, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT)", "data": "synthetic",
-            "config": {"workload": "cfg2: synthetic 1280x560 stream, 300 feats, 4-level pyramid KLT fwd+bwd (BA not yet in the step)",
-                       "streams_per_gpu": 1},
+            "config": {"workload": WORKLOAD if not args.no_ba else WORKLOAD_KLT, "streams_per_gpu": 1},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": info[1], "kind": info[0], "sample": info[2]},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -182,25 +231,26 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from ic_gvins_b200 import lib
+    from ic_gvins_b200.ba import BaProblem, BaSummary, WindowSolver, imu_preintegrate, to_struct
     from ic_gvins_b200.klt import KltTracker
+    import ctypes as C
 
     B = args.streams
-    stream = torch.cuda.Stream(device=dev)
+    use_ba = not args.no_ba
+    stream = torch.cuda.Stream(device=dev)       # KLT stream (tracking thread of the reference)
+    stream_ba = torch.cuda.Stream(device=dev)    # BA stream (optimization thread of the reference)
     frames, pts = make_stream(1234 + rank)
     n_slots = NFRAMES * B
     trk = KltTracker(W, H, n_slots=n_slots, max_points=B * NPTS, device=local_rank, stream=stream.cuda_stream)
 
-    # pinned host frames (one copy per frame index; every stream uploads its own device copy)
+    # ---- KLT inputs: pinned host frames; level-0 planes resident in HBM: slot = f * B + b
     h_frames = [torch.from_numpy(f.copy()).pin_memory() for f in frames]
-    # level-0 planes resident in HBM: slot = f * B + b
     for f in range(NFRAMES):
         for b in range(B):
             trk.upload_ptr(f * B + b, h_frames[f].data_ptr(), W, build=False)
     trk.sync()
-
     total = args.warmup + args.steps
     seq = frame_sequence(total + 1)
-    # per-step point sets (host, pinned) and device buffers
     n_total = B * NPTS
     h_prev = torch.empty((total, n_total, 2), dtype=torch.float32).pin_memory()
     h_init = torch.empty((total, n_total, 2), dtype=torch.float32).pin_memory()
@@ -213,65 +263,110 @@ def run_b200(args):
             h_init[s, b * NPTS:(b + 1) * NPTS] = torch.from_numpy(i)
             h_slots[s, b * NPTS:(b + 1) * NPTS, 0] = fa * B + b
             h_slots[s, b * NPTS:(b + 1) * NPTS, 1] = fb * B + b
-    d_prev = h_prev.to(dev)
-    d_init = h_init.to(dev)
-    d_slots = h_slots.to(dev)
+    d_prev, d_init, d_slots = h_prev.to(dev), h_init.to(dev), h_slots.to(dev)
     d_fwd = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
     d_bwd = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
     d_st = torch.empty((n_total,), dtype=torch.uint8, device=dev)
     h_fwd = torch.empty((n_total, 2), dtype=torch.float32).pin_memory()
     h_st = torch.empty((n_total,), dtype=torch.uint8).pin_memory()
-    # e2e staging buffers on the device for per-step point uploads
     e_prev = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
     e_init = torch.empty((n_total, 2), dtype=torch.float32, device=dev)
     e_slots = torch.empty((n_total, 2), dtype=torch.int32, device=dev)
 
-    def step_resident(s):
+    # ---- BA inputs: one cfg-3 window per stream (the product's own host-side preintegration builds the IMU factors)
+    solver = None
+    if use_ba:
+        def pre(st, iewn, g, nz, imu):
+            blob, end = imu_preintegrate(st, iewn, g, nz, imu)
+            return blob, np.zeros((imu.shape[0] - 1, 4)), end
+        windows = make_windows(B, pre, seed0=2024 + 1000 * rank)
+        maxF = max(w_["F"] for w_ in windows)
+        solver = WindowSolver(max_windows=B, max_K=10, max_L=300, max_F=maxF, max_gnss=8, max_marg_r=1, device=local_rank,
+                              stream=stream_ba.cuda_stream)
+        import copy
+        win_e2e = [copy.deepcopy(w_) for w_ in windows]
+        solver.upload(windows)
+        solver.sync()
+        # e2e: the struct array over host arrays is what the reference's optimization thread would hand over each keyframe
+        e2e_init = [{k: np.array(w_[k], copy=True) for k in ("pose", "mix", "ext", "invdepth", "f_active", "gnss_std")} for w_ in win_e2e]
+        e2e_arr = (BaProblem * B)(*[to_struct(w_) for w_ in win_e2e])
+        e2e_sum = (BaSummary * (2 * B))()
+        ba_h2d = int(sum(w_["F"] * (14 * 8 + 12 + 1) + 10 * 16 * 8 + 8 * 8 + 300 * 8 + 9 * 480 * 8 + 5 * 52 for w_ in windows))
+        ba_d2h = int(sum(10 * 16 * 8 + 8 * 8 + 300 * 8 + w_["F"] for w_ in windows))
+    else:
+        ba_h2d = ba_d2h = 0
+
+    def klt_resident(s):
         fb = seq[s + 1]
         trk.build_pyramids(fb * B, B)
         trk.track_batch_dev(n_total, d_slots[s].data_ptr(), d_prev[s].data_ptr(), d_init[s].data_ptr(), d_fwd.data_ptr(),
                             d_bwd.data_ptr(), d_st.data_ptr(), 1)
 
+    def step_resident(s):
+        klt_resident(s)
+        if use_ba:
+            solver.run_gvins(20, restart=True)
+
     def step_e2e(s):
         fb = seq[s + 1]
         for b in range(B):  # H2D of this step's B new frames from pinned host memory
             trk.upload_ptr(fb * B + b, h_frames[fb].data_ptr(), W, build=False)
-        e_prev.copy_(h_prev[s], non_blocking=True)
-        e_init.copy_(h_init[s], non_blocking=True)
-        e_slots.copy_(h_slots[s], non_blocking=True)
+        with torch.cuda.stream(stream):
+            e_prev.copy_(h_prev[s], non_blocking=True)
+            e_init.copy_(h_init[s], non_blocking=True)
+            e_slots.copy_(h_slots[s], non_blocking=True)
         trk.build_pyramids(fb * B, B)
         trk.track_batch_dev(n_total, e_slots.data_ptr(), e_prev.data_ptr(), e_init.data_ptr(), d_fwd.data_ptr(), d_bwd.data_ptr(),
                             d_st.data_ptr(), 1)
-        h_fwd.copy_(d_fwd, non_blocking=True)
-        h_st.copy_(d_st, non_blocking=True)
+        with torch.cuda.stream(stream):
+            h_fwd.copy_(d_fwd, non_blocking=True)
+            h_st.copy_(d_st, non_blocking=True)
+        if use_ba:
+            for w_, init in zip(win_e2e, e2e_init):  # fresh initial guess every step (the solve updates in place)
+                for k, v in init.items():
+                    w_[k][...] = v
+            rc = lib().icg_ba_gvins_optimization(solver._h, B, e2e_arr, 20, e2e_sum, None)  # upload + solve + download (synchronous)
+            if rc != 0:
+                raise RuntimeError(lib().icg_last_error().decode())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, per_kernel=False):
-        with torch.cuda.stream(stream):
-            for s in range(args.warmup):
+    def timed(step_fn, mode="step"):
+        for s in range(args.warmup):
+            if step_fn is not None:
                 step_fn(s)
-            barrier()
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            kev = []
-            ev0.record(stream)
-            for s in range(args.warmup, total):
-                if per_kernel:
-                    fb = seq[s + 1]
-                    trk.build_pyramids(fb * B, B)
-                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    trk.track_batch_dev(n_total, d_slots[s].data_ptr(), d_prev[s].data_ptr(), d_init[s].data_ptr(), d_fwd.data_ptr(),
-                                        d_bwd.data_ptr(), d_st.data_ptr(), 1)
-                    b_.record(stream)
-                    kev.append((a, b_))
-                else:
-                    step_fn(s)
-            ev1.record(stream)
-            barrier()
+            elif mode == "ba_only":
+                solver.run_gvins(20, restart=True)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kev = []
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        stream_ba.wait_stream(stream)
+        for s in range(args.warmup, total):
+            if mode == "klt_kernel":
+                fb = seq[s + 1]
+                trk.build_pyramids(fb * B, B)
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                trk.track_batch_dev(n_total, d_slots[s].data_ptr(), d_prev[s].data_ptr(), d_init[s].data_ptr(), d_fwd.data_ptr(),
+                                    d_bwd.data_ptr(), d_st.data_ptr(), 1)
+                b_.record(stream)
+                kev.append((a, b_))
+            elif mode == "ba_only":
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream_ba)
+                solver.run_gvins(20, restart=True)
+                b_.record(stream_ba)
+                kev.append((a, b_))
+            else:
+                step_fn(s)
+        stream.wait_stream(stream_ba)   # the step ends when both the tracking and the optimization stream are done
+        ev1.record(stream)
+        barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -285,9 +380,17 @@ def run_b200(args):
         ms_res, _ = timed(step_resident)
         launches = int(lib().icg_launch_count())
         ms_e2e, _ = timed(step_e2e)
-        _, kms = timed(step_resident, per_kernel=True)
+        _, kms = timed(klt_resident, mode="klt_kernel")
+        bms = timed(None, mode="ba_only")[1] if use_ba else []
+        ms_klt, _ = timed(klt_resident)
     clocks = clk.summary()
     good = int(d_st.sum().item())
+    ba_info = None
+    if use_ba:
+        sm = solver.download(write_back=False)
+        ba_info = {"ms_per_batch": float(np.mean(bms)), "windows_per_batch": B, "solves_per_s": B / (float(np.mean(bms)) / 1e3) * world,
+                   "mean_lm_iterations_pass2": float(np.mean([x["iterations"] for x in sm])),
+                   "final_cost_mean": float(np.mean([x["final_cost"] for x in sm]))}
 
     frames_per_step = B * world
     value = frames_per_step * args.steps / (ms_res / 1e3)
@@ -303,25 +406,34 @@ def run_b200(args):
     line = {
         "metric": "frames/sec (KLT+BA) 1280x560 300-feat 10-KF window", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT)", "data": "synthetic",
-        "config": {"workload": "cfg5-style throughput mode, KLT leg (cfg2 x B): B independent synthetic 1280x560 streams per GPU, per frame: "
-                               "pyramid levels 1..3 + fused fwd+bwd 21x21 LK of 300 pts (BA solve per frame not yet in the step)",
-                   "streams_per_gpu": B, "points_per_frame": NPTS, "l2": f"inputs larger than L2: {B * 2 * 1.127:.0f} MB of pyramids touched per step"},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24), "d2h_bytes_per_step": B * NPTS * 9},
+        "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT), f64 (BA)", "data": "synthetic",
+        "config": {"workload": WORKLOAD if use_ba else WORKLOAD_KLT, "streams_per_gpu": B, "points_per_frame": NPTS,
+                   "l2": f"inputs larger than L2: {B * 2 * 1.127:.0f} MB of pyramids touched per step"},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24) + ba_h2d,
+                "d2h_bytes_per_step": B * NPTS * 9 + ba_d2h},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "klt_track_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": B * KLT_BYTES_PER_FRAME_TRACK},
+        "klt_only": {"value": frames_per_step * args.steps / (ms_klt / 1e3), "unit": "frames/s"},
+        "ba_only": ba_info,
         "tracked_fraction": good / float(n_total),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, args.cpu_seconds, os.cpu_count() or 1)
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, args.cpu_seconds * (0.5 if use_ba else 1.0), os.cpu_count() or 1)
+        if use_ba:
+            sps, bsample = cpu_ba_solves_per_sec(args.cpu_seconds * 0.5)
+            line["cpu_baseline"] = {"value": 1.0 / (1.0 / fps + 1.0 / sps), "unit": "frames/s", "cores": cores, "kind": "reference(cv2 KLT) + port(BA oracle, 4 threads)",
+                                    "sample": sample + " + " + bsample, "klt_frames_per_s": fps, "ba_solves_per_s": sps}
+        else:
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
     if rank == 0:
         print(json.dumps(line))
     trk.close()
+    if solver:
+        solver.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -69,6 +69,8 @@ def _declare(L: C.CDLL) -> None:
     L.icg_ba_run.argtypes = [vp, C.c_int, C.c_int]
     L.icg_ba_download.argtypes = [vp, C.c_int, vp, vp]
     L.icg_ba_sync.argtypes = [vp]
+    L.icg_ba_gvins_optimization.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp]
+    L.icg_ba_run_gvins.argtypes = [vp, C.c_int, C.c_int]
     L.icg_ba_residual_costs.argtypes = [vp, vp, vp, vp]
     L.icg_ba_reproj_evaluate.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp]
     L.icg_ba_imu_evaluate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
@@ -81,5 +83,5 @@ EXPORTS = [
     "icg_klt_upload_level0", "icg_klt_slot_level0", "icg_klt_slot_level", "icg_klt_build_pyramids",
     "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
     "icg_imu_preintegrate", "icg_ba_create", "icg_ba_destroy", "icg_ba_solve", "icg_ba_upload", "icg_ba_run", "icg_ba_download",
-    "icg_ba_sync", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate",
+    "icg_ba_sync", "icg_ba_gvins_optimization", "icg_ba_run_gvins", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate",
 ]

@@ -135,6 +135,21 @@ class WindowSolver:
               "icg_ba_residual_costs")
         return rc, gc
 
+    def gvins_optimization_batch(self, problems, num_iterations=20):
+        """GVINS::gvinsOptimization on a list of windows in one device-resident call (icg_ba_gvins_optimization)."""
+        n = len(problems)
+        arr = (BaProblem * n)(*[to_struct(p) for p in problems])
+        summ = (BaSummary * (2 * n))()
+        culled = (C.c_int32 * (2 * n))()
+        check(lib().icg_ba_gvins_optimization(self._h, n, arr, num_iterations, summ, culled), "icg_ba_gvins_optimization")
+        f = lambda s: dict(iterations=s.iterations, num_successful_steps=s.num_successful_steps, termination=s.termination,
+                           initial_cost=s.initial_cost, final_cost=s.final_cost, final_radius=s.final_radius)
+        return [dict(pass1=f(summ[2 * w]), pass2=f(summ[2 * w + 1]), reproj_removed=culled[2 * w], gnss_reweighted=culled[2 * w + 1])
+                for w in range(n)]
+
+    def run_gvins(self, num_iterations: int = 20, restart: bool = False):
+        check(lib().icg_ba_run_gvins(self._h, num_iterations, 1 if restart else 0), "icg_ba_run_gvins")
+
     def gvins_optimization(self, prob, num_iterations=20):
         """GVINS::gvinsOptimization (IG/ic_gvins.cc:1130-1239): pass 1 (N/4 iterations, Huber on GNSS + reprojection),
         GNSS chi2 re-weighting (:1241-1267), reprojection chi2 removal (:1269-1297), pass 2 (N - N/4, GNSS without loss)."""

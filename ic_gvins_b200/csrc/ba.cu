@@ -881,6 +881,53 @@ __global__ void ba_lin_done(BaDev D, int NW) {
     if (w < NW && !D.st[w].done && D.st[w].need_lin) D.st[w].need_lin = 0;
 }
 
+// ------------------------------------------------------------------------------------------------ LM state reset (device side)
+__global__ void ba_reset_state(BaDev D, LmState *save, int n, int max_iter) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    if (save) save[w] = D.st[w];
+    LmState st;
+    memset(&st, 0, sizeof(st));
+    st.radius = 1e4, st.decrease_factor = 2.0;  // Ceres initial_trust_region_radius
+    st.need_lin = 1, st.fresh_lin = 1, st.first = 1, st.last_success = 1, st.max_iter = max_iter;
+    D.st[w] = st;
+}
+
+// The outlier pass between the two solves of GVINS::gvinsOptimization (IG/ic_gvins.cc:1196-1207):
+//   gnssOutlierCullingByChi2 (:1241-1267): chi2 = 2 cost > 7.815 -> std *= sqrt(chi2 / 7.815)
+//   removeReprojectionFactorsByChi2 (:1269-1297): chi2 = 2 cost > 5.991 -> RemoveResidualBlock
+//   GNSS factors re-added without loss function (:1202-1207)
+__global__ void __launch_bounds__(128) ba_chi2_cull(BaCaps C, BaDev D, int *counters) {
+    const int w = blockIdx.y;
+    WinDims &dm = D.dims[w];
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    const double *pose = D.pose + (size_t) w * C.K * 7, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
+    if (t < dm.F && D.f_active[(size_t) w * C.F + t]) {
+        double r[2];
+        reproj_eval(pose + D.f_ref[(size_t) w * C.F + t] * 7, pose + D.f_obs[(size_t) w * C.F + t] * 7, ext, rho[D.f_lm[(size_t) w * C.F + t]], ext[7],
+                    D.f_const + ((size_t) w * C.F + t) * 14, dm.reproj_sinv, false, r, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if ((r[0] * r[0] + r[1] * r[1]) > 5.991) {
+            D.f_active[(size_t) w * C.F + t] = 0;
+            atomicAdd(&counters[2 * w], 1);
+        }
+    }
+    if (t < dm.n_gnss) {
+        double r[3];
+        double *sd = D.gnss_std + ((size_t) w * C.G + t) * 3;
+        gnss_eval(pose + D.gnss_node[(size_t) w * C.G + t] * 7, D.gnss_blh + ((size_t) w * C.G + t) * 3, sd, D.lever + (size_t) w * 3, false, r, nullptr);
+        double chi2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+        if (chi2 > 7.815) {
+            double sc = sqrt(chi2 / 7.815);
+            sd[0] *= sc, sd[1] *= sc, sd[2] *= sc;
+            atomicAdd(&counters[2 * w + 1], 1);
+        }
+    }
+}
+__global__ void ba_set_gnss_huber(BaDev D, int n, int v) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < n) D.dims[w].gnss_huber = v;
+}
+
 // ------------------------------------------------------------------------------------------------ utility kernels
 __global__ void ba_residual_costs_kernel(BaCaps C, BaDev D, double *reproj_cost, double *gnss_cost) {
     const int w = 0;
@@ -1011,6 +1058,8 @@ struct icg_ba {
     HostDev<uint8_t> f_active;
     std::vector<void *> dev_only;
     HostDev<double> scratch;  // single-factor evaluation
+    HostDev<LmState> st_save;   // pass-1 LM state of the two-pass protocol
+    HostDev<int> cull_counters; // per window: reprojection factors removed, GNSS fixes re-weighted
 };
 
 static int dmalloc(icg_ba *h, double **p, size_t n) {
@@ -1182,7 +1231,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * 64 * 9)
     HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
     HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * 64) HD(marg_node, NW * 64) HD(f_active, NW * C.F)
-    HD(scratch, 1024)
+    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW)
 #undef HD
     BaDev &D = h->D;
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
@@ -1232,7 +1281,7 @@ void icg_ba_destroy(icg_ba *h) {
     h->imu_blob.release(), h->imu_U.release(), h->gnss_blh.release(), h->gnss_std.release(), h->lever.release(), h->pose_prior.release();
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
-    h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release();
+    h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release();
     for (void *p : h->dev_only) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1372,30 +1421,11 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     return ICG_OK;
 }
 
-// enqueue the LM iterations for the uploaded problems (asynchronous; device-resident decisions)
-int icg_ba_run(icg_ba *h, int max_num_iterations, int restart) {
-    if (!h || h->cur_windows < 1 || max_num_iterations < 0) {
-        set_error("icg_ba_run: no problems uploaded");
-        return ICG_EINVAL;
-    }
-    ICG_CUDA(cudaSetDevice(h->device));
+static int enqueue_lm(icg_ba *h, int max_num_iterations) {
     const BaCaps &C = h->C;
     const BaDev &D = h->D;
     const int n = h->cur_windows;
     cudaStream_t s = h->stream;
-    if (restart) {
-        ICG_CUDA(cudaMemcpyAsync(D.pose, D.pose_0, sizeof(double) * (size_t) n * C.K * 7, cudaMemcpyDeviceToDevice, s));
-        ICG_CUDA(cudaMemcpyAsync(D.mix, D.mix_0, sizeof(double) * (size_t) n * C.K * 9, cudaMemcpyDeviceToDevice, s));
-        ICG_CUDA(cudaMemcpyAsync(D.ext, D.ext_0, sizeof(double) * (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
-        ICG_CUDA(cudaMemcpyAsync(D.rho, D.rho_0, sizeof(double) * (size_t) n * C.L, cudaMemcpyDeviceToDevice, s));
-    }
-    for (int w = 0; w < n; w++) {
-        LmState &st = h->st.h[w];
-        memset(&st, 0, sizeof(st));
-        st.radius = 1e4, st.decrease_factor = 2.0;  // initial_trust_region_radius (Ceres default)
-        st.need_lin = 1, st.fresh_lin = 1, st.first = 1, st.last_success = 1, st.max_iter = max_num_iterations;
-    }
-    ICG_CUDA(h->st.up(s, n));
     const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L + 7) / 8, n), g_sj(BA_SPLIT_J, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis + 1, n);
     // iteration 0 linearisation + (max_iter) x [schur syrk, solve, cost, accept, re-linearise]; one extra solve call
     // performs the final termination bookkeeping.
@@ -1415,6 +1445,69 @@ int icg_ba_run(icg_ba *h, int max_num_iterations, int restart) {
     }
     ICG_CHECK_LAUNCH();
     return ICG_OK;
+}
+
+static int restore_params(icg_ba *h) {
+    const BaCaps &C = h->C;
+    const BaDev &D = h->D;
+    const int n = h->cur_windows;
+    cudaStream_t s = h->stream;
+    ICG_CUDA(cudaMemcpyAsync(D.pose, D.pose_0, sizeof(double) * (size_t) n * C.K * 7, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.mix, D.mix_0, sizeof(double) * (size_t) n * C.K * 9, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.ext, D.ext_0, sizeof(double) * (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.rho, D.rho_0, sizeof(double) * (size_t) n * C.L, cudaMemcpyDeviceToDevice, s));
+    // problem data the two-pass protocol mutates: factor activity, GNSS std, GNSS loss flag
+    ICG_CUDA(h->f_active.up(s, (size_t) n * C.F));
+    ICG_CUDA(h->gnss_std.up(s, (size_t) n * C.G * 3));
+    ICG_CUDA(h->dims.up(s, n));
+    return ICG_OK;
+}
+
+// enqueue the LM iterations for the uploaded problems (asynchronous; device-resident decisions)
+int icg_ba_run(icg_ba *h, int max_num_iterations, int restart) {
+    if (!h || h->cur_windows < 1 || max_num_iterations < 0) {
+        set_error("icg_ba_run: no problems uploaded");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    const int n = h->cur_windows;
+    if (restart) {
+        int rc = restore_params(h);
+        if (rc != ICG_OK) return rc;
+    }
+    ba_reset_state<<<(n + 127) / 128, 128, 0, h->stream>>>(h->D, nullptr, n, max_num_iterations);
+    count_launch();
+    return enqueue_lm(h, max_num_iterations);
+}
+
+// GVINS::gvinsOptimization (IG/ic_gvins.cc:1130-1239) entirely on the stream: pass 1 (N/4 iterations, Huber on GNSS),
+// chi-square culling, pass 2 (N - N/4 iterations, GNSS without loss).  No host round trip between the passes.
+int icg_ba_run_gvins(icg_ba *h, int num_iterations, int restart) {
+    if (!h || h->cur_windows < 1 || num_iterations < 1) {
+        set_error("icg_ba_run_gvins: no problems uploaded");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    const BaCaps &C = h->C;
+    const int n = h->cur_windows;
+    const int first = num_iterations / 4, second = num_iterations - first;  // IG/ic_gvins.cc:1131-1132
+    if (restart) {
+        int rc = restore_params(h);
+        if (rc != ICG_OK) return rc;
+    }
+    cudaStream_t s = h->stream;
+    ba_set_gnss_huber<<<(n + 127) / 128, 128, 0, s>>>(h->D, n, 1);
+    ba_reset_state<<<(n + 127) / 128, 128, 0, s>>>(h->D, nullptr, n, first);
+    count_launch(2);
+    int rc = enqueue_lm(h, first);
+    if (rc != ICG_OK) return rc;
+    ICG_CUDA(cudaMemsetAsync(h->cull_counters.d, 0, sizeof(int) * 2 * (size_t) n, s));
+    const dim3 g_cull((std::max(C.F, C.G) + 127) / 128, n);
+    ba_chi2_cull<<<g_cull, 128, 0, s>>>(C, h->D, h->cull_counters.d);
+    ba_set_gnss_huber<<<(n + 127) / 128, 128, 0, s>>>(h->D, n, 0);
+    ba_reset_state<<<(n + 127) / 128, 128, 0, s>>>(h->D, h->st_save.d, n, second);
+    count_launch(3);
+    return enqueue_lm(h, second);
 }
 
 int icg_ba_download(icg_ba *h, int n, const icg_ba_problem *P, icg_ba_summary *summaries) {
@@ -1453,6 +1546,42 @@ int icg_ba_solve(icg_ba *h, int n_windows, const icg_ba_problem *problems, int m
     rc = icg_ba_run(h, max_num_iterations, 0);
     if (rc != ICG_OK) return rc;
     return icg_ba_download(h, n_windows, problems, summaries);
+}
+
+static void fill_summary(const LmState &st, icg_ba_summary &o) {
+    o.iterations = st.iter, o.num_successful_steps = st.n_success;
+    o.termination = st.done == 2 ? 1 : st.done == 3 ? 2 : 0;
+    o.reserved = 0;
+    o.initial_cost = st.initial_cost, o.final_cost = st.x_cost, o.final_radius = st.radius;
+}
+
+int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations, icg_ba_summary *summaries,
+                              int32_t *culled) {
+    int rc = icg_ba_upload(h, n_windows, problems);
+    if (rc != ICG_OK) return rc;
+    rc = icg_ba_run_gvins(h, num_iterations, 0);
+    if (rc != ICG_OK) return rc;
+    const BaCaps &C = h->C;
+    cudaStream_t s = h->stream;
+    ICG_CUDA(h->st_save.down(s, n_windows));
+    ICG_CUDA(h->cull_counters.down(s, 2 * (size_t) n_windows));
+    ICG_CUDA(h->f_active.down(s, (size_t) n_windows * C.F));
+    ICG_CUDA(h->gnss_std.down(s, (size_t) n_windows * C.G * 3));
+    std::vector<icg_ba_summary> second(n_windows);
+    rc = icg_ba_download(h, n_windows, problems, second.data());
+    if (rc != ICG_OK) return rc;
+    for (int w = 0; w < n_windows; w++) {
+        const icg_ba_problem &p = problems[w];
+        // the reference mutates gnss->std in place and removes residual blocks from the problem: mirror both
+        if (p.f_active) memcpy(const_cast<uint8_t *>(p.f_active), h->f_active.h + (size_t) w * C.F, p.F);
+        if (p.n_gnss) memcpy(const_cast<double *>(p.gnss_std), h->gnss_std.h + (size_t) w * C.G * 3, sizeof(double) * 3 * p.n_gnss);
+        if (summaries) {
+            fill_summary(h->st_save.h[w], summaries[2 * w]);
+            summaries[2 * w + 1] = second[w];
+        }
+        if (culled) culled[2 * w] = h->cull_counters.h[2 * w], culled[2 * w + 1] = h->cull_counters.h[2 * w + 1];
+    }
+    return ICG_OK;
 }
 
 int icg_ba_sync(icg_ba *h) {

@@ -187,6 +187,21 @@ int icg_ba_solve(icg_ba *h, int n_windows, const icg_ba_problem *problems, int m
 int icg_ba_upload(icg_ba *h, int n_windows, const icg_ba_problem *problems);
 int icg_ba_run(icg_ba *h, int max_num_iterations, int restart);
 int icg_ba_download(icg_ba *h, int n_windows, const icg_ba_problem *problems, icg_ba_summary *summaries);
+/*
+ * Drop-in for the body of GVINS::gvinsOptimization (IG/ic_gvins.cc:1130-1239) on n_windows problems:
+ *   Solve(max_num_iterations = N/4) with HuberLoss on GNSS + reprojection         (:1183)
+ *   gnssOutlierCullingByChi2 (chi2 > 7.815 -> std *= sqrt(chi2/7.815))            (:1241-1267)
+ *   removeReprojectionFactorsByChi2(5.991)                                        (:1269-1297)
+ *   GNSS factors re-added without loss, Solve(max_num_iterations = N - N/4)       (:1202-1217)
+ * entirely on the device (no host round trip between the passes).  Parameters are updated in place; the problems'
+ * f_active (must be non-NULL to receive the removals) and gnss_std arrays are updated in place too, as the reference mutates
+ * `gnss->std` and removes residual blocks.  summaries: 2 per window (pass 1, pass 2), may be NULL.
+ * culled: 2 ints per window (reprojection factors removed, GNSS fixes re-weighted), may be NULL.
+ * icg_ba_run_gvins is the asynchronous device-only stage for problems already uploaded.
+ */
+int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations, icg_ba_summary *summaries,
+                              int32_t *culled);
+int icg_ba_run_gvins(icg_ba *h, int num_iterations, int restart);
 int icg_ba_sync(icg_ba *h);
 /* Problem::EvaluateResidualBlock(id, false, &cost, NULL, NULL) for every reprojection / GNSS block
  * (the two chi-square passes, IG/ic_gvins.cc:1251,1278): cost = 0.5 |r|^2 without the loss function. */

@@ -168,3 +168,25 @@ def test_capacity_errors(solver, olib):
     prob["K"] = 11
     with pytest.raises(IcgError):
         solver.solve(prob, 2)
+
+
+def test_device_resident_two_pass_equals_host_protocol(olib, solver):
+    """icg_ba_gvins_optimization (culling on the device, no host round trip) == the host-driven protocol, bitwise."""
+    probs = []
+    for i in range(3):
+        p, _ = make(olib, K=10, L=200, seed=90 + i)
+        p["ext_const"], p["td_const"] = 1, 1
+        fc = p["f_const"].reshape(-1, 14)
+        fc[7 + i, 3] += 0.2
+        p["gnss_blh"][3:6] += np.array([1.0, -0.8, 0.5])
+        probs.append(p)
+    host = copy.deepcopy(probs)
+    infos_h = [solver.gvins_optimization(p, 20) for p in host]
+    dev = copy.deepcopy(probs)
+    infos_d = solver.gvins_optimization_batch(dev, 20)
+    for a, b, ia, ib in zip(dev, host, infos_d, infos_h):
+        assert ia["reproj_removed"] == ib["reproj_removed"] >= 1 and ia["gnss_reweighted"] == ib["gnss_reweighted"] >= 1
+        assert np.array_equal(a["f_active"], b["f_active"])
+        assert ia["pass1"]["iterations"] == ib["pass1"]["iterations"] and ia["pass2"]["iterations"] == ib["pass2"]["iterations"]
+        for key in ("pose", "mix", "invdepth", "ext", "gnss_std"):
+            assert np.array_equal(a[key], b[key]), key
