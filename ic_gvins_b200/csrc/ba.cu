@@ -30,8 +30,9 @@
 namespace icg {
 using namespace bam;
 
-constexpr int BA_SPLIT_J = 4;   // row splits of the J^T J SYRK (partials summed in fixed order -> deterministic)
-constexpr int BA_SPLIT_W = 1;
+constexpr int BA_SPLIT_J = 1;   // the vision Gram matrix is produced whole by ba_pair_gram
+constexpr int BA_SPLIT_W = 4;   // row splits of the Schur SYRK (partials summed in fixed order -> deterministic)
+constexpr int BA_CHOL_NB = 8;   // Cholesky block width
 constexpr int BA_MAX_TILES = 3; // 4x4 register tiles per SYRK thread (256 threads): (NCA/4)(NCA/4+1)/2 <= 768
 
 struct BaCaps {
@@ -60,7 +61,9 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     double *f_const;
     uint8_t *f_active;
     int *lm_off, *lm_fidx;
-    double *AJ, *AW, *CJ, *CW;  // SYRK inputs / partial outputs
+    int *pair_off, *pair_ro, *pair_fidx, *npairs;  // factors grouped by (reference node, observing node)
+    double *Mp;                                    // per-pair 20x20 Gram matrices (upper, 210 entries)
+    double *AW, *CJ, *CW;  // Schur SYRK input; vision Gram matrix; Schur partials
     double *jcomp, *jrho, *costf;  // per-factor compact Jacobian (38), rho-Jacobian rows (2), cost
     double *hl, *gl, *scale_l, *scale_c;
     double *Hc, *gc;
@@ -88,8 +91,6 @@ __global__ void __launch_bounds__(128) ba_lin_vis(BaCaps C, BaDev D) {
     const WinDims dm = D.dims[w];
     const int f = blockIdx.x * 128 + threadIdx.x;
     if (f >= dm.F) return;
-    const int K = dm.K, NCV = 6 * K + 7;
-    double *AJ = D.AJ + (size_t) w * C.NCA * C.RJ;
     const int lm = D.f_lm[(size_t) w * C.F + f], i = D.f_ref[(size_t) w * C.F + f], j = D.f_obs[(size_t) w * C.F + f];
     double r[2], Ji[12], Jj[12], Je[12], Jr[2], Jt[2], cost = 0;
     const bool active = D.f_active[(size_t) w * C.F + f] != 0;
@@ -113,15 +114,6 @@ __global__ void __launch_bounds__(128) ba_lin_vis(BaCaps C, BaDev D) {
         for (int k = 0; k < 12; k++) Ji[k] = Jj[k] = Je[k] = 0;
         Jr[0] = Jr[1] = Jt[0] = Jt[1] = r[0] = r[1] = 0;
     }
-    // dense column-major rows 2f, 2f+1 (the untouched columns were zero-filled at upload and never change)
-    const size_t row = 2 * (size_t) f;
-    for (int c = 0; c < 6; c++) {
-        *(double2 *) &AJ[(size_t) (col_pose(i) + c) * C.RJ + row] = make_double2(Ji[c], Ji[6 + c]);
-        *(double2 *) &AJ[(size_t) (col_pose(j) + c) * C.RJ + row] = make_double2(Jj[c], Jj[6 + c]);
-        *(double2 *) &AJ[(size_t) (col_ext(K) + c) * C.RJ + row] = make_double2(Je[c], Je[6 + c]);
-    }
-    *(double2 *) &AJ[(size_t) col_td(K) * C.RJ + row] = make_double2(Jt[0], Jt[1]);
-    *(double2 *) &AJ[(size_t) NCV * C.RJ + row] = make_double2(r[0], r[1]);
     double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
     for (int k = 0; k < 12; k++) jc[k] = Ji[k], jc[12 + k] = Jj[k], jc[24 + k] = Je[k];
     jc[36] = Jt[0], jc[37] = Jt[1], jc[38] = r[0], jc[39] = r[1];
@@ -131,61 +123,161 @@ __global__ void __launch_bounds__(128) ba_lin_vis(BaCaps C, BaDev D) {
 }
 
 // ------------------------------------------------------------------------------------------------ lin_lm
+// One thread per (landmark, vision column): w_l[c] = sum over the landmark's factors of J_f[:, c]^T j_rho,f  (zero when the factor
+// does not touch column c); column NCV carries g_l = sum j_rho^T r, and that thread also produces h_l and the Jacobi scale.
+// A_W is landmark-major [l][NCA] so that a warp writes one contiguous row segment.
 __global__ void __launch_bounds__(256) ba_lin_lm(BaCaps C, BaDev D) {
     const int w = blockIdx.y;
-    LmState &st = D.st[w];
+    const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
     const WinDims dm = D.dims[w];
-    const int lane = threadIdx.x & 31;
-    const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int K = dm.K, NCV = 6 * K + 7, NCA = 4 * ((NCV + 1 + 3) / 4);
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int l = t / NCA, c = t - l * NCA;
     if (l >= dm.L) return;
-    const int K = dm.K, NCV = 6 * K + 7;
     const int *off = D.lm_off + (size_t) w * (C.L + 1);
     const int *fidx = D.lm_fidx + (size_t) w * C.F;
     const int f0 = off[l], f1 = off[l + 1];
-    double h = 0, g = 0;
-    for (int q = f0; q < f1; q++) {
-        const int f = fidx[q];
-        const double *jr = D.jrho + ((size_t) w * C.F + f) * 2;
-        const double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
-        h += jr[0] * jr[0] + jr[1] * jr[1];
-        g += jr[0] * jc[38] + jr[1] * jc[39];
-    }
-    double *AW = D.AW + (size_t) w * C.NCA * C.LP;
-    const int NCA = 4 * ((NCV + 1 + 3) / 4);
-    for (int c = lane; c < NCA; c += 32) {
-        double v = 0;
-        if (c == NCV) {
-            v = g;
-        } else if (c < NCV) {
-            for (int q = f0; q < f1; q++) {
-                const int f = fidx[q];
-                const double *jr = D.jrho + ((size_t) w * C.F + f) * 2;
-                const double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
-                const int i = D.f_ref[(size_t) w * C.F + f], j = D.f_obs[(size_t) w * C.F + f];
-                const double *blk = nullptr;
-                int cc = 0;
-                if (c >= col_pose(i) && c < col_pose(i) + 6) blk = jc, cc = c - col_pose(i);
-                else if (c >= col_pose(j) && c < col_pose(j) + 6) blk = jc + 12, cc = c - col_pose(j);
-                else if (c >= col_ext(K) && c < col_ext(K) + 6) blk = jc + 24, cc = c - col_ext(K);
-                if (blk)
-                    v += blk[cc] * jr[0] + blk[6 + cc] * jr[1];
-                else if (c == col_td(K))
-                    v += jc[36] * jr[0] + jc[37] * jr[1];
+    double v = 0, h = 0;
+    if (c <= NCV) {
+        for (int q = f0; q < f1; q++) {
+            const int f = fidx[q];
+            const double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
+            const double *jr = D.jrho + ((size_t) w * C.F + f) * 2;
+            if (c == NCV) {
+                v += jr[0] * jc[38] + jr[1] * jc[39];
+                h += jr[0] * jr[0] + jr[1] * jr[1];
+                continue;
             }
+            const int i = D.f_ref[(size_t) w * C.F + f], j = D.f_obs[(size_t) w * C.F + f];
+            int o = -1;
+            if (c >= col_pose(i) && c < col_pose(i) + 6) o = c - col_pose(i);
+            else if (c >= col_pose(j) && c < col_pose(j) + 6) o = 12 + c - col_pose(j);
+            else if (c >= col_ext(K) && c < col_ext(K) + 6) o = 24 + c - col_ext(K);
+            if (o >= 0)
+                v += jc[o] * jr[0] + jc[o + 6] * jr[1];
+            else if (c == col_td(K))
+                v += jc[36] * jr[0] + jc[37] * jr[1];
         }
-        AW[(size_t) c * C.LP + l] = v;
     }
-    if (lane == 0) {
+    D.AW[((size_t) w * C.LP + l) * C.NCA + c] = v;
+    if (c == NCV) {
         D.hl[(size_t) w * C.L + l] = h;
-        D.gl[(size_t) w * C.L + l] = g;
+        D.gl[(size_t) w * C.L + l] = v;
         if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(h));  // jacobi_scaling, once (iteration 0)
     }
+}
+
+// ------------------------------------------------------------------------------------------------ pair_gram: vision part of H_cc, g_c
+// Factors are grouped by (reference node, observing node).  Within a group every factor has the same 19 camera-side columns
+// [ref pose 6 | obs pose 6 | extrinsic 6 | td 1] (+ the residual as a 20th column), so the group's contribution is the dense
+// 20x20 Gram matrix of its stacked 2x20 rows: stage 1 (warp / group) computes it, stage 2 (thread / output entry) gathers the
+// groups into the symmetric (NCV+1)^2 matrix [H_vis g_vis; g_vis^T r^T r].  No atomics: every output has one writer.
+__device__ __forceinline__ int jc_off(int a) { return a < 18 ? (a / 6) * 12 + (a % 6) : 36 + 2 * (a - 18); }  // row 0 offset in a record
+__device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }                                           // + this for row 1
+__device__ __forceinline__ int tri20(int la, int lb) {  // index of (la <= lb) in the packed upper 20x20
+    return la * 20 - la * (la - 1) / 2 + (lb - la);
+}
+constexpr int PG_CHUNK = 16;  // factors staged per warp pass
+// stage 1: one warp per (window, group): the group's packed 20x20 Gram matrix -> Mp (global, L2 resident)
+__global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) {
+    __shared__ double s_stage[8][PG_CHUNK * 40];
+    __shared__ unsigned char s_ea[210], s_eb[210];
+    const int w = blockIdx.y;
+    const LmState &st = D.st[w];
+    if (st.done || !st.need_lin) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PM = C.K * (C.K - 1);
+    const int P = D.npairs[w];
+    if ((int) blockIdx.x * 8 >= P) return;
+    const int *poff = D.pair_off + (size_t) w * (PM + 1), *pfidx = D.pair_fidx + (size_t) w * C.F;
+    double *Mp = D.Mp + (size_t) w * PM * 210;
+    if (tid < 210) {
+        int e = tid, a = 0;
+        while (e >= 20 - a) e -= 20 - a, a++;
+        s_ea[tid] = (unsigned char) a, s_eb[tid] = (unsigned char) (a + e);
+    }
+    __syncthreads();
+    const int p = blockIdx.x * 8 + warp;
+    if (p >= P) return;
+    int oa[7], ob[7], ra[7], rb[7];
+    double acc[7];
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+        const int e = lane + 32 * q;
+        const int a = e < 210 ? s_ea[e] : 0, b = e < 210 ? s_eb[e] : 0;
+        oa[q] = jc_off(a), ob[q] = jc_off(b), ra[q] = jc_row1(a), rb[q] = jc_row1(b);
+        acc[q] = 0;
+    }
+    double *stg = s_stage[warp];
+    for (int base = poff[p]; base < poff[p + 1]; base += PG_CHUNK) {
+        const int cnt = min(PG_CHUNK, poff[p + 1] - base);
+        __syncwarp();
+        for (int e = lane; e < cnt * 40; e += 32) {
+            const int fi = e / 40, k = e - fi * 40;
+            stg[e] = D.jcomp[((size_t) w * C.F + pfidx[base + fi]) * 40 + k];
+        }
+        __syncwarp();
+        for (int fi = 0; fi < cnt; fi++) {
+            const double *jc = stg + fi * 40;
+#pragma unroll
+            for (int q = 0; q < 7; q++) acc[q] += jc[oa[q]] * jc[ob[q]] + jc[oa[q] + ra[q]] * jc[ob[q] + rb[q]];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 7; q++)
+        if (lane + 32 * q < 210) Mp[(size_t) p * 210 + lane + 32 * q] = acc[q];
+}
+
+// stage 2: one thread per output entry gathers the groups that touch both of its blocks (one writer per entry, no atomics)
+__global__ void __launch_bounds__(256) ba_pair_gram2(BaCaps C, BaDev D) {
+    __shared__ short s_slot[32 * 32];
+    const int w = blockIdx.y;
+    const LmState &st = D.st[w];
+    if (st.done || !st.need_lin) return;
+    const WinDims dm = D.dims[w];
+    const int tid = threadIdx.x;
+    const int K = dm.K, NCV = 6 * K + 7, PM = C.K * (C.K - 1), nn = NCV + 1;
+    if ((int) blockIdx.x * 256 >= nn * nn) return;
+    const int P = D.npairs[w];
+    const int *pro = D.pair_ro + (size_t) w * PM;
+    const double *Mp = D.Mp + (size_t) w * PM * 210;
+    for (int e = tid; e < K * K; e += 256) s_slot[e] = -1;
+    __syncthreads();
+    for (int p = tid; p < P; p += 256) s_slot[(pro[p] >> 8) * K + (pro[p] & 255)] = (short) p;
+    __syncthreads();
+    double *Cout = D.CJ + (size_t) w * C.NCA * C.NCA;
+    const int t = blockIdx.x * 256 + tid;
+    if (t >= nn * nn) return;
+    const int A = t / nn, B = t - A * nn;
+    if (B < A) return;
+    const int bA = A < 6 * K ? A / 6 : K, bB = B < 6 * K ? B / 6 : K;
+    const int a = A - 6 * bA, b = B - 6 * bB;  // offsets inside the block (global block: 0..7 = ext 6, td, residual)
+    const int ga = 12 + a, gb = 12 + b;          // local column of a global-block column
+    double sum = 0;
+    if (bA == K) {  // (global, global): every group
+        const int idx = tri20(ga, gb);
+        for (int p = 0; p < P; p++) sum += Mp[(size_t) p * 210 + idx];
+    } else if (bB == K || bB == bA) {  // (pose, global) or the pose's diagonal block
+        const int i1 = tri20(a, bB == K ? gb : b), i2 = tri20(6 + a, bB == K ? gb : 6 + b);
+        for (int o = 0; o < K; o++) {
+            const int p1 = s_slot[bA * K + o], p2 = s_slot[o * K + bA];  // bA as reference node / as observing node
+            if (p1 >= 0) sum += Mp[(size_t) p1 * 210 + i1];
+            if (p2 >= 0) sum += Mp[(size_t) p2 * 210 + i2];
+        }
+    } else {  // two different poses: the (bA -> bB) and (bB -> bA) groups
+        const int p1 = s_slot[bA * K + bB], p2 = s_slot[bB * K + bA];
+        if (p1 >= 0) sum += Mp[(size_t) p1 * 210 + tri20(a, 6 + b)];
+        if (p2 >= 0) sum += Mp[(size_t) p2 * 210 + tri20(b, 6 + a)];
+    }
+    Cout[(size_t) A * C.NCA + B] = sum;
+    Cout[(size_t) B * C.NCA + A] = sum;
 }
 
 // ------------------------------------------------------------------------------------------------ syrk: C = A^T diag(w) A
 // A column-major [NCA][ld] (rows contiguous).  mode 0: A_J, rows = 2F, no weights.  mode 1: A_W, rows = L,
 // weight_l = s_l^2 / (s_l^2 h_l + clamp(s_l^2 h_l) / radius)  (the LM-damped landmark pivot).
+template <int NT>
 __global__ void __launch_bounds__(256) ba_syrk(BaCaps C, BaDev D, int mode) {
     extern __shared__ double s_tile[];  // [NCA][33]
     const int w = blockIdx.y, split = blockIdx.x;
@@ -194,18 +286,17 @@ __global__ void __launch_bounds__(256) ba_syrk(BaCaps C, BaDev D, int mode) {
     if (mode == 0 && !st.need_lin) return;
     const WinDims dm = D.dims[w];
     const int NCV = 6 * dm.K + 7, NCA = 4 * ((NCV + 1 + 3) / 4), nt = NCA / 4;
-    const int rows = mode == 0 ? 2 * dm.F : dm.L;
-    const int ld = mode == 0 ? C.RJ : C.LP;
+    const int rows = dm.L;
     const int nsplit = mode == 0 ? BA_SPLIT_J : BA_SPLIT_W;
-    const double *A = (mode == 0 ? D.AJ + (size_t) w * C.NCA * C.RJ : D.AW + (size_t) w * C.NCA * C.LP);
+    const double *A = D.AW + (size_t) w * C.LP * C.NCA;  // landmark-major [l][NCA]
     double *Cout = (mode == 0 ? D.CJ + ((size_t) w * BA_SPLIT_J + split) * C.NCA * C.NCA : D.CW + ((size_t) w * BA_SPLIT_W + split) * C.NCA * C.NCA);
     __shared__ double s_wt[32];
     const int tid = threadIdx.x;
     const int ntiles = nt * (nt + 1) / 2;
-    int ti[BA_MAX_TILES], tj[BA_MAX_TILES];
-    double acc[BA_MAX_TILES][16];
+    int ti[NT], tj[NT];
+    double acc[NT][16];
 #pragma unroll
-    for (int q = 0; q < BA_MAX_TILES; q++) {
+    for (int q = 0; q < NT; q++) {
         int t = tid + q * 256, a = 0;
         if (t < ntiles) {
             while (t >= nt - a) t -= nt - a, a++;
@@ -222,8 +313,8 @@ __global__ void __launch_bounds__(256) ba_syrk(BaCaps C, BaDev D, int mode) {
         const int r0 = ch * 32;
         __syncthreads();
         for (int e = tid; e < NCA * 32; e += 256) {
-            int c = e >> 5, rr = e & 31;
-            s_tile[c * 33 + rr] = (r0 + rr < rows) ? A[(size_t) c * ld + r0 + rr] : 0.0;
+            int rr = e / NCA, c = e - rr * NCA;
+            s_tile[c * 33 + rr] = (r0 + rr < rows) ? A[(size_t) (r0 + rr) * C.NCA + c] : 0.0;
         }
         if (tid < 32) {
             double wt = 1.0;
@@ -239,7 +330,7 @@ __global__ void __launch_bounds__(256) ba_syrk(BaCaps C, BaDev D, int mode) {
         }
         __syncthreads();
 #pragma unroll
-        for (int q = 0; q < BA_MAX_TILES; q++) {
+        for (int q = 0; q < NT; q++) {
             if (ti[q] < 0) continue;
             const double *pa = s_tile + (4 * ti[q]) * 33, *pb = s_tile + (4 * tj[q]) * 33;
 #pragma unroll 4
@@ -255,7 +346,7 @@ __global__ void __launch_bounds__(256) ba_syrk(BaCaps C, BaDev D, int mode) {
         }
     }
 #pragma unroll
-    for (int q = 0; q < BA_MAX_TILES; q++) {
+    for (int q = 0; q < NT; q++) {
         if (ti[q] < 0) continue;
 #pragma unroll
         for (int a = 0; a < 4; a++)
@@ -568,7 +659,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
     double *s_rhs = s_g + C.NS;         // N   -> step' (scaled space)
     double *s_d2 = s_rhs + C.NS;        // N
     double *s_diag = s_d2 + C.NS;       // N   Cholesky diagonal
-    double *S = use_global_S ? D.Sglobal + (size_t) w * ((size_t) C.N * (C.N + 1) / 2) : s_diag + C.NS;  // packed lower
+    double *S = use_global_S ? D.Sglobal + (size_t) w * ((size_t) (C.N + 1) * (C.N + 2) / 2) : s_diag + C.NS;  // packed lower, N + 1 rows
     const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS;
     const double *CJ = D.CJ + (size_t) w * BA_SPLIT_J * C.NCA * C.NCA, *CW = D.CW + (size_t) w * BA_SPLIT_W * C.NCA * C.NCA;
     double *scale_c = D.scale_c + (size_t) w * C.NS;
@@ -654,58 +745,125 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
             S[i * (i + 1) / 2 + j] = v;
         }
     }
+    // augmented row N = rhs': the factorisation then leaves y = L^-1 rhs' in it (forward substitution for free)
+    for (int a = tid; a < N; a += SOLVE_THREADS) S[N * (N + 1) / 2 + a] = s_rhs[a];
     __syncthreads();
-    // ---- packed Cholesky (right-looking); failure -> invalid step
+    // ---- blocked left-looking Cholesky on the packed lower triangle (3 barriers per 8 columns); failure -> invalid step
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     __syncthreads();
-    for (int k = 0; k < N; k++) {
-        const double akk = S[k * (k + 1) / 2 + k];
-        if (!(akk > 0.0) || !isfinite(akk)) {
-            if (tid == 0) s_fail = 1;
-            break;
+    const int NR = N + 1;
+    for (int J0 = 0; J0 < N; J0 += BA_CHOL_NB) {
+        const int nb = min(BA_CHOL_NB, N - J0);
+        // (1) panel update with all previous columns
+        if (J0 > 0) {
+            for (int t = tid; t < (NR - J0) * nb; t += SOLVE_THREADS) {
+                const int i = J0 + t / nb, c = J0 + t % nb;
+                if (c > i) continue;
+                const double *ri = S + i * (i + 1) / 2, *rc = S + c * (c + 1) / 2;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                int k = 0;
+                for (; k + 4 <= J0; k += 4) s0 += ri[k] * rc[k], s1 += ri[k + 1] * rc[k + 1], s2 += ri[k + 2] * rc[k + 2], s3 += ri[k + 3] * rc[k + 3];
+                for (; k < J0; k++) s0 += ri[k] * rc[k];
+                S[i * (i + 1) / 2 + c] -= (s0 + s1) + (s2 + s3);
+            }
+            __syncthreads();
         }
-        const double d = sqrt(akk);
-        const double dinv = 1.0 / d;
-        __syncthreads();  // everyone has read akk before it is overwritten
-        for (int i = k + tid; i < N; i += SOLVE_THREADS) {
-            double v = S[i * (i + 1) / 2 + k];
-            S[i * (i + 1) / 2 + k] = (i == k) ? d : v * dinv;
+        // (2)+(3) every thread that owns a row i >= J0 factors the (updated) nb x nb diagonal block REDUNDANTLY in registers
+        // (no serial section, no extra barrier), then either writes back its row of L_JJ (rows inside the block) or solves
+        // its row of the panel against it (rows below, including the augmented rhs row).
+        {
+            const int i = J0 + tid;
+            if (i < NR) {
+                double Ld[BA_CHOL_NB][BA_CHOL_NB];
+                bool bad = false;
+#pragma unroll
+                for (int a = 0; a < BA_CHOL_NB; a++)
+#pragma unroll
+                    for (int b = 0; b < BA_CHOL_NB; b++) Ld[a][b] = (a < nb && b <= a) ? S[(J0 + a) * (J0 + a + 1) / 2 + J0 + b] : (a == b ? 1.0 : 0.0);
+#pragma unroll
+                for (int j = 0; j < BA_CHOL_NB; j++) {
+                    double d = Ld[j][j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
+                    if (!(d > 0.0) || !isfinite(d)) bad = true;
+                    d = sqrt(d);
+                    Ld[j][j] = d;
+                    const double dinv = 1.0 / d;
+#pragma unroll
+                    for (int a = j + 1; a < BA_CHOL_NB; a++) {
+                        double sum = Ld[a][j];
+#pragma unroll
+                        for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
+                        Ld[a][j] = sum * dinv;
+                    }
+                }
+                if (bad) s_fail = 1;  // benign race: every thread computes the same verdict
+                double *ri = S + i * (i + 1) / 2 + J0;
+                if (i < J0 + nb) {
+                    const int a = i - J0;
+#pragma unroll
+                    for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers
+                        if (a2 != a) continue;
+#pragma unroll
+                        for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
+                        s_diag[i] = 1.0 / Ld[a2][a2];
+                    }
+                } else {
+                    double x[BA_CHOL_NB];
+#pragma unroll
+                    for (int c = 0; c < BA_CHOL_NB; c++) x[c] = c < nb ? ri[c] : 0.0;
+#pragma unroll
+                    for (int c = 0; c < BA_CHOL_NB; c++) {
+                        double sum = x[c];
+#pragma unroll
+                        for (int k = 0; k < c; k++) sum -= x[k] * Ld[c][k];
+                        x[c] = sum / Ld[c][c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < BA_CHOL_NB; c++)
+                        if (c < nb) ri[c] = x[c];
+                }
+            }
         }
         __syncthreads();
-        // trailing update: rows i > k, cols k < j <= i  (16 x 32 thread grid over the packed lower triangle)
-        for (int i = k + 1 + (tid >> 5); i < N; i += SOLVE_THREADS / 32) {
-            const double lik = S[i * (i + 1) / 2 + k];
-            double *Si = S + i * (i + 1) / 2;
-            for (int j = k + 1 + (tid & 31); j <= i; j += 32) Si[j] -= lik * S[j * (j + 1) / 2 + k];
-        }
-        __syncthreads();
+        if (s_fail) break;
     }
     __syncthreads();
     bool valid = !s_fail;
-    // ---- triangular solves by warp 0 (no block barriers): L y = rhs, L^T x = y
-    if (valid && tid < 32) {
-        const int lane = tid;
-        for (int i = 0; i < N; i++) {
-            double s = 0;
-            for (int k = lane; k < i; k += 32) s += S[i * (i + 1) / 2 + k] * s_rhs[k];
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_rhs[i] = (s_rhs[i] - s) / S[i * (i + 1) / 2 + i];
-            __syncwarp();
-        }
-        for (int i = N - 1; i >= 0; i--) {
-            double s = 0;
-            for (int k = i + 1 + lane; k < N; k += 32) s += S[k * (k + 1) / 2 + i] * s_rhs[k];
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) s_rhs[i] = (s_rhs[i] - s) / S[i * (i + 1) / 2 + i];
-            __syncwarp();
+    // ---- blocked backward substitution L^T x = y: per block, 8 warps reduce the 8 column dot products with the already
+    //      solved unknowns, then one lane-serial 8x8 triangular solve with pre-inverted diagonal
+    if (valid) {
+        const double *y = S + N * (N + 1) / 2;
+        for (int a = tid; a < N; a += SOLVE_THREADS) s_rhs[a] = y[a];
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        const int nblk = (N + BA_CHOL_NB - 1) / BA_CHOL_NB;
+        for (int jb = nblk - 1; jb >= 0; jb--) {
+            const int J0 = jb * BA_CHOL_NB, nb = min(BA_CHOL_NB, N - J0), J1 = J0 + nb;
+            if (warp < nb) {
+                const int c = J0 + warp;
+                double sum = 0;
+                for (int i2 = J1 + lane; i2 < N; i2 += 32) sum += S[i2 * (i2 + 1) / 2 + c] * s_rhs[i2];
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) s_red[warp] = sum;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int c = J1 - 1; c >= J0; c--) {
+                    double sum = s_rhs[c] - s_red[c - J0];
+                    for (int k = c + 1; k < J1; k++) sum -= S[k * (k + 1) / 2 + c] * s_rhs[k];
+                    s_rhs[c] = sum * s_diag[c];
+                }
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
     // ---- landmark back-substitution + model cost change  (-1/2 step'.g' + 1/2 step'.D^2 step', exact identity of
     //      Ceres' -(J' step)^T (r + J' step / 2) for the damped normal-equation solution)
     double *step_l = D.step_l + (size_t) w * C.L;
-    const double *AW = D.AW + (size_t) w * C.NCA * C.LP;
+    const double *AW = D.AW + (size_t) w * C.LP * C.NCA;  // landmark-major
     double part = 0;
     bool finite = true;
     if (valid) {
@@ -717,7 +875,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
         for (int l = tid; l < L; l += SOLVE_THREADS) {
             double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
             double dotp = 0;
-            for (int c = 0; c < NCV; c++) dotp += AW[(size_t) c * C.LP + l] * (s_scale[c] * s_rhs[c]);
+            for (int c = 0; c < NCV; c++) dotp += AW[(size_t) l * C.NCA + c] * (s_scale[c] * s_rhs[c]);
             double sp = (-sl * gl[l] - sl * dotp) / (hs + d2);
             finite = finite && isfinite(sp);
             step_l[l] = sp;
@@ -1048,13 +1206,14 @@ struct icg_ba {
     bool own_stream;
     int nblk_vis;
     int cur_windows;
-    size_t smem_cam, smem_solve, smem_syrk;
+    size_t smem_cam, smem_solve, smem_syrk, smem_gram;
+    int mp_in_smem, syrk_one_tile;
     int use_global_S;
     HostDev<WinDims> dims;
     HostDev<LmState> st;
     HostDev<double> pose, mix, ext, rho, f_const, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
         marg_H0, marg_b0, marg_c0;
-    HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node;
+    HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
     HostDev<uint8_t> f_active;
     std::vector<void *> dev_only;
     HostDev<double> scratch;  // single-factor evaluation
@@ -1220,6 +1379,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
         return ICG_EUNSUPPORTED;
     }
     h->nblk_vis = (max_F + 255) / 256;
+    h->syrk_one_tile = (nt * (nt + 1) / 2 <= 256) ? 1 : 0;
     const size_t NW = max_windows;
 #define HD(field, count)                                                       \
     if (h->field.alloc(count) != ICG_OK) {                                     \
@@ -1232,10 +1392,12 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
     HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * 64) HD(marg_node, NW * 64) HD(f_active, NW * C.F)
     HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW)
+    HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
 #undef HD
     BaDev &D = h->D;
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
     D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
+    D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
     D.lm_off = h->lm_off.d, D.lm_fidx = h->lm_fidx.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
     D.gnss_node = h->gnss_node.d, D.gnss_blh = h->gnss_blh.d, D.gnss_std = h->gnss_std.d, D.lever = h->lever.d;
     D.pose_prior = h->pose_prior.d, D.pose_prior_sinfo = h->pose_prior_sinfo.d, D.mix_prior = h->mix_prior.d, D.mix_prior_std = h->mix_prior_std.d;
@@ -1245,7 +1407,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     if (rc == ICG_OK) rc = dmalloc(h, &D.field, count);
     DM(pose_c, NW * C.K * 7) DM(mix_c, NW * C.K * 9) DM(ext_c, NW * 8) DM(rho_c, NW * C.L)
     DM(pose_0, NW * C.K * 7) DM(mix_0, NW * C.K * 9) DM(ext_0, NW * 8) DM(rho_0, NW * C.L)
-    DM(AJ, NW * C.NCA * C.RJ) DM(AW, NW * C.NCA * C.LP) DM(CJ, NW * BA_SPLIT_J * C.NCA * C.NCA) DM(CW, NW * BA_SPLIT_W * C.NCA * C.NCA)
+    DM(AW, NW * C.NCA * C.LP) DM(Mp, NW * (size_t) C.K * (C.K - 1) * 210) DM(CJ, NW * BA_SPLIT_J * C.NCA * C.NCA) DM(CW, NW * BA_SPLIT_W * C.NCA * C.NCA)
     DM(jcomp, NW * C.F * 40) DM(jrho, NW * C.F * 2) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
     DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
 #undef DM
@@ -1254,11 +1416,11 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     h->smem_cam = sizeof(double) * ((size_t) C.K * 480 + (size_t) C.G * 24 + 48 + 16 + 2 * (size_t) C.R + 8) + sizeof(int) * (size_t) C.R + 64;
     h->smem_syrk = sizeof(double) * (size_t) C.NCA * 33;
     size_t vec = sizeof(double) * (40 + 5 * (size_t) C.NS);
-    size_t packed = sizeof(double) * ((size_t) C.N * (C.N + 1) / 2);
+    size_t packed = sizeof(double) * ((size_t) (C.N + 1) * (C.N + 2) / 2);
     h->use_global_S = (vec + packed > 220 * 1024) ? 1 : 0;
     h->smem_solve = vec + (h->use_global_S ? 0 : packed);
     if (h->use_global_S) {
-        rc = dmalloc(h, &D.Sglobal, NW * ((size_t) C.N * (C.N + 1) / 2));
+        rc = dmalloc(h, &D.Sglobal, NW * ((size_t) (C.N + 1) * (C.N + 2) / 2));
         if (rc != ICG_OK) return rc;
     } else {
         D.Sglobal = nullptr;
@@ -1266,7 +1428,9 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     ICG_CUDA(cudaFuncSetAttribute(ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve));
     ICG_CUDA(cudaFuncSetAttribute(ba_lin_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
     ICG_CUDA(cudaFuncSetAttribute(ba_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
-    ICG_CUDA(cudaFuncSetAttribute(ba_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
+    ICG_CUDA(cudaFuncSetAttribute(ba_syrk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
+    ICG_CUDA(cudaFuncSetAttribute(ba_syrk<BA_MAX_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
+    h->mp_in_smem = 0, h->smem_gram = 0;
     ICG_CUDA(cudaStreamSynchronize(h->stream));
     h->cur_windows = 0;
     *out = h;
@@ -1281,7 +1445,7 @@ void icg_ba_destroy(icg_ba *h) {
     h->imu_blob.release(), h->imu_U.release(), h->gnss_blh.release(), h->gnss_std.release(), h->lever.release(), h->pose_prior.release();
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
-    h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release();
+    h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     for (void *p : h->dev_only) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1334,6 +1498,25 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
         {
             std::vector<int> cur(off, off + p.L);
             for (int f = 0; f < p.F; f++) fidx[cur[p.f_lm[f]]++] = f;
+        }
+        // CSR by (reference node, observing node) pair
+        {
+            const int PM = C.K * (C.K - 1);
+            int *poff = h->pair_off.h + (size_t) w * (PM + 1), *pro = h->pair_ro.h + (size_t) w * PM, *pfidx = h->pair_fidx.h + (size_t) w * C.F;
+            std::vector<int> cnt((size_t) p.K * p.K, 0), slot((size_t) p.K * p.K, -1);
+            for (int f = 0; f < p.F; f++) cnt[(size_t) p.f_ref[f] * p.K + p.f_obs[f]]++;
+            int P = 0;
+            poff[0] = 0;
+            for (int key = 0; key < p.K * p.K; key++)
+                if (cnt[key]) {
+                    slot[key] = P;
+                    pro[P] = ((key / p.K) << 8) | (key % p.K);
+                    poff[P + 1] = poff[P] + cnt[key];
+                    P++;
+                }
+            std::vector<int> cur(poff, poff + P);
+            for (int f = 0; f < p.F; f++) pfidx[cur[slot[(size_t) p.f_ref[f] * p.K + p.f_obs[f]]]++] = f;
+            h->npairs.h[w] = P;
         }
         for (int k = 0; k < p.n_imu; k++) {
             const double *b = p.imu_blob + (size_t) k * ICG_IMU_BLOB_DOUBLES;
@@ -1403,7 +1586,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     ICG_CUDA(h->dims.up(s));
     ICG_CUDA(h->pose.up(s)); ICG_CUDA(h->mix.up(s)); ICG_CUDA(h->ext.up(s)); ICG_CUDA(h->rho.up(s));
     ICG_CUDA(h->f_lm.up(s)); ICG_CUDA(h->f_ref.up(s)); ICG_CUDA(h->f_obs.up(s)); ICG_CUDA(h->f_const.up(s)); ICG_CUDA(h->f_active.up(s));
-    ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
+    ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
     ICG_CUDA(h->gnss_node.up(s)); ICG_CUDA(h->gnss_blh.up(s)); ICG_CUDA(h->gnss_std.up(s)); ICG_CUDA(h->lever.up(s));
     ICG_CUDA(h->pose_prior.up(s)); ICG_CUDA(h->pose_prior_sinfo.up(s)); ICG_CUDA(h->mix_prior.up(s)); ICG_CUDA(h->mix_prior_std.up(s));
     ICG_CUDA(h->marg_type.up(s)); ICG_CUDA(h->marg_node.up(s)); ICG_CUDA(h->marg_x0.up(s)); ICG_CUDA(h->marg_H0.up(s)); ICG_CUDA(h->marg_b0.up(s));
@@ -1415,8 +1598,6 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     ICG_CUDA(cudaMemcpyAsync(D.ext_0, D.ext, sizeof(double) * (size_t) C.NW * 8, cudaMemcpyDeviceToDevice, s));
     ICG_CUDA(cudaMemcpyAsync(D.rho_0, D.rho, sizeof(double) * (size_t) C.NW * C.L, cudaMemcpyDeviceToDevice, s));
     // the dense SYRK operands keep a fixed sparsity pattern per problem: zero them once here
-    ICG_CUDA(cudaMemsetAsync(D.AJ, 0, sizeof(double) * (size_t) n * C.NCA * C.RJ, s));
-    ICG_CUDA(cudaMemsetAsync(D.AW, 0, sizeof(double) * (size_t) n * C.NCA * C.LP, s));
     h->cur_windows = n;
     return ICG_OK;
 }
@@ -1426,18 +1607,22 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
     const BaDev &D = h->D;
     const int n = h->cur_windows;
     cudaStream_t s = h->stream;
-    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L + 7) / 8, n), g_sj(BA_SPLIT_J, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis + 1, n);
+    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L * C.NCA + 255) / 256, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis + 1, n);
     // iteration 0 linearisation + (max_iter) x [schur syrk, solve, cost, accept, re-linearise]; one extra solve call
     // performs the final termination bookkeeping.
     for (int it = 0; it <= max_num_iterations; it++) {
         ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
         ba_lin_lm<<<g_lm, 256, 0, s>>>(C, D);
-        ba_syrk<<<g_sj, 256, h->smem_syrk, s>>>(C, D, 0);
+        ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
+        ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
         ba_lin_cam<<<n, 256, h->smem_cam, s>>>(C, D);
         ba_lin_done<<<(n + 127) / 128, 128, 0, s>>>(D, n);
-        ba_syrk<<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
+        if (h->syrk_one_tile)
+            ba_syrk<1><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
+        else
+            ba_syrk<BA_MAX_TILES><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
         ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
-        count_launch(7);
+        count_launch(8);
         if (it == max_num_iterations) break;
         ba_cost<<<g_cost, 256, h->smem_cam, s>>>(C, D, h->nblk_vis);
         ba_accept<<<n, 128, 0, s>>>(C, D, h->nblk_vis);
