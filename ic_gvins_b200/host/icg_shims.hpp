@@ -1,0 +1,123 @@
+// icg_shims.hpp -- header-only C++ shims that keep the reference's call signatures and forward to the C ABI
+// (include/icgvins_b200.h).  A maintainer includes this in IG/tracking/tracking.cc and IG/ic_gvins.cc; see INTEGRATION.md.
+//
+// When OpenCV headers are present the shims take cv:: types; otherwise (this image has no OpenCV C++ headers) minimal
+// stand-ins with the same data layout are used so that the header still compiles and can be unit-tested.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/icgvins_b200.h"
+
+#if __has_include(<opencv2/core.hpp>)
+#include <opencv2/core.hpp>
+namespace icg_b200 {
+using Point2f = cv::Point2f;
+using Mat = cv::Mat;
+using Size = cv::Size;
+using TermCriteria = cv::TermCriteria;
+inline const uint8_t *mat_data(const Mat &m) { return m.data; }
+inline int mat_stride(const Mat &m) { return (int) m.step; }
+inline int mat_cols(const Mat &m) { return m.cols; }
+inline int mat_rows(const Mat &m) { return m.rows; }
+}  // namespace icg_b200
+#else
+namespace icg_b200 {
+struct Point2f {
+    float x, y;
+};
+struct Size {
+    int width, height;
+    Size(int w = 0, int h = 0) : width(w), height(h) {}
+};
+struct TermCriteria {
+    enum { COUNT = 1, EPS = 2 };
+    int type, maxCount;
+    double epsilon;
+    TermCriteria(int t = 3, int c = 30, double e = 0.01) : type(t), maxCount(c), epsilon(e) {}
+};
+struct Mat {  // 8-bit single channel view
+    const uint8_t *data;
+    int rows, cols, step;
+};
+inline const uint8_t *mat_data(const Mat &m) { return m.data; }
+inline int mat_stride(const Mat &m) { return m.step; }
+inline int mat_cols(const Mat &m) { return m.cols; }
+inline int mat_rows(const Mat &m) { return m.rows; }
+}  // namespace icg_b200
+#endif
+
+namespace icg_b200 {
+
+inline void check(int rc, const char *what) {
+    if (rc != ICG_OK) throw std::runtime_error(std::string(what) + ": " + icg_last_error());
+}
+
+// One tracker per Tracking object (single tracking thread, IG/ic_gvins.cc:535).
+class KltContext {
+public:
+    KltContext(int width, int height, int max_points = 4096, int device = 0) { check(icg_klt_create(&h_, width, height, 4, max_points, device, nullptr), "icg_klt_create"); }
+    ~KltContext() { icg_klt_destroy(h_); }
+    KltContext(const KltContext &) = delete;
+    KltContext &operator=(const KltContext &) = delete;
+
+    // cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err, winSize, maxLevel, criteria, flags)
+    // exactly as called at IG/tracking/tracking.cc:385,390,487,493.
+    void calcOpticalFlowPyrLK(const Mat &prev, const Mat &next, const std::vector<Point2f> &prevPts, std::vector<Point2f> &nextPts,
+                              std::vector<uint8_t> &status, std::vector<float> &err, Size winSize, int maxLevel, TermCriteria criteria, int flags) {
+        const int n = (int) prevPts.size();
+        if (!(flags & ICG_OPTFLOW_USE_INITIAL_FLOW)) nextPts = prevPts;
+        nextPts.resize(n);
+        status.resize(n);
+        err.resize(n);
+        const int max_iter = (criteria.type & 1) ? criteria.maxCount : 30;
+        const double eps = (criteria.type & 2) ? criteria.epsilon : 0.0;
+        check(icg_klt_calc_optical_flow_pyr_lk(h_, mat_data(prev), mat_data(next), mat_stride(prev), reinterpret_cast<const float *>(prevPts.data()),
+                                               reinterpret_cast<float *>(nextPts.data()), status.data(), err.data(), n, winSize.width, maxLevel, max_iter, eps,
+                                               flags),
+              "icg_klt_calc_optical_flow_pyr_lk");
+    }
+
+    // The whole forward + backward + gate block of Tracking::trackMappoint (IG/tracking/tracking.cc:385-403):
+    // status[k] = st_fwd && st_bwd && !isOnBorder(fwd) && ptsDistance(bwd, prev) < 0.5
+    void trackForwardBackward(const Mat &prev, const Mat &next, const std::vector<Point2f> &prevPts, std::vector<Point2f> &nextPts, std::vector<uint8_t> &status) {
+        const int n = (int) prevPts.size();
+        nextPts.resize(n);
+        status.resize(n);
+        check(icg_klt_track_fb(h_, mat_data(prev), mat_data(next), mat_stride(prev), reinterpret_cast<const float *>(prevPts.data()),
+                               reinterpret_cast<float *>(nextPts.data()), nullptr, status.data(), n),
+              "icg_klt_track_fb");
+    }
+
+private:
+    icg_klt *h_ = nullptr;
+};
+
+// The window solve seam: what GVINS::gvinsOptimization hands to ceres::Solver::Solve (IG/ic_gvins.cc:1130-1239).
+class WindowSolver {
+public:
+    WindowSolver(int max_K, int max_L, int max_F, int max_gnss = 16, int max_marg_r = 160, int device = 0) {
+        check(icg_ba_create(&h_, 1, max_K, max_L, max_F, max_gnss, max_marg_r, device, nullptr), "icg_ba_create");
+    }
+    ~WindowSolver() { icg_ba_destroy(h_); }
+    WindowSolver(const WindowSolver &) = delete;
+    WindowSolver &operator=(const WindowSolver &) = delete;
+
+    // solver.Solve(options, &problem, &summary) with options.max_num_iterations = max_iter
+    icg_ba_summary Solve(const icg_ba_problem &problem, int max_iter) {
+        icg_ba_summary s{};
+        check(icg_ba_solve(h_, 1, &problem, max_iter, &s), "icg_ba_solve");
+        return s;
+    }
+    // the two-pass body of gvinsOptimization (first N/4, chi2 culling, then N - N/4 iterations); out[0], out[1] = pass summaries
+    void gvinsOptimization(const icg_ba_problem &problem, int num_iterations, icg_ba_summary out[2], int32_t culled[2]) {
+        check(icg_ba_gvins_optimization(h_, 1, &problem, num_iterations, out, culled), "icg_ba_gvins_optimization");
+    }
+
+private:
+    icg_ba *h_ = nullptr;
+};
+
+}  // namespace icg_b200
