@@ -59,6 +59,12 @@ def _declare(L: C.CDLL) -> None:
     L.icg_klt_track_batch_dev.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_int]
     L.icg_klt_sync.argtypes = [vp]
     L.icg_klt_download_level.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
+    # ---- detection
+    L.icg_detect_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    L.icg_detect_destroy.argtypes = [vp]
+    L.icg_detect_destroy.restype = None
+    L.icg_detect_blocks.argtypes = [vp, vp, vp, C.c_int, C.c_int, vp, vp, C.c_double, C.c_double, C.c_int, vp, vp]
+    L.icg_corner_subpix.argtypes = [vp, vp, C.c_int, vp, C.c_int]
     # ---- BA
     L.icg_imu_preintegrate.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp, vp]
     L.icg_ba_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
@@ -82,6 +88,7 @@ EXPORTS = [
     "icg_klt_create", "icg_klt_destroy", "icg_klt_calc_optical_flow_pyr_lk", "icg_klt_track_fb", "icg_klt_upload",
     "icg_klt_upload_level0", "icg_klt_slot_level0", "icg_klt_slot_level", "icg_klt_build_pyramids",
     "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
+    "icg_detect_create", "icg_detect_destroy", "icg_detect_blocks", "icg_corner_subpix",
     "icg_imu_preintegrate", "icg_ba_create", "icg_ba_destroy", "icg_ba_solve", "icg_ba_upload", "icg_ba_run", "icg_ba_download",
     "icg_ba_sync", "icg_ba_gvins_optimization", "icg_ba_run_gvins", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate",
 ]

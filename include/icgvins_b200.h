@@ -99,6 +99,29 @@ int icg_klt_track_batch_dev(icg_klt *h, int n_total, const int32_t *dev_slots, c
                             int mode);
 int icg_klt_sync(icg_klt *h);
 
+/* ----- detection leg of path A: Tracking::featuresDetection (IG/tracking/tracking.cc:576-688) ----- */
+typedef struct icg_rect {
+    int32_t x, y, w, h;
+} icg_rect;
+typedef struct icg_detect icg_detect;
+/* width x height frames; up to max_blocks ROIs per call, each at most max_roi_pixels pixels, at most
+ * max_corners_per_block corners returned per block. */
+int icg_detect_create(icg_detect **h, int width, int height, int max_blocks, int max_corners_per_block, int max_roi_pixels, int device, void *stream);
+void icg_detect_destroy(icg_detect *h);
+/*
+ * The body of the tbb::parallel_for over blocks (IG/tracking/tracking.cc:627-656) for all blocks in one call:
+ *   cv::goodFeaturesToTrack(frame(roi), out, max_corners[b], quality, min_distance, mask(roi))          (:647)
+ *   cv::cornerSubPix(frame(roi), out, Size(5,5), Size(-1,-1), TermCriteria(COUNT+EPS, 20, 0.01))        (:651, when do_subpix)
+ * with C++ ROI semantics (the derivative of a block reads the frame beyond the block edge).  img / mask are full frames
+ * (mask may be NULL == all 255).  out_xy: n_blocks x max_corners_per_block x 2 floats, block-LOCAL coordinates in
+ * OpenCV's order (strength descending, ties by address descending); out_n: corners per block.  Host buffers, synchronous.
+ * A single ROI covering the frame reproduces the stand-alone cv::goodFeaturesToTrack / cv::cornerSubPix calls.
+ */
+int icg_detect_blocks(icg_detect *h, const uint8_t *img, const uint8_t *mask, int stride, int n_blocks, const icg_rect *rois,
+                      const int32_t *max_corners, double quality, double min_distance, int do_subpix, float *out_xy, int32_t *out_n);
+/* Drop-in for cv::cornerSubPix(img, corners, Size(5,5), Size(-1,-1), (COUNT+EPS, 20, 0.01)) on the whole frame; corners in/out */
+int icg_corner_subpix(icg_detect *h, const uint8_t *img, int stride, float *corners_xy, int n);
+
 /* ===================================================================================================== *
  *  Path B: sliding-window factor-graph solve
  * ===================================================================================================== */

@@ -122,3 +122,58 @@ def pose_plus(lib, x, d):
     out = np.zeros(7)
     lib.icgo_pose_plus(_p(x), _p(d), _p(out))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ detection oracle
+def declare_detect(lib):
+    lib.icgo_min_eig_roi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    lib.icgo_min_eig_roi.restype = None
+    lib.icgo_good_features_from_eig.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp]
+    lib.icgo_good_features_from_eig.restype = C.c_int
+    lib.icgo_corner_subpix_roi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_double]
+    lib.icgo_corner_subpix_roi.restype = None
+    lib.icgo_detect_block.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp]
+    lib.icgo_detect_block.restype = C.c_int
+
+
+def min_eig_roi(lib, img, roi):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape
+    x0, y0, w, h = roi
+    eig = np.zeros((h, w), np.float32)
+    lib.icgo_min_eig_roi(_p(img), W, H, W, x0, y0, w, h, _p(eig))
+    return eig
+
+
+def good_features(lib, img, n, quality, min_dist, mask=None, roi=None):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape
+    roi = roi or (0, 0, W, H)
+    eig = min_eig_roi(lib, img, roi)
+    x0, y0, w, h = roi
+    out = np.zeros((max(1, n), 2), np.float32)
+    m = None
+    if mask is not None:
+        m = np.ascontiguousarray(mask)
+        mp = C.c_void_p(m.ctypes.data + y0 * W + x0)
+    cnt = lib.icgo_good_features_from_eig(_p(eig), w, h, mp if mask is not None else None, W, n, quality, min_dist, _p(out))
+    return out[:cnt].copy()
+
+
+def corner_subpix(lib, img, pts, roi=None):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape
+    x0, y0, w, h = roi or (0, 0, W, H)
+    p = np.array(pts, np.float32).reshape(-1, 2).copy()
+    lib.icgo_corner_subpix_roi(_p(img), W, H, W, x0, y0, w, h, _p(p), p.shape[0], 5, 20, 0.01)
+    return p
+
+
+def detect_block(lib, img, mask, roi, n, quality, min_dist):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape
+    x0, y0, w, h = roi
+    out = np.zeros((max(1, n), 2), np.float32)
+    m = np.ascontiguousarray(mask) if mask is not None else None
+    cnt = lib.icgo_detect_block(_p(img), _p(m) if m is not None else None, W, H, W, x0, y0, w, h, n, quality, min_dist, _p(out))
+    return out[:cnt].copy()
