@@ -113,19 +113,41 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
 struct WarpSmem {
     uint8_t *iw;    // 48x24 template window, origin ((ipx-1) & ~15, ipy-1)
     uint8_t *jw;    // 48x32 search window, origin (jx0 (16-aligned), jy0)
-    int *dv;        // 22x22 packed (Ix | Iy << 16)
-    uint64_t *bar;  // mbarrier
-    uint32_t phase;
+    int *pg;        // 23 x 24 ints: Q14 bilinear grid P (interior windows) or 22 x 22 packed Scharr taps (border windows)
+    uint64_t *bar_i, *bar_j;  // mbarriers: template window, search window
+    uint32_t phase_i, phase_j;
 };
+
+// Box origin for a (need_w x need_h) window whose top-left pixel is (px, py): keep `margin` pixels of slack on the low side, align x
+// to 16 bytes (TMA), and -- when the needed window lies inside the image -- slide the box back inside the image so that TMA never
+// zero-fills and no border patching is needed.  Only windows that really cross the image border keep an out-of-image box.
+__device__ __forceinline__ void box_origin(int px, int py, int need_w, int need_h, int margin, int box_h, const KltLevel &L, int &bx, int &by) {
+    bx = (px - margin) & ~15;
+    by = py - margin;
+    if (px >= 0 && py >= 0 && px + need_w <= L.W && py + need_h <= L.H) {
+        const int bx_max = (L.W - KLT_BOXW) & ~15, by_max = L.H - box_h;
+        if (bx_max >= 0) {
+            const int cb = max(0, min(bx, bx_max));
+            if (px - cb + need_w <= KLT_BOXW) bx = cb;  // (W - 48) & ~15 may stop short of the last columns of an odd-sized image
+        }
+        if (by_max >= 0) by = max(0, min(by, by_max));
+    }
+}
 
 __device__ __forceinline__ void window_fixup(uint8_t *w, int x0, int y0, int rows, const KltLevel &L, int slot, int lane) {
     // TMA zero-fills outside the tensor; OpenCV's pyramid is reflect-101 padded: patch the out-of-image bytes.
     if (x0 >= 0 && y0 >= 0 && x0 + KLT_BOXW <= L.W && y0 + rows <= L.H) return;
     const uint8_t *img = L.base + (size_t) slot * L.slot_stride;
-    for (int i = lane; i < KLT_BOXW * rows; i += 32) {
-        int r = i / KLT_BOXW, c = i - r * KLT_BOXW;
-        int x = x0 + c, y = y0 + r;
-        if (x < 0 || x >= L.W || y < 0 || y >= L.H) w[i] = img[(size_t) reflect101(y, L.H) * L.pitch + reflect101(x, L.W)];
+    const bool cols_in = x0 >= 0 && x0 + KLT_BOXW <= L.W;
+    for (int r = 0; r < rows; r++) {
+        const int y = y0 + r;
+        const bool row_out = y < 0 || y >= L.H;
+        if (!row_out && cols_in) continue;  // nothing to patch in this row
+        const int ry = reflect101(y, L.H);
+        for (int c = lane; c < KLT_BOXW; c += 32) {
+            const int x = x0 + c;
+            if (row_out || x < 0 || x >= L.W) w[r * KLT_BOXW + c] = img[(size_t) ry * L.pitch + reflect101(x, L.W)];
+        }
     }
     __syncwarp();
 }
@@ -163,6 +185,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
     float err_val = 0.f;
     float2 nextPt = make_float2(0.f, 0.f);
     const int maxLevel = A.n_levels - 1;
+    bool i_pending = false;  // a template-window TMA for the upcoming level is in flight
 
     for (int level = maxLevel; level >= 0; level--) {
         const KltLevel &L = A.lv[level];
@@ -190,64 +213,127 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         float nx = nextPt.x - half, ny = nextPt.y - half;
         int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
         const bool j_ok = !(inx < -KLT_WIN || inx >= L.W || iny < -KLT_WIN || iny >= L.H);
-        int jx0 = (inx - KLT_MARGIN) & ~15, jy0 = iny - KLT_MARGIN;
-        const int ix0 = (ipx - 1) & ~15;   // 16-byte aligned TMA x origin of the template window
-        const int oxI = ipx - 1 - ix0;     // 0..15
+        int jx0, jy0, ix0, iy0;
+        box_origin(inx, iny, 22, 22, KLT_MARGIN, KLT_BOXH_J, L, jx0, jy0);
+        box_origin(ipx - 1, ipy - 1, 24, 24, 0, KLT_BOXH_I, L, ix0, iy0);  // template window: 21 + 1 (bilinear) + 2 (Scharr)
+        const int oxI = ipx - 1 - ix0 + (ipy - 1 - iy0) * KLT_BOXW;        // byte offset of pixel (ipx-1, ipy-1) inside the staged window
+        // all 24x24 template taps inside the image <=> OpenCV's zero derivative border is never touched
+        const bool t_in = ipx - 1 >= 0 && ipy - 1 >= 0 && ipx + 23 <= L.W && ipy + 23 <= L.H;
 
-        // ---- stage template window (+ first search window) with TMA
+        // ---- stage the windows with TMA: the template window may already be in flight (prefetched by the previous level)
         __syncwarp();
         if (lane == 0) {
             fence_proxy_async();
-            mbar_expect_tx(S.bar, KLT_BOXW * KLT_BOXH_I + (j_ok ? KLT_BOXW * KLT_BOXH_J : 0));
-            tma_load_3d(S.iw, &maps.mi[level], ix0, ipy - 1, sI, S.bar);
-            if (j_ok) tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar);
+            if (!i_pending) {
+                mbar_expect_tx(S.bar_i, KLT_BOXW * KLT_BOXH_I);
+                tma_load_3d(S.iw, &maps.mi[level], ix0, iy0, sI, S.bar_i);
+            }
+            if (j_ok) {
+                mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
+                tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar_j);
+            }
         }
-        mbar_wait(S.bar, S.phase);
-        S.phase ^= 1;
-        window_fixup(S.iw, ix0, ipy - 1, KLT_BOXH_I, L, sI, lane);
-        if (j_ok) window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
+        i_pending = false;
+        mbar_wait(S.bar_i, S.phase_i);
+        S.phase_i ^= 1;
+        window_fixup(S.iw, ix0, iy0, KLT_BOXH_I, L, sI, lane);
 
-        // ---- Scharr derivatives on the 22x22 tap grid (zero outside the image: OpenCV pads derivI with zeros)
-        for (int i = lane; i < 22 * 22; i += 32) {
-            int dy = i / 22, dx = i - dy * 22;
-            const uint8_t *r0 = S.iw + dy * KLT_BOXW + dx + oxI;
-            const uint8_t *r1 = r0 + KLT_BOXW, *r2 = r1 + KLT_BOXW;
-            int t0m = 3 * (r0[0] + r2[0]) + 10 * r1[0];
-            int t0p = 3 * (r0[2] + r2[2]) + 10 * r1[2];
-            int t1m = r2[0] - r0[0], t1c = r2[1] - r0[1], t1p = r2[2] - r0[2];
-            int gx = t0p - t0m, gy = 3 * (t1m + t1p) + 10 * t1c;
-            int X = ipx + dx, Y = ipy + dy;
-            if (X < 0 || X >= L.W || Y < 0 || Y >= L.H) gx = gy = 0;
-            S.dv[i] = (gx & 0xFFFF) | (gy << 16);
-        }
-        __syncwarp();
-
-        // ---- template patch + structure tensor
         float a = px - (float) ipx, b = py - (float) ipy;
         int iw00, iw01, iw10, iw11;
         bilinear_weights(a, b, iw00, iw01, iw10, iw11);
         int Ireg[KLT_PXL], Greg[KLT_PXL];
         int sA11 = 0, sA12 = 0, sA22 = 0;
-#pragma unroll
-        for (int k = 0; k < KLT_PXL; k++) {
-            if (lane + 32 * k < KLT_WIN * KLT_WIN) {
-                int idx = lane + 32 * k;
-                int y = (idx * 3121) >> 16, x = idx - 21 * y;
-                const uint8_t *s = S.iw + (y + 1) * KLT_BOXW + x + 1 + oxI;
-                int ival = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
-                const int *d = S.dv + y * 22 + x;
-                int d00 = d[0], d01 = d[1], d10 = d[22], d11 = d[23];
-                int ixv = ((short) d00 * iw00 + (short) d01 * iw01 + (short) d10 * iw10 + (short) d11 * iw11 + (1 << 13)) >> 14;
-                int iyv = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
-                Ireg[k] = ival;
-                Greg[k] = (ixv & 0xFFFF) | (iyv << 16);
-                sA11 += ixv * ixv;
-                sA12 += ixv * iyv;
-                sA22 += iyv * iyv;
-            } else {
-                Ireg[k] = 0;
-                Greg[k] = 0;
+        if (t_in) {
+            // ---- interpolate first, differentiate second.  Scharr is linear and OpenCV rounds only AFTER interpolating, so
+            //      sum_taps w * Ix(tap) == Scharr_x(P) with P = sum_taps w * I(tap) (exact Q14 integers, |.| < 2^27):
+            //      one 23x23 grid gives I, Ix and Iy of the whole 21x21 template.
+            const uint8_t *w0 = S.iw + oxI;
+            if (lane < 23) {
+#pragma unroll 4
+                for (int gy = 0; gy < 23; gy++) {
+                    const uint8_t *sp = w0 + gy * KLT_BOXW + lane;
+                    S.pg[gy * 24 + lane] = sp[0] * iw00 + sp[1] * iw01 + sp[KLT_BOXW] * iw10 + sp[KLT_BOXW + 1] * iw11;
+                }
             }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < KLT_PXL; k++) {
+                if (lane + 32 * k < KLT_WIN * KLT_WIN) {
+                    const int idx = lane + 32 * k;
+                    const int y = (idx * 3121) >> 16, x = idx - 21 * y;
+                    const int *pp = S.pg + y * 24 + x;
+                    const int p00 = pp[0], p01 = pp[1], p02 = pp[2], p10 = pp[24], p11 = pp[25], p12 = pp[26], p20 = pp[48], p21 = pp[49], p22 = pp[50];
+                    const int ival = (p11 + (1 << 8)) >> 9;
+                    const int ixv = (3 * ((p02 - p00) + (p22 - p20)) + 10 * (p12 - p10) + (1 << 13)) >> 14;
+                    const int iyv = (3 * ((p20 - p00) + (p22 - p02)) + 10 * (p21 - p01) + (1 << 13)) >> 14;
+                    Ireg[k] = ival;
+                    Greg[k] = (ixv & 0xFFFF) | (iyv << 16);
+                    sA11 += ixv * ixv;
+                    sA12 += ixv * iyv;
+                    sA22 += iyv * iyv;
+                } else {
+                    Ireg[k] = 0;
+                    Greg[k] = 0;
+                }
+            }
+        } else {
+            // ---- window touches the image border: Scharr taps first (zero outside the image: OpenCV pads derivI with zeros)
+            for (int i = lane; i < 22 * 22; i += 32) {
+                int dy = i / 22, dx = i - dy * 22;
+                const uint8_t *r0 = S.iw + dy * KLT_BOXW + dx + oxI;
+                const uint8_t *r1 = r0 + KLT_BOXW, *r2 = r1 + KLT_BOXW;
+                int t0m = 3 * (r0[0] + r2[0]) + 10 * r1[0];
+                int t0p = 3 * (r0[2] + r2[2]) + 10 * r1[2];
+                int t1m = r2[0] - r0[0], t1c = r2[1] - r0[1], t1p = r2[2] - r0[2];
+                int gx = t0p - t0m, gy = 3 * (t1m + t1p) + 10 * t1c;
+                int X = ipx + dx, Y = ipy + dy;
+                if (X < 0 || X >= L.W || Y < 0 || Y >= L.H) gx = gy = 0;
+                S.pg[i] = (gx & 0xFFFF) | (gy << 16);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < KLT_PXL; k++) {
+                if (lane + 32 * k < KLT_WIN * KLT_WIN) {
+                    int idx = lane + 32 * k;
+                    int y = (idx * 3121) >> 16, x = idx - 21 * y;
+                    const uint8_t *sp = S.iw + (y + 1) * KLT_BOXW + x + 1 + oxI;
+                    int ival = (sp[0] * iw00 + sp[1] * iw01 + sp[KLT_BOXW] * iw10 + sp[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
+                    const int *d = S.pg + y * 22 + x;
+                    int d00 = d[0], d01 = d[1], d10 = d[22], d11 = d[23];
+                    int ixv = ((short) d00 * iw00 + (short) d01 * iw01 + (short) d10 * iw10 + (short) d11 * iw11 + (1 << 13)) >> 14;
+                    int iyv = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
+                    Ireg[k] = ival;
+                    Greg[k] = (ixv & 0xFFFF) | (iyv << 16);
+                    sA11 += ixv * ixv;
+                    sA12 += ixv * iyv;
+                    sA22 += iyv * iyv;
+                } else {
+                    Ireg[k] = 0;
+                    Greg[k] = 0;
+                }
+            }
+        }
+        // ---- the template now lives in registers: prefetch the NEXT level's template window while this level iterates
+        if (level > 0) {
+            const KltLevel &Ln = A.lv[level - 1];
+            const float sn = (float) (1. / (1 << (level - 1)));
+            const int npx = __float2int_rd(prev.x * sn - half), npy = __float2int_rd(prev.y * sn - half);
+            if (!(npx < -KLT_WIN || npx >= Ln.W || npy < -KLT_WIN || npy >= Ln.H)) {
+                int nx0, ny0;
+                box_origin(npx - 1, npy - 1, 24, 24, 0, KLT_BOXH_I, Ln, nx0, ny0);
+                __syncwarp();  // every lane is done reading the template window
+                if (lane == 0) {
+                    fence_proxy_async();
+                    mbar_expect_tx(S.bar_i, KLT_BOXW * KLT_BOXH_I);
+                    tma_load_3d(S.iw, &maps.mi[level - 1], nx0, ny0, sI, S.bar_i);
+                }
+                i_pending = true;
+            }
+        }
+        if (j_ok) {
+            mbar_wait(S.bar_j, S.phase_j);
+            S.phase_j ^= 1;
+            window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
         }
         // per-lane partials fit int32 (14 * 4080^2 < 2^28); the warp total needs 64 bits
         const float A11 = (float) warp_sum_exact(sA11) * FLT_SCALE;
@@ -272,19 +358,18 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             int ox = inx - jx0, oy = iny - jy0;
             if (ox < 0 || ox > KLT_BOXW - 22 || oy < 0 || oy > KLT_BOXH_J - 22) {
                 // the track left the staged window: re-centre it
-                jx0 = (inx - KLT_MARGIN) & ~15;
-                jy0 = iny - KLT_MARGIN;
+                box_origin(inx, iny, 22, 22, KLT_MARGIN, KLT_BOXH_J, L, jx0, jy0);
                 __syncwarp();
                 if (lane == 0) {
                     fence_proxy_async();
-                    mbar_expect_tx(S.bar, KLT_BOXW * KLT_BOXH_J);
-                    tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar);
+                    mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
+                    tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar_j);
                 }
-                mbar_wait(S.bar, S.phase);
-                S.phase ^= 1;
+                mbar_wait(S.bar_j, S.phase_j);
+                S.phase_j ^= 1;
                 window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
                 ox = inx - jx0;
-                oy = KLT_MARGIN;
+                oy = iny - jy0;
             }
             a = nx - (float) inx;
             b = ny - (float) iny;
@@ -326,19 +411,18 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             } else if (err_out != nullptr) {
                 int ox = fix - jx0, oy = fiy - jy0;
                 if (ox < 0 || ox > KLT_BOXW - 22 || oy < 0 || oy > KLT_BOXH_J - 22) {
-                    jx0 = (fix - KLT_MARGIN) & ~15;
-                    jy0 = fiy - KLT_MARGIN;
+                    box_origin(fix, fiy, 22, 22, KLT_MARGIN, KLT_BOXH_J, L, jx0, jy0);
                     __syncwarp();
                     if (lane == 0) {
                         fence_proxy_async();
-                        mbar_expect_tx(S.bar, KLT_BOXW * KLT_BOXH_J);
-                        tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar);
+                        mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
+                        tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar_j);
                     }
-                    mbar_wait(S.bar, S.phase);
-                    S.phase ^= 1;
+                    mbar_wait(S.bar_j, S.phase_j);
+                    S.phase_j ^= 1;
                     window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
                     ox = fix - jx0;
-                    oy = KLT_MARGIN;
+                    oy = fiy - jy0;
                 }
                 a = fx - (float) fix;
                 b = fy - (float) fiy;
@@ -364,13 +448,14 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
 __global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid_constant__ KltMaps maps, const KltArgs A) {
     __shared__ __align__(128) uint8_t s_iw[KLT_WPB][KLT_BOXW * KLT_BOXH_I];
     __shared__ __align__(128) uint8_t s_jw[KLT_WPB][KLT_BOXW * KLT_BOXH_J];
-    __shared__ int s_dv[KLT_WPB][22 * 22];
-    __shared__ __align__(8) uint64_t s_bar[KLT_WPB];
+    __shared__ int s_pg[KLT_WPB][23 * 24];
+    __shared__ __align__(8) uint64_t s_bar[KLT_WPB][2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int task = blockIdx.x * KLT_WPB + warp;
     if (lane == 0) {
-        mbar_init(&s_bar[warp], 1);
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
         fence_mbar_init();
     }
     __syncwarp();
@@ -379,9 +464,10 @@ __global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid
     WarpSmem S;
     S.iw    = s_iw[warp];
     S.jw    = s_jw[warp];
-    S.dv    = s_dv[warp];
-    S.bar   = &s_bar[warp];
-    S.phase = 0;
+    S.pg      = s_pg[warp];
+    S.bar_i   = &s_bar[warp][0];
+    S.bar_j   = &s_bar[warp][1];
+    S.phase_i = S.phase_j = 0;
 
     const int sP = A.slots[2 * task], sN = A.slots[2 * task + 1];
     const float2 prev = A.prev_xy[task];
