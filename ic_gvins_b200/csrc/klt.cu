@@ -30,12 +30,14 @@ constexpr int KLT_BOXW    = 48; // TMA box width in bytes: the innermost TMA coo
 constexpr int KLT_BOXH_J  = 32; // search-window rows (22 needed + 10 slack)
 constexpr int KLT_BOXH_I  = 24; // template-window rows (21 + 1 bilinear + 2 Scharr)
 constexpr int KLT_MARGIN  = 5;  // search window slack kept on the low side when (re-)centring
+constexpr int KLT_PAD     = 48; // reflect-101 padding stored around every pyramid plane: any TMA box the tracker can ask for
+                                // (x in [-41, W+42], y in [-26, H+26]) stays inside the plane, so no border patching is needed
 constexpr int KLT_WPB     = 4;  // warps per block
 constexpr int KLT_PXL     = 14; // template pixels per lane: ceil(441 / 32)
 
 struct KltLevel {
-    const uint8_t *base;
-    int W, H, pitch;
+    const uint8_t *base;  // padded plane origin of slot 0; pixel (x, y) of slot s lives at base + s*slot_stride + (y+PAD)*pitch + x+PAD
+    int W, H, pitch;      // logical size, padded row pitch (multiple of 16)
     size_t slot_stride;
 };
 
@@ -81,8 +83,8 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
     __shared__ uint8_t tile[2 * PD_TH + 4][2 * PD_TW + 4 + 4];
     __shared__ uint16_t hsum[2 * PD_TH + 4][PD_TW];
     const int slot = first_slot + blockIdx.z;
-    src += (size_t) slot * s_slot;
-    dst += (size_t) slot * d_slot;
+    src += (size_t) slot * s_slot + (size_t) KLT_PAD * spitch + KLT_PAD;  // interiors of the padded planes
+    dst += (size_t) slot * d_slot + (size_t) KLT_PAD * dpitch + KLT_PAD;
     const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
     const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
     const int tid = threadIdx.x;
@@ -109,6 +111,41 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
     }
 }
 
+// Fill the reflect-101 padding of all levels of a range of slots (OpenCV pads its pyramid the same way, lkpyramid.cpp).
+struct PadArgs {
+    uint8_t *base[KLT_LEVELS];
+    int W[KLT_LEVELS], H[KLT_LEVELS], pitch[KLT_LEVELS];
+    size_t slot_stride[KLT_LEVELS];
+    int off[KLT_LEVELS + 1];  // prefix sums of the per-level border element counts
+    int first_slot;
+};
+__global__ void __launch_bounds__(256) pad_fill_kernel(PadArgs P) {
+    // one flat index space over the border elements of all levels (prefix table in P.off), one grid row per slot
+    const int slot = P.first_slot + blockIdx.y;
+    const int total = P.off[KLT_LEVELS];
+    for (int g = blockIdx.x * 256 + threadIdx.x; g < total; g += gridDim.x * 256) {
+        int level = 0;
+        while (g >= P.off[level + 1]) level++;
+        const int e = g - P.off[level];
+        const int W = P.W[level], H = P.H[level], PW = W + 2 * KLT_PAD;
+        uint8_t *plane = P.base[level] + (size_t) slot * P.slot_stride[level];
+        // border elements enumerated as: PAD full rows on top, PAD full rows at the bottom, 2*PAD columns for each interior row
+        const int n_top = 2 * KLT_PAD * PW;
+        int xo, yo;
+        if (e < n_top) {
+            yo = e / PW, xo = e - yo * PW;
+            if (yo >= KLT_PAD) yo += H;
+        } else {
+            const int q = e - n_top;
+            yo = KLT_PAD + q / (2 * KLT_PAD);
+            xo = q % (2 * KLT_PAD);
+            if (xo >= KLT_PAD) xo += W;
+        }
+        const int rx = reflect101(xo - KLT_PAD, W), ry = reflect101(yo - KLT_PAD, H);
+        plane[(size_t) yo * P.pitch[level] + xo] = plane[(size_t) (ry + KLT_PAD) * P.pitch[level] + rx + KLT_PAD];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ LK tracker
 struct WarpSmem {
     uint8_t *iw;    // 48x24 template window, origin ((ipx-1) & ~15, ipy-1)
@@ -118,38 +155,10 @@ struct WarpSmem {
     uint32_t phase_i, phase_j;
 };
 
-// Box origin for a (need_w x need_h) window whose top-left pixel is (px, py): keep `margin` pixels of slack on the low side, align x
-// to 16 bytes (TMA), and -- when the needed window lies inside the image -- slide the box back inside the image so that TMA never
-// zero-fills and no border patching is needed.  Only windows that really cross the image border keep an out-of-image box.
-__device__ __forceinline__ void box_origin(int px, int py, int need_w, int need_h, int margin, int box_h, const KltLevel &L, int &bx, int &by) {
+// Box origin for a window whose top-left pixel is (px, py): `margin` pixels of slack on the low side, x aligned to 16 bytes (TMA).
+__device__ __forceinline__ void box_origin(int px, int py, int margin, int &bx, int &by) {
     bx = (px - margin) & ~15;
     by = py - margin;
-    if (px >= 0 && py >= 0 && px + need_w <= L.W && py + need_h <= L.H) {
-        const int bx_max = (L.W - KLT_BOXW) & ~15, by_max = L.H - box_h;
-        if (bx_max >= 0) {
-            const int cb = max(0, min(bx, bx_max));
-            if (px - cb + need_w <= KLT_BOXW) bx = cb;  // (W - 48) & ~15 may stop short of the last columns of an odd-sized image
-        }
-        if (by_max >= 0) by = max(0, min(by, by_max));
-    }
-}
-
-__device__ __forceinline__ void window_fixup(uint8_t *w, int x0, int y0, int rows, const KltLevel &L, int slot, int lane) {
-    // TMA zero-fills outside the tensor; OpenCV's pyramid is reflect-101 padded: patch the out-of-image bytes.
-    if (x0 >= 0 && y0 >= 0 && x0 + KLT_BOXW <= L.W && y0 + rows <= L.H) return;
-    const uint8_t *img = L.base + (size_t) slot * L.slot_stride;
-    const bool cols_in = x0 >= 0 && x0 + KLT_BOXW <= L.W;
-    for (int r = 0; r < rows; r++) {
-        const int y = y0 + r;
-        const bool row_out = y < 0 || y >= L.H;
-        if (!row_out && cols_in) continue;  // nothing to patch in this row
-        const int ry = reflect101(y, L.H);
-        for (int c = lane; c < KLT_BOXW; c += 32) {
-            const int x = x0 + c;
-            if (row_out || x < 0 || x >= L.W) w[r * KLT_BOXW + c] = img[(size_t) ry * L.pitch + reflect101(x, L.W)];
-        }
-    }
-    __syncwarp();
 }
 
 __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, int &iw01, int &iw10, int &iw11) {
@@ -214,8 +223,8 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
         const bool j_ok = !(inx < -KLT_WIN || inx >= L.W || iny < -KLT_WIN || iny >= L.H);
         int jx0, jy0, ix0, iy0;
-        box_origin(inx, iny, 22, 22, KLT_MARGIN, KLT_BOXH_J, L, jx0, jy0);
-        box_origin(ipx - 1, ipy - 1, 24, 24, 0, KLT_BOXH_I, L, ix0, iy0);  // template window: 21 + 1 (bilinear) + 2 (Scharr)
+        box_origin(inx, iny, KLT_MARGIN, jx0, jy0);
+        box_origin(ipx - 1, ipy - 1, 0, ix0, iy0);  // template window: 21 + 1 (bilinear) + 2 (Scharr)
         const int oxI = ipx - 1 - ix0 + (ipy - 1 - iy0) * KLT_BOXW;        // byte offset of pixel (ipx-1, ipy-1) inside the staged window
         // all 24x24 template taps inside the image <=> OpenCV's zero derivative border is never touched
         const bool t_in = ipx - 1 >= 0 && ipy - 1 >= 0 && ipx + 23 <= L.W && ipy + 23 <= L.H;
@@ -226,17 +235,16 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             fence_proxy_async();
             if (!i_pending) {
                 mbar_expect_tx(S.bar_i, KLT_BOXW * KLT_BOXH_I);
-                tma_load_3d(S.iw, &maps.mi[level], ix0, iy0, sI, S.bar_i);
+                tma_load_3d(S.iw, &maps.mi[level], ix0 + KLT_PAD, iy0 + KLT_PAD, sI, S.bar_i);
             }
             if (j_ok) {
                 mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
-                tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar_j);
+                tma_load_3d(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
             }
         }
         i_pending = false;
         mbar_wait(S.bar_i, S.phase_i);
         S.phase_i ^= 1;
-        window_fixup(S.iw, ix0, iy0, KLT_BOXH_I, L, sI, lane);
 
         float a = px - (float) ipx, b = py - (float) ipy;
         int iw00, iw01, iw10, iw11;
@@ -320,12 +328,12 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             const int npx = __float2int_rd(prev.x * sn - half), npy = __float2int_rd(prev.y * sn - half);
             if (!(npx < -KLT_WIN || npx >= Ln.W || npy < -KLT_WIN || npy >= Ln.H)) {
                 int nx0, ny0;
-                box_origin(npx - 1, npy - 1, 24, 24, 0, KLT_BOXH_I, Ln, nx0, ny0);
+                box_origin(npx - 1, npy - 1, 0, nx0, ny0);
                 __syncwarp();  // every lane is done reading the template window
                 if (lane == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(S.bar_i, KLT_BOXW * KLT_BOXH_I);
-                    tma_load_3d(S.iw, &maps.mi[level - 1], nx0, ny0, sI, S.bar_i);
+                    tma_load_3d(S.iw, &maps.mi[level - 1], nx0 + KLT_PAD, ny0 + KLT_PAD, sI, S.bar_i);
                 }
                 i_pending = true;
             }
@@ -333,7 +341,6 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         if (j_ok) {
             mbar_wait(S.bar_j, S.phase_j);
             S.phase_j ^= 1;
-            window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
         }
         // per-lane partials fit int32 (14 * 4080^2 < 2^28); the warp total needs 64 bits
         const float A11 = (float) warp_sum_exact(sA11) * FLT_SCALE;
@@ -358,16 +365,15 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             int ox = inx - jx0, oy = iny - jy0;
             if (ox < 0 || ox > KLT_BOXW - 22 || oy < 0 || oy > KLT_BOXH_J - 22) {
                 // the track left the staged window: re-centre it
-                box_origin(inx, iny, 22, 22, KLT_MARGIN, KLT_BOXH_J, L, jx0, jy0);
+                box_origin(inx, iny, KLT_MARGIN, jx0, jy0);
                 __syncwarp();
                 if (lane == 0) {
                     fence_proxy_async();
                     mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
-                    tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar_j);
+                    tma_load_3d(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
                 }
                 mbar_wait(S.bar_j, S.phase_j);
                 S.phase_j ^= 1;
-                window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
                 ox = inx - jx0;
                 oy = iny - jy0;
             }
@@ -411,16 +417,15 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             } else if (err_out != nullptr) {
                 int ox = fix - jx0, oy = fiy - jy0;
                 if (ox < 0 || ox > KLT_BOXW - 22 || oy < 0 || oy > KLT_BOXH_J - 22) {
-                    box_origin(fix, fiy, 22, 22, KLT_MARGIN, KLT_BOXH_J, L, jx0, jy0);
+                    box_origin(fix, fiy, KLT_MARGIN, jx0, jy0);
                     __syncwarp();
                     if (lane == 0) {
                         fence_proxy_async();
                         mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
-                        tma_load_3d(S.jw, &maps.mj[level], jx0, jy0, sJ, S.bar_j);
+                        tma_load_3d(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
                     }
                     mbar_wait(S.bar_j, S.phase_j);
                     S.phase_j ^= 1;
-                    window_fixup(S.jw, jx0, jy0, KLT_BOXH_J, L, sJ, lane);
                     ox = fix - jx0;
                     oy = fiy - jy0;
                 }
@@ -595,16 +600,16 @@ int icg_klt_create(icg_klt **out, int width, int height, int n_slots, int max_po
             w = (w + 1) / 2;
             hh = (hh + 1) / 2;
         }
-        int pitch = (w + 15) & ~15;
-        size_t slot_stride = (size_t) pitch * hh;
+        int pitch = (w + 2 * KLT_PAD + 15) & ~15;
+        size_t slot_stride = (size_t) pitch * (hh + 2 * KLT_PAD);
         ICG_CUDA(cudaMalloc(&h->planes[l], slot_stride * n_slots));
         ICG_CUDA(cudaMemsetAsync(h->planes[l], 0, slot_stride * n_slots, h->stream));
         h->lv[l] = KltLevel{h->planes[l], w, hh, pitch, slot_stride};
-        int rc = encode_tensor_map_u8_3d(&h->maps.mj[l], h->planes[l], (uint64_t) w, (uint64_t) hh, (uint64_t) n_slots, (uint64_t) pitch,
-                                         (uint64_t) slot_stride, KLT_BOXW, KLT_BOXH_J, 1);
+        int rc = encode_tensor_map_u8_3d(&h->maps.mj[l], h->planes[l], (uint64_t) (w + 2 * KLT_PAD), (uint64_t) (hh + 2 * KLT_PAD), (uint64_t) n_slots,
+                                         (uint64_t) pitch, (uint64_t) slot_stride, KLT_BOXW, KLT_BOXH_J, 1);
         if (rc != ICG_OK) return rc;
-        rc = encode_tensor_map_u8_3d(&h->maps.mi[l], h->planes[l], (uint64_t) w, (uint64_t) hh, (uint64_t) n_slots, (uint64_t) pitch,
-                                     (uint64_t) slot_stride, KLT_BOXW, KLT_BOXH_I, 1);
+        rc = encode_tensor_map_u8_3d(&h->maps.mi[l], h->planes[l], (uint64_t) (w + 2 * KLT_PAD), (uint64_t) (hh + 2 * KLT_PAD), (uint64_t) n_slots,
+                                     (uint64_t) pitch, (uint64_t) slot_stride, KLT_BOXW, KLT_BOXH_I, 1);
         if (rc != ICG_OK) return rc;
     }
     ICG_CUDA(cudaMalloc(&h->d_slots, sizeof(int32_t) * 2 * max_points));
@@ -646,7 +651,7 @@ int icg_klt_slot_level(icg_klt *h, int slot, int level, void **dev_ptr, int *pit
         set_error("icg_klt_slot_level: bad arguments");
         return ICG_EINVAL;
     }
-    if (dev_ptr) *dev_ptr = h->planes[level] + (size_t) slot * h->lv[level].slot_stride;
+    if (dev_ptr) *dev_ptr = h->planes[level] + (size_t) slot * h->lv[level].slot_stride + (size_t) KLT_PAD * h->lv[level].pitch + KLT_PAD;
     if (pitch) *pitch = h->lv[level].pitch;
     if (w) *w = h->lv[level].W;
     if (hgt) *hgt = h->lv[level].H;
@@ -669,6 +674,18 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
         ICG_CHECK_LAUNCH();
         count_launch();
     }
+    {
+        PadArgs P;
+        for (int l = 0; l < KLT_LEVELS; l++) {
+            P.base[l] = h->planes[l], P.W[l] = h->lv[l].W, P.H[l] = h->lv[l].H, P.pitch[l] = h->lv[l].pitch, P.slot_stride[l] = h->lv[l].slot_stride;
+        }
+        P.first_slot = first_slot;
+        P.off[0] = 0;
+        for (int l = 0; l < KLT_LEVELS; l++) P.off[l + 1] = P.off[l] + 2 * KLT_PAD * (h->lv[l].W + 2 * KLT_PAD) + h->lv[l].H * 2 * KLT_PAD;
+        pad_fill_kernel<<<dim3((P.off[KLT_LEVELS] + 1023) / 1024, count), 256, 0, h->stream>>>(P);
+        ICG_CHECK_LAUNCH();
+        count_launch();
+    }
     return ICG_OK;
 }
 
@@ -678,8 +695,8 @@ int icg_klt_upload_level0(icg_klt *h, int slot, const uint8_t *host_img, int str
         return ICG_EINVAL;
     }
     ICG_CUDA(cudaSetDevice(h->device));
-    ICG_CUDA(cudaMemcpy2DAsync(h->planes[0] + (size_t) slot * h->lv[0].slot_stride, h->lv[0].pitch, host_img, stride, h->W, h->H,
-                               cudaMemcpyHostToDevice, h->stream));
+    ICG_CUDA(cudaMemcpy2DAsync(h->planes[0] + (size_t) slot * h->lv[0].slot_stride + (size_t) KLT_PAD * h->lv[0].pitch + KLT_PAD, h->lv[0].pitch, host_img, stride,
+                               h->W, h->H, cudaMemcpyHostToDevice, h->stream));
     h->slot_hash[slot] = 0;
     return ICG_OK;
 }
@@ -697,7 +714,7 @@ int icg_klt_download_level(icg_klt *h, int slot, int level, uint8_t *host_img, i
     }
     ICG_CUDA(cudaSetDevice(h->device));
     const KltLevel &L = h->lv[level];
-    ICG_CUDA(cudaMemcpy2DAsync(host_img, stride, h->planes[level] + (size_t) slot * L.slot_stride, L.pitch, L.W, L.H,
+    ICG_CUDA(cudaMemcpy2DAsync(host_img, stride, h->planes[level] + (size_t) slot * L.slot_stride + (size_t) KLT_PAD * L.pitch + KLT_PAD, L.pitch, L.W, L.H,
                                cudaMemcpyDeviceToHost, h->stream));
     ICG_CUDA(cudaStreamSynchronize(h->stream));
     return ICG_OK;
