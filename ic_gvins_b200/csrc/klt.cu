@@ -74,75 +74,87 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ------------------------------------------------------------------------------------------------ pyrDown
 // cv::pyrDown: dst(y,x) = (sum_{i,j} k_i k_j src(2y+i, 2x+j) + 128) >> 8, k = [1 4 6 4 1], reflect-101.
-// One block produces a 64x16 output tile: stage the (2*64+4) x (2*16+4) input tile in smem (coalesced rows),
-// horizontal pass into int16 smem, vertical pass to the output.
-constexpr int PD_TW = 64, PD_TH = 16;
+// One thread per output pixel: five source rows, each read as two aligned 16-bit loads + one byte (2x-2 is even); neighbouring
+// threads overlap in L1.  HBM-bound: every source byte is fetched from DRAM once (W*H bytes in, W*H/4 out per level).
+__device__ __forceinline__ int pd_row5(const uint8_t *__restrict__ r, int x0) {
+    const unsigned a = *(const unsigned short *) (r + x0), b = *(const unsigned short *) (r + x0 + 2), c = r[x0 + 4];
+    return (int) (a & 0xff) + 4 * (int) (a >> 8) + 6 * (int) (b & 0xff) + 4 * (int) (b >> 8) + (int) c;
+}
 __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict__ src, int sW, int sH, int spitch, size_t s_slot,
                                                        uint8_t *__restrict__ dst, int dW, int dH, int dpitch, size_t d_slot,
                                                        int first_slot) {
-    __shared__ uint8_t tile[2 * PD_TH + 4][2 * PD_TW + 4 + 4];
-    __shared__ uint16_t hsum[2 * PD_TH + 4][PD_TW];
     const int slot = first_slot + blockIdx.z;
     src += (size_t) slot * s_slot + (size_t) KLT_PAD * spitch + KLT_PAD;  // interiors of the padded planes
     dst += (size_t) slot * d_slot + (size_t) KLT_PAD * dpitch + KLT_PAD;
-    const int ox = blockIdx.x * PD_TW, oy = blockIdx.y * PD_TH;
-    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
-    const int tid = threadIdx.x;
-    constexpr int IW = 2 * PD_TW + 4, IH = 2 * PD_TH + 4;
-    for (int i = tid; i < IW * IH; i += 256) {
-        int r = i / IW, c = i - r * IW;
-        int y = reflect101(iy0 + r, sH), x = reflect101(ix0 + c, sW);
-        tile[r][c] = src[(size_t) y * spitch + x];
-    }
-    __syncthreads();
-    for (int i = tid; i < IH * PD_TW; i += 256) {
-        int r = i / PD_TW, c = i - r * PD_TW;
-        const uint8_t *t = &tile[r][2 * c];
-        hsum[r][c] = (uint16_t) (t[0] + 4 * t[1] + 6 * t[2] + 4 * t[3] + t[4]);
-    }
-    __syncthreads();
-    for (int i = tid; i < PD_TH * PD_TW; i += 256) {
-        int r = i / PD_TW, c = i - r * PD_TW;
-        int x = ox + c, y = oy + r;
-        if (x < dW && y < dH) {
-            int s = hsum[2 * r][c] + 4 * hsum[2 * r + 1][c] + 6 * hsum[2 * r + 2][c] + 4 * hsum[2 * r + 3][c] + hsum[2 * r + 4][c];
-            dst[(size_t) y * dpitch + x] = (uint8_t) ((s + 128) >> 8);
+    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    if (x >= dW || y >= dH) return;
+    const int x0 = 2 * x - 2, y0 = 2 * y - 2;
+    int s;
+    if (x0 >= 0 && x0 + 4 < sW && y0 >= 0 && y0 + 4 < sH) {
+        const uint8_t *r = src + (size_t) y0 * spitch;
+        s = pd_row5(r, x0) + 4 * pd_row5(r + spitch, x0) + 6 * pd_row5(r + 2 * (size_t) spitch, x0) + 4 * pd_row5(r + 3 * (size_t) spitch, x0) +
+            pd_row5(r + 4 * (size_t) spitch, x0);
+    } else {
+        const int kk[5] = {1, 4, 6, 4, 1};
+        s = 0;
+        for (int j = 0; j < 5; j++) {
+            const uint8_t *r = src + (size_t) reflect101(y0 + j, sH) * spitch;
+            int rs = 0;
+            for (int i = 0; i < 5; i++) rs += kk[i] * r[reflect101(x0 + i, sW)];
+            s += kk[j] * rs;
         }
     }
+    dst[(size_t) y * dpitch + x] = (uint8_t) ((s + 128) >> 8);
 }
 
 // Fill the reflect-101 padding of all levels of a range of slots (OpenCV pads its pyramid the same way, lkpyramid.cpp).
+// One thread writes one aligned 16-byte chunk: whole rows for the PAD rows above / below, the two 48-byte side strips otherwise.
 struct PadArgs {
     uint8_t *base[KLT_LEVELS];
     int W[KLT_LEVELS], H[KLT_LEVELS], pitch[KLT_LEVELS];
     size_t slot_stride[KLT_LEVELS];
-    int off[KLT_LEVELS + 1];  // prefix sums of the per-level border element counts
+    int off[KLT_LEVELS + 1];  // prefix sums of the per-level chunk counts
     int first_slot;
 };
+__host__ __device__ inline int pad_chunks(int W, int H) {
+    const int row_chunks = (W + 2 * KLT_PAD + 15) / 16;
+    return 2 * KLT_PAD * row_chunks + H * 7;  // side strips: 3 chunks left, 4 chunks from the 16-byte boundary at or below PAD + W
+}
 __global__ void __launch_bounds__(256) pad_fill_kernel(PadArgs P) {
-    // one flat index space over the border elements of all levels (prefix table in P.off), one grid row per slot
     const int slot = P.first_slot + blockIdx.y;
     const int total = P.off[KLT_LEVELS];
     for (int g = blockIdx.x * 256 + threadIdx.x; g < total; g += gridDim.x * 256) {
         int level = 0;
         while (g >= P.off[level + 1]) level++;
-        const int e = g - P.off[level];
-        const int W = P.W[level], H = P.H[level], PW = W + 2 * KLT_PAD;
+        int e = g - P.off[level];
+        const int W = P.W[level], H = P.H[level], pitch = P.pitch[level];
+        const int row_chunks = (W + 2 * KLT_PAD + 15) / 16, side_chunks = 7;
         uint8_t *plane = P.base[level] + (size_t) slot * P.slot_stride[level];
-        // border elements enumerated as: PAD full rows on top, PAD full rows at the bottom, 2*PAD columns for each interior row
-        const int n_top = 2 * KLT_PAD * PW;
-        int xo, yo;
-        if (e < n_top) {
-            yo = e / PW, xo = e - yo * PW;
+        int yo, xo;  // padded coordinates of the chunk's first byte
+        if (e < 2 * KLT_PAD * row_chunks) {
+            yo = e / row_chunks, xo = 16 * (e - yo * row_chunks);
             if (yo >= KLT_PAD) yo += H;
         } else {
-            const int q = e - n_top;
-            yo = KLT_PAD + q / (2 * KLT_PAD);
-            xo = q % (2 * KLT_PAD);
-            if (xo >= KLT_PAD) xo += W;
+            e -= 2 * KLT_PAD * row_chunks;
+            yo = KLT_PAD + e / side_chunks;
+            const int c = e % side_chunks;
+            // left strip: chunks 0..2; right strip: 4 chunks from the 16-byte boundary at or below PAD + W (in-image bytes it
+            // covers are rewritten with their own values)
+            xo = c < 3 ? 16 * c : ((KLT_PAD + W) & ~15) + 16 * (c - 3);
         }
-        const int rx = reflect101(xo - KLT_PAD, W), ry = reflect101(yo - KLT_PAD, H);
-        plane[(size_t) yo * P.pitch[level] + xo] = plane[(size_t) (ry + KLT_PAD) * P.pitch[level] + rx + KLT_PAD];
+        const uint8_t *srow = plane + (size_t) (reflect101(yo - KLT_PAD, H) + KLT_PAD) * pitch + KLT_PAD;  // interior of the source row
+        union {
+            uint4 v;
+            uint8_t b[16];
+        } u;
+        const int lx = xo - KLT_PAD;  // logical x of the first byte
+        if (lx >= 0 && lx + 16 <= W && (((size_t) (srow + lx)) & 15) == 0) {
+            u.v = *(const uint4 *) (srow + lx);  // interior columns of a pad row: straight aligned copy
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) u.b[k] = srow[reflect101(lx + k, W)];
+        }
+        if (xo + 16 <= pitch) *(uint4 *) (plane + (size_t) yo * pitch + xo) = u.v;
     }
 }
 
@@ -168,12 +180,12 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, in
     iw11 = 16384 - iw00 - iw01 - iw10;
 }
 
-__device__ __forceinline__ long long warp_sum_exact(int v) {
-    // exact 64-bit sum of 32 int32 values with two REDUX instructions
+__device__ __forceinline__ float warp_sum_exact(int v) {
+    // exact sum of 32 int32 values (two REDUX on 16-bit halves, recombined exactly in f64), rounded ONCE to f32
     int lo = v & 0xFFFF, hi = v >> 16;
     int slo = __reduce_add_sync(0xffffffffu, lo);
     int shi = __reduce_add_sync(0xffffffffu, hi);
-    return (long long) shi * 65536ll + (long long) slo;
+    return (float) ((double) shi * 65536.0 + (double) slo);
 }
 
 // Track one point from image slot sI to image slot sJ through all levels.  All lanes hold identical scalars.
@@ -249,7 +261,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         float a = px - (float) ipx, b = py - (float) ipy;
         int iw00, iw01, iw10, iw11;
         bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-        int Ireg[KLT_PXL], Greg[KLT_PXL];
+        int Ireg[KLT_PXL], Gxr[KLT_PXL], Gyr[KLT_PXL];
         int sA11 = 0, sA12 = 0, sA22 = 0;
         if (t_in) {
             // ---- interpolate first, differentiate second.  Scharr is linear and OpenCV rounds only AFTER interpolating, so
@@ -275,13 +287,13 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                     const int ixv = (3 * ((p02 - p00) + (p22 - p20)) + 10 * (p12 - p10) + (1 << 13)) >> 14;
                     const int iyv = (3 * ((p20 - p00) + (p22 - p02)) + 10 * (p21 - p01) + (1 << 13)) >> 14;
                     Ireg[k] = ival;
-                    Greg[k] = (ixv & 0xFFFF) | (iyv << 16);
+                    Gxr[k] = ixv, Gyr[k] = iyv;
                     sA11 += ixv * ixv;
                     sA12 += ixv * iyv;
                     sA22 += iyv * iyv;
                 } else {
                     Ireg[k] = 0;
-                    Greg[k] = 0;
+                    Gxr[k] = Gyr[k] = 0;
                 }
             }
         } else {
@@ -311,13 +323,13 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                     int ixv = ((short) d00 * iw00 + (short) d01 * iw01 + (short) d10 * iw10 + (short) d11 * iw11 + (1 << 13)) >> 14;
                     int iyv = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
                     Ireg[k] = ival;
-                    Greg[k] = (ixv & 0xFFFF) | (iyv << 16);
+                    Gxr[k] = ixv, Gyr[k] = iyv;
                     sA11 += ixv * ixv;
                     sA12 += ixv * iyv;
                     sA22 += iyv * iyv;
                 } else {
                     Ireg[k] = 0;
-                    Greg[k] = 0;
+                    Gxr[k] = Gyr[k] = 0;
                 }
             }
         }
@@ -343,9 +355,9 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             S.phase_j ^= 1;
         }
         // per-lane partials fit int32 (14 * 4080^2 < 2^28); the warp total needs 64 bits
-        const float A11 = (float) warp_sum_exact(sA11) * FLT_SCALE;
-        const float A12 = (float) warp_sum_exact(sA12) * FLT_SCALE;
-        const float A22 = (float) warp_sum_exact(sA22) * FLT_SCALE;
+        const float A11 = warp_sum_exact(sA11) * FLT_SCALE;
+        const float A12 = warp_sum_exact(sA12) * FLT_SCALE;
+        const float A22 = warp_sum_exact(sA22) * FLT_SCALE;
         float D = A11 * A22 - A12 * A12;
         const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float) (2 * KLT_WIN * KLT_WIN);
         if ((double) minEig < A.min_eig_thr || D < 1.192092896e-07f) {
@@ -387,11 +399,11 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 const uint8_t *s = jb + joff[k];
                 int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
                 int diff = v - Ireg[k];
-                sb1 += diff * (int) (short) Greg[k];
-                sb2 += diff * (Greg[k] >> 16);
+                sb1 += diff * Gxr[k];
+                sb2 += diff * Gyr[k];
             }
-            const float b1 = (float) warp_sum_exact(sb1) * FLT_SCALE;
-            const float b2 = (float) warp_sum_exact(sb2) * FLT_SCALE;
+            const float b1 = warp_sum_exact(sb1) * FLT_SCALE;
+            const float b2 = warp_sum_exact(sb2) * FLT_SCALE;
             const float dx = (A12 * b2 - A22 * b1) * D;
             const float dy = (A12 * b1 - A11 * b2) * D;
             nx += dx;
@@ -442,7 +454,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                         se += abs(v - Ireg[k]);
                     }
                 }
-                err_val = (float) warp_sum_exact(se) * 1.f / (float) (32 * KLT_WIN * KLT_WIN);
+                err_val = warp_sum_exact(se) * 1.f / (float) (32 * KLT_WIN * KLT_WIN);
             }
         }
     }
@@ -668,7 +680,7 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
     ICG_CUDA(cudaSetDevice(h->device));
     for (int l = 1; l < KLT_LEVELS; l++) {
         const KltLevel &s = h->lv[l - 1], &d = h->lv[l];
-        dim3 grid((d.W + PD_TW - 1) / PD_TW, (d.H + PD_TH - 1) / PD_TH, count);
+        dim3 grid((d.W + 63) / 64, (d.H + 3) / 4, count);
         pyr_down_kernel<<<grid, 256, 0, h->stream>>>(s.base, s.W, s.H, s.pitch, s.slot_stride, h->planes[l], d.W, d.H, d.pitch,
                                                      d.slot_stride, first_slot);
         ICG_CHECK_LAUNCH();
@@ -681,8 +693,8 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
         }
         P.first_slot = first_slot;
         P.off[0] = 0;
-        for (int l = 0; l < KLT_LEVELS; l++) P.off[l + 1] = P.off[l] + 2 * KLT_PAD * (h->lv[l].W + 2 * KLT_PAD) + h->lv[l].H * 2 * KLT_PAD;
-        pad_fill_kernel<<<dim3((P.off[KLT_LEVELS] + 1023) / 1024, count), 256, 0, h->stream>>>(P);
+        for (int l = 0; l < KLT_LEVELS; l++) P.off[l + 1] = P.off[l] + pad_chunks(h->lv[l].W, h->lv[l].H);
+        pad_fill_kernel<<<dim3((P.off[KLT_LEVELS] + 255) / 256, count), 256, 0, h->stream>>>(P);
         ICG_CHECK_LAUNCH();
         count_launch();
     }
