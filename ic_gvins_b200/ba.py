@@ -63,6 +63,40 @@ def to_struct(prob: dict) -> BaProblem:
     return s
 
 
+def shard_window(prob: dict, rank: int, world: int) -> dict:
+    """Landmark shard `rank` of `world` of one window problem: block partition of the landmarks, each landmark keeps
+    all of its reprojection factors (the per-landmark loop at IG/ic_gvins.cc:1777-1834); the camera-side problem is replicated.
+    Returns a new dict whose `invdepth`, `f_*` arrays are the local slices (landmark indices remapped) plus `lm_lo`, `lm_hi`
+    (global landmark range) and `f_index` (global factor indices) for merging results back."""
+    L, F = prob["L"], prob["F"]
+    lo, hi = (L * rank) // world, (L * (rank + 1)) // world
+    f_lm = np.asarray(prob["f_lm"])
+    sel = np.nonzero((f_lm >= lo) & (f_lm < hi))[0]
+    out = dict(prob)
+    out.update(L=hi - lo, F=len(sel), invdepth=np.array(prob["invdepth"][lo:hi], np.float64),
+               f_lm=(f_lm[sel] - lo).astype(np.int32), f_ref=np.asarray(prob["f_ref"])[sel].astype(np.int32),
+               f_obs=np.asarray(prob["f_obs"])[sel].astype(np.int32),
+               f_const=np.asarray(prob["f_const"], np.float64).reshape(-1, 14)[sel].reshape(-1).copy(),
+               f_active=np.asarray(prob["f_active"], np.uint8)[sel].copy(), lm_lo=lo, lm_hi=hi, f_index=sel)
+    for k in ("pose", "mix", "ext", "gnss_std"):
+        out[k] = np.array(prob[k], copy=True)
+    return out
+
+
+def merge_shard(prob: dict, shard: dict) -> None:
+    """Write a solved shard's landmark results back into the full problem dict (camera-side blocks are identical on all shards)."""
+    prob["invdepth"][shard["lm_lo"]:shard["lm_hi"]] = shard["invdepth"]
+    prob["f_active"][shard["f_index"]] = shard["f_active"]
+    for k in ("pose", "mix", "ext", "gnss_std"):
+        prob[k][...] = shard[k]
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    check(lib().icg_nccl_unique_id(buf), "icg_nccl_unique_id")
+    return bytes(buf)
+
+
 def imu_preintegrate(state16, iewn, gravity, noise5, imu):
     """B3 host-side propagation in the product library (PreintegrationEarth::integrationProcess, preintegration_earth.cc:205-303)."""
     imu = np.ascontiguousarray(imu, np.float64)
@@ -93,6 +127,11 @@ class WindowSolver:
             self.close()
         except Exception:
             pass
+
+    def set_shard(self, rank: int, world: int, unique_id: bytes | None = None):
+        """Make this handle solve landmark shard `rank` of `world` (one process per GPU; NCCL all-reduce per LM attempt)."""
+        buf = (C.c_uint8 * 128)(*unique_id) if unique_id else None
+        check(lib().icg_ba_set_shard(self._h, rank, world, buf), "icg_ba_set_shard")
 
     def solve(self, problems, max_num_iterations: int):
         """ceres::Solver::Solve on a list of problem dicts (updated in place).  Returns a list of summaries."""

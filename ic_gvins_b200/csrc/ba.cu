@@ -18,7 +18,9 @@
 //   solve     : one CTA / window -> Jacobi scaling, LM diagonal, S = s(H - Schur)s + D^2, packed Cholesky in shared
 //               memory, triangular solves, landmark back-substitution, model cost change, candidate x (+) delta
 //   cost      : candidate cost (all factors, residuals only);   accept : Ceres step acceptance + radius update
+#include <dlfcn.h>
 #include <math.h>
+#include <nccl.h>
 #include <string.h>
 
 #include <algorithm>
@@ -48,7 +50,7 @@ struct WinDims {  // per-window actual sizes
 
 struct LmState {
     double radius, decrease_factor, x_cost, x_norm, cand_cost, model_cost_change, step_norm, gmax, initial_cost, cost_cam;
-    int iter, n_success, n_invalid, done, need_lin, last_success, first, step_valid, fresh_lin, max_iter;
+    int iter, n_success, n_invalid, done, need_lin, last_success, first, step_valid, fresh_lin, max_iter, chol_ok;
 };
 
 struct BaDev {  // device pointers (flat, capacity-strided by window)
@@ -74,6 +76,10 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     int *marg_type, *marg_node;
     double *marg_x0, *marg_H0, *marg_b0, *marg_c0;
     double *cost_part;  // [NW][ncost_blocks]
+    double *red;        // [NW][2*NCA*NCA + 8]: vision Gram | Schur term | scalars -- the operand of the landmark-shard all-reduce
+    double *redmax;     // [NW] max |g_l| over the local landmarks (max-reduced)
+    double *red2;       // [NW][4]: model cost change, step norm^2, non-finite count, candidate cost (sum-reduced)
+    int rank, world;    // landmark shard of this process (camera-only terms are counted on rank 0 only)
     double *step_c, *step_l;
     double *Sglobal;    // fallback Cholesky workspace when the packed system does not fit shared memory
 };
@@ -609,6 +615,58 @@ __global__ void __launch_bounds__(256) ba_lin_cam(BaCaps C, BaDev D) {
     if (threadIdx.x == 0) st.cost_cam = c;
 }
 
+__device__ __forceinline__ double block_sum(double v, double *s_red);
+__device__ __forceinline__ double block_max(double v, double *s_red);
+
+// ------------------------------------------------------------------------------------------------ reduction operands
+// Everything a landmark shard contributes to the window's reduced camera system goes into ONE contiguous buffer per window, so that
+// a sharded solve needs a single all-reduce (sum) per attempt: [H_vis g_vis | Schur term | vision cost, sum rho^2].
+__global__ void __launch_bounds__(256) ba_pack1(BaCaps C, BaDev D) {
+    __shared__ double s_red[40];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    const int NN = C.NCA * C.NCA;
+    double *R = D.red + (size_t) w * (2 * NN + 8);
+    const double *CJ = D.CJ + (size_t) w * BA_SPLIT_J * NN, *CW = D.CW + (size_t) w * BA_SPLIT_W * NN;
+    for (int e = tid; e < NN; e += 256) {
+        R[e] = CJ[e];
+        double s = 0;
+        for (int k = 0; k < BA_SPLIT_W; k++) s += CW[(size_t) k * NN + e];
+        R[NN + e] = s;
+    }
+    double c = 0, q = 0, gm = 0;
+    for (int f = tid; f < dm.F; f += 256) c += D.costf[(size_t) w * C.F + f];
+    for (int l = tid; l < dm.L; l += 256) {
+        const double r = D.rho[(size_t) w * C.L + l];
+        q += r * r;
+        gm = fmax(gm, fabs(D.gl[(size_t) w * C.L + l]));
+    }
+    c = block_sum(c, s_red);
+    q = block_sum(q, s_red);
+    gm = block_max(gm, s_red);
+    if (tid == 0) {
+        R[2 * NN] = c, R[2 * NN + 1] = q;
+        for (int k = 2; k < 8; k++) R[2 * NN + k] = 0;
+        D.redmax[w] = gm;
+    }
+}
+
+__global__ void ba_pack2(BaCaps C, BaDev D, int n, int nblk_vis) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const LmState &st = D.st[w];
+    if (st.done || !st.step_valid) return;
+    const WinDims dm = D.dims[w];
+    const double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
+    double cand = 0;
+    const int nb = (dm.F + 255) / 256;
+    for (int b = 0; b < nb; b++) cand += part[b];
+    if (D.rank == 0) cand += part[nblk_vis];  // camera-only factors are replicated on every shard: count them once
+    D.red2[(size_t) w * 4 + 3] = cand;
+}
+
 // ------------------------------------------------------------------------------------------------ solve (one CTA per window)
 constexpr int SOLVE_THREADS = 512;
 
@@ -661,17 +719,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
     double *s_diag = s_d2 + C.NS;       // N   Cholesky diagonal
     double *S = use_global_S ? D.Sglobal + (size_t) w * ((size_t) (C.N + 1) * (C.N + 2) / 2) : s_diag + C.NS;  // packed lower, N + 1 rows
     const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS;
-    const double *CJ = D.CJ + (size_t) w * BA_SPLIT_J * C.NCA * C.NCA, *CW = D.CW + (size_t) w * BA_SPLIT_W * C.NCA * C.NCA;
+    const double *RED = D.red + (size_t) w * (2 * C.NCA * C.NCA + 8);
+    const double *CJ = RED, *CW = RED + C.NCA * C.NCA;  // all-reduced (identical on every shard)
+    const double camw = D.rank == 0 ? 1.0 : 0.0;       // camera-side partial sums are counted on shard 0 only
     double *scale_c = D.scale_c + (size_t) w * C.NS;
     const double *hl = D.hl + (size_t) w * C.L, *gl = D.gl + (size_t) w * C.L, *scale_l = D.scale_l + (size_t) w * C.L;
 
     // ---- after a fresh linearisation: total cost, gradient, (first time) Jacobi scaling
     for (int a = tid; a < N; a += SOLVE_THREADS) {
         double g = gcam[a];
-        if (a < NCV) g += syrk_get(CJ, BA_SPLIT_J, C.NCA, a, NCV);
+        if (a < NCV) g += syrk_get(CJ, 1, C.NCA, a, NCV);
         s_g[a] = g;
         if (f_first) {
-            double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? syrk_get(CJ, BA_SPLIT_J, C.NCA, a, a) : 0.0);
+            double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? syrk_get(CJ, 1, C.NCA, a, a) : 0.0);
             scale_c[a] = 1.0 / (1.0 + sqrt(h));
         }
     }
@@ -679,13 +739,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
     for (int a = tid; a < N; a += SOLVE_THREADS) s_scale[a] = scale_c[a];
     double gmax_now = st.gmax;
     if (f_fresh) {
-        double c = 0;
-        for (int f = tid; f < dm.F; f += SOLVE_THREADS) c += D.costf[(size_t) w * C.F + f];
-        c = block_sum(c, s_red);
+        const double c = RED[2 * C.NCA * C.NCA];  // vision cost, summed over the landmark shards
         double gm = 0;
         for (int a = tid; a < N; a += SOLVE_THREADS) gm = fmax(gm, fabs(s_g[a]));
-        for (int l = tid; l < L; l += SOLVE_THREADS) gm = fmax(gm, fabs(gl[l]));
-        gm = block_max(gm, s_red);
+        gm = fmax(block_max(gm, s_red), D.redmax[w]);
         gmax_now = gm;
         if (tid == 0) {
             st.x_cost = c + st.cost_cam;
@@ -696,20 +753,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
         __syncthreads();
     }
     if (f_first) {
-        // x_norm (Ceres: x_.norm() of the reduced program)
-        double s = 0;
-        const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
-        for (int e = tid; e < K * 7; e += SOLVE_THREADS) s += pose[e] * pose[e];
-        for (int e = tid; e < K * 9; e += SOLVE_THREADS) s += mix[e] * mix[e];
-        if (tid < 7 && !dm.ext_const) s += ext[tid] * ext[tid];
-        if (tid == 7 && !dm.td_const) s += ext[7] * ext[7];
-        for (int e = tid; e < L; e += SOLVE_THREADS) s += rho[e] * rho[e];
-        s = block_sum(s, s_red);
-        if (tid == 0) {
-            st.x_norm = sqrt(s);
-            st.first = 0;
-        }
         __syncthreads();
+        if (tid == 0) st.first = 0;
     }
     // ---- TrustRegionMinimizer::FinalizeIterationAndCheckIfMinimizerCanContinue
     {
@@ -729,17 +774,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
 
     // ---- assemble S' = s (H - Schur) s + D^2 (packed lower), rhs' = -s (g - W phi g_l)
     for (int a = tid; a < N; a += SOLVE_THREADS) {
-        double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? syrk_get(CJ, BA_SPLIT_J, C.NCA, a, a) : 0.0);
+        double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? syrk_get(CJ, 1, C.NCA, a, a) : 0.0);
         double hs = s_scale[a] * s_scale[a] * h;
         s_d2[a] = fmin(fmax(hs, 1e-6), 1e32) / radius;
-        double gw = a < NCV ? syrk_get(CW, BA_SPLIT_W, C.NCA, a, NCV) : 0.0;
+        double gw = a < NCV ? syrk_get(CW, 1, C.NCA, a, NCV) : 0.0;
         s_rhs[a] = -s_scale[a] * (s_g[a] - gw);
     }
     __syncthreads();
     for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
         for (int j = tid & 31; j <= i; j += 32) {
             double h = Hc[(size_t) j * C.NS + i];
-            if (i < NCV) h += syrk_get(CJ, BA_SPLIT_J, C.NCA, j, i) - syrk_get(CW, BA_SPLIT_W, C.NCA, j, i);
+            if (i < NCV) h += syrk_get(CJ, 1, C.NCA, j, i) - syrk_get(CW, 1, C.NCA, j, i);
             double v = s_scale[i] * s_scale[j] * h;
             if (i == j) v += s_d2[i];
             S[i * (i + 1) / 2 + j] = v;
@@ -866,37 +911,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
     const double *AW = D.AW + (size_t) w * C.LP * C.NCA;  // landmark-major
     double part = 0;
     bool finite = true;
-    if (valid) {
-        for (int a = tid; a < N; a += SOLVE_THREADS) {
-            double sp = s_rhs[a];
-            finite = finite && isfinite(sp);
-            part += -0.5 * sp * (s_scale[a] * s_g[a]) + 0.5 * s_d2[a] * sp * sp;
-        }
-        for (int l = tid; l < L; l += SOLVE_THREADS) {
-            double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
-            double dotp = 0;
-            for (int c = 0; c < NCV; c++) dotp += AW[(size_t) l * C.NCA + c] * (s_scale[c] * s_rhs[c]);
-            double sp = (-sl * gl[l] - sl * dotp) / (hs + d2);
-            finite = finite && isfinite(sp);
-            step_l[l] = sp;
-            part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
-        }
-    }
-    double mcc = block_sum(part, s_red);
-    double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
-    valid = valid && nfin == 0.0 && mcc > 0.0;
+    double *R2 = D.red2 + (size_t) w * 4;
     if (!valid) {
-        // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
+        // Cholesky breakdown (identical on every shard): the step is invalid; ba_accept applies HandleInvalidStep
         if (tid == 0) {
-            st.step_valid = 0;
-            st.n_invalid++;
-            if (st.n_invalid >= 5) st.done = 3;  // FAILURE
-            st.radius *= 0.5;
-            st.last_success = 0;
+            st.chol_ok = 0, st.step_valid = 0;
+            R2[0] = 0, R2[1] = 0, R2[2] = 1, R2[3] = 0;
         }
         return;
     }
-    // ---- candidate point x (+) delta, delta = step' * scale; step_norm = |x - x_cand| over active blocks
+    for (int a = tid; a < N; a += SOLVE_THREADS) {
+        double sp = s_rhs[a];
+        finite = finite && isfinite(sp);
+        part += camw * (-0.5 * sp * (s_scale[a] * s_g[a]) + 0.5 * s_d2[a] * sp * sp);
+    }
+    for (int l = tid; l < L; l += SOLVE_THREADS) {
+        double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
+        double dotp = 0;
+        for (int c = 0; c < NCV; c++) dotp += AW[(size_t) l * C.NCA + c] * (s_scale[c] * s_rhs[c]);
+        double sp = (-sl * gl[l] - sl * dotp) / (hs + d2);
+        finite = finite && isfinite(sp);
+        step_l[l] = sp;
+        part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
+    }
+    const double mcc = block_sum(part, s_red);
+    const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
+    // ---- candidate point x (+) delta, delta = step' * scale; |x - x_cand|^2 over active blocks (camera part counted on shard 0)
     const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
     double *pose_c = D.pose_c + (size_t) w * C.K * 7, *mix_c = D.mix_c + (size_t) w * C.K * 9, *ext_c = D.ext_c + (size_t) w * 8, *rho_c = D.rho_c + (size_t) w * C.L;
     double sn = 0;
@@ -911,14 +951,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
             double d[6];
             for (int e = 0; e < 6; e++) d[e] = s_rhs[c0 + e] * s_scale[c0 + e];
             pose_plus(x, d, xc);
-            for (int e = 0; e < 7; e++) sn += (x[e] - xc[e]) * (x[e] - xc[e]);
+            for (int e = 0; e < 7; e++) sn += camw * (x[e] - xc[e]) * (x[e] - xc[e]);
         }
     }
     for (int e = tid; e < K * 9; e += SOLVE_THREADS) {
         int k = e / 9, q = e - 9 * k, c = col_mix(K, k) + q;
         double v = mix[e] + s_rhs[c] * s_scale[c];
         mix_c[e] = v;
-        sn += (mix[e] - v) * (mix[e] - v);
+        sn += camw * (mix[e] - v) * (mix[e] - v);
     }
     if (tid == 0) {
         if (dm.td_const) {
@@ -926,7 +966,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
         } else {
             double v = ext[7] + s_rhs[col_td(K)] * s_scale[col_td(K)];
             ext_c[7] = v;
-            sn += (ext[7] - v) * (ext[7] - v);
+            sn += camw * (ext[7] - v) * (ext[7] - v);
         }
     }
     for (int l = tid; l < L; l += SOLVE_THREADS) {
@@ -936,10 +976,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int
     }
     sn = block_sum(sn, s_red);
     if (tid == 0) {
-        st.step_valid = 1;
-        st.n_invalid = 0;
-        st.model_cost_change = mcc;
-        st.step_norm = sqrt(sn);
+        st.chol_ok = 1, st.step_valid = 1;  // provisional: ba_accept validates with the reduced model cost change
+        R2[0] = mcc, R2[1] = sn, R2[2] = nfin, R2[3] = 0;
     }
 }
 
@@ -978,41 +1016,66 @@ __global__ void __launch_bounds__(256) ba_cost(BaCaps C, BaDev D, int nblk_vis) 
 // ------------------------------------------------------------------------------------------------ accept / reject
 __global__ void __launch_bounds__(128) ba_accept(BaCaps C, BaDev D, int nblk_vis) {
     __shared__ int s_accept;
+    __shared__ double s_camsq;
+    __shared__ double s_red[40];
     const int w = blockIdx.x, tid = threadIdx.x;
     LmState &st = D.st[w];
-    if (st.done || !st.step_valid) return;
+    if (st.done) return;
     const WinDims dm = D.dims[w];
+    const int chol_ok = st.chol_ok;
+    const double *R2 = D.red2 + (size_t) w * 4;
+    // |x|^2 of the camera-side blocks (replicated on every shard); the landmark part comes from the reduced operand
+    {
+        const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8;
+        double s = 0;
+        for (int e = tid; e < dm.K * 7; e += 128) s += pose[e] * pose[e];
+        for (int e = tid; e < dm.K * 9; e += 128) s += mix[e] * mix[e];
+        if (tid < 7 && !dm.ext_const) s += ext[tid] * ext[tid];
+        if (tid == 7 && !dm.td_const) s += ext[7] * ext[7];
+        s = block_sum(s, s_red);
+        if (tid == 0) s_camsq = s;
+    }
+    __syncthreads();
     if (tid == 0) {
-        const double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
-        double cand = 0;
-        const int nb = (dm.F + 255) / 256;
-        for (int b = 0; b < nb; b++) cand += part[b];
-        cand += part[nblk_vis];
-        st.cand_cost = cand;
         s_accept = 0;
-        // ParameterToleranceReached / FunctionToleranceReached (Ceres trust_region_minimizer.cc)
-        if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) {
-            st.done = 2;
-        } else if (fabs(st.x_cost - cand) <= 1e-6 * st.x_cost) {
-            st.done = 2;
+        const double mcc = R2[0], sn = R2[1], nfin = R2[2], cand = R2[3];
+        if (!chol_ok || nfin != 0.0 || !(mcc > 0.0)) {
+            // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
+            st.step_valid = 0;
+            st.n_invalid++;
+            if (st.n_invalid >= 5) st.done = 3;  // FAILURE
+            st.radius *= 0.5;
+            st.last_success = 0;
         } else {
-            const double rel = (st.x_cost - cand) / st.model_cost_change;
-            if (rel > 1e-3) {
-                s_accept = 1;
-                st.n_success++;
-                // LevenbergMarquardtStrategy::StepAccepted
-                double t = 2.0 * rel - 1.0;
-                st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
-                st.decrease_factor = 2.0;
-                st.last_success = 1;
-                st.need_lin = 1;
-                st.fresh_lin = 1;
+            st.n_invalid = 0;
+            st.model_cost_change = mcc;
+            st.step_norm = sqrt(sn);
+            st.x_norm = sqrt(s_camsq + D.red[(size_t) w * (2 * C.NCA * C.NCA + 8) + 2 * C.NCA * C.NCA + 1]);
+            st.cand_cost = cand;
+            // ParameterToleranceReached / FunctionToleranceReached (Ceres trust_region_minimizer.cc)
+            if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) {
+                st.done = 2;
+            } else if (fabs(st.x_cost - cand) <= 1e-6 * st.x_cost) {
+                st.done = 2;
             } else {
-                // StepRejected
-                st.radius = st.radius / st.decrease_factor;
-                st.decrease_factor *= 2.0;
-                st.last_success = 0;
-                st.need_lin = 0;
+                const double rel = (st.x_cost - cand) / mcc;
+                if (rel > 1e-3) {
+                    s_accept = 1;
+                    st.n_success++;
+                    // LevenbergMarquardtStrategy::StepAccepted
+                    double t = 2.0 * rel - 1.0;
+                    st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+                    st.decrease_factor = 2.0;
+                    st.last_success = 1;
+                    st.need_lin = 1;
+                    st.fresh_lin = 1;
+                } else {
+                    // StepRejected
+                    st.radius = st.radius / st.decrease_factor;
+                    st.decrease_factor *= 2.0;
+                    st.last_success = 0;
+                    st.need_lin = 0;
+                }
             }
         }
     }
@@ -1020,17 +1083,10 @@ __global__ void __launch_bounds__(128) ba_accept(BaCaps C, BaDev D, int nblk_vis
     if (!s_accept) return;
     double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
     const double *pose_c = D.pose_c + (size_t) w * C.K * 7, *mix_c = D.mix_c + (size_t) w * C.K * 9, *ext_c = D.ext_c + (size_t) w * 8, *rho_c = D.rho_c + (size_t) w * C.L;
-    __shared__ double s_red[40];
-    double s = 0;
-    for (int e = tid; e < dm.K * 7; e += 128) pose[e] = pose_c[e], s += pose_c[e] * pose_c[e];
-    for (int e = tid; e < dm.K * 9; e += 128) mix[e] = mix_c[e], s += mix_c[e] * mix_c[e];
-    if (tid < 8) {
-        ext[tid] = ext_c[tid];
-        if ((tid < 7 && !dm.ext_const) || (tid == 7 && !dm.td_const)) s += ext_c[tid] * ext_c[tid];
-    }
-    for (int e = tid; e < dm.L; e += 128) rho[e] = rho_c[e], s += rho_c[e] * rho_c[e];
-    s = block_sum(s, s_red);
-    if (tid == 0) st.x_norm = sqrt(s);
+    for (int e = tid; e < dm.K * 7; e += 128) pose[e] = pose_c[e];
+    for (int e = tid; e < dm.K * 9; e += 128) mix[e] = mix_c[e];
+    if (tid < 8) ext[tid] = ext_c[tid];
+    for (int e = tid; e < dm.L; e += 128) rho[e] = rho_c[e];
 }
 
 // mark need_lin consumed after the linearisation kernels ran
@@ -1219,6 +1275,7 @@ struct icg_ba {
     HostDev<double> scratch;  // single-factor evaluation
     HostDev<LmState> st_save;   // pass-1 LM state of the two-pass protocol
     HostDev<int> cull_counters; // per window: reprojection factors removed, GNSS fixes re-weighted
+    void *comm = nullptr;       // ncclComm_t when this handle solves a landmark shard
 };
 
 static int dmalloc(icg_ba *h, double **p, size_t n) {
@@ -1230,6 +1287,43 @@ static int dmalloc(icg_ba *h, double **p, size_t n) {
     h->dev_only.push_back(*p);
     return ICG_OK;
 }
+
+// ---- NCCL, loaded at run time (only landmark-sharded solves need it; the KLT / single-GPU paths never touch it)
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl_api() {
+    static NcclApi api;
+    if (!api.lib) {
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) {
+            api.GetUniqueId = (decltype(api.GetUniqueId)) dlsym(api.lib, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank)) dlsym(api.lib, "ncclCommInitRank");
+            api.AllReduce = (decltype(api.AllReduce)) dlsym(api.lib, "ncclAllReduce");
+            api.CommDestroy = (decltype(api.CommDestroy)) dlsym(api.lib, "ncclCommDestroy");
+            api.GetErrorString = (decltype(api.GetErrorString)) dlsym(api.lib, "ncclGetErrorString");
+        }
+    }
+    return api;
+}
+}  // namespace
+
+static int nccl_allreduce(icg_ba *h, double *buf, size_t count, int op_max) {
+    NcclApi &a = nccl_api();
+    ncclResult_t r = a.AllReduce(buf, buf, count, ncclDouble, op_max ? ncclMax : ncclSum, (ncclComm_t) h->comm, h->stream);
+    if (r != ncclSuccess) {
+        set_error("ncclAllReduce failed: %s", a.GetErrorString ? a.GetErrorString(r) : "?");
+        return ICG_ENCCL;
+    }
+    return ICG_OK;
+}
+
 
 extern "C" {
 
@@ -1395,6 +1489,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
 #undef HD
     BaDev &D = h->D;
+    D.rank = 0, D.world = 1;
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
     D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
     D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
@@ -1409,7 +1504,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     DM(pose_0, NW * C.K * 7) DM(mix_0, NW * C.K * 9) DM(ext_0, NW * 8) DM(rho_0, NW * C.L)
     DM(AW, NW * C.NCA * C.LP) DM(Mp, NW * (size_t) C.K * (C.K - 1) * 210) DM(CJ, NW * BA_SPLIT_J * C.NCA * C.NCA) DM(CW, NW * BA_SPLIT_W * C.NCA * C.NCA)
     DM(jcomp, NW * C.F * 40) DM(jrho, NW * C.F * 2) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
-    DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
+    DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(red, NW * (2 * (size_t) C.NCA * C.NCA + 8)) DM(redmax, NW) DM(red2, NW * 4) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
 #undef DM
     if (rc != ICG_OK) return rc;
     // shared-memory budgets
@@ -1446,6 +1541,7 @@ void icg_ba_destroy(icg_ba *h) {
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
     h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
+    if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
     for (void *p : h->dev_only) cudaFree(p);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -1621,12 +1717,24 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
             ba_syrk<1><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
         else
             ba_syrk<BA_MAX_TILES><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
+        ba_pack1<<<n, 256, 0, s>>>(C, D);
+        if (h->comm) {  // landmark-sharded window: one sum all-reduce of [H_vis g | Schur | cost, |rho|^2] + one max all-reduce
+            int rc = nccl_allreduce(h, D.red, (size_t) n * (2 * (size_t) C.NCA * C.NCA + 8), 0);
+            if (rc != ICG_OK) return rc;
+            rc = nccl_allreduce(h, D.redmax, (size_t) n, 1);
+            if (rc != ICG_OK) return rc;
+        }
         ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
-        count_launch(8);
+        count_launch(9);
         if (it == max_num_iterations) break;
         ba_cost<<<g_cost, 256, h->smem_cam, s>>>(C, D, h->nblk_vis);
+        ba_pack2<<<(n + 127) / 128, 128, 0, s>>>(C, D, n, h->nblk_vis);
+        if (h->comm) {
+            int rc = nccl_allreduce(h, D.red2, (size_t) n * 4, 0);
+            if (rc != ICG_OK) return rc;
+        }
         ba_accept<<<n, 128, 0, s>>>(C, D, h->nblk_vis);
-        count_launch(2);
+        count_launch(3);
     }
     ICG_CHECK_LAUNCH();
     return ICG_OK;
@@ -1766,6 +1874,52 @@ int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *pr
         }
         if (culled) culled[2 * w] = h->cull_counters.h[2 * w], culled[2 * w + 1] = h->cull_counters.h[2 * w + 1];
     }
+    return ICG_OK;
+}
+
+int icg_nccl_unique_id(uint8_t *id128) {
+    NcclApi &a = nccl_api();
+    if (!a.lib || !a.GetUniqueId) {
+        set_error("icg_nccl_unique_id: libnccl.so.2 not loadable");
+        return ICG_ENCCL;
+    }
+    ncclUniqueId id;
+    ncclResult_t r = a.GetUniqueId(&id);
+    if (r != ncclSuccess) {
+        set_error("ncclGetUniqueId failed: %s", a.GetErrorString(r));
+        return ICG_ENCCL;
+    }
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(id128, &id, 128);
+    return ICG_OK;
+}
+
+int icg_ba_set_shard(icg_ba *h, int rank, int world, const uint8_t *id128) {
+    if (!h || rank < 0 || world < 1 || rank >= world) {
+        set_error("icg_ba_set_shard: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    NcclApi &a = nccl_api();
+    if (h->comm) {
+        a.CommDestroy((ncclComm_t) h->comm);
+        h->comm = nullptr;
+    }
+    h->D.rank = rank, h->D.world = world;
+    if (world == 1) return ICG_OK;
+    if (!id128 || !a.lib || !a.CommInitRank) {
+        set_error("icg_ba_set_shard: libnccl.so.2 not loadable or null id");
+        return ICG_ENCCL;
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm;
+    ncclResult_t r = a.CommInitRank(&comm, world, id, rank);
+    if (r != ncclSuccess) {
+        set_error("ncclCommInitRank failed: %s", a.GetErrorString(r));
+        return ICG_ENCCL;
+    }
+    h->comm = comm;
     return ICG_OK;
 }
 

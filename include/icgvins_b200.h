@@ -226,6 +226,17 @@ int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *pr
                               int32_t *culled);
 int icg_ba_run_gvins(icg_ba *h, int num_iterations, int restart);
 int icg_ba_sync(icg_ba *h);
+/*
+ * Landmark sharding of the window solve across the GPUs of one box: every process (one per GPU) uploads the same
+ * camera-side problem but only ITS landmarks and their reprojection factors; per LM attempt one NCCL sum all-reduce of the packed
+ * [vision Gram matrix + gradient | Schur term | vision cost, sum rho^2] buffer (+ an n-double max / 4n-double sum) makes the
+ * reduced camera system identical on all ranks, which then factorise it redundantly (deterministic, no broadcast) and
+ * back-substitute their own landmarks.  Camera-only factors (IMU, GNSS, priors) are evaluated by every rank and counted on rank 0.
+ * icg_nccl_unique_id: rank 0 creates the 128-byte ncclUniqueId, the caller distributes it (e.g. torch.distributed broadcast);
+ * icg_ba_set_shard(world = 1) returns the handle to single-GPU operation.  NCCL is dlopen-ed (libnccl.so.2) on first use.
+ */
+int icg_nccl_unique_id(uint8_t *id128);
+int icg_ba_set_shard(icg_ba *h, int rank, int world, const uint8_t *id128);
 /* Problem::EvaluateResidualBlock(id, false, &cost, NULL, NULL) for every reprojection / GNSS block
  * (the two chi-square passes, IG/ic_gvins.cc:1251,1278): cost = 0.5 |r|^2 without the loss function. */
 int icg_ba_residual_costs(icg_ba *h, const icg_ba_problem *problem, double *reproj_cost /* F */, double *gnss_cost /* n_gnss */);
