@@ -39,10 +39,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=148, help="independent streams (frames in flight) per GPU")
+    ap.add_argument("--streams", type=int, default=296, help="independent streams (frames in flight) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-ba", action="store_true")
+    ap.add_argument("--ba-handles", type=int, default=2, help="solver handles (CUDA streams) the B windows are split over")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the cfg-4 landmark-sharded BA section")
     return ap.parse_args()
 
 
@@ -274,27 +276,35 @@ def run_b200(args):
     e_slots = torch.empty((n_total, 2), dtype=torch.int32, device=dev)
 
     # ---- BA inputs: one cfg-3 window per stream (the product's own host-side preintegration builds the IMU factors)
-    solver = None
+    solvers = []
     if use_ba:
         def pre(st, iewn, g, nz, imu):
             blob, end = imu_preintegrate(st, iewn, g, nz, imu)
             return blob, np.zeros((imu.shape[0] - 1, 4)), end
-        windows = make_windows(B, pre, seed0=2024 + 1000 * rank)
-        maxF = max(w_["F"] for w_ in windows)
-        solver = WindowSolver(max_windows=B, max_K=10, max_L=300, max_F=maxF, max_gnss=8, max_marg_r=1, device=local_rank,
-                              stream=stream_ba.cuda_stream)
         import copy
-        win_e2e = [copy.deepcopy(w_) for w_ in windows]
-        solver.upload(windows)
-        solver.sync()
-        # e2e: the struct array over host arrays is what the reference's optimization thread would hand over each keyframe
-        e2e_init = [{k: np.array(w_[k], copy=True) for k in ("pose", "mix", "ext", "invdepth", "f_active", "gnss_std")} for w_ in win_e2e]
-        e2e_arr = (BaProblem * B)(*[to_struct(w_) for w_ in win_e2e])
-        e2e_sum = (BaSummary * (2 * B))()
+        base = make_windows(min(B, 64), pre, seed0=2024 + 1000 * rank)  # 64 distinct windows, repeated to fill the batch
+        windows = [copy.deepcopy(base[i % len(base)]) for i in range(B)]
+        maxF = max(w_["F"] for w_ in windows)
+        NH = max(1, min(args.ba_handles, B))
+        bounds = [(B * k) // NH for k in range(NH + 1)]
+        ba_streams = [stream_ba] + [torch.cuda.Stream(device=dev) for _ in range(NH - 1)]
+        e2e_parts = []
+        for k in range(NH):
+            part = windows[bounds[k]:bounds[k + 1]]
+            sv = WindowSolver(max_windows=len(part), max_K=10, max_L=300, max_F=maxF, max_gnss=8, max_marg_r=1, device=local_rank,
+                              stream=ba_streams[k].cuda_stream)
+            sv.upload(part)
+            sv.sync()
+            solvers.append(sv)
+            # e2e: the struct array over host arrays is what the reference's optimization thread would hand over each keyframe
+            pe = [copy.deepcopy(w_) for w_ in part]
+            init = [{q: np.array(w_[q], copy=True) for q in ("pose", "mix", "ext", "invdepth", "f_active", "gnss_std")} for w_ in pe]
+            e2e_parts.append((pe, init, (BaProblem * len(pe))(*[to_struct(w_) for w_ in pe]), (BaSummary * (2 * len(pe)))()))
         ba_h2d = int(sum(w_["F"] * (14 * 8 + 12 + 1) + 10 * 16 * 8 + 8 * 8 + 300 * 8 + 9 * 480 * 8 + 5 * 52 for w_ in windows))
         ba_d2h = int(sum(10 * 16 * 8 + 8 * 8 + 300 * 8 + w_["F"] for w_ in windows))
     else:
         ba_h2d = ba_d2h = 0
+        ba_streams = []
 
     def klt_resident(s):
         fb = seq[s + 1]
@@ -304,8 +314,8 @@ def run_b200(args):
 
     def step_resident(s):
         klt_resident(s)
-        if use_ba:
-            solver.run_gvins(20, restart=True)
+        for sv in solvers:
+            sv.run_gvins(20, restart=True)
 
     def step_e2e(s):
         fb = seq[s + 1]
@@ -321,11 +331,15 @@ def run_b200(args):
         with torch.cuda.stream(stream):
             h_fwd.copy_(d_fwd, non_blocking=True)
             h_st.copy_(d_st, non_blocking=True)
-        if use_ba:
-            for w_, init in zip(win_e2e, e2e_init):  # fresh initial guess every step (the solve updates in place)
-                for k, v in init.items():
-                    w_[k][...] = v
-            rc = lib().icg_ba_gvins_optimization(solver._h, B, e2e_arr, 20, e2e_sum, None)  # upload + solve + download (synchronous)
+        for sv, (pe, init, arr, summ) in zip(solvers, e2e_parts):
+            for w_, ini in zip(pe, init):  # fresh initial guess every step (the solve updates in place)
+                for q, v in ini.items():
+                    w_[q][...] = v
+            rc = lib().icg_ba_gvins_optimization_begin(sv._h, len(pe), arr, 20)  # pack + upload + enqueue (asynchronous)
+            if rc != 0:
+                raise RuntimeError(lib().icg_last_error().decode())
+        for sv, (pe, init, arr, summ) in zip(solvers, e2e_parts):
+            rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)  # synchronise + write back
             if rc != 0:
                 raise RuntimeError(lib().icg_last_error().decode())
 
@@ -339,13 +353,15 @@ def run_b200(args):
             if step_fn is not None:
                 step_fn(s)
             elif mode == "ba_only":
-                solver.run_gvins(20, restart=True)
+                for sv in solvers:
+                    sv.run_gvins(20, restart=True)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kev = []
         torch.cuda.synchronize()
         ev0.record(stream)
-        stream_ba.wait_stream(stream)
+        for bs in ba_streams:
+            bs.wait_stream(stream)
         for s in range(args.warmup, total):
             if mode == "klt_kernel":
                 fb = seq[s + 1]
@@ -358,13 +374,19 @@ def run_b200(args):
                 kev.append((a, b_))
             elif mode == "ba_only":
                 a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream_ba)
-                solver.run_gvins(20, restart=True)
-                b_.record(stream_ba)
+                a.record(stream)
+                for bs in ba_streams:
+                    bs.wait_stream(stream)
+                for sv in solvers:
+                    sv.run_gvins(20, restart=True)
+                for bs in ba_streams:
+                    stream.wait_stream(bs)
+                b_.record(stream)
                 kev.append((a, b_))
             else:
                 step_fn(s)
-        stream.wait_stream(stream_ba)   # the step ends when both the tracking and the optimization stream are done
+        for bs in ba_streams:
+            stream.wait_stream(bs)      # the step ends when the tracking and all optimization streams are done
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -387,10 +409,46 @@ def run_b200(args):
     good = int(d_st.sum().item())
     ba_info = None
     if use_ba:
-        sm = solver.download(write_back=False)
+        sm = [x for sv in solvers for x in sv.download(write_back=False)]
         ba_info = {"ms_per_batch": float(np.mean(bms)), "windows_per_batch": B, "solves_per_s": B / (float(np.mean(bms)) / 1e3) * world,
                    "mean_lm_iterations_pass2": float(np.mean([x["iterations"] for x in sm])),
                    "final_cost_mean": float(np.mean([x["final_cost"] for x in sm]))}
+
+    # ---- cfg 4: 20-KF / 2000-landmark windows, landmarks sharded over the ranks with an NCCL all-reduce per LM attempt
+    sharded = None
+    if use_ba and not args.no_sharded:
+        from ic_gvins_b200.ba import nccl_unique_id, shard_window
+        NW4 = 8
+        big = [__import__("datagen.synth_ba", fromlist=["x"]).make_window(pre, K=20, L=2000, seed=4000 + i)[0] for i in range(NW4)]
+        shards = [shard_window(p_, rank, world) for p_ in big]
+        s4 = WindowSolver(max_windows=NW4, max_K=20, max_L=max(x["L"] for x in shards), max_F=max(x["F"] for x in shards), max_gnss=16,
+                          max_marg_r=1, device=local_rank, stream=stream_ba.cuda_stream)
+        if world > 1:
+            ids = [nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            s4.set_shard(rank, world, ids[0])
+        s4.upload(shards)
+        for _ in range(2):
+            s4.run_gvins(20, restart=True)
+        barrier()
+        a4, b4 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps4 = 5
+        a4.record(stream_ba)
+        for _ in range(reps4):
+            s4.run_gvins(20, restart=True)
+        b4.record(stream_ba)
+        barrier()
+        ms4 = a4.elapsed_time(b4) / reps4
+        if world > 1:
+            t4 = torch.tensor([ms4], device=dev, dtype=torch.float64)
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            ms4 = float(t4.item())
+        sm4 = s4.download(write_back=False)
+        sharded = {"workload": "cfg4: 20-KF window, 2000 landmarks, landmarks block-partitioned over the ranks, NCCL all-reduce of the packed "
+                               "reduced-camera operands per LM attempt (strong scaling of one batch)", "windows": NW4, "ranks": world,
+                   "factors_per_window": int(np.mean([p_["F"] for p_ in big])), "ms_per_batch": ms4, "window_solves_per_s": NW4 / (ms4 / 1e3),
+                   "allreduce_bytes_per_attempt": int(NW4 * (2 * 128 * 128 + 8 + 1 + 4) * 8), "final_cost_window0": sm4[0]["final_cost"]}
+        s4.close()
 
     frames_per_step = B * world
     value = frames_per_step * args.steps / (ms_res / 1e3)
@@ -407,7 +465,7 @@ def run_b200(args):
         "metric": "frames/sec (KLT+BA) 1280x560 300-feat 10-KF window", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT), f64 (BA)", "data": "synthetic",
-        "config": {"workload": WORKLOAD if use_ba else WORKLOAD_KLT, "streams_per_gpu": B, "points_per_frame": NPTS,
+        "config": {"workload": WORKLOAD if use_ba else WORKLOAD_KLT, "streams_per_gpu": B, "points_per_frame": NPTS, "ba_solver_handles": len(solvers),
                    "l2": f"inputs larger than L2: {B * 2 * 1.127:.0f} MB of pyramids touched per step"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24) + ba_h2d,
                 "d2h_bytes_per_step": B * NPTS * 9 + ba_d2h},
@@ -419,6 +477,7 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": B * KLT_BYTES_PER_FRAME_TRACK},
         "klt_only": {"value": frames_per_step * args.steps / (ms_klt / 1e3), "unit": "frames/s"},
         "ba_only": ba_info,
+        "sharded_ba": sharded,
         "tracked_fraction": good / float(n_total),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -432,8 +491,8 @@ def run_b200(args):
     if rank == 0:
         print(json.dumps(line))
     trk.close()
-    if solver:
-        solver.close()
+    for sv in solvers:
+        sv.close()
     if world > 1:
         dist.destroy_process_group()
 

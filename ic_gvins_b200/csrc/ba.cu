@@ -187,7 +187,7 @@ __device__ __forceinline__ int tri20(int la, int lb) {  // index of (la <= lb) i
 constexpr int PG_CHUNK = 16;  // factors staged per warp pass
 // stage 1: one warp per (window, group): the group's packed 20x20 Gram matrix -> Mp (global, L2 resident)
 __global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) {
-    __shared__ double s_stage[8][PG_CHUNK * 40];
+    __shared__ __align__(16) double s_stage[8][PG_CHUNK * 40];
     __shared__ unsigned char s_ea[210], s_eb[210];
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
@@ -215,20 +215,38 @@ __global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) {
         oa[q] = jc_off(a), ob[q] = jc_off(b), ra[q] = jc_row1(a), rb[q] = jc_row1(b);
         acc[q] = 0;
     }
-    double *stg = s_stage[warp];
-    for (int base = poff[p]; base < poff[p + 1]; base += PG_CHUNK) {
-        const int cnt = min(PG_CHUNK, poff[p + 1] - base);
-        __syncwarp();
-        for (int e = lane; e < cnt * 40; e += 32) {
-            const int fi = e / 40, k = e - fi * 40;
-            stg[e] = D.jcomp[((size_t) w * C.F + pfidx[base + fi]) * 40 + k];
+    // double-buffered staging with cp.async (LDGSTS): the next chunk of records streams in while this one is multiplied
+    double *stg0 = s_stage[warp], *stg1 = s_stage[warp] + (PG_CHUNK / 2) * 40;
+    const int HC = PG_CHUNK / 2;
+    auto stage = [&](double *dst, int base, int cnt) {
+        for (int e = lane; e < cnt * 20; e += 32) {  // 16-byte pieces: 20 per 320-byte record
+            const int fi = e / 20, k = e - fi * 20;
+            const double *src = D.jcomp + ((size_t) w * C.F + pfidx[base + fi]) * 40 + 2 * k;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + fi * 40 + 2 * k)), "l"(src) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int pbeg = poff[p], pend = poff[p + 1];
+    int buf = 0;
+    if (pbeg < pend) stage(stg0, pbeg, min(HC, pend - pbeg));
+    for (int base = pbeg; base < pend; base += HC) {
+        const int cnt = min(HC, pend - base);
+        const int nbase = base + HC;
+        if (nbase < pend) {
+            stage(buf ? stg0 : stg1, nbase, min(HC, pend - nbase));
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncwarp();
+        const double *stg = buf ? stg1 : stg0;
         for (int fi = 0; fi < cnt; fi++) {
             const double *jc = stg + fi * 40;
 #pragma unroll
             for (int q = 0; q < 7; q++) acc[q] += jc[oa[q]] * jc[ob[q]] + jc[oa[q] + ra[q]] * jc[ob[q] + rb[q]];
         }
+        __syncwarp();
+        buf ^= 1;
     }
 #pragma unroll
     for (int q = 0; q < 7; q++)
@@ -668,7 +686,7 @@ __global__ void ba_pack2(BaCaps C, BaDev D, int n, int nblk_vis) {
 }
 
 // ------------------------------------------------------------------------------------------------ solve (one CTA per window)
-constexpr int SOLVE_THREADS = 512;
+constexpr int SOLVE_THREADS = 256;  // 2 CTAs (windows) per SM: 107 KB shared memory and <= 128 registers each
 
 __device__ __forceinline__ double block_sum(double v, double *s_red) {
     // deterministic block reduction (fixed tree)
@@ -700,7 +718,7 @@ __device__ __forceinline__ double block_max(double v, double *s_red) {
     return s_red[32];
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve(BaCaps C, BaDev D, int use_global_S) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, int use_global_S) {
     extern __shared__ double sm[];
     const int w = blockIdx.x, tid = threadIdx.x;
     LmState &st = D.st[w];
@@ -1848,12 +1866,18 @@ static void fill_summary(const LmState &st, icg_ba_summary &o) {
     o.initial_cost = st.initial_cost, o.final_cost = st.x_cost, o.final_radius = st.radius;
 }
 
-int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations, icg_ba_summary *summaries,
-                              int32_t *culled) {
+int icg_ba_gvins_optimization_begin(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations) {
     int rc = icg_ba_upload(h, n_windows, problems);
     if (rc != ICG_OK) return rc;
-    rc = icg_ba_run_gvins(h, num_iterations, 0);
-    if (rc != ICG_OK) return rc;
+    return icg_ba_run_gvins(h, num_iterations, 0);
+}
+
+int icg_ba_gvins_optimization_end(icg_ba *h, int n_windows, const icg_ba_problem *problems, icg_ba_summary *summaries, int32_t *culled) {
+    if (!h || !problems || n_windows < 1 || n_windows > h->cur_windows) {
+        set_error("icg_ba_gvins_optimization_end: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
     const BaCaps &C = h->C;
     cudaStream_t s = h->stream;
     ICG_CUDA(h->st_save.down(s, n_windows));
@@ -1861,7 +1885,7 @@ int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *pr
     ICG_CUDA(h->f_active.down(s, (size_t) n_windows * C.F));
     ICG_CUDA(h->gnss_std.down(s, (size_t) n_windows * C.G * 3));
     std::vector<icg_ba_summary> second(n_windows);
-    rc = icg_ba_download(h, n_windows, problems, second.data());
+    int rc = icg_ba_download(h, n_windows, problems, second.data());
     if (rc != ICG_OK) return rc;
     for (int w = 0; w < n_windows; w++) {
         const icg_ba_problem &p = problems[w];
@@ -1875,6 +1899,13 @@ int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *pr
         if (culled) culled[2 * w] = h->cull_counters.h[2 * w], culled[2 * w + 1] = h->cull_counters.h[2 * w + 1];
     }
     return ICG_OK;
+}
+
+int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations, icg_ba_summary *summaries,
+                              int32_t *culled) {
+    int rc = icg_ba_gvins_optimization_begin(h, n_windows, problems, num_iterations);
+    if (rc != ICG_OK) return rc;
+    return icg_ba_gvins_optimization_end(h, n_windows, problems, summaries, culled);
 }
 
 int icg_nccl_unique_id(uint8_t *id128) {

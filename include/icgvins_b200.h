@@ -225,6 +225,10 @@ int icg_ba_download(icg_ba *h, int n_windows, const icg_ba_problem *problems, ic
 int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations, icg_ba_summary *summaries,
                               int32_t *culled);
 int icg_ba_run_gvins(icg_ba *h, int num_iterations, int restart);
+/* The same call split in two so that a caller driving several handles (streams) can overlap them: _begin packs, uploads and
+ * enqueues (asynchronous on the handle's stream), _end synchronises and writes the results back. */
+int icg_ba_gvins_optimization_begin(icg_ba *h, int n_windows, const icg_ba_problem *problems, int num_iterations);
+int icg_ba_gvins_optimization_end(icg_ba *h, int n_windows, const icg_ba_problem *problems, icg_ba_summary *summaries, int32_t *culled);
 int icg_ba_sync(icg_ba *h);
 /*
  * Landmark sharding of the window solve across the GPUs of one box: every process (one per GPU) uploads the same
