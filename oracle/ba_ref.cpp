@@ -1002,6 +1002,194 @@ void gnss_costs(const WindowProblem &Wc, std::vector<double> &cost) {
     }
 }
 
+
+// ===================================================================================== sliding-window marginalization (B10)
+// Restates GVINS::gvinsMarginalization (ic_gvins/ic_gvins/ic_gvins.cc:1412-1640) + MarginalizationInfo
+// (ic_gvins/ic_gvins/factors/marginalization_info.h:73-253) + ResidualBlockInfo::Evaluate (residual_block_info.h:45-91).
+// Eigen::SelfAdjointEigenSolver is un-vendored; a cyclic two-sided Jacobi eigensolver stands in for it (same decomposition up
+// to rounding; the decomposition is pinned against numpy.linalg.eigh in tests/test_oracle_marg.py).
+void sym_eig_jacobi(std::vector<double> &A, int n, std::vector<double> &evals, std::vector<double> &V) {
+    // A: n x n row-major symmetric (destroyed); V columns = eigenvectors
+    V.assign((size_t) n * n, 0.0);
+    for (int i = 0; i < n; i++) V[(size_t) i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = 0, diag = 0;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) (i == j ? diag : off) += A[(size_t) i * n + j] * A[(size_t) i * n + j];
+        if (off <= 1e-60 || off <= 1e-34 * diag) break;
+        for (int p = 0; p < n - 1; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = A[(size_t) p * n + q];
+                if (apq == 0.0) continue;
+                const double app = A[(size_t) p * n + p], aqq = A[(size_t) q * n + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; k++) {  // columns p, q
+                    const double akp = A[(size_t) k * n + p], akq = A[(size_t) k * n + q];
+                    A[(size_t) k * n + p] = c * akp - s * akq;
+                    A[(size_t) k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; k++) {  // rows p, q
+                    const double apk = A[(size_t) p * n + k], aqk = A[(size_t) q * n + k];
+                    A[(size_t) p * n + k] = c * apk - s * aqk;
+                    A[(size_t) q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    const double vkp = V[(size_t) k * n + p], vkq = V[(size_t) k * n + q];
+                    V[(size_t) k * n + p] = c * vkp - s * vkq;
+                    V[(size_t) k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    evals.resize(n);
+    for (int i = 0; i < n; i++) evals[i] = A[(size_t) i * n + i];
+}
+
+void marginalize(WindowProblem &W, int num_marg, MargOut &out) {
+    const double EPS = 1e-8;  // MarginalizationInfo::EPS (marginalization_info.h:256)
+    const int K = W.K, L = W.L, F = (int) W.f_lm.size();
+    // ---- parameter blocks (ids in the order of ic_gvins.cc:1438-1476; no block is constant here: ResidualBlockInfo asks
+    //      the cost functions for every Jacobian, residual_block_info.h:49-57)
+    Program P;
+    for (int k = 0; k < K; k++) {
+        P.blocks.push_back({&W.pose[7 * k], 7, 6, true, false, 0});
+        P.blocks.push_back({&W.mix[9 * k], 9, 9, false, false, 0});
+    }
+    P.blocks.push_back({W.ext, 7, 6, true, false, 0});
+    P.blocks.push_back({&W.ext[7], 1, 1, false, false, 0});
+    P.lm_block0 = (int) P.blocks.size();
+    for (int l = 0; l < L; l++) P.blocks.push_back({&W.invdepth[l], 1, 1, false, false, 0});
+    const int NB = (int) P.blocks.size();
+    std::vector<char> is_marg(NB, 0), touched(NB, 0);
+    auto add = [&](const CostFunction *c, bool own, std::vector<int> blocks, std::vector<int> marg_idx) {
+        if (own) P.owned.push_back(c);
+        for (int b : blocks) touched[b] = 1;
+        for (int i : marg_idx) is_marg[blocks[i]] = 1;
+        P.residuals.push_back({c, false /* loss_function == nullptr everywhere, ic_gvins.cc:1499,1510,1532,1543,1605 */, std::move(blocks), true});
+    };
+    // the previous prior (ic_gvins.cc:1485-1501)
+    if (W.has_marg) {
+        std::vector<int> bl, mi;
+        for (size_t i = 0; i < W.marg_block_type.size(); i++) {
+            const int t = W.marg_block_type[i], nd = W.marg_block_node[i];
+            bl.push_back(t == 0 ? 2 * nd : t == 1 ? 2 * nd + 1 : t == 2 ? 2 * K : 2 * K + 1);
+            if ((t == 0 || t == 1) && nd < num_marg) mi.push_back((int) i);
+        }
+        add(&W.marg, false, bl, mi);
+    }
+    // GNSS factors at the removed nodes (:1505-1516)
+    for (size_t g = 0; g < W.gnss_node.size(); g++)
+        if (W.gnss_node[g] < num_marg)
+            add(new GnssFactor({W.gnss_blh[3 * g], W.gnss_blh[3 * g + 1], W.gnss_blh[3 * g + 2]}, {W.gnss_std[3 * g], W.gnss_std[3 * g + 1], W.gnss_std[3 * g + 2]},
+                               W.lever),
+                true, {2 * W.gnss_node[g]}, {0});
+    // preintegration factors (:1520-1538)
+    for (int k = 0; k < num_marg && k < (int) W.preint.size(); k++)
+        add(new PreintegrationFactor(&W.preint[k]), true, {2 * k, 2 * k + 1, 2 * k + 2, 2 * k + 3},
+            k == num_marg - 1 ? std::vector<int>{0, 1} : std::vector<int>{0, 1, 2, 3});
+    // first-window priors (:1542-1554)
+    if (W.has_pose_prior) add(&W.pose_prior, false, {0}, {0});
+    if (W.has_mix_prior) add(&W.mix_prior, false, {1}, {0});
+    // reprojection factors of the landmarks anchored in the oldest keyframe (:1559-1611)
+    for (int f = 0; f < F; f++) {
+        if (!W.f_active.empty() && !W.f_active[f]) continue;
+        if (W.f_ref[f] >= num_marg) continue;
+        const double *c = &W.f_const[14 * f];
+        add(new ReprojectionFactor({c[0], c[1], c[2]}, {c[3], c[4], c[5]}, {c[6], c[7], c[8]}, {c[9], c[10], c[11]}, c[12], c[13], W.reproj_std), true,
+            {2 * W.f_ref[f], 2 * W.f_obs[f], 2 * K, P.lm_block0 + W.f_lm[f], 2 * K + 1}, {0, 3});
+    }
+    // ---- updateParameterBlocksIndex (marginalization_info.h:228-251): marginalized blocks first.  The reference iterates
+    //      unordered_maps, so the order inside each group is implementation-defined; it only permutes rows / columns.  Here:
+    //      marginalized = [pose_k, mix_k (k < num_marg), landmarks ascending]; remained = [pose_k, mix_k (k >= num_marg), ext, td].
+    std::vector<int> col(NB, -1);
+    int idx = 0;
+    for (int b = 0; b < NB; b++)
+        if (touched[b] && is_marg[b]) col[b] = idx, idx += P.blocks[b].lsize;
+    const int m = idx;
+    out.block_type.clear(), out.block_node.clear(), out.x0.clear();
+    for (int b = 0; b < NB; b++)
+        if (touched[b] && !is_marg[b]) {
+            col[b] = idx, idx += P.blocks[b].lsize;
+            const int t = b < 2 * K ? (b & 1) : b == 2 * K ? 2 : 3;
+            out.block_type.push_back(t);
+            out.block_node.push_back(b < 2 * K ? b / 2 - num_marg : 0);  // node index in the window AFTER the removal
+            for (int k = 0; k < P.blocks[b].gsize; k++) out.x0.push_back(P.blocks[b].data[k]);  // preMarginalization copies the data (:270-283)
+        }
+    const int n0 = idx, r = n0 - m;
+    out.m = m, out.r = r;
+    if (m == 0) return;
+    // ---- preMarginalization + constructEquation (:195-226, 253-285)
+    std::vector<double> H0((size_t) n0 * n0, 0.0), b0(n0, 0.0);
+    for (const Residual &R : P.residuals) {
+        EvalBlock E;
+        evaluate_block(P, R, true, E);
+        const int nb = (int) R.blocks.size();
+        for (int i = 0; i < nb; i++) {
+            const int row0 = col[R.blocks[i]], rows = P.blocks[R.blocks[i]].lsize;
+            for (int j = i; j < nb; j++) {
+                const int col0 = col[R.blocks[j]], cols = P.blocks[R.blocks[j]].lsize;
+                for (int a = 0; a < rows; a++)
+                    for (int b = 0; b < cols; b++) {
+                        double s = 0;
+                        for (int k = 0; k < E.nres; k++) s += E.J[i][(size_t) k * rows + a] * E.J[j][(size_t) k * cols + b];
+                        H0[(size_t) (row0 + a) * n0 + col0 + b] += s;
+                        if (i != j) H0[(size_t) (col0 + b) * n0 + row0 + a] = H0[(size_t) (row0 + a) * n0 + col0 + b];
+                    }
+            }
+            for (int a = 0; a < rows; a++) {
+                double s = 0;
+                for (int k = 0; k < E.nres; k++) s += E.J[i][(size_t) k * rows + a] * E.r[k];
+                b0[row0 + a] -= s;
+            }
+        }
+    }
+    // ---- schurElimination (:170-193)
+    std::vector<double> Hmm((size_t) m * m), ev, V;
+    for (int i = 0; i < m; i++)
+        for (int j = 0; j < m; j++) Hmm[(size_t) i * m + j] = 0.5 * (H0[(size_t) i * n0 + j] + H0[(size_t) j * n0 + i]);
+    sym_eig_jacobi(Hmm, m, ev, V);
+    std::vector<double> Hinv((size_t) m * m, 0.0);
+    for (int k = 0; k < m; k++) {
+        if (!(ev[k] > EPS)) continue;
+        const double inv = 1.0 / ev[k];
+        for (int i = 0; i < m; i++)
+            for (int j = 0; j < m; j++) Hinv[(size_t) i * m + j] += V[(size_t) i * m + k] * inv * V[(size_t) j * m + k];
+    }
+    std::vector<double> T((size_t) r * m, 0.0);  // Hrm * Hmm^-1
+    for (int i = 0; i < r; i++)
+        for (int j = 0; j < m; j++) {
+            double s = 0;
+            for (int k = 0; k < m; k++) s += H0[(size_t) (m + i) * n0 + k] * Hinv[(size_t) k * m + j];
+            T[(size_t) i * m + j] = s;
+        }
+    out.Hp.assign((size_t) r * r, 0.0), out.bp.assign(r, 0.0);
+    for (int i = 0; i < r; i++) {
+        for (int j = 0; j < r; j++) {
+            double s = 0;
+            for (int k = 0; k < m; k++) s += T[(size_t) i * m + k] * H0[(size_t) k * n0 + m + j];
+            out.Hp[(size_t) i * r + j] = H0[(size_t) (m + i) * n0 + m + j] - s;
+        }
+        double s = 0;
+        for (int k = 0; k < m; k++) s += T[(size_t) i * m + k] * b0[k];
+        out.bp[i] = b0[m + i] - s;
+    }
+    // ---- linearization (:153-168)
+    std::vector<double> Hp = out.Hp, S, V2;
+    sym_eig_jacobi(Hp, r, S, V2);
+    out.J0.assign((size_t) r * r, 0.0), out.e0.assign(r, 0.0);
+    for (int k = 0; k < r; k++) {
+        const double s = S[k] > EPS ? S[k] : 0.0, sinv = S[k] > EPS ? 1.0 / S[k] : 0.0;
+        const double ss = std::sqrt(s), ssi = std::sqrt(sinv);
+        double d = 0;
+        for (int j = 0; j < r; j++) {
+            out.J0[(size_t) k * r + j] = ss * V2[(size_t) j * r + k];
+            d += V2[(size_t) j * r + k] * -out.bp[j];
+        }
+        out.e0[k] = ssi * d;
+    }
+}
+
 }  // namespace icgo
 
 // ===================================================================================== C API (ctypes) over the public problem struct
@@ -1181,6 +1369,35 @@ int icgo_pose_prior_eval(const double *pose, const double *prior7, const double 
     double *Jp[1] = {J};
     f.Evaluate(params, r, J ? Jp : nullptr);
     return 0;
+}
+
+// MarginalizationInfo::marginalization on the window held by `p` (num_marg oldest nodes + the landmarks anchored there).
+// Outputs are sized by the caller for r <= 15*K+7: block list, x0, J0 (r x r row-major), e0, Hp, bp.  Returns r (0: nothing to do).
+int icgo_ba_marginalize(const icg_ba_problem *p, const double *pn, const int32_t *pn_off, int num_marg, int32_t *m_out, int32_t *nblocks_out,
+                        int32_t *block_type, int32_t *block_node, double *x0, double *J0, double *e0, double *Hp, double *bp) {
+    WindowProblem W;
+    to_window(p, pn, pn_off, W);
+    MargOut M;
+    marginalize(W, num_marg, M);
+    if (m_out) *m_out = M.m;
+    if (nblocks_out) *nblocks_out = (int32_t) M.block_type.size();
+    for (size_t i = 0; i < M.block_type.size(); i++) block_type[i] = M.block_type[i], block_node[i] = M.block_node[i];
+    std::memcpy(x0, M.x0.data(), sizeof(double) * M.x0.size());
+    if (M.m > 0) {
+        std::memcpy(J0, M.J0.data(), sizeof(double) * M.J0.size());
+        std::memcpy(e0, M.e0.data(), sizeof(double) * M.e0.size());
+        if (Hp) std::memcpy(Hp, M.Hp.data(), sizeof(double) * M.Hp.size());
+        if (bp) std::memcpy(bp, M.bp.data(), sizeof(double) * M.bp.size());
+    }
+    return M.r;
+}
+
+// symmetric eigendecomposition used by the marginalization restatement (checked against numpy.linalg.eigh in the tests)
+void icgo_sym_eig(const double *A, int n, double *evals, double *V) {
+    std::vector<double> a(A, A + (size_t) n * n), e, v;
+    sym_eig_jacobi(a, n, e, v);
+    std::memcpy(evals, e.data(), sizeof(double) * n);
+    std::memcpy(V, v.data(), sizeof(double) * (size_t) n * n);
 }
 
 void icgo_pose_plus(const double *x, const double *delta, double *out) { pose_plus(x, delta, out); }

@@ -240,4 +240,16 @@ SolveSummary solve(WindowProblem &P, int max_num_iterations, int num_threads);
 void reproj_costs(const WindowProblem &P, std::vector<double> &cost);
 void gnss_costs(const WindowProblem &P, std::vector<double> &cost);
 
+// MarginalizationInfo::marginalization driven as GVINS::gvinsMarginalization does (ic_gvins.cc:1412-1640,
+// factors/marginalization_info.h:73-253): removes the num_marg oldest nodes and the landmarks anchored in them.
+struct MargOut {
+    int m = 0, r = 0;                         // marginalizedSize(), remainedSize()
+    std::vector<int> block_type, block_node;  // remained blocks (type 0 pose 1 mix 2 ext 3 td; node index after the removal)
+    std::vector<double> x0;                   // remainedBlockData(), concatenated global sizes
+    std::vector<double> J0, e0;               // linearizedJacobians() (r x r row-major), linearizedResiduals()
+    std::vector<double> Hp, bp;               // the Schur complement itself (for invariant comparisons)
+};
+void marginalize(WindowProblem &W, int num_marg, MargOut &out);
+void sym_eig_jacobi(std::vector<double> &A, int n, std::vector<double> &evals, std::vector<double> &V);
+
 }  // namespace icgo

@@ -66,6 +66,9 @@ def declare_ba(lib):
     lib.icgo_pose_prior_eval.argtypes = [vp, vp, vp, vp, vp]
     lib.icgo_pose_plus.argtypes = [vp, vp, vp]
     lib.icgo_pose_plus.restype = None
+    lib.icgo_ba_marginalize.argtypes = [C.POINTER(BaProblem), vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.icgo_sym_eig.argtypes = [vp, C.c_int, vp, vp]
+    lib.icgo_sym_eig.restype = None
 
 
 def preintegrate(lib, state16, iewn, gravity, noise5, imu):
@@ -97,6 +100,33 @@ def ba_residual_costs(lib, prob):
     gc = np.zeros(prob["n_gnss"])
     lib.icgo_ba_residual_costs(C.byref(s), _p(rc), _p(gc))
     return rc, gc
+
+
+def ba_marginalize(lib, prob, num_marg=1):
+    """MarginalizationInfo::marginalization on the window (oracle).  Returns a dict with the new prior in the layout
+    icg_ba_problem.marg_* uses (node indices already shifted by num_marg) + the Schur complement (Hp, bp)."""
+    from ic_gvins_b200.ba import to_struct
+    s = to_struct(prob)
+    pn = np.ascontiguousarray(prob["pn"], np.float64)
+    off = np.ascontiguousarray(prob["pn_off"], np.int32)
+    rmax = 15 * prob["K"] + 7
+    m = np.zeros(1, np.int32); nb = np.zeros(1, np.int32)
+    bt = np.zeros(2 * prob["K"] + 2, np.int32); bn = np.zeros(2 * prob["K"] + 2, np.int32)
+    x0 = np.zeros(16 * prob["K"] + 8); J0 = np.zeros(rmax * rmax); e0 = np.zeros(rmax); Hp = np.zeros(rmax * rmax); bp = np.zeros(rmax)
+    r = lib.icgo_ba_marginalize(C.byref(s), _p(pn), _p(off), num_marg, _p(m), _p(nb), _p(bt), _p(bn), _p(x0), _p(J0), _p(e0), _p(Hp), _p(bp))
+    nb = int(nb[0])
+    gs = {0: 7, 1: 9, 2: 7, 3: 1}
+    nx = sum(gs[int(t)] for t in bt[:nb])
+    return dict(m=int(m[0]), r=r, block_type=bt[:nb].copy(), block_node=bn[:nb].copy(), x0=x0[:nx].copy(),
+                J0=J0[:r * r].reshape(r, r).copy(), e0=e0[:r].copy(), Hp=Hp[:r * r].reshape(r, r).copy(), bp=bp[:r].copy())
+
+
+def sym_eig(lib, A):
+    A = np.ascontiguousarray(A, np.float64)
+    n = A.shape[0]
+    ev = np.zeros(n); V = np.zeros((n, n))
+    lib.icgo_sym_eig(_p(A), n, _p(ev), _p(V))
+    return ev, V
 
 
 def reproj_eval(lib, pose0, pose1, ext, rho, td, c14, std, want_jac=True):
