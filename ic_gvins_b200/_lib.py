@@ -84,6 +84,7 @@ def _declare(L: C.CDLL) -> None:
     L.icg_ba_residual_costs.argtypes = [vp, vp, vp, vp]
     L.icg_ba_reproj_evaluate.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp]
     L.icg_ba_imu_evaluate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.icg_ba_marginalize.argtypes = [vp, C.c_int, vp, vp, vp]
 
 
 # every symbol include/icgvins_b200.h declares (checked by tests/test_abi.py against the header text)
@@ -94,5 +95,5 @@ EXPORTS = [
     "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
     "icg_detect_create", "icg_detect_destroy", "icg_detect_blocks", "icg_corner_subpix",
     "icg_imu_preintegrate", "icg_ba_create", "icg_ba_destroy", "icg_ba_solve", "icg_ba_upload", "icg_ba_run", "icg_ba_download",
-    "icg_ba_sync", "icg_nccl_unique_id", "icg_ba_set_shard", "icg_ba_gvins_optimization", "icg_ba_run_gvins", "icg_ba_gvins_optimization_begin", "icg_ba_gvins_optimization_end", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate",
+    "icg_ba_sync", "icg_nccl_unique_id", "icg_ba_set_shard", "icg_ba_gvins_optimization", "icg_ba_run_gvins", "icg_ba_gvins_optimization_begin", "icg_ba_gvins_optimization_end", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate", "icg_ba_marginalize",
 ]

@@ -34,6 +34,12 @@ class BaProblem(C.Structure):
     ]
 
 
+class BaPrior(C.Structure):
+    """ctypes image of `icg_ba_prior`."""
+    _fields_ = [("m", C.c_int32), ("r", C.c_int32), ("nblocks", C.c_int32), ("rcap", C.c_int32), ("block_type", ip), ("block_node", ip),
+                ("x0", dp), ("J0", dp), ("e0", dp), ("Hp", dp), ("bp", dp)]
+
+
 class BaSummary(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("num_successful_steps", C.c_int32), ("termination", C.c_int32), ("reserved", C.c_int32),
                 ("initial_cost", C.c_double), ("final_cost", C.c_double), ("final_radius", C.c_double)]
@@ -211,6 +217,38 @@ class WindowSolver:
         prob["gnss_huber"] = 0
         s2 = self.solve(prob, second)[0]
         return dict(pass1=s1, pass2=s2, reproj_removed=int(out.sum()), gnss_reweighted=n_gnss_out)
+
+    def marginalize(self, problems, num_marg=1, want_schur=True):
+        """MarginalizationInfo::marginalization as GVINS::gvinsMarginalization drives it (IG/ic_gvins.cc:1412-1640) on a list of
+        windows: removes the `num_marg` oldest nodes + the landmarks anchored in them.  Returns one dict per window with the new
+        prior in the layout the problem dict's marg_* entries use (node indices already shifted)."""
+        if isinstance(problems, dict):
+            problems = [problems]
+        n = len(problems)
+        nm = np.full(n, num_marg, np.int32) if np.isscalar(num_marg) else np.ascontiguousarray(num_marg, np.int32)
+        arr = (BaProblem * n)(*[to_struct(p) for p in problems])
+        pri = (BaPrior * n)()
+        bufs = []
+        for w, p in enumerate(problems):
+            rcap = 15 * p["K"] + 7
+            b = dict(bt=np.zeros(2 * p["K"] + 2, np.int32), bn=np.zeros(2 * p["K"] + 2, np.int32), x0=np.zeros(16 * p["K"] + 8),
+                     J0=np.zeros(rcap * rcap), e0=np.zeros(rcap), Hp=np.zeros(rcap * rcap), bp=np.zeros(rcap))
+            bufs.append(b)
+            pri[w].rcap = rcap
+            pri[w].block_type, pri[w].block_node = b["bt"].ctypes.data_as(ip), b["bn"].ctypes.data_as(ip)
+            pri[w].x0, pri[w].J0, pri[w].e0 = b["x0"].ctypes.data_as(dp), b["J0"].ctypes.data_as(dp), b["e0"].ctypes.data_as(dp)
+            if want_schur:
+                pri[w].Hp, pri[w].bp = b["Hp"].ctypes.data_as(dp), b["bp"].ctypes.data_as(dp)
+        check(lib().icg_ba_marginalize(self._h, n, arr, vp(nm.ctypes.data), pri), "icg_ba_marginalize")
+        out = []
+        gs = {0: 7, 1: 9, 2: 7, 3: 1}
+        for w, b in enumerate(bufs):
+            r, nb = pri[w].r, pri[w].nblocks
+            nx = sum(gs[int(t)] for t in b["bt"][:nb])
+            out.append(dict(m=pri[w].m, r=r, block_type=b["bt"][:nb].copy(), block_node=b["bn"][:nb].copy(), x0=b["x0"][:nx].copy(),
+                            J0=b["J0"][:r * r].reshape(r, r).copy(), e0=b["e0"][:r].copy(),
+                            Hp=b["Hp"][:r * r].reshape(r, r).copy() if want_schur else None, bp=b["bp"][:r].copy() if want_schur else None))
+        return out
 
     # -- single-factor Evaluate (Ceres CostFunction contract), computed on the device
     def reproj_evaluate(self, pose0, pose1, ext, invdepth, td, const14, std, want_jac=True):

@@ -129,48 +129,58 @@ __global__ void __launch_bounds__(128) ba_lin_vis(BaCaps C, BaDev D) {
 }
 
 // ------------------------------------------------------------------------------------------------ lin_lm
-// One thread per (landmark, vision column): w_l[c] = sum over the landmark's factors of J_f[:, c]^T j_rho,f  (zero when the factor
-// does not touch column c); column NCV carries g_l = sum j_rho^T r, and that thread also produces h_l and the Jacobi scale.
-// A_W is landmark-major [l][NCA] so that a warp writes one contiguous row segment.
+// One warp per landmark: w_l[c] = sum over the landmark's factors of J_f[:, c]^T j_rho,f.  All factors of a landmark share the
+// reference node, the extrinsic and td (lanes 0..5, 12..17, 18 accumulate over the factors); each observing node appears once
+// (lanes 6..11 write their block directly).  Lane 19 produces g_l = sum j_rho^T r, lane 20 h_l = sum |j_rho|^2 (+ the Jacobi scale).
+// A_W is landmark-major [l][NCA]: the warp zeroes its row, then fills the <= 13 + 6 n_obs non-zeros.
+__device__ __forceinline__ int jc_off(int a) { return a < 18 ? (a / 6) * 12 + (a % 6) : 36 + 2 * (a - 18); }  // row 0 offset in a record
+__device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }                                           // + this for row 1
 __global__ void __launch_bounds__(256) ba_lin_lm(BaCaps C, BaDev D) {
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
     const WinDims dm = D.dims[w];
     const int K = dm.K, NCV = 6 * K + 7, NCA = 4 * ((NCV + 1 + 3) / 4);
-    const int t = blockIdx.x * 256 + threadIdx.x;
-    const int l = t / NCA, c = t - l * NCA;
+    const int lane = threadIdx.x & 31;
+    const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (l >= dm.L) return;
     const int *off = D.lm_off + (size_t) w * (C.L + 1);
     const int *fidx = D.lm_fidx + (size_t) w * C.F;
     const int f0 = off[l], f1 = off[l + 1];
-    double v = 0, h = 0;
-    if (c <= NCV) {
-        for (int q = f0; q < f1; q++) {
-            const int f = fidx[q];
-            const double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
-            const double *jr = D.jrho + ((size_t) w * C.F + f) * 2;
-            if (c == NCV) {
-                v += jr[0] * jc[38] + jr[1] * jc[39];
-                h += jr[0] * jr[0] + jr[1] * jr[1];
-                continue;
-            }
-            const int i = D.f_ref[(size_t) w * C.F + f], j = D.f_obs[(size_t) w * C.F + f];
-            int o = -1;
-            if (c >= col_pose(i) && c < col_pose(i) + 6) o = c - col_pose(i);
-            else if (c >= col_pose(j) && c < col_pose(j) + 6) o = 12 + c - col_pose(j);
-            else if (c >= col_ext(K) && c < col_ext(K) + 6) o = 24 + c - col_ext(K);
-            if (o >= 0)
-                v += jc[o] * jr[0] + jc[o + 6] * jr[1];
-            else if (c == col_td(K))
-                v += jc[36] * jr[0] + jc[37] * jr[1];
+    double *row = D.AW + ((size_t) w * C.LP + l) * C.NCA;
+    for (int c = lane; c < NCA; c += 32) row[c] = 0.0;
+    __syncwarp();
+    const int o0 = jc_off(lane < 19 ? lane : 0), o1 = o0 + jc_row1(lane < 19 ? lane : 0);
+    double acc = 0;
+    int ref = 0;
+    for (int q = f0; q < f1; q++) {
+        const int f = fidx[q];
+        const double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
+        const double jr0 = D.jrho[((size_t) w * C.F + f) * 2], jr1 = D.jrho[((size_t) w * C.F + f) * 2 + 1];
+        if (q == f0) ref = D.f_ref[(size_t) w * C.F + f];
+        if (lane < 19) {
+            const double v = jc[o0] * jr0 + jc[o1] * jr1;
+            if (lane >= 6 && lane < 12)
+                row[col_pose(D.f_obs[(size_t) w * C.F + f]) + lane - 6] += v;
+            else
+                acc += v;
+        } else if (lane == 19) {
+            acc += jr0 * jc[38] + jr1 * jc[39];
+        } else if (lane == 20) {
+            acc += jr0 * jr0 + jr1 * jr1;
         }
     }
-    D.AW[((size_t) w * C.LP + l) * C.NCA + c] = v;
-    if (c == NCV) {
-        D.hl[(size_t) w * C.L + l] = h;
-        D.gl[(size_t) w * C.L + l] = v;
-        if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(h));  // jacobi_scaling, once (iteration 0)
+    if (f1 > f0) {
+        if (lane < 6) row[col_pose(ref) + lane] = acc;
+        else if (lane >= 12 && lane < 18) row[col_ext(K) + lane - 12] = acc;
+        else if (lane == 18) row[col_td(K)] = acc;
+    }
+    if (lane == 19) {
+        row[NCV] = acc;
+        D.gl[(size_t) w * C.L + l] = acc;
+    } else if (lane == 20) {
+        D.hl[(size_t) w * C.L + l] = acc;
+        if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(acc));  // jacobi_scaling, once (iteration 0)
     }
 }
 
@@ -179,78 +189,68 @@ __global__ void __launch_bounds__(256) ba_lin_lm(BaCaps C, BaDev D) {
 // [ref pose 6 | obs pose 6 | extrinsic 6 | td 1] (+ the residual as a 20th column), so the group's contribution is the dense
 // 20x20 Gram matrix of its stacked 2x20 rows: stage 1 (warp / group) computes it, stage 2 (thread / output entry) gathers the
 // groups into the symmetric (NCV+1)^2 matrix [H_vis g_vis; g_vis^T r^T r].  No atomics: every output has one writer.
-__device__ __forceinline__ int jc_off(int a) { return a < 18 ? (a / 6) * 12 + (a % 6) : 36 + 2 * (a - 18); }  // row 0 offset in a record
-__device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }                                           // + this for row 1
 __device__ __forceinline__ int tri20(int la, int lb) {  // index of (la <= lb) in the packed upper 20x20
     return la * 20 - la * (la - 1) / 2 + (lb - la);
 }
-constexpr int PG_CHUNK = 16;  // factors staged per warp pass
-// stage 1: one warp per (window, group): the group's packed 20x20 Gram matrix -> Mp (global, L2 resident)
+// stage 1: one warp per (window, group): the group's packed 20x20 Gram matrix -> Mp (global, L2 resident).
+// FP64 tensor cores (DMMA.8x8x4): the stacked 2x20 rows X of the group are multiplied as X^T X, 4 rows (2 factors) per k-step.
+// With the m8n8k4 fragment layout (A: lane -> (row lane/4, k lane%4); B: lane -> (k lane%4, col lane/4)) the A operand of
+// X^T X and the B operand are the SAME register: lane loads X[k = lane%4][8 t + lane/4] for the three column tiles t and issues
+// the six upper-triangular tile products.  Records are read straight from L2 (each 320-byte record is consumed whole by the warp).
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 __global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) {
-    __shared__ __align__(16) double s_stage[8][PG_CHUNK * 40];
-    __shared__ unsigned char s_ea[210], s_eb[210];
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PM = C.K * (C.K - 1);
     const int P = D.npairs[w];
-    if ((int) blockIdx.x * 8 >= P) return;
-    const int *poff = D.pair_off + (size_t) w * (PM + 1), *pfidx = D.pair_fidx + (size_t) w * C.F;
-    double *Mp = D.Mp + (size_t) w * PM * 210;
-    if (tid < 210) {
-        int e = tid, a = 0;
-        while (e >= 20 - a) e -= 20 - a, a++;
-        s_ea[tid] = (unsigned char) a, s_eb[tid] = (unsigned char) (a + e);
-    }
-    __syncthreads();
     const int p = blockIdx.x * 8 + warp;
     if (p >= P) return;
-    int oa[7], ob[7], ra[7], rb[7];
-    double acc[7];
+    const int *poff = D.pair_off + (size_t) w * (PM + 1), *pfidx = D.pair_fidx + (size_t) w * C.F;
+    double *Mp = D.Mp + (size_t) w * PM * 210;
+    const int kk = lane & 3, g = lane >> 2;  // k index inside the step (factor kk/2, residual row kk%2), column inside the tile
+    int o[3];
 #pragma unroll
-    for (int q = 0; q < 7; q++) {
-        const int e = lane + 32 * q;
-        const int a = e < 210 ? s_ea[e] : 0, b = e < 210 ? s_eb[e] : 0;
-        oa[q] = jc_off(a), ob[q] = jc_off(b), ra[q] = jc_row1(a), rb[q] = jc_row1(b);
-        acc[q] = 0;
+    for (int t = 0; t < 3; t++) {
+        const int a = 8 * t + g;
+        o[t] = a < 20 ? jc_off(a) + (kk & 1) * jc_row1(a) : -1;
     }
-    // double-buffered staging with cp.async (LDGSTS): the next chunk of records streams in while this one is multiplied
-    double *stg0 = s_stage[warp], *stg1 = s_stage[warp] + (PG_CHUNK / 2) * 40;
-    const int HC = PG_CHUNK / 2;
-    auto stage = [&](double *dst, int base, int cnt) {
-        for (int e = lane; e < cnt * 20; e += 32) {  // 16-byte pieces: 20 per 320-byte record
-            const int fi = e / 20, k = e - fi * 20;
-            const double *src = D.jcomp + ((size_t) w * C.F + pfidx[base + fi]) * 40 + 2 * k;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + fi * 40 + 2 * k)), "l"(src) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
+    double c00[2] = {0, 0}, c01[2] = {0, 0}, c02[2] = {0, 0}, c11[2] = {0, 0}, c12[2] = {0, 0}, c22[2] = {0, 0};
     const int pbeg = poff[p], pend = poff[p + 1];
-    int buf = 0;
-    if (pbeg < pend) stage(stg0, pbeg, min(HC, pend - pbeg));
-    for (int base = pbeg; base < pend; base += HC) {
-        const int cnt = min(HC, pend - base);
-        const int nbase = base + HC;
-        if (nbase < pend) {
-            stage(buf ? stg0 : stg1, nbase, min(HC, pend - nbase));
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncwarp();
-        const double *stg = buf ? stg1 : stg0;
-        for (int fi = 0; fi < cnt; fi++) {
-            const double *jc = stg + fi * 40;
+    const double *rec = D.jcomp + (size_t) w * C.F * 40;
+    constexpr int UNR = 4;  // k-steps in flight (8 factors)
+    for (int base = pbeg; base < pend; base += 2 * UNR) {
+        double x[UNR][3];
 #pragma unroll
-            for (int q = 0; q < 7; q++) acc[q] += jc[oa[q]] * jc[ob[q]] + jc[oa[q] + ra[q]] * jc[ob[q] + rb[q]];
+        for (int u = 0; u < UNR; u++) {
+            const int q = base + 2 * u + (kk >> 1);
+            const bool ok = q < pend;
+            const int f = ok ? pfidx[q] : 0;
+#pragma unroll
+            for (int t = 0; t < 3; t++) x[u][t] = (ok && o[t] >= 0) ? rec[(size_t) f * 40 + o[t]] : 0.0;
         }
-        __syncwarp();
-        buf ^= 1;
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            dmma884(c00[0], c00[1], x[u][0], x[u][0]);
+            dmma884(c01[0], c01[1], x[u][0], x[u][1]);
+            dmma884(c02[0], c02[1], x[u][0], x[u][2]);
+            dmma884(c11[0], c11[1], x[u][1], x[u][1]);
+            dmma884(c12[0], c12[1], x[u][1], x[u][2]);
+            dmma884(c22[0], c22[1], x[u][2], x[u][2]);
+        }
     }
+    // C fragment: lane holds (row lane/4, cols 2 (lane%4) + {0,1}) of each 8x8 tile
+    auto put = [&](int ti, int tj, const double *c) {
 #pragma unroll
-    for (int q = 0; q < 7; q++)
-        if (lane + 32 * q < 210) Mp[(size_t) p * 210 + lane + 32 * q] = acc[q];
+        for (int e = 0; e < 2; e++) {
+            const int la = 8 * ti + g, lb = 8 * tj + 2 * kk + e;
+            if (la <= lb && lb < 20) Mp[(size_t) p * 210 + tri20(la, lb)] = c[e];
+        }
+    };
+    put(0, 0, c00), put(0, 1, c01), put(0, 2, c02), put(1, 1, c11), put(1, 2, c12), put(2, 2, c22);
 }
 
 // stage 2: one thread per output entry gathers the groups that touch both of its blocks (one writer per entry, no atomics)
@@ -398,9 +398,9 @@ constexpr double IMU_AB_STD = 2.0e4 * 1.0e-5;
 // one warp evaluates one IMU factor: whitened residual rw[15] and (optionally) whitened local Jacobian Jw[15x30] in shared memory
 __device__ void imu_factor_warp(const double *blob, const double *U, const double *pose0, const double *mix0, const double *pose1,
                                 const double *mix1, bool want_j, double *rw, double *Jw, int lane) {
-    __shared__ ImuMid s_mid[8];
+    __shared__ ImuMid s_mid[16];
     double *raw_r = rw + 15;  // scratch behind rw (caller provides 30 doubles)
-    const int wslot = (threadIdx.x >> 5) & 7;
+    const int wslot = (threadIdx.x >> 5) & 15;
     if (want_j)
         for (int e = lane; e < 450; e += 32) Jw[e] = 0;
     __syncwarp();
@@ -623,7 +623,8 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
     return s_total;
 }
 
-__global__ void __launch_bounds__(256) ba_lin_cam(BaCaps C, BaDev D) {
+constexpr int CAM_THREADS = 320;  // 10 warps: the K - 1 = 9 IMU factors of a 10-node window are evaluated in one round (warp per factor)
+__global__ void __launch_bounds__(CAM_THREADS) ba_lin_cam(BaCaps C, BaDev D) {
     extern __shared__ double smem[];
     const int w = blockIdx.x;
     LmState &st = D.st[w];
@@ -639,21 +640,29 @@ __device__ __forceinline__ double block_max(double v, double *s_red);
 // ------------------------------------------------------------------------------------------------ reduction operands
 // Everything a landmark shard contributes to the window's reduced camera system goes into ONE contiguous buffer per window, so that
 // a sharded solve needs a single all-reduce (sum) per attempt: [H_vis g_vis | Schur term | vision cost, sum rho^2].
+constexpr int PACK1_SPLIT = 4;  // CTAs per window
 __global__ void __launch_bounds__(256) ba_pack1(BaCaps C, BaDev D) {
     __shared__ double s_red[40];
-    const int w = blockIdx.x, tid = threadIdx.x;
+    const int w = blockIdx.x, tid = threadIdx.x, part = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done) return;
     const WinDims dm = D.dims[w];
     const int NN = C.NCA * C.NCA;
     double *R = D.red + (size_t) w * (2 * NN + 8);
     const double *CJ = D.CJ + (size_t) w * BA_SPLIT_J * NN, *CW = D.CW + (size_t) w * BA_SPLIT_W * NN;
-    for (int e = tid; e < NN; e += 256) {
-        R[e] = CJ[e];
+    const int e0 = (int) ((long long) NN * part / PACK1_SPLIT), e1 = (int) ((long long) NN * (part + 1) / PACK1_SPLIT);
+    for (int e = e0 + tid; e < e1; e += 256) {
+        const double cj = CJ[e];
+        double p[BA_SPLIT_W];
+#pragma unroll
+        for (int k = 0; k < BA_SPLIT_W; k++) p[k] = CW[(size_t) k * NN + e];
         double s = 0;
-        for (int k = 0; k < BA_SPLIT_W; k++) s += CW[(size_t) k * NN + e];
+#pragma unroll
+        for (int k = 0; k < BA_SPLIT_W; k++) s += p[k];
+        R[e] = cj;
         R[NN + e] = s;
     }
+    if (part != 0) return;
     double c = 0, q = 0, gm = 0;
     for (int f = tid; f < dm.F; f += 256) c += D.costf[(size_t) w * C.F + f];
     for (int l = tid; l < dm.L; l += 256) {
@@ -800,12 +809,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     }
     __syncthreads();
     for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
-        for (int j = tid & 31; j <= i; j += 32) {
-            double h = Hc[(size_t) j * C.NS + i];
-            if (i < NCV) h += syrk_get(CJ, 1, C.NCA, j, i) - syrk_get(CW, 1, C.NCA, j, i);
-            double v = s_scale[i] * s_scale[j] * h;
-            if (i == j) v += s_d2[i];
-            S[i * (i + 1) / 2 + j] = v;
+        // one warp per row; all global loads of the row are issued before the first shared-memory store (memory-level parallelism)
+        constexpr int MAXQ = 16;  // N <= 512
+        double hv[MAXQ];
+        const int nq = i / 32 + 1;
+#pragma unroll
+        for (int q = 0; q < MAXQ; q++) {
+            const int j = (tid & 31) + 32 * q;
+            hv[q] = 0;
+            if (q < nq && j <= i) {
+                double h = Hc[(size_t) j * C.NS + i];
+                if (i < NCV) h += CJ[(size_t) j * C.NCA + i] - CW[(size_t) j * C.NCA + i];  // j <= i: upper storage
+                hv[q] = h;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < MAXQ; q++) {
+            const int j = (tid & 31) + 32 * q;
+            if (q < nq && j <= i) {
+                double v = s_scale[i] * s_scale[j] * hv[q];
+                if (i == j) v += s_d2[i];
+                S[i * (i + 1) / 2 + j] = v;
+            }
         }
     }
     // augmented row N = rhs': the factorisation then leaves y = L^-1 rhs' in it (forward substitution for free)
@@ -818,27 +843,44 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     const int NR = N + 1;
     for (int J0 = 0; J0 < N; J0 += BA_CHOL_NB) {
         const int nb = min(BA_CHOL_NB, N - J0);
-        // (1) panel update with all previous columns
+        // (1) panel update with all previous columns on the FP64 tensor cores: S[J0:, J0:J0+8] -= L[J0:, :J0] L[J0:J0+8, :J0]^T.
+        //     One warp per 8-row tile; A fragment = L[i0 + g][k0 + kk], B fragment = L[J0 + g][k0 + kk] (DMMA.8x8x4, J0 % 8 == 0).
         if (J0 > 0) {
-            for (int t = tid; t < (NR - J0) * nb; t += SOLVE_THREADS) {
-                const int i = J0 + t / nb, c = J0 + t % nb;
-                if (c > i) continue;
-                const double *ri = S + i * (i + 1) / 2, *rc = S + c * (c + 1) / 2;
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                int k = 0;
-                for (; k + 4 <= J0; k += 4) s0 += ri[k] * rc[k], s1 += ri[k + 1] * rc[k + 1], s2 += ri[k + 2] * rc[k + 2], s3 += ri[k + 3] * rc[k + 3];
-                for (; k < J0; k++) s0 += ri[k] * rc[k];
-                S[i * (i + 1) / 2 + c] -= (s0 + s1) + (s2 + s3);
+            const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, kk = lane & 3;
+            const int ntile = (NR - J0 + 7) / 8;
+            const int cb = J0 + g;                                     // row of L that is the B operand's column
+            const double *rb = S + (cb < NR ? cb * (cb + 1) / 2 : 0);
+            const bool okb = cb < NR;
+            for (int tI = warp; tI < ntile; tI += SOLVE_THREADS / 32) {
+                const int ia = J0 + 8 * tI + g;
+                const bool oka = ia < NR;
+                const double *ra = S + (oka ? ia * (ia + 1) / 2 : 0);
+                double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+                int k0 = 0;
+                for (; k0 + 8 <= J0; k0 += 8) {  // two independent accumulator pairs hide the DMMA latency
+                    const double a0 = oka ? ra[k0 + kk] : 0.0, b0 = okb ? rb[k0 + kk] : 0.0;
+                    const double a1 = oka ? ra[k0 + 4 + kk] : 0.0, b1 = okb ? rb[k0 + 4 + kk] : 0.0;
+                    dmma884(c0, c1, a0, b0);
+                    dmma884(d0, d1, a1, b1);
+                }
+                c0 += d0, c1 += d1;
+                const int i = J0 + 8 * tI + g;
+                if (i < NR) {
+                    const int ca = J0 + 2 * kk;
+                    if (ca < J0 + nb && ca <= i) S[i * (i + 1) / 2 + ca] -= c0;
+                    if (ca + 1 < J0 + nb && ca + 1 <= i) S[i * (i + 1) / 2 + ca + 1] -= c1;
+                }
             }
             __syncthreads();
         }
         // (2)+(3) every thread that owns a row i >= J0 factors the (updated) nb x nb diagonal block REDUNDANTLY in registers
         // (no serial section, no extra barrier), then either writes back its row of L_JJ (rows inside the block) or solves
-        // its row of the panel against it (rows below, including the augmented rhs row).
+        // its row of the panel against it (rows below, including the augmented rhs row).  1/sqrt(d) comes from rsqrt (one
+        // dependent op per column instead of sqrt + divide); the row solve multiplies by it.
         {
             const int i = J0 + tid;
             if (i < NR) {
-                double Ld[BA_CHOL_NB][BA_CHOL_NB];
+                double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
                 bool bad = false;
 #pragma unroll
                 for (int a = 0; a < BA_CHOL_NB; a++)
@@ -850,15 +892,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
 #pragma unroll
                     for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
                     if (!(d > 0.0) || !isfinite(d)) bad = true;
-                    d = sqrt(d);
-                    Ld[j][j] = d;
-                    const double dinv = 1.0 / d;
+                    const double di = rsqrt(d);
+                    dinv[j] = di;
+                    Ld[j][j] = d * di;
 #pragma unroll
                     for (int a = j + 1; a < BA_CHOL_NB; a++) {
                         double sum = Ld[a][j];
 #pragma unroll
                         for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
-                        Ld[a][j] = sum * dinv;
+                        Ld[a][j] = sum * di;
                     }
                 }
                 if (bad) s_fail = 1;  // benign race: every thread computes the same verdict
@@ -870,7 +912,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                         if (a2 != a) continue;
 #pragma unroll
                         for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
-                        s_diag[i] = 1.0 / Ld[a2][a2];
+                        s_diag[i] = dinv[a2];
                     }
                 } else {
                     double x[BA_CHOL_NB];
@@ -881,7 +923,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                         double sum = x[c];
 #pragma unroll
                         for (int k = 0; k < c; k++) sum -= x[k] * Ld[c][k];
-                        x[c] = sum / Ld[c][c];
+                        x[c] = sum * dinv[c];
                     }
 #pragma unroll
                     for (int c = 0; c < BA_CHOL_NB; c++)
@@ -943,15 +985,34 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         finite = finite && isfinite(sp);
         part += camw * (-0.5 * sp * (s_scale[a] * s_g[a]) + 0.5 * s_d2[a] * sp * sp);
     }
-    for (int l = tid; l < L; l += SOLVE_THREADS) {
-        double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
-        double dotp = 0;
-        for (int c = 0; c < NCV; c++) dotp += AW[(size_t) l * C.NCA + c] * (s_scale[c] * s_rhs[c]);
-        double sp = (-sl * gl[l] - sl * dotp) / (hs + d2);
-        finite = finite && isfinite(sp);
-        step_l[l] = sp;
-        part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
+    // landmark back-substitution: one warp per landmark, the coupling row is read coalesced (two landmarks in flight per warp)
+    double *s_sx = s_diag;  // s_diag is dead after the back-substitution: scaled camera step s_c * step'_c
+    __syncthreads();
+    for (int a = tid; a < NCV; a += SOLVE_THREADS) s_sx[a] = s_scale[a] * s_rhs[a];
+    __syncthreads();
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int l0 = 2 * warp; l0 < L; l0 += 2 * (SOLVE_THREADS / 32)) {
+            const int l1 = l0 + 1;
+            double d0 = 0, d1 = 0;
+            for (int c = lane; c < NCV; c += 32) {
+                d0 += AW[(size_t) l0 * C.NCA + c] * s_sx[c];
+                if (l1 < L) d1 += AW[(size_t) l1 * C.NCA + c] * s_sx[c];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, o), d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            if (lane < 2 && l0 + lane < L) {
+                const int l = l0 + lane;
+                const double dotp = lane ? d1 : d0;
+                double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
+                double sp = (-sl * gl[l] - sl * dotp) / (hs + d2);
+                finite = finite && isfinite(sp);
+                step_l[l] = sp;
+                part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
+            }
+        }
     }
+    __syncthreads();
     const double mcc = block_sum(part, s_red);
     const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
     // ---- candidate point x (+) delta, delta = step' * scale; |x - x_cand|^2 over active blocks (camera part counted on shard 0)
@@ -1000,20 +1061,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
 }
 
 // ------------------------------------------------------------------------------------------------ candidate cost
-__global__ void __launch_bounds__(256) ba_cost(BaCaps C, BaDev D, int nblk_vis) {
+// camera-only factors at the candidate point (one CTA per window; runs beside the vision blocks on the handle's second stream)
+__global__ void __launch_bounds__(CAM_THREADS) ba_cost_cam(BaCaps C, BaDev D, int nblk_vis) {
     extern __shared__ double smem[];
+    const int w = blockIdx.x;
+    const LmState &st = D.st[w];
+    if (st.done || !st.step_valid) return;
+    const WinDims dm = D.dims[w];
+    double c = cam_factors(C, D, w, dm, D.pose_c + (size_t) w * C.K * 7, D.mix_c + (size_t) w * C.K * 9, D.ext_c + (size_t) w * 8, false, smem);
+    if (threadIdx.x == 0) D.cost_part[(size_t) w * (nblk_vis + 1) + nblk_vis] = c;
+}
+__global__ void __launch_bounds__(256) ba_cost(BaCaps C, BaDev D, int nblk_vis) {
     __shared__ double s_red[40];
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.step_valid) return;
     const WinDims dm = D.dims[w];
-    const double *pose = D.pose_c + (size_t) w * C.K * 7, *mix = D.mix_c + (size_t) w * C.K * 9, *ext = D.ext_c + (size_t) w * 8, *rho = D.rho_c + (size_t) w * C.L;
+    const double *pose = D.pose_c + (size_t) w * C.K * 7, *ext = D.ext_c + (size_t) w * 8, *rho = D.rho_c + (size_t) w * C.L;
     double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
-    if ((int) blockIdx.x == nblk_vis) {
-        double c = cam_factors(C, D, w, dm, pose, mix, ext, false, smem);
-        if (threadIdx.x == 0) part[nblk_vis] = c;
-        return;
-    }
     const int f = blockIdx.x * 256 + threadIdx.x;
     double cost = 0;
     if (f < dm.F && D.f_active[(size_t) w * C.F + f]) {
@@ -1202,6 +1267,8 @@ __global__ void ba_imu_eval_kernel(const double *blob, const double *U, const do
 
 }  // namespace icg
 
+#include "ba_marg.cuh"
+
 // ======================================================================================================= host side
 using namespace icg;
 
@@ -1277,6 +1344,8 @@ struct icg_ba {
     BaDev D;
     int device;
     cudaStream_t stream;
+    cudaStream_t stream_cam = nullptr;  // the camera-only factors are linearised concurrently with the vision chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream;
     int nblk_vis;
     int cur_windows;
@@ -1294,6 +1363,11 @@ struct icg_ba {
     HostDev<LmState> st_save;   // pass-1 LM state of the two-pass protocol
     HostDev<int> cull_counters; // per window: reprojection factors removed, GNSS fixes re-weighted
     void *comm = nullptr;       // ncclComm_t when this handle solves a landmark shard
+    // marginalization workspace (allocated on the first icg_ba_marginalize call)
+    bool marg_ready = false;
+    MargDev M;
+    HostDev<int> marg_map;
+    HostDev<double> marg_oJ0, marg_oe0, marg_oHp, marg_obp;
 };
 
 static int dmalloc(icg_ba *h, double **p, size_t n) {
@@ -1481,6 +1555,9 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
         h->stream = (cudaStream_t) stream;
     else
         ICG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    ICG_CUDA(cudaStreamCreateWithFlags(&h->stream_cam, cudaStreamNonBlocking));
+    ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     BaCaps &C = h->C;
     C.NW = max_windows, C.K = max_K, C.L = max_L, C.F = max_F, C.G = std::max(1, max_gnss), C.R = std::max(1, max_marg_r);
     C.NCV = 6 * max_K + 7, C.N = 15 * max_K + 7, C.NS = (C.N + 3) & ~3, C.NCA = 4 * ((C.NCV + 1 + 3) / 4);
@@ -1540,7 +1617,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     }
     ICG_CUDA(cudaFuncSetAttribute(ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve));
     ICG_CUDA(cudaFuncSetAttribute(ba_lin_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
-    ICG_CUDA(cudaFuncSetAttribute(ba_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
+    ICG_CUDA(cudaFuncSetAttribute(ba_cost_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
     ICG_CUDA(cudaFuncSetAttribute(ba_syrk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
     ICG_CUDA(cudaFuncSetAttribute(ba_syrk<BA_MAX_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
     h->mp_in_smem = 0, h->smem_gram = 0;
@@ -1560,7 +1637,11 @@ void icg_ba_destroy(icg_ba *h) {
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
     h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
+    if (h->marg_ready) h->marg_map.release(), h->marg_oJ0.release(), h->marg_oe0.release(), h->marg_oHp.release(), h->marg_obp.release();
     for (void *p : h->dev_only) cudaFree(p);
+    if (h->stream_cam) cudaStreamSynchronize(h->stream_cam), cudaStreamDestroy(h->stream_cam);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1721,21 +1802,26 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
     const BaDev &D = h->D;
     const int n = h->cur_windows;
     cudaStream_t s = h->stream;
-    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L * C.NCA + 255) / 256, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis + 1, n);
+    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L + 7) / 8, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis, n);
     // iteration 0 linearisation + (max_iter) x [schur syrk, solve, cost, accept, re-linearise]; one extra solve call
     // performs the final termination bookkeeping.
     for (int it = 0; it <= max_num_iterations; it++) {
+        // fork: IMU / GNSS / prior factors (one latency-bound CTA per window) run beside the vision chain
+        ICG_CUDA(cudaEventRecord(h->ev_fork, s));
+        ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
+        ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+        ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
         ba_lin_lm<<<g_lm, 256, 0, s>>>(C, D);
         ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
         ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
-        ba_lin_cam<<<n, 256, h->smem_cam, s>>>(C, D);
-        ba_lin_done<<<(n + 127) / 128, 128, 0, s>>>(D, n);
         if (h->syrk_one_tile)
             ba_syrk<1><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
         else
             ba_syrk<BA_MAX_TILES><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
-        ba_pack1<<<n, 256, 0, s>>>(C, D);
+        ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+        ba_lin_done<<<(n + 127) / 128, 128, 0, s>>>(D, n);
+        ba_pack1<<<dim3(n, PACK1_SPLIT), 256, 0, s>>>(C, D);
         if (h->comm) {  // landmark-sharded window: one sum all-reduce of [H_vis g | Schur | cost, |rho|^2] + one max all-reduce
             int rc = nccl_allreduce(h, D.red, (size_t) n * (2 * (size_t) C.NCA * C.NCA + 8), 0);
             if (rc != ICG_OK) return rc;
@@ -1745,14 +1831,19 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
         count_launch(9);
         if (it == max_num_iterations) break;
-        ba_cost<<<g_cost, 256, h->smem_cam, s>>>(C, D, h->nblk_vis);
+        ICG_CUDA(cudaEventRecord(h->ev_fork, s));
+        ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
+        ba_cost_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D, h->nblk_vis);
+        ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        ba_cost<<<g_cost, 256, 0, s>>>(C, D, h->nblk_vis);
+        ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
         ba_pack2<<<(n + 127) / 128, 128, 0, s>>>(C, D, n, h->nblk_vis);
         if (h->comm) {
             int rc = nccl_allreduce(h, D.red2, (size_t) n * 4, 0);
             if (rc != ICG_OK) return rc;
         }
         ba_accept<<<n, 128, 0, s>>>(C, D, h->nblk_vis);
-        count_launch(3);
+        count_launch(4);
     }
     ICG_CHECK_LAUNCH();
     return ICG_OK;
@@ -1906,6 +1997,149 @@ int icg_ba_gvins_optimization(icg_ba *h, int n_windows, const icg_ba_problem *pr
     int rc = icg_ba_gvins_optimization_begin(h, n_windows, problems, num_iterations);
     if (rc != ICG_OK) return rc;
     return icg_ba_gvins_optimization_end(h, n_windows, problems, summaries, culled);
+}
+
+// ---- marginalization (B10)
+static int marg_alloc(icg_ba *h) {
+    if (h->marg_ready) return ICG_OK;
+    const BaCaps &C = h->C;
+    MargDev &M = h->M;
+    const size_t NW = C.NW;
+    M.rcap = C.N, M.mcap = 15 * C.K + C.L, M.n0cap = C.N + C.L;
+    if (M.mcap > 512) {
+        set_error("icg_ba_marginalize: max_K=%d / max_L=%d exceed the Jacobi kernel's 512-row limit", C.K, C.L);
+        return ICG_EUNSUPPORTED;
+    }
+    M.map_stride = MARG_MAP_HDR + 2 * C.K + C.L;
+    if (h->marg_map.alloc(NW * M.map_stride) != ICG_OK || h->marg_oJ0.alloc(NW * (size_t) M.rcap * M.rcap) != ICG_OK || h->marg_oe0.alloc(NW * M.rcap) != ICG_OK ||
+        h->marg_oHp.alloc(NW * (size_t) M.rcap * M.rcap) != ICG_OK || h->marg_obp.alloc(NW * M.rcap) != ICG_OK) {
+        set_error("icg_ba_marginalize: workspace allocation failed");
+        return ICG_ENOMEM;
+    }
+    M.map = h->marg_map.d, M.J0 = h->marg_oJ0.d, M.e0 = h->marg_oe0.d, M.Hp = h->marg_oHp.d, M.bp = h->marg_obp.d;
+    int rc = ICG_OK;
+    double *fl = nullptr;
+#define DM(ptr, count) \
+    if (rc == ICG_OK) rc = dmalloc(h, &ptr, count);
+    DM(M.H0, NW * (size_t) M.n0cap * M.n0cap) DM(M.b0, NW * M.n0cap) DM(M.G1, NW * (size_t) M.mcap * M.mcap) DM(M.V1, NW * (size_t) M.mcap * M.mcap)
+    DM(M.G2, NW * (size_t) M.rcap * M.rcap) DM(M.V2, NW * (size_t) M.rcap * M.rcap) DM(M.lam1, NW * M.mcap) DM(M.lam2, NW * M.rcap)
+    DM(M.Z, NW * (size_t) M.mcap * (M.rcap + 1)) DM(fl, NW * 2)
+#undef DM
+    if (rc != ICG_OK) return rc;
+    M.flags = (int *) fl;
+    const size_t smem = sizeof(double) * (8 * 480 + 2 * (size_t) C.R) + sizeof(int) * (size_t) C.R + 64;
+    ICG_CUDA(cudaFuncSetAttribute(marg_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    h->marg_ready = true;
+    return ICG_OK;
+}
+
+int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out) {
+    if (!h || !problems || !num_marg || !out || n_windows < 1 || n_windows > h->C.NW) {
+        set_error("icg_ba_marginalize: bad arguments");
+        return ICG_EINVAL;
+    }
+    if (h->comm) {
+        set_error("icg_ba_marginalize: not available on a landmark-sharded handle (icg_ba_set_shard(world = 1) first)");
+        return ICG_EUNSUPPORTED;
+    }
+    int rc = icg_ba_upload(h, n_windows, problems);
+    if (rc != ICG_OK) return rc;
+    rc = marg_alloc(h);
+    if (rc != ICG_OK) return rc;
+    const BaCaps &C = h->C;
+    MargDev &M = h->M;
+    const int n = n_windows;
+    // ---- updateParameterBlocksIndex (marginalization_info.h:228-251) on the host: structure only.  The reference iterates
+    //      unordered_maps (implementation-defined order inside each group); here: marginalized = [pose_k, mix_k (k < num_marg),
+    //      landmarks ascending], remained = [pose_k, mix_k (k >= num_marg, only blocks some factor touches), ext, td].
+    for (int w = 0; w < n; w++) {
+        const icg_ba_problem &p = problems[w];
+        const int nm = num_marg[w];
+        icg_ba_prior &o = out[w];
+        if (nm < 1 || nm >= p.K || !o.block_type || !o.block_node || !o.x0 || !o.J0 || !o.e0 || o.rcap < 15 * (p.K - nm) + 7) {
+            set_error("icg_ba_marginalize: window %d: num_marg=%d out of range or output arrays missing / too small (rcap=%d)", w, nm, o.rcap);
+            return ICG_EINVAL;
+        }
+        int *map = h->marg_map.h + (size_t) w * M.map_stride;
+        int *pose_col = map + MARG_MAP_HDR, *mix_col = pose_col + C.K, *lm_col = mix_col + C.K;
+        std::vector<char> tp(p.K, 0), tm(p.K, 0), tl(p.L, 0);
+        bool any_vis = false;
+        for (int f = 0; f < p.F; f++) {
+            if ((p.f_active && !p.f_active[f]) || p.f_ref[f] >= nm) continue;
+            tl[p.f_lm[f]] = 1, tp[p.f_obs[f]] = 1, any_vis = true;
+        }
+        bool has_ext = any_vis, has_td = any_vis;
+        for (int k = 0; k < nm; k++) tp[k] = tm[k] = 1;
+        if (p.n_imu >= nm) tp[nm] = tm[nm] = 1;  // factor nm-1 joins node nm-1 and node nm
+        for (int b = 0; b < p.marg_nblocks && p.marg_r > 0; b++) {
+            const int t = p.marg_block_type[b], nd = p.marg_block_node[b];
+            if (t == 0) tp[nd] = 1;
+            else if (t == 1) tm[nd] = 1;
+            else if (t == 2) has_ext = true;
+            else has_td = true;
+        }
+        int idx = 0;
+        for (int k = 0; k < C.K; k++) pose_col[k] = mix_col[k] = -1;
+        for (int k = 0; k < nm; k++) pose_col[k] = idx, idx += 6, mix_col[k] = idx, idx += 9;
+        for (int l = 0; l < C.L; l++) lm_col[l] = -1;
+        for (int l = 0; l < p.L; l++)
+            if (tl[l]) lm_col[l] = idx++;
+        const int m = idx;
+        int nb = 0, xo = 0;
+        for (int k = nm; k < p.K; k++) {
+            if (tp[k]) pose_col[k] = idx, idx += 6, o.block_type[nb] = 0, o.block_node[nb++] = k - nm, xo += 7;
+            if (tm[k]) mix_col[k] = idx, idx += 9, o.block_type[nb] = 1, o.block_node[nb++] = k - nm, xo += 9;
+        }
+        int ext_col = -1, td_col = -1;
+        if (has_ext) ext_col = idx, idx += 6, o.block_type[nb] = 2, o.block_node[nb++] = 0, xo += 7;
+        if (has_td) td_col = idx, idx += 1, o.block_type[nb] = 3, o.block_node[nb++] = 0, xo += 1;
+        // a reprojection factor always carries ext and td columns; give them (unused) columns when only camera factors exist
+        if (ext_col < 0) ext_col = 0;
+        if (td_col < 0) td_col = 0;
+        map[0] = m, map[1] = idx - m, map[2] = idx, map[3] = nm, map[4] = ext_col, map[5] = td_col, map[6] = map[7] = 0;
+        o.m = m, o.r = idx - m, o.nblocks = nb;
+    }
+    cudaStream_t s = h->stream;
+    ICG_CUDA(h->marg_map.up(s, (size_t) n * M.map_stride));
+    const BaDev &D = h->D;
+    const size_t smem = sizeof(double) * (8 * 480 + 2 * (size_t) C.R) + sizeof(int) * (size_t) C.R + 64;
+    marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 0);
+    ba_lin_vis<<<dim3((C.F + 127) / 128, n), 128, 0, s>>>(C, D);
+    ba_lin_lm<<<dim3((C.L + 7) / 8, n), 256, 0, s>>>(C, D);
+    ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
+    marg_assemble<<<n, 256, smem, s>>>(C, D, M);
+    marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, 0);
+    marg_schur<<<n, MARG_THREADS, 0, s>>>(M);
+    marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, 1);
+    marg_finish<<<n, MARG_THREADS, 0, s>>>(M);
+    marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 1);
+    ICG_CHECK_LAUNCH();
+    count_launch(10);
+    ICG_CUDA(h->marg_oJ0.down(s, (size_t) n * M.rcap * M.rcap));
+    ICG_CUDA(h->marg_oe0.down(s, (size_t) n * M.rcap));
+    ICG_CUDA(h->marg_oHp.down(s, (size_t) n * M.rcap * M.rcap));
+    ICG_CUDA(h->marg_obp.down(s, (size_t) n * M.rcap));
+    ICG_CUDA(cudaStreamSynchronize(s));
+    for (int w = 0; w < n; w++) {
+        const icg_ba_problem &p = problems[w];
+        icg_ba_prior &o = out[w];
+        const int nm = num_marg[w], r = o.r;
+        // preMarginalization copies the parameter data of every block: x0 of the remained blocks (marginalization_info.h:270-283)
+        int xo = 0;
+        for (int b = 0; b < o.nblocks; b++) {
+            const int t = o.block_type[b], nd = o.block_node[b] + nm;
+            const double *src = t == 0 ? p.pose + 7 * nd : t == 1 ? p.mix + 9 * nd : t == 2 ? p.ext : p.ext + 7;
+            const int gs = t == 1 ? 9 : t == 3 ? 1 : 7;
+            memcpy(o.x0 + xo, src, sizeof(double) * gs);
+            xo += gs;
+        }
+        if (o.m <= 0) continue;
+        memcpy(o.J0, h->marg_oJ0.h + (size_t) w * M.rcap * M.rcap, sizeof(double) * (size_t) r * r);
+        memcpy(o.e0, h->marg_oe0.h + (size_t) w * M.rcap, sizeof(double) * r);
+        if (o.Hp) memcpy(o.Hp, h->marg_oHp.h + (size_t) w * M.rcap * M.rcap, sizeof(double) * (size_t) r * r);
+        if (o.bp) memcpy(o.bp, h->marg_obp.h + (size_t) w * M.rcap, sizeof(double) * r);
+    }
+    return ICG_OK;
 }
 
 int icg_nccl_unique_id(uint8_t *id128) {

@@ -231,6 +231,27 @@ int icg_ba_gvins_optimization_begin(icg_ba *h, int n_windows, const icg_ba_probl
 int icg_ba_gvins_optimization_end(icg_ba *h, int n_windows, const icg_ba_problem *problems, icg_ba_summary *summaries, int32_t *culled);
 int icg_ba_sync(icg_ba *h);
 /*
+ * Drop-in for `MarginalizationInfo::marginalization()` as GVINS::gvinsMarginalization drives it (IG/ic_gvins.cc:1412-1640,
+ * IG/factors/marginalization_info.h:73-253): for each window, the num_marg oldest nodes (pose + mix) and the inverse depths of the
+ * landmarks anchored in them are marginalized out of [previous prior, GNSS at those nodes, preintegration factors 0..num_marg-1,
+ * first-window pose / mix priors, reprojection factors of those landmarks] (no loss functions, every Jacobian, as
+ * ResidualBlockInfo::Evaluate does), linearised at the parameter values in `problems`.  Output: the new prior in the layout
+ * icg_ba_problem.marg_* consumes -- remained blocks (node indices already shifted by num_marg), x0 = remainedBlockData(),
+ * J0 = linearizedJacobians() (r x r row-major, rows in ascending eigenvalue order), e0 = linearizedResiduals() -- plus, optionally,
+ * the Schur complement itself (Hp, bp).  Arrays are caller-allocated: block_type/block_node 2K+2 ints, x0 16K+8, J0/Hp rcap*rcap,
+ * e0/bp rcap doubles with rcap >= 15*(K - num_marg) + 7.  Column order inside the marginalized / remained groups is
+ * [pose_k, mix_k ascending k | landmarks ascending] / [pose_k, mix_k (touched blocks only) | ext | td]; the reference's order is that of
+ * an unordered_map (implementation-defined) and only permutes rows / columns.
+ */
+typedef struct icg_ba_prior {
+    int32_t m, r, nblocks;            /* out: marginalizedSize(), remainedSize(), number of remained blocks */
+    int32_t rcap;                     /* in: capacity of J0 / e0 / Hp / bp */
+    int32_t *block_type, *block_node; /* out */
+    double *x0, *J0, *e0;             /* out */
+    double *Hp, *bp;                  /* out, may be NULL */
+} icg_ba_prior;
+int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out);
+/*
  * Landmark sharding of the window solve across the GPUs of one box: every process (one per GPU) uploads the same
  * camera-side problem but only ITS landmarks and their reprojection factors; per LM attempt one NCCL sum all-reduce of the packed
  * [vision Gram matrix + gradient | Schur term | vision cost, sum rho^2] buffer (+ an n-double max / 4n-double sum) makes the
