@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--ba-handles", type=int, default=2, help="solver handles (CUDA streams) the B windows are split over")
     ap.add_argument("--no-sharded", action="store_true", help="skip the cfg-4 landmark-sharded BA section")
+    ap.add_argument("--no-marg", action="store_true", help="skip the marginalization section")
     return ap.parse_args()
 
 
@@ -414,6 +415,34 @@ def run_b200(args):
                    "mean_lm_iterations_pass2": float(np.mean([x["iterations"] for x in sm])),
                    "final_cost_mean": float(np.mean([x["final_cost"] for x in sm]))}
 
+    # ---- gvinsMarginalization: the step that follows the solve at every keyframe, through the host-buffer C ABI
+    marg = None
+    if use_ba and not args.no_marg:
+        part = windows[bounds[0]:bounds[1]]
+        solvers[0].marginalize(part[:2], 1, want_schur=False)  # workspace allocation + warm-up
+        barrier()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pri = solvers[0].marginalize(part, 1, want_schur=False)
+        dtm = (time.perf_counter() - t0) / reps
+        marg = {"workload": "icg_ba_marginalize: oldest node + the landmarks anchored in it out of a cfg-3 window (host buffers in, prior out; "
+                            "upload + linearisation + two Jacobi eigendecompositions + D2H inside the timed region)",
+                "windows_per_call": len(part), "ms_per_call": dtm * 1e3, "windows_per_s": len(part) / dtm * world,
+                "m": int(pri[0]["m"]), "r": int(pri[0]["r"])}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            import ctypes as C
+            import oracle
+            from tests import oracle_api as oa
+            olib = C.CDLL(oracle.build())
+            oa.declare_ba(olib)
+            pw = make_windows(1, lambda *a: oa.preintegrate(olib, *a))[0]
+            oa.ba_marginalize(olib, pw, 1)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                oa.ba_marginalize(olib, pw, 1)
+            marg["cpu_port_ms_per_window"] = (time.perf_counter() - t0) / 3 * 1e3
+
     # ---- cfg 4: 20-KF / 2000-landmark windows, landmarks sharded over the ranks with an NCCL all-reduce per LM attempt
     sharded = None
     if use_ba and not args.no_sharded:
@@ -478,6 +507,7 @@ def run_b200(args):
         "klt_only": {"value": frames_per_step * args.steps / (ms_klt / 1e3), "unit": "frames/s"},
         "ba_only": ba_info,
         "sharded_ba": sharded,
+        "marginalization": marg,
         "tracked_fraction": good / float(n_total),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

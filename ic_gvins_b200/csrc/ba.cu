@@ -10,17 +10,21 @@
 //
 // Per window: n = 15K+7 camera-side columns laid out [pose_0..pose_{K-1} (6 each) | extrinsic 6 | td 1 | mix_0..mix_{K-1} (9 each)];
 // the vision factors only touch the first NCV = 6K+7 ("vision columns").  Landmarks (inverse depths) are eliminated:
-//   lin_vis   : thread / reprojection factor -> residual, local Jacobians, Huber correction; dense column-major rows A_J
-//   lin_lm    : warp / landmark -> h_l, g_l and the dense coupling row w_l (A_W)
-//   syrk      : C = A^T diag(w) A on 4x4 register tiles (A_J -> vision part of H_cc and g_c;  A_W with
-//               w_l = s_l^2 / (s_l^2 h_l + D_l^2) -> the Schur complement term).  HBM-/L2-bound streaming of A.
-//   lin_cam   : one CTA / window -> IMU preintegration, GNSS, bias, prior and marginalization factors -> H_c, g_c
-//   solve     : one CTA / window -> Jacobi scaling, LM diagonal, S = s(H - Schur)s + D^2, packed Cholesky in shared
-//               memory, triangular solves, landmark back-substitution, model cost change, candidate x (+) delta
-//   cost      : candidate cost (all factors, residuals only);   accept : Ceres step acceptance + radius update
+//   lin_vis    : thread / reprojection factor -> residual, local Jacobians, Huber correction -> 40-double record
+//   lin_lm     : warp / landmark -> h_l, g_l and the dense coupling row w_l (A_W, landmark-major)
+//   pair_gram  : factors grouped by (reference node, observing node): 20x20 Gram matrix per group on the FP64 tensor cores
+//                (DMMA.8x8x4), then a one-writer-per-entry gather into the vision part of H_cc and g_c
+//   schur_dmma : sum_l phi_l w_l w_l^T with phi_l = s_l^2 / (s_l^2 h_l + D_l^2) on the FP64 tensor cores
+//   lin_cam    : one CTA / window (second stream, beside the vision chain) -> IMU preintegration, GNSS, bias, prior and
+//                marginalization factors -> H_c, g_c
+//   solve      : one CTA / window -> Jacobi scaling, LM diagonal, S = s(H - Schur)s + D^2, packed Cholesky in shared memory
+//                (panel updates on DMMA), triangular solves, landmark back-substitution, model cost change, candidate x (+) delta
+//   cost       : candidate cost (all factors, residuals only);   accept : Ceres step acceptance + radius update
+//   ba_marg.cuh: sliding-window marginalization (MarginalizationInfo) on the same device-resident linearisation
 #include <dlfcn.h>
 #include <math.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -35,7 +39,6 @@ using namespace bam;
 constexpr int BA_SPLIT_J = 1;   // the vision Gram matrix is produced whole by ba_pair_gram
 constexpr int BA_SPLIT_W = 4;   // row splits of the Schur SYRK (partials summed in fixed order -> deterministic)
 constexpr int BA_CHOL_NB = 8;   // Cholesky block width
-constexpr int BA_MAX_TILES = 3; // 4x4 register tiles per SYRK thread (256 threads): (NCA/4)(NCA/4+1)/2 <= 768
 
 struct BaCaps {
     int NW, K, L, F, G, R;     // capacities
@@ -63,6 +66,7 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     double *f_const;
     uint8_t *f_active;
     int *lm_off, *lm_fidx;
+    int *f_slot;  // position of factor f in landmark-CSR order: the per-factor records are stored in that order
     int *pair_off, *pair_ro, *pair_fidx, *npairs;  // factors grouped by (reference node, observing node)
     double *Mp;                                    // per-pair 20x20 Gram matrices (upper, 210 entries)
     double *AW, *CJ, *CW;  // Schur SYRK input; vision Gram matrix; Schur partials
@@ -90,7 +94,7 @@ __device__ __forceinline__ int col_td(int K) { return 6 * K + 6; }
 __device__ __forceinline__ int col_mix(int K, int k) { return 6 * K + 7 + 9 * k; }
 
 // ------------------------------------------------------------------------------------------------ lin_vis
-__global__ void __launch_bounds__(128) ba_lin_vis(BaCaps C, BaDev D) {
+__global__ void __launch_bounds__(128, 3) ba_lin_vis(BaCaps C, BaDev D) {
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
@@ -120,11 +124,12 @@ __global__ void __launch_bounds__(128) ba_lin_vis(BaCaps C, BaDev D) {
         for (int k = 0; k < 12; k++) Ji[k] = Jj[k] = Je[k] = 0;
         Jr[0] = Jr[1] = Jt[0] = Jt[1] = r[0] = r[1] = 0;
     }
-    double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
+    const size_t slot = (size_t) w * C.F + D.f_slot[(size_t) w * C.F + f];  // records live in landmark-CSR order (lin_lm streams them)
+    double *jc = D.jcomp + slot * 40;
     for (int k = 0; k < 12; k++) jc[k] = Ji[k], jc[12 + k] = Jj[k], jc[24 + k] = Je[k];
     jc[36] = Jt[0], jc[37] = Jt[1], jc[38] = r[0], jc[39] = r[1];
-    D.jrho[((size_t) w * C.F + f) * 2] = Jr[0];
-    D.jrho[((size_t) w * C.F + f) * 2 + 1] = Jr[1];
+    double *jr = D.jrho + slot * 4;  // [j_rho (2) | observing node | reference node]
+    jr[0] = Jr[0], jr[1] = Jr[1], jr[2] = (double) j, jr[3] = (double) i;
     D.costf[(size_t) w * C.F + f] = cost;
 }
 
@@ -145,29 +150,42 @@ __global__ void __launch_bounds__(256) ba_lin_lm(BaCaps C, BaDev D) {
     const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (l >= dm.L) return;
     const int *off = D.lm_off + (size_t) w * (C.L + 1);
-    const int *fidx = D.lm_fidx + (size_t) w * C.F;
     const int f0 = off[l], f1 = off[l + 1];
     double *row = D.AW + ((size_t) w * C.LP + l) * C.NCA;
     for (int c = lane; c < NCA; c += 32) row[c] = 0.0;
     __syncwarp();
-    const int o0 = jc_off(lane < 19 ? lane : 0), o1 = o0 + jc_row1(lane < 19 ? lane : 0);
+    // lane's two record offsets: columns 0..18 -> Jacobian rows 0 / 1, lane 19 -> residual (g_l), lane 20 -> j_rho itself (h_l)
+    const int o0 = lane < 19 ? jc_off(lane) : 38, o1 = lane < 19 ? o0 + jc_row1(lane) : 39;
     double acc = 0;
     int ref = 0;
-    for (int q = f0; q < f1; q++) {
-        const int f = fidx[q];
-        const double *jc = D.jcomp + ((size_t) w * C.F + f) * 40;
-        const double jr0 = D.jrho[((size_t) w * C.F + f) * 2], jr1 = D.jrho[((size_t) w * C.F + f) * 2 + 1];
-        if (q == f0) ref = D.f_ref[(size_t) w * C.F + f];
-        if (lane < 19) {
-            const double v = jc[o0] * jr0 + jc[o1] * jr1;
-            if (lane >= 6 && lane < 12)
-                row[col_pose(D.f_obs[(size_t) w * C.F + f]) + lane - 6] += v;
-            else
-                acc += v;
-        } else if (lane == 19) {
-            acc += jr0 * jc[38] + jr1 * jc[39];
-        } else if (lane == 20) {
-            acc += jr0 * jr0 + jr1 * jr1;
+    constexpr int UNR = 4;  // factor records in flight (contiguous: slots f0 .. f1-1)
+    for (int q0 = f0; q0 < f1; q0 += UNR) {
+        int ob[UNR];
+        double a0[UNR], a1[UNR], r0[UNR], r1[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            const bool ok = q0 + u < f1;
+            const size_t fo = (size_t) w * C.F + (ok ? q0 + u : f0);
+            const double *jr = D.jrho + fo * 4;
+            a0[u] = ok ? D.jcomp[fo * 40 + o0] : 0.0;
+            a1[u] = ok ? D.jcomp[fo * 40 + o1] : 0.0;
+            r0[u] = ok ? jr[0] : 0.0;
+            r1[u] = ok ? jr[1] : 0.0;
+            ob[u] = ok ? (int) jr[2] : 0;
+            if (u == 0 && q0 == f0) ref = (int) jr[3];
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; u++) {
+            if (q0 + u >= f1) continue;
+            if (lane == 20) {
+                acc += r0[u] * r0[u] + r1[u] * r1[u];
+            } else {
+                const double v = a0[u] * r0[u] + a1[u] * r1[u];
+                if (lane >= 6 && lane < 12)
+                    row[col_pose(ob[u]) + lane - 6] = v;  // a landmark is observed at most once per node (checked by icg_ba_upload)
+                else
+                    acc += v;
+            }
         }
     }
     if (f1 > f0) {
@@ -298,84 +316,100 @@ __global__ void __launch_bounds__(256) ba_pair_gram2(BaCaps C, BaDev D) {
     Cout[(size_t) B * C.NCA + A] = sum;
 }
 
-// ------------------------------------------------------------------------------------------------ syrk: C = A^T diag(w) A
-// A column-major [NCA][ld] (rows contiguous).  mode 0: A_J, rows = 2F, no weights.  mode 1: A_W, rows = L,
-// weight_l = s_l^2 / (s_l^2 h_l + clamp(s_l^2 h_l) / radius)  (the LM-damped landmark pivot).
-template <int NT>
-__global__ void __launch_bounds__(256) ba_syrk(BaCaps C, BaDev D, int mode) {
-    extern __shared__ double s_tile[];  // [NCA][33]
+// ------------------------------------------------------------------------------------------------ Schur term
+// Schur SYRK on the FP64 tensor cores: CW[split] = sum over the split's landmarks of phi_l w_l w_l^T (stored symmetric), with
+// phi_l = s_l^2 / (s_l^2 h_l + clamp(s_l^2 h_l) / radius) the LM-damped landmark pivot.  DMMA.8x8x4 with k = 4 landmarks per step; as in
+// ba_pair_gram1 the A and B fragments of X^T X share one layout: lane reads A_W[l0 + lane%4][8 t + lane/4].  The CTA stages its
+// landmark rows (and phi) in shared memory once per pass -- leading dimension = 8 mod 16 doubles, so a fragment read is the minimal
+// two wavefronts -- and every warp accumulates two 16x16 super-tiles (2x2 DMMA tiles each) of the upper triangle per pass.
+// The BA_SPLIT_W landmark splits are separate CTAs whose partials ba_pack1 sums in fixed order (deterministic).
+constexpr int SCHUR_RCH = 80;  // landmark rows staged per chunk (multiple of 4)
+__global__ void __launch_bounds__(256) ba_schur_dmma(BaCaps C, BaDev D, int ld) {
+    extern __shared__ double sA[];  // [SCHUR_RCH][ld] rows, then phi[SCHUR_RCH]
     const int w = blockIdx.y, split = blockIdx.x;
     const LmState &st = D.st[w];
     if (st.done) return;
-    if (mode == 0 && !st.need_lin) return;
     const WinDims dm = D.dims[w];
-    const int NCV = 6 * dm.K + 7, NCA = 4 * ((NCV + 1 + 3) / 4), nt = NCA / 4;
-    const int rows = dm.L;
-    const int nsplit = mode == 0 ? BA_SPLIT_J : BA_SPLIT_W;
-    const double *A = D.AW + (size_t) w * C.LP * C.NCA;  // landmark-major [l][NCA]
-    double *Cout = (mode == 0 ? D.CJ + ((size_t) w * BA_SPLIT_J + split) * C.NCA * C.NCA : D.CW + ((size_t) w * BA_SPLIT_W + split) * C.NCA * C.NCA);
-    __shared__ double s_wt[32];
-    const int tid = threadIdx.x;
-    const int ntiles = nt * (nt + 1) / 2;
-    int ti[NT], tj[NT];
-    double acc[NT][16];
-#pragma unroll
-    for (int q = 0; q < NT; q++) {
-        int t = tid + q * 256, a = 0;
-        if (t < ntiles) {
-            while (t >= nt - a) t -= nt - a, a++;
-            ti[q] = a, tj[q] = a + t;
-        } else {
-            ti[q] = -1, tj[q] = 0;
-        }
-#pragma unroll
-        for (int e = 0; e < 16; e++) acc[q][e] = 0;
-    }
+    const int NCV = 6 * dm.K + 7, NCA = 4 * ((NCV + 1 + 3) / 4);
+    const int T2 = (NCA + 15) / 16, nsuper = T2 * (T2 + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, kk = lane & 3;
+    double *sphi = sA + (size_t) SCHUR_RCH * ld;
+    const double *A = D.AW + (size_t) w * C.LP * C.NCA;
+    double *Cout = D.CW + ((size_t) w * BA_SPLIT_W + split) * C.NCA * C.NCA;
     const double radius = st.radius;
-    const int nchunks = (rows + 31) / 32;
-    for (int ch = split; ch < nchunks; ch += nsplit) {
-        const int r0 = ch * 32;
-        __syncthreads();
-        for (int e = tid; e < NCA * 32; e += 256) {
-            int rr = e / NCA, c = e - rr * NCA;
-            s_tile[c * 33 + rr] = (r0 + rr < rows) ? A[(size_t) (r0 + rr) * C.NCA + c] : 0.0;
+    const int nsteps = (dm.L + 3) / 4;
+    const int r_beg = 4 * (int) ((long long) nsteps * split / BA_SPLIT_W), r_end = min(dm.L, 4 * (int) ((long long) nsteps * (split + 1) / BA_SPLIT_W));
+    const int npass = (nsuper + 15) / 16;
+    for (int pass = 0; pass < npass; pass++) {
+        int si[2], sj[2];
+        bool on[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+            const int su = (2 * pass + h2) * 8 + warp;
+            on[h2] = su < nsuper;
+            int a = 0, e = on[h2] ? su : 0;
+            while (e >= T2 - a) e -= T2 - a, a++;
+            si[h2] = a, sj[h2] = a + e;
         }
-        if (tid < 32) {
-            double wt = 1.0;
-            if (mode == 1) {
-                int l = r0 + tid;
-                wt = 0;
-                if (l < rows) {
-                    double s = D.scale_l[(size_t) w * C.L + l], hs = s * s * D.hl[(size_t) w * C.L + l];
-                    wt = s * s / (hs + fmin(fmax(hs, 1e-6), 1e32) / radius);
+        double acc[2][4][2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[h2][q][0] = acc[h2][q][1] = 0;
+        for (int r0 = r_beg; r0 < r_end; r0 += SCHUR_RCH) {
+            const int nr = min(SCHUR_RCH, r_end - r0), nr4 = (nr + 3) & ~3;
+            __syncthreads();
+            for (int e0 = tid; e0 < nr4 * ld; e0 += 256 * 8) {  // 8 independent loads per thread in flight
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int e = e0 + 256 * u, rr = e / ld, c = e - rr * ld;
+                    v[u] = (e < nr4 * ld && rr < nr && c < NCA) ? A[(size_t) (r0 + rr) * C.NCA + c] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++)
+                    if (e0 + 256 * u < nr4 * ld) sA[e0 + 256 * u] = v[u];
+            }
+            for (int rr = tid; rr < nr4; rr += 256) {
+                double ph = 0;
+                if (rr < nr) {
+                    const int l = r0 + rr;
+                    const double sl = D.scale_l[(size_t) w * C.L + l], hs = sl * sl * D.hl[(size_t) w * C.L + l];
+                    ph = sl * sl / (hs + fmin(fmax(hs, 1e-6), 1e32) / radius);
+                }
+                sphi[rr] = ph;
+            }
+            __syncthreads();
+            for (int ks = 0; ks < nr4 / 4; ks++) {
+                const double *row = sA + (size_t) (4 * ks + kk) * ld;
+                const double ph = sphi[4 * ks + kk];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; h2++) {
+                    if (!on[h2]) continue;
+                    const double xb0 = row[16 * sj[h2] + g], xb1 = row[16 * sj[h2] + 8 + g];
+                    const double a0 = row[16 * si[h2] + g] * ph, a1 = row[16 * si[h2] + 8 + g] * ph;
+                    dmma884(acc[h2][0][0], acc[h2][0][1], a0, xb0);
+                    dmma884(acc[h2][1][0], acc[h2][1][1], a0, xb1);
+                    dmma884(acc[h2][2][0], acc[h2][2][1], a1, xb0);
+                    dmma884(acc[h2][3][0], acc[h2][3][1], a1, xb1);
                 }
             }
-            s_wt[tid] = wt;
         }
-        __syncthreads();
 #pragma unroll
-        for (int q = 0; q < NT; q++) {
-            if (ti[q] < 0) continue;
-            const double *pa = s_tile + (4 * ti[q]) * 33, *pb = s_tile + (4 * tj[q]) * 33;
-#pragma unroll 4
-            for (int rr = 0; rr < 32; rr++) {
-                const double wt = s_wt[rr];
-                double a0 = pa[rr] * wt, a1 = pa[33 + rr] * wt, a2 = pa[66 + rr] * wt, a3 = pa[99 + rr] * wt;
-                double b0 = pb[rr], b1 = pb[33 + rr], b2 = pb[66 + rr], b3 = pb[99 + rr];
-                acc[q][0] += a0 * b0, acc[q][1] += a0 * b1, acc[q][2] += a0 * b2, acc[q][3] += a0 * b3;
-                acc[q][4] += a1 * b0, acc[q][5] += a1 * b1, acc[q][6] += a1 * b2, acc[q][7] += a1 * b3;
-                acc[q][8] += a2 * b0, acc[q][9] += a2 * b1, acc[q][10] += a2 * b2, acc[q][11] += a2 * b3;
-                acc[q][12] += a3 * b0, acc[q][13] += a3 * b1, acc[q][14] += a3 * b2, acc[q][15] += a3 * b3;
+        for (int h2 = 0; h2 < 2; h2++) {
+            if (!on[h2]) continue;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {  // C fragment: (row g, cols 2 kk + {0, 1}) of tile (2 si + q/2, 2 sj + q%2)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int r = 8 * (2 * si[h2] + (q >> 1)) + g, cc = 8 * (2 * sj[h2] + (q & 1)) + 2 * kk + e;
+                    if (r <= cc && cc < NCA) {
+                        Cout[(size_t) r * C.NCA + cc] = acc[h2][q][e];
+                        Cout[(size_t) cc * C.NCA + r] = acc[h2][q][e];  // stored symmetric: ba_solve reads rows contiguously
+                    }
+                }
             }
         }
-    }
-#pragma unroll
-    for (int q = 0; q < NT; q++) {
-        if (ti[q] < 0) continue;
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-            for (int b = 0; b < 4; b++) Cout[(size_t) (4 * ti[q] + a) * C.NCA + 4 * tj[q] + b] = acc[q][4 * a + b];
     }
 }
 
@@ -746,9 +780,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     double *s_diag = s_d2 + C.NS;       // N   Cholesky diagonal
     double *S = use_global_S ? D.Sglobal + (size_t) w * ((size_t) (C.N + 1) * (C.N + 2) / 2) : s_diag + C.NS;  // packed lower, N + 1 rows
     const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS;
-    const double *RED = D.red + (size_t) w * (2 * C.NCA * C.NCA + 8);
-    const double *CJ = RED, *CW = RED + C.NCA * C.NCA;  // all-reduced (identical on every shard)
+    // Reduction operands.  Landmark-sharded solve: the packed, all-reduced buffer (identical on every shard, written by ba_pack1).
+    // Single GPU: read the producers' outputs directly (vision Gram matrix; the BA_SPLIT_W Schur partials summed in fixed order).
+    const bool sharded = D.world > 1;
+    const int NN = C.NCA * C.NCA;
+    const double *RED = D.red + (size_t) w * (2 * NN + 8);
+    const double *CJ = sharded ? RED : D.CJ + (size_t) w * BA_SPLIT_J * NN;
+    const double *CWp = sharded ? RED + NN : D.CW + (size_t) w * BA_SPLIT_W * NN;
+    auto cw_get = [&](int a, int b) {  // symmetric storage: any (a, b)
+        if (sharded) return CWp[(size_t) a * C.NCA + b];
+        double s2 = 0;
+#pragma unroll
+        for (int k = 0; k < BA_SPLIT_W; k++) s2 += CWp[(size_t) k * NN + (size_t) a * C.NCA + b];
+        return s2;
+    };
     const double camw = D.rank == 0 ? 1.0 : 0.0;       // camera-side partial sums are counted on shard 0 only
+    if (tid == 0 && st.need_lin) st.need_lin = 0;      // the linearisation kernels of this iteration have run (stream order)
     double *scale_c = D.scale_c + (size_t) w * C.NS;
     const double *hl = D.hl + (size_t) w * C.L, *gl = D.gl + (size_t) w * C.L, *scale_l = D.scale_l + (size_t) w * C.L;
 
@@ -766,10 +813,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     for (int a = tid; a < N; a += SOLVE_THREADS) s_scale[a] = scale_c[a];
     double gmax_now = st.gmax;
     if (f_fresh) {
-        const double c = RED[2 * C.NCA * C.NCA];  // vision cost, summed over the landmark shards
+        double c, gml;
+        if (sharded) {
+            c = RED[2 * NN];  // vision cost, summed over the landmark shards
+            gml = D.redmax[w];
+        } else {
+            double cs = 0, gq = 0;
+            for (int f = tid; f < dm.F; f += SOLVE_THREADS) cs += D.costf[(size_t) w * C.F + f];
+            for (int l = tid; l < L; l += SOLVE_THREADS) gq = fmax(gq, fabs(gl[l]));
+            c = block_sum(cs, s_red);
+            gml = block_max(gq, s_red);
+        }
         double gm = 0;
         for (int a = tid; a < N; a += SOLVE_THREADS) gm = fmax(gm, fabs(s_g[a]));
-        gm = fmax(block_max(gm, s_red), D.redmax[w]);
+        gm = fmax(block_max(gm, s_red), gml);
         gmax_now = gm;
         if (tid == 0) {
             st.x_cost = c + st.cost_cam;
@@ -804,7 +861,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? syrk_get(CJ, 1, C.NCA, a, a) : 0.0);
         double hs = s_scale[a] * s_scale[a] * h;
         s_d2[a] = fmin(fmax(hs, 1e-6), 1e32) / radius;
-        double gw = a < NCV ? syrk_get(CW, 1, C.NCA, a, NCV) : 0.0;
+        double gw = a < NCV ? cw_get(a, NCV) : 0.0;
         s_rhs[a] = -s_scale[a] * (s_g[a] - gw);
     }
     __syncthreads();
@@ -818,8 +875,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
             const int j = (tid & 31) + 32 * q;
             hv[q] = 0;
             if (q < nq && j <= i) {
-                double h = Hc[(size_t) j * C.NS + i];
-                if (i < NCV) h += CJ[(size_t) j * C.NCA + i] - CW[(size_t) j * C.NCA + i];  // j <= i: upper storage
+                double h = Hc[(size_t) i * C.NS + j];  // H_c, the vision Gram matrix and the Schur term are stored symmetric:
+                if (i < NCV) h += CJ[(size_t) i * C.NCA + j] - cw_get(i, j);  // row i is read contiguously
                 hv[q] = h;
             }
         }
@@ -936,32 +993,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     }
     __syncthreads();
     bool valid = !s_fail;
-    // ---- blocked backward substitution L^T x = y: per block, 8 warps reduce the 8 column dot products with the already
-    //      solved unknowns, then one lane-serial 8x8 triangular solve with pre-inverted diagonal
+    // ---- backward substitution L^T x = y, column oriented, by ONE warp with y in registers: for j = N-1 .. 0:
+    //      x_j = y_j / L_jj (owner lane, broadcast by shuffle), then y_i -= L_ji x_j for i < j -- row j of the packed lower triangle
+    //      is contiguous, so every step is one coalesced shared-memory row read and no reduction or block barrier.
     if (valid) {
         const double *y = S + N * (N + 1) / 2;
-        for (int a = tid; a < N; a += SOLVE_THREADS) s_rhs[a] = y[a];
-        __syncthreads();
-        const int lane = tid & 31, warp = tid >> 5;
-        const int nblk = (N + BA_CHOL_NB - 1) / BA_CHOL_NB;
-        for (int jb = nblk - 1; jb >= 0; jb--) {
-            const int J0 = jb * BA_CHOL_NB, nb = min(BA_CHOL_NB, N - J0), J1 = J0 + nb;
-            if (warp < nb) {
-                const int c = J0 + warp;
-                double sum = 0;
-                for (int i2 = J1 + lane; i2 < N; i2 += 32) sum += S[i2 * (i2 + 1) / 2 + c] * s_rhs[i2];
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0) s_red[warp] = sum;
-            }
-            __syncthreads();
-            if (tid == 0) {
-                for (int c = J1 - 1; c >= J0; c--) {
-                    double sum = s_rhs[c] - s_red[c - J0];
-                    for (int k = c + 1; k < J1; k++) sum -= S[k * (k + 1) / 2 + c] * s_rhs[k];
-                    s_rhs[c] = sum * s_diag[c];
+        const int lane = tid & 31;
+        if (tid < 32) {
+            constexpr int MAXQ = 16;  // N <= 512
+            double yr[MAXQ];
+#pragma unroll
+            for (int q = 0; q < MAXQ; q++) yr[q] = lane + 32 * q < N ? y[lane + 32 * q] : 0.0;
+            for (int j = N - 1; j >= 0; j--) {
+                const int oq = j >> 5, ol = j & 31;
+                double xj = 0;
+#pragma unroll
+                for (int q = 0; q < MAXQ; q++)
+                    if (q == oq) xj = yr[q];
+                xj = __shfl_sync(0xffffffffu, xj, ol) * s_diag[j];
+                if (lane == ol) s_rhs[j] = xj;
+                const double *rj = S + j * (j + 1) / 2;
+#pragma unroll
+                for (int q = 0; q < MAXQ; q++) {
+                    const int i2 = lane + 32 * q;
+                    if (q <= oq && i2 < j) yr[q] -= rj[i2] * xj;
                 }
             }
-            __syncthreads();
         }
     }
     __syncthreads();
@@ -992,20 +1049,27 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     __syncthreads();
     {
         const int lane = tid & 31, warp = tid >> 5;
-        for (int l0 = 2 * warp; l0 < L; l0 += 2 * (SOLVE_THREADS / 32)) {
-            const int l1 = l0 + 1;
-            double d0 = 0, d1 = 0;
-            for (int c = lane; c < NCV; c += 32) {
-                d0 += AW[(size_t) l0 * C.NCA + c] * s_sx[c];
-                if (l1 < L) d1 += AW[(size_t) l1 * C.NCA + c] * s_sx[c];
-            }
+        constexpr int LB = 4;  // landmarks in flight per warp (the coupling rows come from L2)
+        for (int l0 = LB * warp; l0 < L; l0 += LB * (SOLVE_THREADS / 32)) {
+            double d[LB];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) d0 += __shfl_xor_sync(0xffffffffu, d0, o), d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            if (lane < 2 && l0 + lane < L) {
+            for (int u = 0; u < LB; u++) d[u] = 0;
+            for (int c = lane; c < NCV; c += 32) {
+                const double sx = s_sx[c];
+#pragma unroll
+                for (int u = 0; u < LB; u++) d[u] += (l0 + u < L ? AW[(size_t) (l0 + u) * C.NCA + c] : 0.0) * sx;
+            }
+            double mine = 0;  // lane u keeps landmark l0 + u
+#pragma unroll
+            for (int u = 0; u < LB; u++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+                if (lane == u) mine = d[u];
+            }
+            if (lane < LB && l0 + lane < L) {
                 const int l = l0 + lane;
-                const double dotp = lane ? d1 : d0;
                 double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
-                double sp = (-sl * gl[l] - sl * dotp) / (hs + d2);
+                double sp = (-sl * gl[l] - sl * mine) / (hs + d2);
                 finite = finite && isfinite(sp);
                 step_l[l] = sp;
                 part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
@@ -1099,7 +1163,7 @@ __global__ void __launch_bounds__(256) ba_cost(BaCaps C, BaDev D, int nblk_vis) 
 // ------------------------------------------------------------------------------------------------ accept / reject
 __global__ void __launch_bounds__(128) ba_accept(BaCaps C, BaDev D, int nblk_vis) {
     __shared__ int s_accept;
-    __shared__ double s_camsq;
+    __shared__ double s_camsq, s_rhosq;
     __shared__ double s_red[40];
     const int w = blockIdx.x, tid = threadIdx.x;
     LmState &st = D.st[w];
@@ -1116,12 +1180,27 @@ __global__ void __launch_bounds__(128) ba_accept(BaCaps C, BaDev D, int nblk_vis
         if (tid < 7 && !dm.ext_const) s += ext[tid] * ext[tid];
         if (tid == 7 && !dm.td_const) s += ext[7] * ext[7];
         s = block_sum(s, s_red);
-        if (tid == 0) s_camsq = s;
+        double q = 0;  // |rho|^2: from the reduced operand when the landmarks are sharded
+        if (D.world == 1) {
+            for (int l = tid; l < dm.L; l += 128) q += D.rho[(size_t) w * C.L + l] * D.rho[(size_t) w * C.L + l];
+            q = block_sum(q, s_red);
+        } else {
+            q = D.red[(size_t) w * (2 * C.NCA * C.NCA + 8) + 2 * C.NCA * C.NCA + 1];
+        }
+        if (tid == 0) s_camsq = s, s_rhosq = q;
     }
     __syncthreads();
     if (tid == 0) {
         s_accept = 0;
-        const double mcc = R2[0], sn = R2[1], nfin = R2[2], cand = R2[3];
+        const double mcc = R2[0], sn = R2[1], nfin = R2[2];
+        double cand = R2[3];
+        if (D.world == 1 && st.step_valid) {  // single GPU: sum the candidate-cost partials here (ba_pack2 does it before the all-reduce otherwise)
+            const double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
+            cand = 0;
+            const int nb = (dm.F + 255) / 256;
+            for (int b = 0; b < nb; b++) cand += part[b];
+            cand += part[nblk_vis];
+        }
         if (!chol_ok || nfin != 0.0 || !(mcc > 0.0)) {
             // HandleInvalidStep + LevenbergMarquardtStrategy::StepIsInvalid
             st.step_valid = 0;
@@ -1133,7 +1212,7 @@ __global__ void __launch_bounds__(128) ba_accept(BaCaps C, BaDev D, int nblk_vis
             st.n_invalid = 0;
             st.model_cost_change = mcc;
             st.step_norm = sqrt(sn);
-            st.x_norm = sqrt(s_camsq + D.red[(size_t) w * (2 * C.NCA * C.NCA + 8) + 2 * C.NCA * C.NCA + 1]);
+            st.x_norm = sqrt(s_camsq + s_rhosq);
             st.cand_cost = cand;
             // ParameterToleranceReached / FunctionToleranceReached (Ceres trust_region_minimizer.cc)
             if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) {
@@ -1170,12 +1249,6 @@ __global__ void __launch_bounds__(128) ba_accept(BaCaps C, BaDev D, int nblk_vis
     for (int e = tid; e < dm.K * 9; e += 128) mix[e] = mix_c[e];
     if (tid < 8) ext[tid] = ext_c[tid];
     for (int e = tid; e < dm.L; e += 128) rho[e] = rho_c[e];
-}
-
-// mark need_lin consumed after the linearisation kernels ran
-__global__ void ba_lin_done(BaDev D, int NW) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w < NW && !D.st[w].done && D.st[w].need_lin) D.st[w].need_lin = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ LM state reset (device side)
@@ -1349,13 +1422,14 @@ struct icg_ba {
     bool own_stream;
     int nblk_vis;
     int cur_windows;
-    size_t smem_cam, smem_solve, smem_syrk, smem_gram;
-    int mp_in_smem, syrk_one_tile;
+    size_t smem_cam, smem_solve, smem_schur;
+    int ld_schur;
     int use_global_S;
     HostDev<WinDims> dims;
     HostDev<LmState> st;
     HostDev<double> pose, mix, ext, rho, f_const, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
         marg_H0, marg_b0, marg_c0;
+    HostDev<int> f_slot;
     HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
     HostDev<uint8_t> f_active;
     std::vector<void *> dev_only;
@@ -1363,12 +1437,25 @@ struct icg_ba {
     HostDev<LmState> st_save;   // pass-1 LM state of the two-pass protocol
     HostDev<int> cull_counters; // per window: reprojection factors removed, GNSS fixes re-weighted
     void *comm = nullptr;       // ncclComm_t when this handle solves a landmark shard
+    // in-situ stage timing (ICG_BA_PROFILE=1): events between the kernels of the LM sequence on the main stream, read back in
+    // icg_ba_sync / icg_ba_download and printed by icg_ba_destroy (warm caches, real launch gaps -- unlike an ncu replay)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_tag;
+    size_t prof_used = 0;
+    double prof_ms[16] = {0};
+    long prof_cnt[16] = {0};
     // marginalization workspace (allocated on the first icg_ba_marginalize call)
     bool marg_ready = false;
     MargDev M;
     HostDev<int> marg_map;
     HostDev<double> marg_oJ0, marg_oe0, marg_oHp, marg_obp;
 };
+
+extern "C" {
+static void prof_collect(icg_ba *h);
+static void prof_print(icg_ba *h);
+}
 
 static int dmalloc(icg_ba *h, double **p, size_t n) {
     if (cudaMalloc(p, sizeof(double) * n) != cudaSuccess) {
@@ -1558,17 +1645,12 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     ICG_CUDA(cudaStreamCreateWithFlags(&h->stream_cam, cudaStreamNonBlocking));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->prof = getenv("ICG_BA_PROFILE") != nullptr;
     BaCaps &C = h->C;
     C.NW = max_windows, C.K = max_K, C.L = max_L, C.F = max_F, C.G = std::max(1, max_gnss), C.R = std::max(1, max_marg_r);
     C.NCV = 6 * max_K + 7, C.N = 15 * max_K + 7, C.NS = (C.N + 3) & ~3, C.NCA = 4 * ((C.NCV + 1 + 3) / 4);
     C.RJ = (2 * max_F + 31) & ~31, C.LP = (max_L + 31) & ~31;
-    const int nt = C.NCA / 4;
-    if (nt * (nt + 1) / 2 > 256 * BA_MAX_TILES) {
-        set_error("icg_ba_create: max_K=%d exceeds the SYRK tile budget", max_K);
-        return ICG_EUNSUPPORTED;
-    }
     h->nblk_vis = (max_F + 255) / 256;
-    h->syrk_one_tile = (nt * (nt + 1) / 2 <= 256) ? 1 : 0;
     const size_t NW = max_windows;
 #define HD(field, count)                                                       \
     if (h->field.alloc(count) != ICG_OK) {                                     \
@@ -1580,7 +1662,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * 64 * 9)
     HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
     HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * 64) HD(marg_node, NW * 64) HD(f_active, NW * C.F)
-    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW)
+    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F)
     HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
 #undef HD
     BaDev &D = h->D;
@@ -1588,6 +1670,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
     D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
     D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
+    D.f_slot = h->f_slot.d;
     D.lm_off = h->lm_off.d, D.lm_fidx = h->lm_fidx.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
     D.gnss_node = h->gnss_node.d, D.gnss_blh = h->gnss_blh.d, D.gnss_std = h->gnss_std.d, D.lever = h->lever.d;
     D.pose_prior = h->pose_prior.d, D.pose_prior_sinfo = h->pose_prior_sinfo.d, D.mix_prior = h->mix_prior.d, D.mix_prior_std = h->mix_prior_std.d;
@@ -1598,13 +1681,12 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     DM(pose_c, NW * C.K * 7) DM(mix_c, NW * C.K * 9) DM(ext_c, NW * 8) DM(rho_c, NW * C.L)
     DM(pose_0, NW * C.K * 7) DM(mix_0, NW * C.K * 9) DM(ext_0, NW * 8) DM(rho_0, NW * C.L)
     DM(AW, NW * C.NCA * C.LP) DM(Mp, NW * (size_t) C.K * (C.K - 1) * 210) DM(CJ, NW * BA_SPLIT_J * C.NCA * C.NCA) DM(CW, NW * BA_SPLIT_W * C.NCA * C.NCA)
-    DM(jcomp, NW * C.F * 40) DM(jrho, NW * C.F * 2) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
+    DM(jcomp, NW * C.F * 40) DM(jrho, NW * C.F * 4) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
     DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(red, NW * (2 * (size_t) C.NCA * C.NCA + 8)) DM(redmax, NW) DM(red2, NW * 4) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
 #undef DM
     if (rc != ICG_OK) return rc;
     // shared-memory budgets
     h->smem_cam = sizeof(double) * ((size_t) C.K * 480 + (size_t) C.G * 24 + 48 + 16 + 2 * (size_t) C.R + 8) + sizeof(int) * (size_t) C.R + 64;
-    h->smem_syrk = sizeof(double) * (size_t) C.NCA * 33;
     size_t vec = sizeof(double) * (40 + 5 * (size_t) C.NS);
     size_t packed = sizeof(double) * ((size_t) (C.N + 1) * (C.N + 2) / 2);
     h->use_global_S = (vec + packed > 220 * 1024) ? 1 : 0;
@@ -1616,11 +1698,11 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
         D.Sglobal = nullptr;
     }
     ICG_CUDA(cudaFuncSetAttribute(ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve));
+    h->ld_schur = 16 * ((C.NCA + 15) / 16) + 8;  // = 8 mod 16 doubles: conflict-free fragment reads
+    h->smem_schur = sizeof(double) * ((size_t) SCHUR_RCH * h->ld_schur + SCHUR_RCH);
+    ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_schur));
     ICG_CUDA(cudaFuncSetAttribute(ba_lin_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
     ICG_CUDA(cudaFuncSetAttribute(ba_cost_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
-    ICG_CUDA(cudaFuncSetAttribute(ba_syrk<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
-    ICG_CUDA(cudaFuncSetAttribute(ba_syrk<BA_MAX_TILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_syrk));
-    h->mp_in_smem = 0, h->smem_gram = 0;
     ICG_CUDA(cudaStreamSynchronize(h->stream));
     h->cur_windows = 0;
     *out = h;
@@ -1631,11 +1713,14 @@ void icg_ba_destroy(icg_ba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    prof_collect(h);
+    prof_print(h);
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
     h->dims.release(), h->st.release(), h->pose.release(), h->mix.release(), h->ext.release(), h->rho.release(), h->f_const.release();
     h->imu_blob.release(), h->imu_U.release(), h->gnss_blh.release(), h->gnss_std.release(), h->lever.release(), h->pose_prior.release();
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
-    h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
+    h->f_slot.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
     if (h->marg_ready) h->marg_map.release(), h->marg_oJ0.release(), h->marg_oe0.release(), h->marg_oHp.release(), h->marg_obp.release();
     for (void *p : h->dev_only) cudaFree(p);
@@ -1677,6 +1762,19 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
                 return ICG_EINVAL;
             }
         }
+        {   // a map point has one reference frame and at most one observation per keyframe (IG/ic_gvins.cc:1777-1834): lin_lm relies on it
+            std::vector<int> refof(p.L, -1);
+            std::vector<unsigned> seen((size_t) p.L, 0u);
+            for (int f = 0; f < p.F; f++) {
+                const int l = p.f_lm[f];
+                if (refof[l] < 0) refof[l] = p.f_ref[f];
+                if (refof[l] != p.f_ref[f] || (seen[l] >> p.f_obs[f]) & 1u) {
+                    set_error("icg_ba_upload: window %d factor %d: landmark %d has two reference nodes or two observations in node %d", w, f, l, p.f_obs[f]);
+                    return ICG_EINVAL;
+                }
+                seen[l] |= 1u << p.f_obs[f];
+            }
+        }
         memcpy(h->f_lm.h + (size_t) w * C.F, p.f_lm, sizeof(int) * p.F);
         memcpy(h->f_ref.h + (size_t) w * C.F, p.f_ref, sizeof(int) * p.F);
         memcpy(h->f_obs.h + (size_t) w * C.F, p.f_obs, sizeof(int) * p.F);
@@ -1690,9 +1788,10 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
         for (int l = 0; l <= p.L; l++) off[l] = 0;
         for (int f = 0; f < p.F; f++) off[p.f_lm[f] + 1]++;
         for (int l = 0; l < p.L; l++) off[l + 1] += off[l];
+        int *fslot = h->f_slot.h + (size_t) w * C.F;
         {
             std::vector<int> cur(off, off + p.L);
-            for (int f = 0; f < p.F; f++) fidx[cur[p.f_lm[f]]++] = f;
+            for (int f = 0; f < p.F; f++) fslot[f] = cur[p.f_lm[f]], fidx[cur[p.f_lm[f]]++] = f;
         }
         // CSR by (reference node, observing node) pair
         {
@@ -1710,7 +1809,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
                     P++;
                 }
             std::vector<int> cur(poff, poff + P);
-            for (int f = 0; f < p.F; f++) pfidx[cur[slot[(size_t) p.f_ref[f] * p.K + p.f_obs[f]]]++] = f;
+            for (int f = 0; f < p.F; f++) pfidx[cur[slot[(size_t) p.f_ref[f] * p.K + p.f_obs[f]]]++] = fslot[f];  // record slots, not factor ids
             h->npairs.h[w] = P;
         }
         for (int k = 0; k < p.n_imu; k++) {
@@ -1781,7 +1880,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     ICG_CUDA(h->dims.up(s));
     ICG_CUDA(h->pose.up(s)); ICG_CUDA(h->mix.up(s)); ICG_CUDA(h->ext.up(s)); ICG_CUDA(h->rho.up(s));
     ICG_CUDA(h->f_lm.up(s)); ICG_CUDA(h->f_ref.up(s)); ICG_CUDA(h->f_obs.up(s)); ICG_CUDA(h->f_const.up(s)); ICG_CUDA(h->f_active.up(s));
-    ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
+    ICG_CUDA(h->f_slot.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
     ICG_CUDA(h->gnss_node.up(s)); ICG_CUDA(h->gnss_blh.up(s)); ICG_CUDA(h->gnss_std.up(s)); ICG_CUDA(h->lever.up(s));
     ICG_CUDA(h->pose_prior.up(s)); ICG_CUDA(h->pose_prior_sinfo.up(s)); ICG_CUDA(h->mix_prior.up(s)); ICG_CUDA(h->mix_prior_std.up(s));
     ICG_CUDA(h->marg_type.up(s)); ICG_CUDA(h->marg_node.up(s)); ICG_CUDA(h->marg_x0.up(s)); ICG_CUDA(h->marg_H0.up(s)); ICG_CUDA(h->marg_b0.up(s));
@@ -1795,6 +1894,41 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     // the dense SYRK operands keep a fixed sparsity pattern per problem: zero them once here
     h->cur_windows = n;
     return ICG_OK;
+}
+
+// ---- in-situ stage timing
+static const char *PROF_NAMES[16] = {"(gap/other)", "lin_vis", "lin_lm", "pair_gram1", "pair_gram2", "schur_dmma", "join lin_cam + lin_done",
+                                     "pack1", "solve", "cost (+cost_cam)", "pack2", "accept", "", "", "", ""};
+static void prof_mark(icg_ba *h, int tag) {
+    if (!h->prof) return;
+    if (h->prof_used == h->prof_ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_ev.push_back(e);
+        h->prof_tag.push_back(0);
+    }
+    h->prof_tag[h->prof_used] = tag;
+    cudaEventRecord(h->prof_ev[h->prof_used++], h->stream);
+}
+static void prof_collect(icg_ba *h) {  // call after the stream has been synchronised
+    if (!h->prof) return;
+    for (size_t i = 1; i < h->prof_used; i++) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->prof_ev[i - 1], h->prof_ev[i]) == cudaSuccess) {
+            h->prof_ms[h->prof_tag[i]] += ms;
+            h->prof_cnt[h->prof_tag[i]]++;
+        }
+    }
+    h->prof_used = 0;
+}
+static void prof_print(icg_ba *h) {
+    if (!h->prof) return;
+    double tot = 0;
+    for (int t = 0; t < 16; t++) tot += h->prof_ms[t];
+    fprintf(stderr, "[icg_ba profile] handle %p, %d windows: stage totals over all recorded LM sequences (ms, mean us, share)\n", (void *) h, h->cur_windows);
+    for (int t = 0; t < 16; t++)
+        if (h->prof_cnt[t])
+            fprintf(stderr, "  %-28s %9.3f ms  %8.1f us  %5.1f %%\n", PROF_NAMES[t], h->prof_ms[t], 1e3 * h->prof_ms[t] / h->prof_cnt[t], 100.0 * h->prof_ms[t] / tot);
 }
 
 static int enqueue_lm(icg_ba *h, int max_num_iterations) {
@@ -1811,25 +1945,30 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
         ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
         ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        prof_mark(h, 0);
         ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
+        prof_mark(h, 1);
         ba_lin_lm<<<g_lm, 256, 0, s>>>(C, D);
+        prof_mark(h, 2);
         ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
+        prof_mark(h, 3);
         ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
-        if (h->syrk_one_tile)
-            ba_syrk<1><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
-        else
-            ba_syrk<BA_MAX_TILES><<<g_sw, 256, h->smem_syrk, s>>>(C, D, 1);
+        prof_mark(h, 4);
+        ba_schur_dmma<<<g_sw, 256, h->smem_schur, s>>>(C, D, h->ld_schur);
+        prof_mark(h, 5);
         ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-        ba_lin_done<<<(n + 127) / 128, 128, 0, s>>>(D, n);
-        ba_pack1<<<dim3(n, PACK1_SPLIT), 256, 0, s>>>(C, D);
+        prof_mark(h, 6);
         if (h->comm) {  // landmark-sharded window: one sum all-reduce of [H_vis g | Schur | cost, |rho|^2] + one max all-reduce
+            ba_pack1<<<dim3(n, PACK1_SPLIT), 256, 0, s>>>(C, D);
+            prof_mark(h, 7);
             int rc = nccl_allreduce(h, D.red, (size_t) n * (2 * (size_t) C.NCA * C.NCA + 8), 0);
             if (rc != ICG_OK) return rc;
             rc = nccl_allreduce(h, D.redmax, (size_t) n, 1);
             if (rc != ICG_OK) return rc;
         }
         ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
-        count_launch(9);
+        prof_mark(h, 8);
+        count_launch(h->comm ? 8 : 7);
         if (it == max_num_iterations) break;
         ICG_CUDA(cudaEventRecord(h->ev_fork, s));
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
@@ -1837,13 +1976,16 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         ba_cost<<<g_cost, 256, 0, s>>>(C, D, h->nblk_vis);
         ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-        ba_pack2<<<(n + 127) / 128, 128, 0, s>>>(C, D, n, h->nblk_vis);
+        prof_mark(h, 9);
         if (h->comm) {
+            ba_pack2<<<(n + 127) / 128, 128, 0, s>>>(C, D, n, h->nblk_vis);
+            prof_mark(h, 10);
             int rc = nccl_allreduce(h, D.red2, (size_t) n * 4, 0);
             if (rc != ICG_OK) return rc;
         }
         ba_accept<<<n, 128, 0, s>>>(C, D, h->nblk_vis);
-        count_launch(4);
+        prof_mark(h, 11);
+        count_launch(h->comm ? 4 : 3);
     }
     ICG_CHECK_LAUNCH();
     return ICG_OK;
@@ -2192,6 +2334,7 @@ int icg_ba_sync(icg_ba *h) {
     if (!h) return ICG_EINVAL;
     ICG_CUDA(cudaSetDevice(h->device));
     ICG_CUDA(cudaStreamSynchronize(h->stream));
+    prof_collect(h);
     return ICG_OK;
 }
 

@@ -60,7 +60,7 @@ __global__ void marg_prepare(BaDev D, MargDev M, int n, int restore) {
 // H0, b0 of constructEquation.  One CTA per window; every stage has one writer per entry, stages are separated by barriers.
 __global__ void __launch_bounds__(256) marg_assemble(BaCaps C, BaDev D, MargDev M) {
     extern __shared__ double smem[];
-    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WinDims dm = D.dims[w];
     const int *map = M.map + (size_t) w * M.map_stride;
     const int m = map[0], n0 = map[2], nm = map[3], ext_col = map[4], td_col = map[5];

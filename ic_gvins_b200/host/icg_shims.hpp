@@ -116,8 +116,60 @@ public:
         check(icg_ba_gvins_optimization(h_, 1, &problem, num_iterations, out, culled), "icg_ba_gvins_optimization");
     }
 
+    // marginalization_info->marginalization() as GVINS::gvinsMarginalization drives it (IG/ic_gvins.cc:1412-1640): the prior that
+    // replaces last_marginalization_info_ / last_marginalization_parameter_blocks_.  Vectors are sized here.
+    struct Prior {
+        int m = 0, r = 0;
+        std::vector<int32_t> block_type, block_node;  // remainedBlock*: type 0 pose 1 mix 2 extrinsic 3 td; node index after the removal
+        std::vector<double> x0, J0, e0;               // remainedBlockData(), linearizedJacobians() (r x r row-major), linearizedResiduals()
+    };
+    Prior marginalization(const icg_ba_problem &problem, int num_marg) {
+        Prior P;
+        const int rcap = 15 * problem.K + 7;
+        P.block_type.resize(2 * problem.K + 2), P.block_node.resize(2 * problem.K + 2);
+        P.x0.resize(16 * problem.K + 8), P.J0.resize((size_t) rcap * rcap), P.e0.resize(rcap);
+        icg_ba_prior o{};
+        o.rcap = rcap, o.block_type = P.block_type.data(), o.block_node = P.block_node.data(), o.x0 = P.x0.data(), o.J0 = P.J0.data(), o.e0 = P.e0.data();
+        const int32_t nm = num_marg;
+        check(icg_ba_marginalize(h_, 1, &problem, &nm, &o), "icg_ba_marginalize");
+        P.m = o.m, P.r = o.r;
+        P.block_type.resize(o.nblocks), P.block_node.resize(o.nblocks);
+        P.J0.resize((size_t) o.r * o.r), P.e0.resize(o.r);
+        return P;
+    }
+
 private:
     icg_ba *h_ = nullptr;
+};
+
+// Tracking::featuresDetection's tbb::parallel_for body (IG/tracking/tracking.cc:627-656) for all blocks in one call.
+class BlockDetector {
+public:
+    BlockDetector(int width, int height, int max_blocks, int max_corners_per_block, int max_roi_pixels, int device = 0) : cap_(max_corners_per_block) {
+        check(icg_detect_create(&h_, width, height, max_blocks, max_corners_per_block, max_roi_pixels, device, nullptr), "icg_detect_create");
+    }
+    ~BlockDetector() { icg_detect_destroy(h_); }
+    BlockDetector(const BlockDetector &) = delete;
+    BlockDetector &operator=(const BlockDetector &) = delete;
+
+    // goodFeaturesToTrack(frame(roi), out, max_corners[b], quality, min_distance, mask(roi)) + cornerSubPix(...) per block;
+    // features[b] holds block-local coordinates in OpenCV's order
+    void detect(const Mat &frame, const Mat *mask, const std::vector<icg_rect> &rois, const std::vector<int32_t> &max_corners, double quality,
+                double min_distance, std::vector<std::vector<Point2f>> &features) {
+        const int nb = (int) rois.size();
+        std::vector<float> xy((size_t) nb * cap_ * 2);
+        std::vector<int32_t> cnt(nb);
+        check(icg_detect_blocks(h_, mat_data(frame), mask ? mat_data(*mask) : nullptr, mat_stride(frame), nb, rois.data(), max_corners.data(), quality,
+                                min_distance, 1, xy.data(), cnt.data()),
+              "icg_detect_blocks");
+        features.assign(nb, {});
+        for (int b = 0; b < nb; b++)
+            for (int k = 0; k < cnt[b]; k++) features[b].push_back(Point2f{xy[((size_t) b * cap_ + k) * 2], xy[((size_t) b * cap_ + k) * 2 + 1]});
+    }
+
+private:
+    icg_detect *h_ = nullptr;
+    int cap_;
 };
 
 }  // namespace icg_b200

@@ -6,7 +6,7 @@ mkdir -p $O
 timeout 900 python -m pytest tests -m gpu -x -q > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest.log
 [ -x scripts/fp64_probe ] && timeout 60 scripts/fp64_probe > $O/${T}_fp64.txt 2>&1
 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sharded > $O/${T}_bench.json 2> $O/${T}_bench.err
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sharded --ba-handles 4 > $O/${T}_bench_h4.json 2> $O/${T}_bench_h4.err
+timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sharded --ba-handles 4 --streams 592 > $O/${T}_bench_h4.json 2> $O/${T}_bench_h4.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${T}_ba_launches.csv python scripts/prof_ba.py 148 1 > $O/${T}_ncu_ba.log 2>&1
 tail -15 $O/${T}_pytest.log; cat $O/${T}_fp64.txt; for f in $O/${T}_bench.json $O/${T}_bench_h4.json; do python - "$f" <<'PY'
 import json,sys

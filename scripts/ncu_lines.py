@@ -1,7 +1,9 @@
-"""Aggregate an ncu source-page CSV by CUDA source line: stall samples + instructions.  usage: ncu_lines.py rep [topN]"""
+"""Aggregate an ncu source-page CSV by CUDA source line: stall samples + instructions.  usage: ncu_lines.py rep [topN] [kernel-regex]"""
 import csv, subprocess, sys, collections
 rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]
+if len(sys.argv) > 3: cmd += ["--kernel-name", "regex:" + sys.argv[3]]
+out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "# Samples" in r)
 hdr = rows[hi]
