@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--ba-handles", type=int, default=2, help="solver handles (CUDA streams) the B windows are split over")
     ap.add_argument("--no-sharded", action="store_true", help="skip the cfg-4 landmark-sharded BA section")
     ap.add_argument("--no-marg", action="store_true", help="skip the marginalization section")
+    ap.add_argument("--no-detect", action="store_true", help="skip the block-detection section")
     return ap.parse_args()
 
 
@@ -415,6 +416,40 @@ def run_b200(args):
                    "mean_lm_iterations_pass2": float(np.mean([x["iterations"] for x in sm])),
                    "final_cost_mean": float(np.mean([x["final_cost"] for x in sm]))}
 
+    # ---- featuresDetection: all 18 blocks of a frame in one host-buffer call (image H2D + corners D2H inside)
+    detect = None
+    if not args.no_detect:
+        from ic_gvins_b200.detect import Detector, block_rois
+        det = Detector(W, H, max_blocks=32, max_corners_per_block=64, device=local_rank)
+        rois, quota, min_dist, _ = block_rois(W, H, NPTS)
+        want = [quota] * len(rois)
+        got = det.detect_blocks(frames[0], rois, want, 0.01, float(min_dist), None, subpix=True)
+        barrier()
+        reps = 20
+        t0 = time.perf_counter()
+        for k in range(reps):
+            det.detect_blocks(frames[k % NFRAMES], rois, want, 0.01, float(min_dist), None, subpix=True)
+        dtd = (time.perf_counter() - t0) / reps
+        detect = {"workload": "icg_detect_blocks: goodFeaturesToTrack + cornerSubPix on the 18 blocks of a 1280x560 frame, empty mask, "
+                              "host buffers (synchronous call, one frame at a time: the reference's per-keyframe use)",
+                  "ms_per_frame": dtd * 1e3, "frames_per_s": 1.0 / dtd * world, "corners": int(sum(len(g) for g in got))}
+        det.close()
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                import cv2
+                cv2.setNumThreads(os.cpu_count() or 1)
+                t0 = time.perf_counter()
+                for k in range(5):
+                    img = frames[k % NFRAMES]
+                    for (x0, y0, bw, bh), n in zip(rois, want):  # cv2 on numpy slices (the C++ ROI reads beyond the block edge; timing only)
+                        blk = np.ascontiguousarray(img[y0:y0 + bh, x0:x0 + bw])
+                        c = cv2.goodFeaturesToTrack(blk, n, 0.01, float(min_dist))
+                        if c is not None and len(c):
+                            cv2.cornerSubPix(blk, c, (5, 5), (-1, -1), (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 20, 0.01))
+                detect["cpu_cv2_ms_per_frame"] = (time.perf_counter() - t0) / 5 * 1e3
+            except Exception:
+                pass
+
     # ---- gvinsMarginalization: the step that follows the solve at every keyframe, through the host-buffer C ABI
     marg = None
     if use_ba and not args.no_marg:
@@ -508,6 +543,7 @@ def run_b200(args):
         "ba_only": ba_info,
         "sharded_ba": sharded,
         "marginalization": marg,
+        "detection": detect,
         "tracked_fraction": good / float(n_total),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -28,6 +28,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "ba_math.cuh"
@@ -67,12 +69,15 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     uint8_t *f_active;
     int *lm_off, *lm_fidx;
     int *f_slot;  // position of factor f in landmark-CSR order: the per-factor records are stored in that order
+    int *f_meta_s;       // per record slot: (landmark, reference node, observing node, factor id)
+    double *f_const_s;   // per record slot: the factor's 14 constants (copy of f_const in slot order)
     int *pair_off, *pair_ro, *pair_fidx, *npairs;  // factors grouped by (reference node, observing node)
     double *Mp;                                    // per-pair 20x20 Gram matrices (upper, 210 entries)
     double *AW, *CJ, *CW;  // Schur SYRK input; vision Gram matrix; Schur partials
     double *jcomp, *jrho, *costf;  // per-factor compact Jacobian (38), rho-Jacobian rows (2), cost
     double *hl, *gl, *scale_l, *scale_c;
     double *Hc, *gc;
+    double *Hs;  // H_c + vision Gram - Schur term (lower triangle, ld NS): the operand ba_solve scales and factorises
     double *imu_blob, *imu_U;
     int *gnss_node;
     double *gnss_blh, *gnss_std, *lever;
@@ -94,43 +99,64 @@ __device__ __forceinline__ int col_td(int K) { return 6 * K + 6; }
 __device__ __forceinline__ int col_mix(int K, int k) { return 6 * K + 7 + 9 * k; }
 
 // ------------------------------------------------------------------------------------------------ lin_vis
-__global__ void __launch_bounds__(128, 3) ba_lin_vis(BaCaps C, BaDev D) {
+// One thread per reprojection factor, in record (landmark-CSR slot) order: thread q evaluates factor f = meta[q].f and the warp's 32
+// records (40 + 4 doubles each) are transposed through shared memory so that they leave as contiguous, fully used 128-byte lines
+// (a thread-per-record store pattern costs 32 sectors per instruction and made the store pipe the bottleneck of this kernel).
+constexpr int LV_REC = 44, LV_LD = 45;  // record doubles (40 Jacobian/residual + 4 j_rho/meta), padded row (odd: conflict-free)
+__global__ void __launch_bounds__(128, 4) ba_lin_vis(BaCaps C, BaDev D) {
+    __shared__ double s_rec[4][32][LV_LD];
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
     const WinDims dm = D.dims[w];
-    const int f = blockIdx.x * 128 + threadIdx.x;
-    if (f >= dm.F) return;
-    const int lm = D.f_lm[(size_t) w * C.F + f], i = D.f_ref[(size_t) w * C.F + f], j = D.f_obs[(size_t) w * C.F + f];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q0 = blockIdx.x * 128 + 32 * warp, q = q0 + lane;
+    if (q0 >= dm.F) return;  // whole warp
     double r[2], Ji[12], Jj[12], Je[12], Jr[2], Jt[2], cost = 0;
-    const bool active = D.f_active[(size_t) w * C.F + f] != 0;
-    if (active) {
-        const double *ext = D.ext + (size_t) w * 8;
-        reproj_eval(D.pose + ((size_t) w * C.K + i) * 7, D.pose + ((size_t) w * C.K + j) * 7, ext, D.rho[(size_t) w * C.L + lm], ext[7],
-                    D.f_const + ((size_t) w * C.F + f) * 14, dm.reproj_sinv, true, r, Ji, Jj, Je, Jr, Jt);
-        if (dm.ext_const)
-            for (int k = 0; k < 12; k++) Je[k] = 0;
-        if (dm.td_const) Jt[0] = Jt[1] = 0;
-        double sq = r[0] * r[0] + r[1] * r[1], sc = 1.0;
-        if (dm.reproj_huber)
-            huber(sq, cost, sc);
-        else
-            cost = 0.5 * sq;
-        if (sc != 1.0) {
-            for (int k = 0; k < 12; k++) Ji[k] *= sc, Jj[k] *= sc, Je[k] *= sc;
-            Jr[0] *= sc, Jr[1] *= sc, Jt[0] *= sc, Jt[1] *= sc, r[0] *= sc, r[1] *= sc;
+    int i = 0, j = 0, f = -1;
+    if (q < dm.F) {
+        const int4 meta = ((const int4 *) D.f_meta_s)[(size_t) w * C.F + q];  // (landmark, reference node, observing node, factor id)
+        i = meta.y, j = meta.z, f = meta.w;
+        if (D.f_active[(size_t) w * C.F + f] != 0) {
+            const double *ext = D.ext + (size_t) w * 8;
+            reproj_eval(D.pose + ((size_t) w * C.K + i) * 7, D.pose + ((size_t) w * C.K + j) * 7, ext, D.rho[(size_t) w * C.L + meta.x], ext[7],
+                        D.f_const_s + ((size_t) w * C.F + q) * 14, dm.reproj_sinv, true, r, Ji, Jj, Je, Jr, Jt);
+            if (dm.ext_const)
+                for (int k = 0; k < 12; k++) Je[k] = 0;
+            if (dm.td_const) Jt[0] = Jt[1] = 0;
+            double sq = r[0] * r[0] + r[1] * r[1], sc = 1.0;
+            if (dm.reproj_huber)
+                huber(sq, cost, sc);
+            else
+                cost = 0.5 * sq;
+            if (sc != 1.0) {
+                for (int k = 0; k < 12; k++) Ji[k] *= sc, Jj[k] *= sc, Je[k] *= sc;
+                Jr[0] *= sc, Jr[1] *= sc, Jt[0] *= sc, Jt[1] *= sc, r[0] *= sc, r[1] *= sc;
+            }
+        } else {
+            for (int k = 0; k < 12; k++) Ji[k] = Jj[k] = Je[k] = 0;
+            Jr[0] = Jr[1] = Jt[0] = Jt[1] = r[0] = r[1] = 0;
         }
-    } else {
-        for (int k = 0; k < 12; k++) Ji[k] = Jj[k] = Je[k] = 0;
-        Jr[0] = Jr[1] = Jt[0] = Jt[1] = r[0] = r[1] = 0;
+        D.costf[(size_t) w * C.F + f] = cost;
+        double *sr = s_rec[warp][lane];
+#pragma unroll
+        for (int k = 0; k < 12; k++) sr[k] = Ji[k], sr[12 + k] = Jj[k], sr[24 + k] = Je[k];
+        sr[36] = Jt[0], sr[37] = Jt[1], sr[38] = r[0], sr[39] = r[1];
+        sr[40] = Jr[0], sr[41] = Jr[1], sr[42] = (double) j, sr[43] = (double) i;  // [j_rho (2) | observing node | reference node]
     }
-    const size_t slot = (size_t) w * C.F + D.f_slot[(size_t) w * C.F + f];  // records live in landmark-CSR order (lin_lm streams them)
-    double *jc = D.jcomp + slot * 40;
-    for (int k = 0; k < 12; k++) jc[k] = Ji[k], jc[12 + k] = Jj[k], jc[24 + k] = Je[k];
-    jc[36] = Jt[0], jc[37] = Jt[1], jc[38] = r[0], jc[39] = r[1];
-    double *jr = D.jrho + slot * 4;  // [j_rho (2) | observing node | reference node]
-    jr[0] = Jr[0], jr[1] = Jr[1], jr[2] = (double) j, jr[3] = (double) i;
-    D.costf[(size_t) w * C.F + f] = cost;
+    __syncwarp();
+    const int nrec = min(32, dm.F - q0);
+    double *gj = D.jcomp + ((size_t) w * C.F + q0) * 40, *gr = D.jrho + ((size_t) w * C.F + q0) * 4;
+#pragma unroll 8
+    for (int t = 0; t < 40; t++) {
+        const int idx = lane + 32 * t, rr = idx / 40, k = idx - 40 * rr;
+        if (rr < nrec) gj[idx] = s_rec[warp][rr][k];
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int idx = lane + 32 * t, rr = idx >> 2, k = idx & 3;
+        if (rr < nrec) gr[idx] = s_rec[warp][rr][40 + k];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ lin_lm
@@ -141,64 +167,77 @@ __global__ void __launch_bounds__(128, 3) ba_lin_vis(BaCaps C, BaDev D) {
 __device__ __forceinline__ int jc_off(int a) { return a < 18 ? (a / 6) * 12 + (a % 6) : 36 + 2 * (a - 18); }  // row 0 offset in a record
 __device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }                                           // + this for row 1
 __global__ void __launch_bounds__(256) ba_lin_lm(BaCaps C, BaDev D) {
+    // four landmarks per warp (8 lanes each): the kernel is a chain of dependent L2 round trips (offsets -> records -> row), so
+    // fewer, fuller warps mean fewer latency-bound waves.  Sub-lane sl owns output columns sl, sl + 8, sl + 16 of the 21
+    // (19 Jacobian columns, 19 -> g_l, 20 -> h_l).
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
     const WinDims dm = D.dims[w];
     const int K = dm.K, NCV = 6 * K + 7, NCA = 4 * ((NCV + 1 + 3) / 4);
-    const int lane = threadIdx.x & 31;
-    const int l = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
+    const int l = 4 * (blockIdx.x * 8 + (threadIdx.x >> 5)) + grp;
     if (l >= dm.L) return;
     const int *off = D.lm_off + (size_t) w * (C.L + 1);
-    const int f0 = off[l], f1 = off[l + 1];
+    const int f0 = off[l], nf = off[l + 1] - f0;
     double *row = D.AW + ((size_t) w * C.LP + l) * C.NCA;
-    for (int c = lane; c < NCA; c += 32) row[c] = 0.0;
+    for (int c = sl; c < NCA; c += 8) row[c] = 0.0;
     __syncwarp();
-    // lane's two record offsets: columns 0..18 -> Jacobian rows 0 / 1, lane 19 -> residual (g_l), lane 20 -> j_rho itself (h_l)
-    const int o0 = lane < 19 ? jc_off(lane) : 38, o1 = lane < 19 ? o0 + jc_row1(lane) : 39;
-    double acc = 0;
+    int o0[3], o1[3];
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        const int c = sl + 8 * t;  // 0..23; 19 -> residual pair (g_l), >= 20 unused (lane 4 of t = 2 accumulates h_l from j_rho)
+        o0[t] = c < 19 ? jc_off(c) : 38, o1[t] = c < 19 ? o0[t] + jc_row1(c) : 39;
+    }
+    const double *jc = D.jcomp + ((size_t) w * C.F + f0) * 40, *jr = D.jrho + ((size_t) w * C.F + f0) * 4;
+    double acc[3] = {0, 0, 0};
     int ref = 0;
-    constexpr int UNR = 4;  // factor records in flight (contiguous: slots f0 .. f1-1)
-    for (int q0 = f0; q0 < f1; q0 += UNR) {
+    if (nf > 0) ref = (int) jr[3];
+    constexpr int UNR = 2;  // factor records in flight per landmark
+    for (int q0 = 0; q0 < nf; q0 += UNR) {
         int ob[UNR];
-        double a0[UNR], a1[UNR], r0[UNR], r1[UNR];
+        double a0[UNR][3], a1[UNR][3], r0[UNR], r1[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-            const bool ok = q0 + u < f1;
-            const size_t fo = (size_t) w * C.F + (ok ? q0 + u : f0);
-            const double *jr = D.jrho + fo * 4;
-            a0[u] = ok ? D.jcomp[fo * 40 + o0] : 0.0;
-            a1[u] = ok ? D.jcomp[fo * 40 + o1] : 0.0;
-            r0[u] = ok ? jr[0] : 0.0;
-            r1[u] = ok ? jr[1] : 0.0;
-            ob[u] = ok ? (int) jr[2] : 0;
-            if (u == 0 && q0 == f0) ref = (int) jr[3];
+            const int q = min(q0 + u, nf - 1);  // clamped: the tail re-reads the last record (its contribution is skipped below)
+#pragma unroll
+            for (int t = 0; t < 3; t++) a0[u][t] = jc[q * 40 + o0[t]], a1[u][t] = jc[q * 40 + o1[t]];
+            r0[u] = jr[q * 4], r1[u] = jr[q * 4 + 1];
+            ob[u] = (int) jr[q * 4 + 2];
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-            if (q0 + u >= f1) continue;
-            if (lane == 20) {
-                acc += r0[u] * r0[u] + r1[u] * r1[u];
-            } else {
-                const double v = a0[u] * r0[u] + a1[u] * r1[u];
-                if (lane >= 6 && lane < 12)
-                    row[col_pose(ob[u]) + lane - 6] = v;  // a landmark is observed at most once per node (checked by icg_ba_upload)
-                else
-                    acc += v;
+            if (q0 + u >= nf) continue;
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const int c = sl + 8 * t;
+                if (c == 20) {
+                    acc[t] += r0[u] * r0[u] + r1[u] * r1[u];
+                } else if (c < 20) {
+                    const double v = a0[u][t] * r0[u] + a1[u][t] * r1[u];
+                    if (c >= 6 && c < 12)
+                        row[col_pose(ob[u]) + c - 6] = v;  // a landmark is observed at most once per node (checked by icg_ba_upload)
+                    else
+                        acc[t] += v;
+                }
             }
         }
     }
-    if (f1 > f0) {
-        if (lane < 6) row[col_pose(ref) + lane] = acc;
-        else if (lane >= 12 && lane < 18) row[col_ext(K) + lane - 12] = acc;
-        else if (lane == 18) row[col_td(K)] = acc;
-    }
-    if (lane == 19) {
-        row[NCV] = acc;
-        D.gl[(size_t) w * C.L + l] = acc;
-    } else if (lane == 20) {
-        D.hl[(size_t) w * C.L + l] = acc;
-        if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(acc));  // jacobi_scaling, once (iteration 0)
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+        const int c = sl + 8 * t;
+        if (nf > 0) {
+            if (c < 6) row[col_pose(ref) + c] = acc[t];
+            else if (c >= 12 && c < 18) row[col_ext(K) + c - 12] = acc[t];
+            else if (c == 18) row[col_td(K)] = acc[t];
+        }
+        if (c == 19) {
+            row[NCV] = acc[t];
+            D.gl[(size_t) w * C.L + l] = acc[t];
+        } else if (c == 20) {
+            D.hl[(size_t) w * C.L + l] = acc[t];
+            if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(acc[t]));  // jacobi_scaling, once (iteration 0)
+        }
     }
 }
 
@@ -359,16 +398,31 @@ __global__ void __launch_bounds__(256) ba_schur_dmma(BaCaps C, BaDev D, int ld) 
         for (int r0 = r_beg; r0 < r_end; r0 += SCHUR_RCH) {
             const int nr = min(SCHUR_RCH, r_end - r0), nr4 = (nr + 3) & ~3;
             __syncthreads();
-            for (int e0 = tid; e0 < nr4 * ld; e0 += 256 * 8) {  // 8 independent loads per thread in flight
-                double v[8];
+            for (int rb = warp; rb < nr4; rb += 8 * 4) {  // warp stages rows rb, rb + 8, rb + 16, rb + 24: 4 rows x 3 column chunks in flight
+                double v[4][3];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int e = e0 + 256 * u, rr = e / ld, c = e - rr * ld;
-                    v[u] = (e < nr4 * ld && rr < nr && c < NCA) ? A[(size_t) (r0 + rr) * C.NCA + c] : 0.0;
+                for (int u = 0; u < 4; u++) {
+                    const int rr = rb + 8 * u;
+#pragma unroll
+                    for (int cchunk = 0; cchunk < 3; cchunk++) {
+                        const int c = lane + 32 * cchunk;
+                        v[u][cchunk] = (rr < nr && c < NCA) ? A[(size_t) (r0 + rr) * C.NCA + c] : 0.0;
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (e0 + 256 * u < nr4 * ld) sA[e0 + 256 * u] = v[u];
+                for (int u = 0; u < 4; u++) {
+                    const int rr = rb + 8 * u;
+#pragma unroll
+                    for (int cchunk = 0; cchunk < 3; cchunk++) {
+                        const int c = lane + 32 * cchunk;
+                        if (rr < nr4 && c < ld) sA[(size_t) rr * ld + c] = v[u][cchunk];
+                    }
+                }
+                for (int c = lane + 96; c < ld; c += 32)  // wider rows (K > 12): remaining columns
+                    for (int u = 0; u < 4; u++) {
+                        const int rr = rb + 8 * u;
+                        if (rr < nr4) sA[(size_t) rr * ld + c] = (rr < nr && c < NCA) ? A[(size_t) (r0 + rr) * C.NCA + c] : 0.0;
+                    }
             }
             for (int rr = tid; rr < nr4; rr += 256) {
                 double ph = 0;
@@ -728,6 +782,34 @@ __global__ void ba_pack2(BaCaps C, BaDev D, int n, int nblk_vis) {
     D.red2[(size_t) w * 4 + 3] = cand;
 }
 
+// ------------------------------------------------------------------------------------------------ reduced camera matrix
+// Hs = H_c + H_vis - Schur term, lower triangle, one thread per entry (wide and coalesced; ba_solve then reads ONE operand per entry
+// instead of gathering 2 + BA_SPLIT_W).  Landmark-sharded solve: the vision / Schur operands are the all-reduced buffer.
+__global__ void __launch_bounds__(256) ba_hsum(BaCaps C, BaDev D) {
+    const int w = blockIdx.y;
+    if (D.st[w].done) return;
+    const int K = D.dims[w].K, NCV = 6 * K + 7, N = 15 * K + 7;
+    const int e = blockIdx.x * 256 + threadIdx.x, i = e / C.NS, j = e - i * C.NS;
+    (void) N;
+    if (i >= NCV || j > i) return;  // rows beyond the vision columns are H_c itself: ba_solve reads them directly
+    const int NN = C.NCA * C.NCA;
+    double h = D.Hc[(size_t) w * C.NS * C.NS + e];
+    {
+        const size_t o = (size_t) i * C.NCA + j;
+        if (D.world > 1) {
+            const double *RED = D.red + (size_t) w * (2 * NN + 8);
+            h += RED[o] - RED[NN + o];
+        } else {
+            const double *CWp = D.CW + (size_t) w * BA_SPLIT_W * NN;
+            double s2 = 0;
+#pragma unroll
+            for (int k = 0; k < BA_SPLIT_W; k++) s2 += CWp[(size_t) k * NN + o];
+            h += D.CJ[(size_t) w * BA_SPLIT_J * NN + o] - s2;
+        }
+    }
+    D.Hs[(size_t) w * C.NS * C.NS + e] = h;
+}
+
 // ------------------------------------------------------------------------------------------------ solve (one CTA per window)
 constexpr int SOLVE_THREADS = 256;  // 2 CTAs (windows) per SM: 107 KB shared memory and <= 128 registers each
 
@@ -779,7 +861,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     double *s_d2 = s_rhs + C.NS;        // N
     double *s_diag = s_d2 + C.NS;       // N   Cholesky diagonal
     double *S = use_global_S ? D.Sglobal + (size_t) w * ((size_t) (C.N + 1) * (C.N + 2) / 2) : s_diag + C.NS;  // packed lower, N + 1 rows
-    const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS;
+    const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS, *Hs = D.Hs + (size_t) w * C.NS * C.NS;
     // Reduction operands.  Landmark-sharded solve: the packed, all-reduced buffer (identical on every shard, written by ba_pack1).
     // Single GPU: read the producers' outputs directly (vision Gram matrix; the BA_SPLIT_W Schur partials summed in fixed order).
     const bool sharded = D.world > 1;
@@ -875,9 +957,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
             const int j = (tid & 31) + 32 * q;
             hv[q] = 0;
             if (q < nq && j <= i) {
-                double h = Hc[(size_t) i * C.NS + j];  // H_c, the vision Gram matrix and the Schur term are stored symmetric:
-                if (i < NCV) h += CJ[(size_t) i * C.NCA + j] - cw_get(i, j);  // row i is read contiguously
-                hv[q] = h;
+                hv[q] = (i < NCV ? Hs : Hc)[(size_t) i * C.NS + j];  // ba_hsum: H_c + vision Gram - Schur (vision rows); row i contiguous
             }
         }
 #pragma unroll
@@ -1004,19 +1084,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
             double yr[MAXQ];
 #pragma unroll
             for (int q = 0; q < MAXQ; q++) yr[q] = lane + 32 * q < N ? y[lane + 32 * q] : 0.0;
-            for (int j = N - 1; j >= 0; j--) {
-                const int oq = j >> 5, ol = j & 31;
-                double xj = 0;
+            // statically indexed: the owner register block oq is an unrolled outer loop, so the per-step critical path is
+            // shuffle -> multiply -> FMA (no register selects); only blocks q <= oq are touched
 #pragma unroll
-                for (int q = 0; q < MAXQ; q++)
-                    if (q == oq) xj = yr[q];
-                xj = __shfl_sync(0xffffffffu, xj, ol) * s_diag[j];
-                if (lane == ol) s_rhs[j] = xj;
-                const double *rj = S + j * (j + 1) / 2;
+            for (int oq = MAXQ - 1; oq >= 0; oq--) {
+                if (32 * oq >= N) continue;
+                for (int ol = min(31, N - 1 - 32 * oq); ol >= 0; ol--) {
+                    const int j = 32 * oq + ol;
+                    const double *rj = S + j * (j + 1) / 2;
+                    double lv[MAXQ];
 #pragma unroll
-                for (int q = 0; q < MAXQ; q++) {
-                    const int i2 = lane + 32 * q;
-                    if (q <= oq && i2 < j) yr[q] -= rj[i2] * xj;
+                    for (int q = 0; q < MAXQ; q++) lv[q] = (q <= oq && lane + 32 * q < j) ? rj[lane + 32 * q] : 0.0;  // off the critical path
+                    const double xj = __shfl_sync(0xffffffffu, yr[oq], ol) * s_diag[j];
+                    if (lane == ol) s_rhs[j] = xj;
+#pragma unroll
+                    for (int q = 0; q < MAXQ; q++)
+                        if (q <= oq) yr[q] -= lv[q] * xj;
                 }
             }
         }
@@ -1418,7 +1501,8 @@ struct icg_ba {
     int device;
     cudaStream_t stream;
     cudaStream_t stream_cam = nullptr;  // the camera-only factors are linearised concurrently with the vision chain
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_gram = nullptr; // pair Gram chain (H_vis) beside lin_lm -> Schur: both only consume lin_vis' records
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     bool own_stream;
     int nblk_vis;
     int cur_windows;
@@ -1429,7 +1513,8 @@ struct icg_ba {
     HostDev<LmState> st;
     HostDev<double> pose, mix, ext, rho, f_const, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
         marg_H0, marg_b0, marg_c0;
-    HostDev<int> f_slot;
+    HostDev<int> f_slot, f_meta_s;
+    HostDev<double> f_const_s;
     HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
     HostDev<uint8_t> f_active;
     std::vector<void *> dev_only;
@@ -1643,6 +1728,9 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     else
         ICG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     ICG_CUDA(cudaStreamCreateWithFlags(&h->stream_cam, cudaStreamNonBlocking));
+    ICG_CUDA(cudaStreamCreateWithFlags(&h->stream_gram, cudaStreamNonBlocking));
+    ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+    ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->prof = getenv("ICG_BA_PROFILE") != nullptr;
@@ -1662,7 +1750,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * 64 * 9)
     HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
     HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * 64) HD(marg_node, NW * 64) HD(f_active, NW * C.F)
-    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F)
+    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F) HD(f_meta_s, NW * C.F * 4) HD(f_const_s, NW * C.F * 14)
     HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
 #undef HD
     BaDev &D = h->D;
@@ -1670,7 +1758,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
     D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
     D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
-    D.f_slot = h->f_slot.d;
+    D.f_slot = h->f_slot.d, D.f_meta_s = h->f_meta_s.d, D.f_const_s = h->f_const_s.d;
     D.lm_off = h->lm_off.d, D.lm_fidx = h->lm_fidx.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
     D.gnss_node = h->gnss_node.d, D.gnss_blh = h->gnss_blh.d, D.gnss_std = h->gnss_std.d, D.lever = h->lever.d;
     D.pose_prior = h->pose_prior.d, D.pose_prior_sinfo = h->pose_prior_sinfo.d, D.mix_prior = h->mix_prior.d, D.mix_prior_std = h->mix_prior_std.d;
@@ -1682,7 +1770,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     DM(pose_0, NW * C.K * 7) DM(mix_0, NW * C.K * 9) DM(ext_0, NW * 8) DM(rho_0, NW * C.L)
     DM(AW, NW * C.NCA * C.LP) DM(Mp, NW * (size_t) C.K * (C.K - 1) * 210) DM(CJ, NW * BA_SPLIT_J * C.NCA * C.NCA) DM(CW, NW * BA_SPLIT_W * C.NCA * C.NCA)
     DM(jcomp, NW * C.F * 40) DM(jrho, NW * C.F * 4) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
-    DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(red, NW * (2 * (size_t) C.NCA * C.NCA + 8)) DM(redmax, NW) DM(red2, NW * 4) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
+    DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(Hs, NW * C.NS * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(red, NW * (2 * (size_t) C.NCA * C.NCA + 8)) DM(redmax, NW) DM(red2, NW * 4) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
 #undef DM
     if (rc != ICG_OK) return rc;
     // shared-memory budgets
@@ -1701,6 +1789,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     h->ld_schur = 16 * ((C.NCA + 15) / 16) + 8;  // = 8 mod 16 doubles: conflict-free fragment reads
     h->smem_schur = sizeof(double) * ((size_t) SCHUR_RCH * h->ld_schur + SCHUR_RCH);
     ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_schur));
+    ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ICG_CUDA(cudaFuncSetAttribute(ba_lin_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
     ICG_CUDA(cudaFuncSetAttribute(ba_cost_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
     ICG_CUDA(cudaStreamSynchronize(h->stream));
@@ -1720,11 +1809,14 @@ void icg_ba_destroy(icg_ba *h) {
     h->imu_blob.release(), h->imu_U.release(), h->gnss_blh.release(), h->gnss_std.release(), h->lever.release(), h->pose_prior.release();
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
-    h->f_slot.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
+    h->f_slot.release(), h->f_meta_s.release(), h->f_const_s.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
     if (h->marg_ready) h->marg_map.release(), h->marg_oJ0.release(), h->marg_oe0.release(), h->marg_oHp.release(), h->marg_obp.release();
     for (void *p : h->dev_only) cudaFree(p);
     if (h->stream_cam) cudaStreamSynchronize(h->stream_cam), cudaStreamDestroy(h->stream_cam);
+    if (h->stream_gram) cudaStreamSynchronize(h->stream_gram), cudaStreamDestroy(h->stream_gram);
+    if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1739,13 +1831,21 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     }
     ICG_CUDA(cudaSetDevice(h->device));
     const BaCaps &C = h->C;
-    for (int w = 0; w < n; w++) {
+    // per-window packing is independent (disjoint slices of the pinned staging arrays): spread it over a few host threads -- it is
+    // memcpy-bound (about 0.4 MB per cfg-3 window) and sits inside the end-to-end path of every keyframe
+#define PK_FAIL(code, ...)                          \
+    do {                                            \
+        char eb_[512];                              \
+        snprintf(eb_, sizeof(eb_), __VA_ARGS__);    \
+        err = eb_;                                  \
+        return code;                                \
+    } while (0)
+    auto pack_one = [&](int w, std::string &err) -> int {
         const icg_ba_problem &p = P[w];
         if (p.K < 2 || p.K > C.K || p.L < 1 || p.L > C.L || p.F < 0 || p.F > C.F || p.n_imu < 0 || p.n_imu > p.K - 1 || p.n_gnss < 0 || p.n_gnss > C.G ||
             p.marg_r < 0 || p.marg_r > C.R || p.marg_nblocks < 0 || p.marg_nblocks > 64 || !p.pose || !p.mix || !p.ext || !p.invdepth) {
-            set_error("icg_ba_upload: window %d exceeds the handle's capacity or has null parameter arrays (K=%d L=%d F=%d gnss=%d marg_r=%d)", w, p.K, p.L, p.F,
+            PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d exceeds the handle's capacity or has null parameter arrays (K=%d L=%d F=%d gnss=%d marg_r=%d)", w, p.K, p.L, p.F,
                       p.n_gnss, p.marg_r);
-            return ICG_EINVAL;
         }
         WinDims &d = h->dims.h[w];
         d.K = p.K, d.L = p.L, d.F = p.F, d.n_imu = p.n_imu, d.n_gnss = p.n_gnss, d.marg_r = p.marg_r, d.marg_nb = p.marg_nblocks;
@@ -1758,8 +1858,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
         memcpy(h->rho.h + (size_t) w * C.L, p.invdepth, sizeof(double) * p.L);
         for (int f = 0; f < p.F; f++) {
             if (p.f_lm[f] < 0 || p.f_lm[f] >= p.L || p.f_ref[f] < 0 || p.f_ref[f] >= p.K || p.f_obs[f] < 0 || p.f_obs[f] >= p.K || p.f_ref[f] == p.f_obs[f]) {
-                set_error("icg_ba_upload: window %d factor %d has invalid indices", w, f);
-                return ICG_EINVAL;
+                PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d factor %d has invalid indices", w, f);
             }
         }
         {   // a map point has one reference frame and at most one observation per keyframe (IG/ic_gvins.cc:1777-1834): lin_lm relies on it
@@ -1769,8 +1868,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
                 const int l = p.f_lm[f];
                 if (refof[l] < 0) refof[l] = p.f_ref[f];
                 if (refof[l] != p.f_ref[f] || (seen[l] >> p.f_obs[f]) & 1u) {
-                    set_error("icg_ba_upload: window %d factor %d: landmark %d has two reference nodes or two observations in node %d", w, f, l, p.f_obs[f]);
-                    return ICG_EINVAL;
+                    PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d factor %d: landmark %d has two reference nodes or two observations in node %d", w, f, l, p.f_obs[f]);
                 }
                 seen[l] |= 1u << p.f_obs[f];
             }
@@ -1792,6 +1890,13 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
         {
             std::vector<int> cur(off, off + p.L);
             for (int f = 0; f < p.F; f++) fslot[f] = cur[p.f_lm[f]], fidx[cur[p.f_lm[f]]++] = f;
+            int *meta = h->f_meta_s.h + (size_t) w * C.F * 4;
+            double *fcs = h->f_const_s.h + (size_t) w * C.F * 14;
+            for (int q = 0; q < p.F; q++) {
+                const int f = fidx[q];
+                meta[4 * q] = p.f_lm[f], meta[4 * q + 1] = p.f_ref[f], meta[4 * q + 2] = p.f_obs[f], meta[4 * q + 3] = f;
+                memcpy(fcs + (size_t) q * 14, p.f_const + (size_t) f * 14, sizeof(double) * 14);
+            }
         }
         // CSR by (reference node, observing node) pair
         {
@@ -1816,14 +1921,12 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
             const double *b = p.imu_blob + (size_t) k * ICG_IMU_BLOB_DOUBLES;
             memcpy(h->imu_blob.h + ((size_t) w * C.K + k) * ICG_IMU_BLOB_DOUBLES, b, sizeof(double) * ICG_IMU_BLOB_DOUBLES);
             if (!host_imu_sqrt_info(b + 252, h->imu_U.h + ((size_t) w * C.K + k) * 225)) {
-                set_error("icg_ba_upload: window %d IMU factor %d has a non positive-definite covariance", w, k);
-                return ICG_EINVAL;
+                PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d IMU factor %d has a non positive-definite covariance", w, k);
             }
         }
         for (int g = 0; g < p.n_gnss; g++) {
             if (p.gnss_node[g] < 0 || p.gnss_node[g] >= p.K) {
-                set_error("icg_ba_upload: window %d GNSS factor %d has an invalid node", w, g);
-                return ICG_EINVAL;
+                PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d GNSS factor %d has an invalid node", w, g);
             }
             h->gnss_node.h[(size_t) w * C.G + g] = p.gnss_node[g];
         }
@@ -1847,8 +1950,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
             for (int b = 0; b < p.marg_nblocks; b++) {
                 int t = p.marg_block_type[b];
                 if (t < 0 || t > 3 || ((t == 0 || t == 1) && (p.marg_block_node[b] < 0 || p.marg_block_node[b] >= p.K))) {
-                    set_error("icg_ba_upload: window %d marginalization block %d invalid", w, b);
-                    return ICG_EINVAL;
+                    PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d marginalization block %d invalid", w, b);
                 }
                 tot += (t == 0 || t == 2) ? 7 : t == 1 ? 9 : 1;
                 cols += (t == 0 || t == 2) ? 6 : t == 1 ? 9 : 1;
@@ -1856,8 +1958,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
                 h->marg_node.h[(size_t) w * 64 + b] = p.marg_block_node[b];
             }
             if (cols != r || tot > 64 * 9) {
-                set_error("icg_ba_upload: window %d marginalization prior size mismatch (blocks give %d columns, marg_r=%d)", w, cols, r);
-                return ICG_EINVAL;
+                PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d marginalization prior size mismatch (blocks give %d columns, marg_r=%d)", w, cols, r);
             }
             memcpy(h->marg_x0.h + (size_t) w * 64 * 9, p.marg_x0, sizeof(double) * tot);
             double *H0 = h->marg_H0.h + (size_t) w * C.R * C.R, *b0 = h->marg_b0.h + (size_t) w * C.R;
@@ -1875,12 +1976,37 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
             for (int k = 0; k < r; k++) c0 += p.marg_e0[k] * p.marg_e0[k];
             h->marg_c0.h[w] = c0;
         }
+            return ICG_OK;
+    };
+#undef PK_FAIL
+    {
+        const int nthreads = std::max(1, std::min({n / 4, 8, (int) std::thread::hardware_concurrency()}));
+        std::vector<int> rcs(nthreads, ICG_OK);
+        std::vector<std::string> errs(nthreads);
+        auto worker = [&](int t) {
+            for (int w = t; w < n; w += nthreads) {
+                const int rc = pack_one(w, errs[t]);
+                if (rc != ICG_OK) {
+                    rcs[t] = rc;
+                    return;
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto &x : th) x.join();
+        for (int t = 0; t < nthreads; t++)
+            if (rcs[t] != ICG_OK) {
+                set_error("%s", errs[t].c_str());
+                return rcs[t];
+            }
     }
     cudaStream_t s = h->stream;
     ICG_CUDA(h->dims.up(s));
     ICG_CUDA(h->pose.up(s)); ICG_CUDA(h->mix.up(s)); ICG_CUDA(h->ext.up(s)); ICG_CUDA(h->rho.up(s));
     ICG_CUDA(h->f_lm.up(s)); ICG_CUDA(h->f_ref.up(s)); ICG_CUDA(h->f_obs.up(s)); ICG_CUDA(h->f_const.up(s)); ICG_CUDA(h->f_active.up(s));
-    ICG_CUDA(h->f_slot.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
+    ICG_CUDA(h->f_slot.up(s)); ICG_CUDA(h->f_meta_s.up(s)); ICG_CUDA(h->f_const_s.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
     ICG_CUDA(h->gnss_node.up(s)); ICG_CUDA(h->gnss_blh.up(s)); ICG_CUDA(h->gnss_std.up(s)); ICG_CUDA(h->lever.up(s));
     ICG_CUDA(h->pose_prior.up(s)); ICG_CUDA(h->pose_prior_sinfo.up(s)); ICG_CUDA(h->mix_prior.up(s)); ICG_CUDA(h->mix_prior_std.up(s));
     ICG_CUDA(h->marg_type.up(s)); ICG_CUDA(h->marg_node.up(s)); ICG_CUDA(h->marg_x0.up(s)); ICG_CUDA(h->marg_H0.up(s)); ICG_CUDA(h->marg_b0.up(s));
@@ -1898,7 +2024,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
 
 // ---- in-situ stage timing
 static const char *PROF_NAMES[16] = {"(gap/other)", "lin_vis", "lin_lm", "pair_gram1", "pair_gram2", "schur_dmma", "join lin_cam + lin_done",
-                                     "pack1", "solve", "cost (+cost_cam)", "pack2", "accept", "", "", "", ""};
+                                     "pack1", "solve", "cost (+cost_cam)", "pack2", "accept", "hsum", "join gram chain", "", ""};
 static void prof_mark(icg_ba *h, int tag) {
     if (!h->prof) return;
     if (h->prof_used == h->prof_ev.size()) {
@@ -1936,7 +2062,7 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
     const BaDev &D = h->D;
     const int n = h->cur_windows;
     cudaStream_t s = h->stream;
-    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L + 7) / 8, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis, n);
+    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L + 31) / 32, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis, n);
     // iteration 0 linearisation + (max_iter) x [schur syrk, solve, cost, accept, re-linearise]; one extra solve call
     // performs the final termination bookkeeping.
     for (int it = 0; it <= max_num_iterations; it++) {
@@ -1948,14 +2074,17 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         prof_mark(h, 0);
         ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
         prof_mark(h, 1);
+        ICG_CUDA(cudaEventRecord(h->ev_fork2, s));
+        ICG_CUDA(cudaStreamWaitEvent(h->stream_gram, h->ev_fork2, 0));
+        ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, h->stream_gram>>>(C, D);
+        ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, h->stream_gram>>>(C, D);
+        ICG_CUDA(cudaEventRecord(h->ev_join2, h->stream_gram));
         ba_lin_lm<<<g_lm, 256, 0, s>>>(C, D);
         prof_mark(h, 2);
-        ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
-        prof_mark(h, 3);
-        ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
-        prof_mark(h, 4);
         ba_schur_dmma<<<g_sw, 256, h->smem_schur, s>>>(C, D, h->ld_schur);
         prof_mark(h, 5);
+        ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
+        prof_mark(h, 13);
         ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
         prof_mark(h, 6);
         if (h->comm) {  // landmark-sharded window: one sum all-reduce of [H_vis g | Schur | cost, |rho|^2] + one max all-reduce
@@ -1966,9 +2095,11 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
             rc = nccl_allreduce(h, D.redmax, (size_t) n, 1);
             if (rc != ICG_OK) return rc;
         }
+        ba_hsum<<<dim3((C.NCV * C.NS + 255) / 256, n), 256, 0, s>>>(C, D);
+        prof_mark(h, 12);
         ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
         prof_mark(h, 8);
-        count_launch(h->comm ? 8 : 7);
+        count_launch(h->comm ? 9 : 8);
         if (it == max_num_iterations) break;
         ICG_CUDA(cudaEventRecord(h->ev_fork, s));
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
@@ -2247,7 +2378,7 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
     const size_t smem = sizeof(double) * (8 * 480 + 2 * (size_t) C.R) + sizeof(int) * (size_t) C.R + 64;
     marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 0);
     ba_lin_vis<<<dim3((C.F + 127) / 128, n), 128, 0, s>>>(C, D);
-    ba_lin_lm<<<dim3((C.L + 7) / 8, n), 256, 0, s>>>(C, D);
+    ba_lin_lm<<<dim3((C.L + 31) / 32, n), 256, 0, s>>>(C, D);
     ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
     marg_assemble<<<n, 256, smem, s>>>(C, D, M);
     marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, 0);

@@ -159,30 +159,33 @@ BAM_HD void reproj_eval(const double *pi, const double *pj, const double *ext, d
     r[0] = sinv * (pts_1.x / d1 - pts_1_td.x);
     r[1] = sinv * (pts_1.y / d1 - pts_1_td.y);
     if (!want_j) return;
-    M3 cb0n = qmat(q0), cnb1 = tr(qmat(q1)), cbc = tr(qmat(qic));
-    double red[6] = {sinv * (1.0 / d1), 0, sinv * (-pts_1.x / (d1 * d1)), 0, sinv * (1.0 / d1), sinv * (-pts_1.y / (d1 * d1))};
-    auto red_m = [&](const M3 &a, double *o, int c0) {
+    // Jacobians (reprojection_factor.h:84-144), evaluated row by row instead of as 3x3 matrix products: with r = a row of the 2x3
+    // reduce matrix and R0 = R(q0), R1 = R(q1), Ric = R(q_ic) (so cb0n = R0, cnb1 = R1^T, cbc = Ric^T) every Jacobian row is a chain
+    // of matrix-VECTOR products   a1 = r^T cbc = Ric r,  a2 = a1^T cnb1 = R1 a1,  a3 = a2^T cb0n = R0^T a2,  a4 = a3^T cbc^T = Ric^T a3
+    // and cross products (a^T [p]x = (a x p)^T).  Same algebra as the reference's matrix form, ~3x fewer flops and far fewer live
+    // registers; the sum of the two skew terms of the extrinsic-rotation block is [tmp_r pts_c_0 + lever]x = [pts_1]x.
+    const M3 R0 = qmat(q0), R1 = qmat(q1), Ric = qmat(qic);
+    const double inv_d = 1.0 / d1;
+    const double redr[2][3] = {{sinv * inv_d, 0.0, sinv * (-pts_1.x / (d1 * d1))}, {0.0, sinv * inv_d, sinv * (-pts_1.y / (d1 * d1))}};
+    const double inv_id0 = 1.0 / id0;
 #pragma unroll
-        for (int rr = 0; rr < 2; rr++)
-#pragma unroll
-            for (int cc = 0; cc < 3; cc++) o[rr * 6 + c0 + cc] = red[3 * rr] * a.m[cc] + red[3 * rr + 1] * a.m[3 + cc] + red[3 * rr + 2] * a.m[6 + cc];
-    };
-    M3 cbc_cnb1 = mul(cbc, cnb1);
-    M3 full = mul(cbc_cnb1, cb0n);
-    red_m(cbc_cnb1, Ji, 0);
-    red_m(neg(mul(full, skew(pts_b_0))), Ji, 3);
-    red_m(neg(cbc_cnb1), Jj, 0);
-    red_m(mul(cbc, skew(pts_b_1)), Jj, 3);
-    M3 tmp_r = mul(full, tr(cbc));
-    red_m(mul(cbc, sub(mul(cnb1, cb0n), ident())), Je, 0);
-    V3 lever = mul(cbc, mul(cnb1, mul(cb0n, tic) + p0 - p1) - tic);
-    red_m(add(add(neg(mul(tmp_r, skew(pts_c_0))), skew(mul(tmp_r, pts_c_0))), skew(lever)), Je, 3);
-    V3 v = mul(tmp_r, pts_0_td) / (id0 * id0);
-    Jr[0] = -(red[0] * v.x + red[1] * v.y + red[2] * v.z);
-    Jr[1] = -(red[3] * v.x + red[4] * v.y + red[5] * v.z);
-    V3 u = mul(tmp_r, vel0) / id0;
-    Jt[0] = -(red[0] * u.x + red[1] * u.y + red[2] * u.z) + sinv * vel1.x;
-    Jt[1] = -(red[3] * u.x + red[4] * u.y + red[5] * u.z) + sinv * vel1.y;
+    for (int rr = 0; rr < 2; rr++) {
+        const V3 r3 = mk(redr[rr][0], redr[rr][1], redr[rr][2]);
+        const V3 a1 = mul(Ric, r3);
+        const V3 a2 = mul(R1, a1);
+        const V3 a3 = mul(tr(R0), a2);
+        const V3 a4 = mul(tr(Ric), a3);
+        const V3 ji_rot = cross(pts_b_0, a3);  // -(a3 x pts_b_0)
+        const V3 jj_rot = cross(a1, pts_b_1);
+        const V3 je_pos = a3 - a1;
+        const V3 je_rot = cross(pts_c_0, a4) + cross(r3, pts_1);  // -(a4 x pts_c_0) + (r x pts_1)
+        double *ji = Ji + 6 * rr, *jj = Jj + 6 * rr, *je = Je + 6 * rr;
+        ji[0] = a2.x, ji[1] = a2.y, ji[2] = a2.z, ji[3] = ji_rot.x, ji[4] = ji_rot.y, ji[5] = ji_rot.z;
+        jj[0] = -a2.x, jj[1] = -a2.y, jj[2] = -a2.z, jj[3] = jj_rot.x, jj[4] = jj_rot.y, jj[5] = jj_rot.z;
+        je[0] = je_pos.x, je[1] = je_pos.y, je[2] = je_pos.z, je[3] = je_rot.x, je[4] = je_rot.y, je[5] = je_rot.z;
+        Jr[rr] = -dot(a4, pts_0_td) * (inv_id0 * inv_id0);
+        Jt[rr] = -dot(a4, vel0) * inv_id0 + sinv * (rr == 0 ? vel1.x : vel1.y);
+    }
 }
 
 // GnssFactor::Evaluate (IG/factors/gnss_factor.h:43-71); J local 3x6 row-major

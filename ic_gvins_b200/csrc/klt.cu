@@ -188,18 +188,59 @@ __device__ __forceinline__ float warp_sum_exact(int v) {
     return (float) ((double) shi * 65536.0 + (double) slo);
 }
 
+// ---- packed-byte bilinear taps ------------------------------------------------------------------------------------------------
+// dp2a with signed 16-bit weights (iw11 = 16384 - iw00 - iw01 - iw10 can be -1 after rounding) and unsigned bytes:
+//   d = c + a.h0 * b.byte[0|2] + a.h1 * b.byte[1|3]
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c) {
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// The 21x21 window is cut into 63 horizontal runs of 7 pixels (3 per row); lane owns runs `lane` and `lane + 32` (lane 31: one run).
+// A run's 8 + 8 tap bytes (two rows) are fetched as aligned 32-bit words and re-aligned with funnel shifts, then every pixel's four taps
+// are two dp2a on packed byte pairs: ~4 instructions per pixel instead of 4 byte loads + 4 multiply-adds.
+__device__ __forceinline__ int pack_w(int lo, int hi) { return (int) (((unsigned) lo & 0xFFFFu) | ((unsigned) hi << 16)); }
+struct RunBytes {
+    unsigned e0, e1, o0, o1;  // even stream: bytes 0..3 | 4..7;  odd stream (shifted by one byte): bytes 1..4 | 5..7
+};
+__device__ __forceinline__ RunBytes run_bytes(const unsigned *wp, int m8) {
+    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    RunBytes r;
+    r.e0 = __funnelshift_r(w0, w1, m8);
+    r.e1 = __funnelshift_r(w1, w2, m8);
+    r.o0 = __funnelshift_r(r.e0, r.e1, 8);
+    r.o1 = r.e1 >> 8;
+    return r;
+}
+// v[i] = c0 + sum of the four Q14-weighted taps of pixel i of the run (i = 0..6, or 0..7 with N8); wt = iw00 | iw01 << 16, wb = iw10 | iw11 << 16
+template <int NPIX>
+__device__ __forceinline__ void run_taps(const RunBytes &t, const RunBytes &b, int wt, int wb, int c0, int *v) {
+    v[0] = dp2a_lo_su(wb, b.e0, dp2a_lo_su(wt, t.e0, c0));
+    v[1] = dp2a_lo_su(wb, b.o0, dp2a_lo_su(wt, t.o0, c0));
+    v[2] = dp2a_hi_su(wb, b.e0, dp2a_hi_su(wt, t.e0, c0));
+    v[3] = dp2a_hi_su(wb, b.o0, dp2a_hi_su(wt, t.o0, c0));
+    v[4] = dp2a_lo_su(wb, b.e1, dp2a_lo_su(wt, t.e1, c0));
+    v[5] = dp2a_lo_su(wb, b.o1, dp2a_lo_su(wt, t.o1, c0));
+    v[6] = dp2a_hi_su(wb, b.e1, dp2a_hi_su(wt, t.e1, c0));
+    if (NPIX == 8) v[7] = 0;  // pixel 7 needs byte 8: handled by the caller
+}
+
 // Track one point from image slot sI to image slot sJ through all levels.  All lanes hold identical scalars.
 __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArgs &A, WarpSmem &S, int lane, int sI, int sJ,
                                                float2 prev, float2 init, bool check_final, float2 &out, int &status,
                                                float *err_out) {
-    // lane's template pixels: idx = lane + 32k -> (x, y) in the 21x21 window
-    int joff[KLT_PXL];
-#pragma unroll
-    for (int k = 0; k < KLT_PXL; k++) {
-        int idx = lane + 32 * k;
-        int y = (idx * 3121) >> 16, x = idx - 21 * y;
-        joff[k] = (idx < KLT_WIN * KLT_WIN) ? (y * KLT_BOXW + x) : 0;  // dead slots (k = 13, lane >= 25) carry I = G = 0
-    }
+    // lane's template pixels: runs rA = lane and rB = lane + 32 of the 63 seven-pixel runs; register k = 7 * run + i <-> pixel
+    // (x0 + i, y) of that run.  Lane 31 has no second run: its slots k = 7..13 carry I = G = 0.
+    const int yA = lane / 3, xA = 7 * (lane - 3 * yA);
+    const bool validB = lane < 31;
+    const int rB = validB ? lane + 32 : 62;
+    const int yB = rB / 3, xB = 7 * (rB - 3 * yB);
+    const int offA = yA * KLT_BOXW + xA, offB = yB * KLT_BOXW + xB;  // byte offset of the run's first tap inside a staged window
     const float half = 10.f;
     const float FLT_SCALE = 1.f / (1 << 20);
     status = 1;
@@ -267,33 +308,55 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             // ---- interpolate first, differentiate second.  Scharr is linear and OpenCV rounds only AFTER interpolating, so
             //      sum_taps w * Ix(tap) == Scharr_x(P) with P = sum_taps w * I(tap) (exact Q14 integers, |.| < 2^27):
             //      one 23x23 grid gives I, Ix and Iy of the whole 21x21 template.
-            const uint8_t *w0 = S.iw + oxI;
-            if (lane < 23) {
-#pragma unroll 4
-                for (int gy = 0; gy < 23; gy++) {
-                    const uint8_t *sp = w0 + gy * KLT_BOXW + lane;
-                    S.pg[gy * 24 + lane] = sp[0] * iw00 + sp[1] * iw01 + sp[KLT_BOXW] * iw10 + sp[KLT_BOXW + 1] * iw11;
+            // P grid (23 x 23, pitch 24): lane = (column run cr of 8, row group rg of 3 rows), 24 lanes; the bottom tap row of one grid
+            // row is the top tap row of the next, so 4 byte rows are fetched for 3 grid rows
+            const int wt = pack_w(iw00, iw01), wb = pack_w(iw10, iw11);
+            if (lane < 24) {
+                const int cr = lane % 3, rg = lane / 3;
+                const uint8_t *bp = S.iw + oxI + (3 * rg) * KLT_BOXW + 8 * cr;
+                const int m8 = ((int) (size_t) bp & 3) * 8;
+                const unsigned *wp = (const unsigned *) ((size_t) bp & ~(size_t) 3);
+                RunBytes top = run_bytes(wp, m8);
+                const unsigned t8 = bp[8];  // 9th byte: right tap of grid column 7 of the run
+                unsigned tb8 = t8;
+#pragma unroll
+                for (int rr = 0; rr < 3; rr++) {
+                    const int gy = 3 * rg + rr;
+                    const RunBytes bot = run_bytes(wp + (rr + 1) * (KLT_BOXW / 4), m8);
+                    const unsigned bb8 = bp[(rr + 1) * KLT_BOXW + 8];
+                    int v[8];
+                    run_taps<8>(top, bot, wt, wb, 0, v);
+                    v[7] = (int) (top.o1 >> 16 & 0xFF) * iw00 + (int) tb8 * iw01 + (int) (bot.o1 >> 16 & 0xFF) * iw10 + (int) bb8 * iw11;
+                    if (gy < 23) {
+                        int4 *dst = (int4 *) (S.pg + gy * 24 + 8 * cr);
+                        dst[0] = make_int4(v[0], v[1], v[2], v[3]);
+                        dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+                    }
+                    top = bot, tb8 = bb8;
                 }
             }
             __syncwarp();
+            // template of the lane's two runs: separable Scharr on the grid (column sums c_j shared along the run)
 #pragma unroll
-            for (int k = 0; k < KLT_PXL; k++) {
-                if (lane + 32 * k < KLT_WIN * KLT_WIN) {
-                    const int idx = lane + 32 * k;
-                    const int y = (idx * 3121) >> 16, x = idx - 21 * y;
-                    const int *pp = S.pg + y * 24 + x;
-                    const int p00 = pp[0], p01 = pp[1], p02 = pp[2], p10 = pp[24], p11 = pp[25], p12 = pp[26], p20 = pp[48], p21 = pp[49], p22 = pp[50];
-                    const int ival = (p11 + (1 << 8)) >> 9;
-                    const int ixv = (3 * ((p02 - p00) + (p22 - p20)) + 10 * (p12 - p10) + (1 << 13)) >> 14;
-                    const int iyv = (3 * ((p20 - p00) + (p22 - p02)) + 10 * (p21 - p01) + (1 << 13)) >> 14;
-                    Ireg[k] = ival;
-                    Gxr[k] = ixv, Gyr[k] = iyv;
+            for (int run = 0; run < 2; run++) {
+                const int *pp = S.pg + (run ? yB * 24 + xB : yA * 24 + xA);
+                int P0[9], P1[9], P2[9];
+#pragma unroll
+                for (int j = 0; j < 9; j++) P0[j] = pp[j], P1[j] = pp[24 + j], P2[j] = pp[48 + j];
+                int c[9];
+#pragma unroll
+                for (int j = 0; j < 9; j++) c[j] = 3 * (P0[j] + P2[j]) + 10 * P1[j];
+                const bool live = run == 0 || validB;
+#pragma unroll
+                for (int i = 0; i < 7; i++) {
+                    const int h0 = 3 * (P0[i] + P0[i + 2]) + 10 * P0[i + 1], h2 = 3 * (P2[i] + P2[i + 2]) + 10 * P2[i + 1];
+                    const int ival = live ? (P1[i + 1] + (1 << 8)) >> 9 : 0;
+                    const int ixv = live ? (c[i + 2] - c[i] + (1 << 13)) >> 14 : 0;
+                    const int iyv = live ? (h2 - h0 + (1 << 13)) >> 14 : 0;
+                    Ireg[7 * run + i] = ival, Gxr[7 * run + i] = ixv, Gyr[7 * run + i] = iyv;
                     sA11 += ixv * ixv;
                     sA12 += ixv * iyv;
                     sA22 += iyv * iyv;
-                } else {
-                    Ireg[k] = 0;
-                    Gxr[k] = Gyr[k] = 0;
                 }
             }
         } else {
@@ -313,9 +376,9 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < KLT_PXL; k++) {
-                if (lane + 32 * k < KLT_WIN * KLT_WIN) {
-                    int idx = lane + 32 * k;
-                    int y = (idx * 3121) >> 16, x = idx - 21 * y;
+                const int run = k / 7, i = k - 7 * run;
+                if (run == 0 || validB) {
+                    const int y = run ? yB : yA, x = (run ? xB : xA) + i;
                     const uint8_t *sp = S.iw + (y + 1) * KLT_BOXW + x + 1 + oxI;
                     int ival = (sp[0] * iw00 + sp[1] * iw01 + sp[KLT_BOXW] * iw10 + sp[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
                     const int *d = S.pg + y * 22 + x;
@@ -393,14 +456,22 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             b = ny - (float) iny;
             bilinear_weights(a, b, iw00, iw01, iw10, iw11);
             const uint8_t *jb = S.jw + oy * KLT_BOXW + ox;
+            const int wt = pack_w(iw00, iw01), wb = pack_w(iw10, iw11);
             int sb1 = 0, sb2 = 0;
 #pragma unroll
-            for (int k = 0; k < KLT_PXL; k++) {
-                const uint8_t *s = jb + joff[k];
-                int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
-                int diff = v - Ireg[k];
-                sb1 += diff * Gxr[k];
-                sb2 += diff * Gyr[k];
+            for (int run = 0; run < 2; run++) {
+                const uint8_t *bp = jb + (run ? offB : offA);
+                const int m8 = ((int) (size_t) bp & 3) * 8;
+                const unsigned *wp = (const unsigned *) ((size_t) bp & ~(size_t) 3);
+                const RunBytes top = run_bytes(wp, m8), bot = run_bytes(wp + KLT_BOXW / 4, m8);
+                int v[7];
+                run_taps<7>(top, bot, wt, wb, 1 << 8, v);
+#pragma unroll
+                for (int i = 0; i < 7; i++) {
+                    const int diff = (v[i] >> 9) - Ireg[7 * run + i];  // dead slots: G = 0
+                    sb1 += diff * Gxr[7 * run + i];
+                    sb2 += diff * Gyr[7 * run + i];
+                }
             }
             const float b1 = warp_sum_exact(sb1) * FLT_SCALE;
             const float b2 = warp_sum_exact(sb2) * FLT_SCALE;
@@ -445,14 +516,19 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 b = fy - (float) fiy;
                 bilinear_weights(a, b, iw00, iw01, iw10, iw11);
                 const uint8_t *jb = S.jw + oy * KLT_BOXW + ox;
+                const int wt = pack_w(iw00, iw01), wb = pack_w(iw10, iw11);
                 int se = 0;
 #pragma unroll
-                for (int k = 0; k < KLT_PXL; k++) {
-                    if (lane + 32 * k < KLT_WIN * KLT_WIN) {
-                        const uint8_t *s = jb + joff[k];
-                        int v = (s[0] * iw00 + s[1] * iw01 + s[KLT_BOXW] * iw10 + s[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
-                        se += abs(v - Ireg[k]);
-                    }
+                for (int run = 0; run < 2; run++) {
+                    if (run == 1 && !validB) continue;
+                    const uint8_t *bp = jb + (run ? offB : offA);
+                    const int m8 = ((int) (size_t) bp & 3) * 8;
+                    const unsigned *wp = (const unsigned *) ((size_t) bp & ~(size_t) 3);
+                    const RunBytes top = run_bytes(wp, m8), bot = run_bytes(wp + KLT_BOXW / 4, m8);
+                    int v[7];
+                    run_taps<7>(top, bot, wt, wb, 1 << 8, v);
+#pragma unroll
+                    for (int i = 0; i < 7; i++) se += abs((v[i] >> 9) - Ireg[7 * run + i]);
                 }
                 err_val = warp_sum_exact(se) * 1.f / (float) (32 * KLT_WIN * KLT_WIN);
             }
@@ -465,7 +541,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
 __global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid_constant__ KltMaps maps, const KltArgs A) {
     __shared__ __align__(128) uint8_t s_iw[KLT_WPB][KLT_BOXW * KLT_BOXH_I];
     __shared__ __align__(128) uint8_t s_jw[KLT_WPB][KLT_BOXW * KLT_BOXH_J];
-    __shared__ int s_pg[KLT_WPB][23 * 24];
+    __shared__ __align__(16) int s_pg[KLT_WPB][23 * 24];
     __shared__ __align__(8) uint64_t s_bar[KLT_WPB][2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -3,13 +3,13 @@
 T=${1:-p}
 O=gpurun_out
 mkdir -p $O
-timeout 600 python -m pytest tests/test_ba_gpu.py tests/test_marg_gpu.py -x -q > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest.log
+timeout 900 python -m pytest ${PYTEST_SEL:-tests/test_ba_gpu.py tests/test_marg_gpu.py} -m gpu -q > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest.log
 ICG_BA_PROFILE=1 timeout 300 python scripts/prof_ba.py 148 4 > $O/${T}_prof1.log 2>&1
 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sharded > $O/${T}_bench.json 2> $O/${T}_bench.err
 if [ -n "${NCU_K:-}" ]; then
 timeout 500 ncu --set full --clock-control none --cache-control none --import-source on -k regex:"$NCU_K" -s ${NCU_S:-5} -c ${NCU_C:-1} -f -o $O/${T}_ncu python scripts/prof_ba.py 148 1 > $O/${T}_ncu.log 2>&1
 fi
-tail -4 $O/${T}_pytest.log; cat $O/${T}_prof1.log
+tail -25 $O/${T}_pytest.log; cat $O/${T}_prof1.log
 python - "$O/${T}_bench.json" <<'PY'
 import json,sys
 try:
