@@ -31,6 +31,9 @@ WORKLOAD_KLT = "cfg2 x B: B independent synthetic 1280x560 streams per GPU, pyra
 NFRAMES = 6           # distinct frames per stream (ping-pong sequence 0..5..0)
 KLT_BYTES_PER_FRAME_TRACK = 2 * 952_000 + 58 * NPTS                     # tracker kernel only (both pyramids + point I/O)
 KLT_BYTES_PER_FRAME_TOTAL = int(W * H * (1 + 5 / 16 + 21 / 64 + 2 * 85 / 64) + 58 * NPTS)  # 3 097 400
+# dram__bytes_read.sum + dram__bytes_write.sum of klt_track_kernel from the ncu --set full capture in profiles/r1_klt_v2_ncu.md
+# (266.787 MB + 5.029 MB for one launch over B = 148 frames), per frame; the bench scales it to its own B
+KLT_DRAM_BYTES_PER_FRAME_NCU = (266_787_072 + 5_028_608) / 148.0
 
 
 def parse():
@@ -537,7 +540,8 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": {"kernel": "klt_track_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "kernel_ms": k_ms,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": int(B * KLT_DRAM_BYTES_PER_FRAME_NCU),
+                     "traffic_source": "ncu --set full, one launch at B = 148 (profiles/r1_klt_v2_ncu.md), scaled to this B", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": B * KLT_BYTES_PER_FRAME_TRACK},
         "klt_only": {"value": frames_per_step * args.steps / (ms_klt / 1e3), "unit": "frames/s"},
         "ba_only": ba_info,

@@ -44,7 +44,7 @@ constexpr int BA_CHOL_NB = 8;   // Cholesky block width
 
 struct BaCaps {
     int NW, K, L, F, G, R;     // capacities
-    int NCV, N, NS, NCA, RJ, LP;  // derived strides: NCV = 6K+7, N = 15K+7, NS = N padded, NCA = roundup4(NCV+1), RJ = 2F padded, LP = L padded
+    int NCV, N, NS, NCA, RJ, LP, NVB;  // derived strides: NCV = 6K+7, N = 15K+7, NS = N padded, NCA = roundup4(NCV+1), RJ = 2F padded, LP = L padded
 };
 
 struct WinDims {  // per-window actual sizes
@@ -68,13 +68,14 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     double *f_const;
     uint8_t *f_active;
     int *lm_off, *lm_fidx;
+    int *vb_lm0;  // [NW][NVB] first landmark of every lin_vis run (runs hold whole landmarks, <= 128 factors); last entry = run count
     int *f_slot;  // position of factor f in landmark-CSR order: the per-factor records are stored in that order
     int *f_meta_s;       // per record slot: (landmark, reference node, observing node, factor id)
     double *f_const_s;   // per record slot: the factor's 14 constants (copy of f_const in slot order)
     int *pair_off, *pair_ro, *pair_fidx, *npairs;  // factors grouped by (reference node, observing node)
     double *Mp;                                    // per-pair 20x20 Gram matrices (upper, 210 entries)
     double *AW, *CJ, *CW;  // Schur SYRK input; vision Gram matrix; Schur partials
-    double *jcomp, *jrho, *costf;  // per-factor compact Jacobian (38), rho-Jacobian rows (2), cost
+    double *jcomp, *costf;  // per-factor record (40 doubles, landmark-CSR order), cost
     double *hl, *gl, *scale_l, *scale_c;
     double *Hc, *gc;
     double *Hs;  // H_c + vision Gram - Schur term (lower triangle, ld NS): the operand ba_solve scales and factorises
@@ -98,25 +99,37 @@ __device__ __forceinline__ int col_ext(int K) { return 6 * K; }
 __device__ __forceinline__ int col_td(int K) { return 6 * K + 6; }
 __device__ __forceinline__ int col_mix(int K, int k) { return 6 * K + 7 + 9 * k; }
 
-// ------------------------------------------------------------------------------------------------ lin_vis
-// One thread per reprojection factor, in record (landmark-CSR slot) order: thread q evaluates factor f = meta[q].f and the warp's 32
-// records (40 + 4 doubles each) are transposed through shared memory so that they leave as contiguous, fully used 128-byte lines
-// (a thread-per-record store pattern costs 32 sectors per instruction and made the store pipe the bottleneck of this kernel).
-constexpr int LV_REC = 44, LV_LD = 45;  // record doubles (40 Jacobian/residual + 4 j_rho/meta), padded row (odd: conflict-free)
+// ------------------------------------------------------------------------------------------------ lin_vis (+ landmark rows)
+__device__ __forceinline__ int jc_off(int a) { return a < 18 ? (a / 6) * 12 + (a % 6) : 36 + 2 * (a - 18); }  // row 0 offset in a record
+__device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }                                           // + this for row 1
+// One CTA linearises a run of WHOLE landmarks (<= 128 reprojection factors; the host packs the runs at upload).
+//  phase 1: thread / factor, in record (landmark-CSR slot) order -> residual, local Jacobians, Huber correction -> 40-double record
+//           [Ji 12 | Jj 12 | Je 12 | Jt 2 | r 2] + [j_rho 2 | observing node | reference node], staged in shared memory;
+//  phase 2: the records leave as contiguous, fully used 128-byte lines (a thread-per-record store pattern costs 32 sectors per
+//           instruction and made the store pipe the bottleneck) -- ba_pair_gram1 consumes them;
+//  phase 3: eight lanes per landmark reduce its records, straight from shared memory, to h_l, g_l and the coupling row
+//           w_l[c] = sum_f J_f[:, c]^T j_rho,f of A_W (landmark-major [l][NCA]: zeroed, then the <= 13 + 6 n_obs non-zeros).  All
+//           factors of a landmark share the reference node, the extrinsic and td (accumulated); each observing node appears once
+//           (written directly; icg_ba_upload checks it).
+constexpr int LV_LD = 45;  // shared-memory record row: 44 doubles padded to an odd length (conflict-free)
 __global__ void __launch_bounds__(128, 4) ba_lin_vis(BaCaps C, BaDev D) {
-    __shared__ double s_rec[4][32][LV_LD];
+    __shared__ double s_rec[128][LV_LD];
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
+    const int *vb = D.vb_lm0 + (size_t) w * C.NVB;
+    if ((int) blockIdx.x >= vb[C.NVB - 1]) return;  // last entry = number of runs of this window
     const WinDims dm = D.dims[w];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q0 = blockIdx.x * 128 + 32 * warp, q = q0 + lane;
-    if (q0 >= dm.F) return;  // whole warp
-    double r[2], Ji[12], Jj[12], Je[12], Jr[2], Jt[2], cost = 0;
-    int i = 0, j = 0, f = -1;
-    if (q < dm.F) {
+    const int tid = threadIdx.x;
+    const int *off = D.lm_off + (size_t) w * (C.L + 1);
+    const int lmA = vb[blockIdx.x], lmB = vb[blockIdx.x + 1];
+    const int s0 = off[lmA], nslot = off[lmB] - s0;
+    // ---- phase 1
+    if (tid < nslot) {
+        const int q = s0 + tid;
+        double r[2], Ji[12], Jj[12], Je[12], Jr[2], Jt[2], cost = 0;
         const int4 meta = ((const int4 *) D.f_meta_s)[(size_t) w * C.F + q];  // (landmark, reference node, observing node, factor id)
-        i = meta.y, j = meta.z, f = meta.w;
+        const int i = meta.y, j = meta.z, f = meta.w;
         if (D.f_active[(size_t) w * C.F + f] != 0) {
             const double *ext = D.ext + (size_t) w * 8;
             reproj_eval(D.pose + ((size_t) w * C.K + i) * 7, D.pose + ((size_t) w * C.K + j) * 7, ext, D.rho[(size_t) w * C.L + meta.x], ext[7],
@@ -138,105 +151,70 @@ __global__ void __launch_bounds__(128, 4) ba_lin_vis(BaCaps C, BaDev D) {
             Jr[0] = Jr[1] = Jt[0] = Jt[1] = r[0] = r[1] = 0;
         }
         D.costf[(size_t) w * C.F + f] = cost;
-        double *sr = s_rec[warp][lane];
+        double *sr = s_rec[tid];
 #pragma unroll
         for (int k = 0; k < 12; k++) sr[k] = Ji[k], sr[12 + k] = Jj[k], sr[24 + k] = Je[k];
         sr[36] = Jt[0], sr[37] = Jt[1], sr[38] = r[0], sr[39] = r[1];
-        sr[40] = Jr[0], sr[41] = Jr[1], sr[42] = (double) j, sr[43] = (double) i;  // [j_rho (2) | observing node | reference node]
+        sr[40] = Jr[0], sr[41] = Jr[1], sr[42] = (double) j, sr[43] = (double) i;
     }
-    __syncwarp();
-    const int nrec = min(32, dm.F - q0);
-    double *gj = D.jcomp + ((size_t) w * C.F + q0) * 40, *gr = D.jrho + ((size_t) w * C.F + q0) * 4;
-#pragma unroll 8
-    for (int t = 0; t < 40; t++) {
-        const int idx = lane + 32 * t, rr = idx / 40, k = idx - 40 * rr;
-        if (rr < nrec) gj[idx] = s_rec[warp][rr][k];
+    __syncthreads();
+    // ---- phase 2
+    {
+        double *gj = D.jcomp + ((size_t) w * C.F + s0) * 40;
+        for (int idx = tid; idx < nslot * 40; idx += 128) {
+            const int rr = idx / 40, k = idx - 40 * rr;
+            gj[idx] = s_rec[rr][k];
+        }
     }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int idx = lane + 32 * t, rr = idx >> 2, k = idx & 3;
-        if (rr < nrec) gr[idx] = s_rec[warp][rr][40 + k];
-    }
-}
-
-// ------------------------------------------------------------------------------------------------ lin_lm
-// One warp per landmark: w_l[c] = sum over the landmark's factors of J_f[:, c]^T j_rho,f.  All factors of a landmark share the
-// reference node, the extrinsic and td (lanes 0..5, 12..17, 18 accumulate over the factors); each observing node appears once
-// (lanes 6..11 write their block directly).  Lane 19 produces g_l = sum j_rho^T r, lane 20 h_l = sum |j_rho|^2 (+ the Jacobi scale).
-// A_W is landmark-major [l][NCA]: the warp zeroes its row, then fills the <= 13 + 6 n_obs non-zeros.
-__device__ __forceinline__ int jc_off(int a) { return a < 18 ? (a / 6) * 12 + (a % 6) : 36 + 2 * (a - 18); }  // row 0 offset in a record
-__device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }                                           // + this for row 1
-__global__ void __launch_bounds__(256) ba_lin_lm(BaCaps C, BaDev D) {
-    // four landmarks per warp (8 lanes each): the kernel is a chain of dependent L2 round trips (offsets -> records -> row), so
-    // fewer, fuller warps mean fewer latency-bound waves.  Sub-lane sl owns output columns sl, sl + 8, sl + 16 of the 21
-    // (19 Jacobian columns, 19 -> g_l, 20 -> h_l).
-    const int w = blockIdx.y;
-    const LmState &st = D.st[w];
-    if (st.done || !st.need_lin) return;
-    const WinDims dm = D.dims[w];
+    // ---- phase 3
     const int K = dm.K, NCV = 6 * K + 7, NCA = 4 * ((NCV + 1 + 3) / 4);
-    const int lane = threadIdx.x & 31, grp = lane >> 3, sl = lane & 7;
-    const int l = 4 * (blockIdx.x * 8 + (threadIdx.x >> 5)) + grp;
-    if (l >= dm.L) return;
-    const int *off = D.lm_off + (size_t) w * (C.L + 1);
-    const int f0 = off[l], nf = off[l + 1] - f0;
-    double *row = D.AW + ((size_t) w * C.LP + l) * C.NCA;
-    for (int c = sl; c < NCA; c += 8) row[c] = 0.0;
-    __syncwarp();
+    const int grp = tid >> 3, sl = tid & 7;
     int o0[3], o1[3];
 #pragma unroll
     for (int t = 0; t < 3; t++) {
-        const int c = sl + 8 * t;  // 0..23; 19 -> residual pair (g_l), >= 20 unused (lane 4 of t = 2 accumulates h_l from j_rho)
+        const int c = sl + 8 * t;  // 0..23; 19 -> residual pair (g_l); 20 -> h_l from j_rho; > 20 unused
         o0[t] = c < 19 ? jc_off(c) : 38, o1[t] = c < 19 ? o0[t] + jc_row1(c) : 39;
     }
-    const double *jc = D.jcomp + ((size_t) w * C.F + f0) * 40, *jr = D.jrho + ((size_t) w * C.F + f0) * 4;
-    double acc[3] = {0, 0, 0};
-    int ref = 0;
-    if (nf > 0) ref = (int) jr[3];
-    constexpr int UNR = 2;  // factor records in flight per landmark
-    for (int q0 = 0; q0 < nf; q0 += UNR) {
-        int ob[UNR];
-        double a0[UNR][3], a1[UNR][3], r0[UNR], r1[UNR];
-#pragma unroll
-        for (int u = 0; u < UNR; u++) {
-            const int q = min(q0 + u, nf - 1);  // clamped: the tail re-reads the last record (its contribution is skipped below)
-#pragma unroll
-            for (int t = 0; t < 3; t++) a0[u][t] = jc[q * 40 + o0[t]], a1[u][t] = jc[q * 40 + o1[t]];
-            r0[u] = jr[q * 4], r1[u] = jr[q * 4 + 1];
-            ob[u] = (int) jr[q * 4 + 2];
-        }
-#pragma unroll
-        for (int u = 0; u < UNR; u++) {
-            if (q0 + u >= nf) continue;
+    for (int l = lmA + grp; l < lmB; l += 16) {
+        const int f0 = off[l] - s0, nf = off[l + 1] - off[l];
+        double *row = D.AW + ((size_t) w * C.LP + l) * C.NCA;
+        for (int c = sl; c < NCA; c += 8) row[c] = 0.0;
+        __syncwarp(0xffu << (tid & 24));  // the landmark's eight lanes: zeros land before the values
+        double acc[3] = {0, 0, 0};
+        for (int q = 0; q < nf; q++) {
+            const double *rec = s_rec[f0 + q];
+            const double r0 = rec[40], r1 = rec[41];
+            const int ob = (int) rec[42];
 #pragma unroll
             for (int t = 0; t < 3; t++) {
                 const int c = sl + 8 * t;
                 if (c == 20) {
-                    acc[t] += r0[u] * r0[u] + r1[u] * r1[u];
+                    acc[t] += r0 * r0 + r1 * r1;
                 } else if (c < 20) {
-                    const double v = a0[u][t] * r0[u] + a1[u][t] * r1[u];
+                    const double v = rec[o0[t]] * r0 + rec[o1[t]] * r1;
                     if (c >= 6 && c < 12)
-                        row[col_pose(ob[u]) + c - 6] = v;  // a landmark is observed at most once per node (checked by icg_ba_upload)
+                        row[col_pose(ob) + c - 6] = v;
                     else
                         acc[t] += v;
                 }
             }
         }
-    }
+        const int ref = nf > 0 ? (int) s_rec[f0][43] : 0;
 #pragma unroll
-    for (int t = 0; t < 3; t++) {
-        const int c = sl + 8 * t;
-        if (nf > 0) {
-            if (c < 6) row[col_pose(ref) + c] = acc[t];
-            else if (c >= 12 && c < 18) row[col_ext(K) + c - 12] = acc[t];
-            else if (c == 18) row[col_td(K)] = acc[t];
-        }
-        if (c == 19) {
-            row[NCV] = acc[t];
-            D.gl[(size_t) w * C.L + l] = acc[t];
-        } else if (c == 20) {
-            D.hl[(size_t) w * C.L + l] = acc[t];
-            if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(acc[t]));  // jacobi_scaling, once (iteration 0)
+        for (int t = 0; t < 3; t++) {
+            const int c = sl + 8 * t;
+            if (nf > 0) {
+                if (c < 6) row[col_pose(ref) + c] = acc[t];
+                else if (c >= 12 && c < 18) row[col_ext(K) + c - 12] = acc[t];
+                else if (c == 18) row[col_td(K)] = acc[t];
+            }
+            if (c == 19) {
+                row[NCV] = acc[t];
+                D.gl[(size_t) w * C.L + l] = acc[t];
+            } else if (c == 20) {
+                D.hl[(size_t) w * C.L + l] = acc[t];
+                if (st.first) D.scale_l[(size_t) w * C.L + l] = 1.0 / (1.0 + sqrt(acc[t]));  // jacobi_scaling, once (iteration 0)
+            }
         }
     }
 }
@@ -257,14 +235,13 @@ __device__ __forceinline__ int tri20(int la, int lb) {  // index of (la <= lb) i
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-__global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) {
-    const int w = blockIdx.y;
+__device__ __forceinline__ void gram1_body(const BaCaps &C, const BaDev &D, int w, int pblock) {
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PM = C.K * (C.K - 1);
     const int P = D.npairs[w];
-    const int p = blockIdx.x * 8 + warp;
+    const int p = pblock * 8 + warp;
     if (p >= P) return;
     const int *poff = D.pair_off + (size_t) w * (PM + 1), *pfidx = D.pair_fidx + (size_t) w * C.F;
     double *Mp = D.Mp + (size_t) w * PM * 210;
@@ -310,28 +287,21 @@ __global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) {
     put(0, 0, c00), put(0, 1, c01), put(0, 2, c02), put(1, 1, c11), put(1, 2, c12), put(2, 2, c22);
 }
 
+__global__ void __launch_bounds__(256) ba_pair_gram1(BaCaps C, BaDev D) { gram1_body(C, D, blockIdx.y, blockIdx.x); }
+
 // stage 2: one thread per output entry gathers the groups that touch both of its blocks (one writer per entry, no atomics)
-__global__ void __launch_bounds__(256) ba_pair_gram2(BaCaps C, BaDev D) {
-    __shared__ short s_slot[32 * 32];
-    const int w = blockIdx.y;
-    const LmState &st = D.st[w];
-    if (st.done || !st.need_lin) return;
-    const WinDims dm = D.dims[w];
-    const int tid = threadIdx.x;
-    const int K = dm.K, NCV = 6 * K + 7, PM = C.K * (C.K - 1), nn = NCV + 1;
-    if ((int) blockIdx.x * 256 >= nn * nn) return;
-    const int P = D.npairs[w];
+// gather of one entry (A <= B) of the symmetric (NCV+1)^2 matrix [H_vis g_vis; g_vis^T r^T r] from the per-pair Gram matrices
+__device__ __forceinline__ void gram2_slots(const BaCaps &C, const BaDev &D, int w, int K, short *s_slot) {
+    const int PM = C.K * (C.K - 1), P = D.npairs[w];
     const int *pro = D.pair_ro + (size_t) w * PM;
+    for (int e = threadIdx.x; e < K * K; e += blockDim.x) s_slot[e] = -1;
+    __syncthreads();
+    for (int p = threadIdx.x; p < P; p += blockDim.x) s_slot[(pro[p] >> 8) * K + (pro[p] & 255)] = (short) p;
+    __syncthreads();
+}
+__device__ __forceinline__ double gram2_entry(const BaCaps &C, const BaDev &D, int w, int K, const short *s_slot, int A, int B) {
+    const int PM = C.K * (C.K - 1), P = D.npairs[w];
     const double *Mp = D.Mp + (size_t) w * PM * 210;
-    for (int e = tid; e < K * K; e += 256) s_slot[e] = -1;
-    __syncthreads();
-    for (int p = tid; p < P; p += 256) s_slot[(pro[p] >> 8) * K + (pro[p] & 255)] = (short) p;
-    __syncthreads();
-    double *Cout = D.CJ + (size_t) w * C.NCA * C.NCA;
-    const int t = blockIdx.x * 256 + tid;
-    if (t >= nn * nn) return;
-    const int A = t / nn, B = t - A * nn;
-    if (B < A) return;
     const int bA = A < 6 * K ? A / 6 : K, bB = B < 6 * K ? B / 6 : K;
     const int a = A - 6 * bA, b = B - 6 * bB;  // offsets inside the block (global block: 0..7 = ext 6, td, residual)
     const int ga = 12 + a, gb = 12 + b;          // local column of a global-block column
@@ -351,6 +321,23 @@ __global__ void __launch_bounds__(256) ba_pair_gram2(BaCaps C, BaDev D) {
         if (p1 >= 0) sum += Mp[(size_t) p1 * 210 + tri20(a, 6 + b)];
         if (p2 >= 0) sum += Mp[(size_t) p2 * 210 + tri20(b, 6 + a)];
     }
+    return sum;
+}
+// stage 2 as its own kernel: landmark-sharded solves only (the vision Gram matrix must exist before the all-reduce)
+__global__ void __launch_bounds__(256) ba_pair_gram2(BaCaps C, BaDev D) {
+    __shared__ short s_slot[32 * 32];
+    const int w = blockIdx.y;
+    const LmState &st = D.st[w];
+    if (st.done || !st.need_lin) return;
+    const int K = D.dims[w].K, NCV = 6 * K + 7, nn = NCV + 1;
+    if ((int) blockIdx.x * 256 >= nn * nn) return;
+    gram2_slots(C, D, w, K, s_slot);
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= nn * nn) return;
+    const int A = t / nn, B = t - A * nn;
+    if (B < A) return;
+    const double sum = gram2_entry(C, D, w, K, s_slot, A, B);
+    double *Cout = D.CJ + (size_t) w * C.NCA * C.NCA;
     Cout[(size_t) A * C.NCA + B] = sum;
     Cout[(size_t) B * C.NCA + A] = sum;
 }
@@ -363,9 +350,7 @@ __global__ void __launch_bounds__(256) ba_pair_gram2(BaCaps C, BaDev D) {
 // two wavefronts -- and every warp accumulates two 16x16 super-tiles (2x2 DMMA tiles each) of the upper triangle per pass.
 // The BA_SPLIT_W landmark splits are separate CTAs whose partials ba_pack1 sums in fixed order (deterministic).
 constexpr int SCHUR_RCH = 80;  // landmark rows staged per chunk (multiple of 4)
-__global__ void __launch_bounds__(256) ba_schur_dmma(BaCaps C, BaDev D, int ld) {
-    extern __shared__ double sA[];  // [SCHUR_RCH][ld] rows, then phi[SCHUR_RCH]
-    const int w = blockIdx.y, split = blockIdx.x;
+__device__ __forceinline__ void schur_body(const BaCaps &C, const BaDev &D, int w, int split, int ld, double *sA /* [SCHUR_RCH][ld] rows, then phi[SCHUR_RCH] */) {
     const LmState &st = D.st[w];
     if (st.done) return;
     const WinDims dm = D.dims[w];
@@ -465,6 +450,11 @@ __global__ void __launch_bounds__(256) ba_schur_dmma(BaCaps C, BaDev D, int ld) 
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) ba_schur_dmma(BaCaps C, BaDev D, int ld) {
+    extern __shared__ double sA[];
+    schur_body(C, D, blockIdx.y, blockIdx.x, ld, sA);
 }
 
 // symmetric read of the summed SYRK partials (upper tiles hold the data)
@@ -786,28 +776,34 @@ __global__ void ba_pack2(BaCaps C, BaDev D, int n, int nblk_vis) {
 // Hs = H_c + H_vis - Schur term, lower triangle, one thread per entry (wide and coalesced; ba_solve then reads ONE operand per entry
 // instead of gathering 2 + BA_SPLIT_W).  Landmark-sharded solve: the vision / Schur operands are the all-reduced buffer.
 __global__ void __launch_bounds__(256) ba_hsum(BaCaps C, BaDev D) {
+    __shared__ short s_slot[32 * 32];
     const int w = blockIdx.y;
     if (D.st[w].done) return;
-    const int K = D.dims[w].K, NCV = 6 * K + 7, N = 15 * K + 7;
-    const int e = blockIdx.x * 256 + threadIdx.x, i = e / C.NS, j = e - i * C.NS;
-    (void) N;
-    if (i >= NCV || j > i) return;  // rows beyond the vision columns are H_c itself: ba_solve reads them directly
+    const int K = D.dims[w].K, NCV = 6 * K + 7, nn = NCV + 1;
     const int NN = C.NCA * C.NCA;
-    double h = D.Hc[(size_t) w * C.NS * C.NS + e];
-    {
-        const size_t o = (size_t) i * C.NCA + j;
-        if (D.world > 1) {
-            const double *RED = D.red + (size_t) w * (2 * NN + 8);
-            h += RED[o] - RED[NN + o];
-        } else {
-            const double *CWp = D.CW + (size_t) w * BA_SPLIT_W * NN;
-            double s2 = 0;
+    if ((int) blockIdx.x * 256 >= nn * nn) return;
+    const bool sharded = D.world > 1;
+    if (!sharded) gram2_slots(C, D, w, K, s_slot);
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= nn * nn) return;
+    const int A = t / nn, B = t - A * nn;  // A <= B: entry (row B, column A) of the lower triangle
+    if (B < A) return;
+    double cj, cw;
+    if (sharded) {
+        const double *RED = D.red + (size_t) w * (2 * NN + 8);
+        cj = RED[(size_t) B * C.NCA + A], cw = RED[NN + (size_t) B * C.NCA + A];
+    } else {
+        // single GPU: the gather of the per-pair Gram matrices (ba_pair_gram2's job) happens here, one kernel less on the path
+        cj = gram2_entry(C, D, w, K, s_slot, A, B);
+        double *Cout = D.CJ + (size_t) w * NN;
+        Cout[(size_t) A * C.NCA + B] = cj;
+        Cout[(size_t) B * C.NCA + A] = cj;
+        const double *CWp = D.CW + (size_t) w * BA_SPLIT_W * NN;
+        cw = 0;
 #pragma unroll
-            for (int k = 0; k < BA_SPLIT_W; k++) s2 += CWp[(size_t) k * NN + o];
-            h += D.CJ[(size_t) w * BA_SPLIT_J * NN + o] - s2;
-        }
+        for (int k = 0; k < BA_SPLIT_W; k++) cw += CWp[(size_t) k * NN + (size_t) B * C.NCA + A];
     }
-    D.Hs[(size_t) w * C.NS * C.NS + e] = h;
+    if (B < NCV) D.Hs[(size_t) w * C.NS * C.NS + (size_t) B * C.NS + A] = D.Hc[(size_t) w * C.NS * C.NS + (size_t) B * C.NS + A] + (cj - cw);
 }
 
 // ------------------------------------------------------------------------------------------------ solve (one CTA per window)
@@ -1501,8 +1497,7 @@ struct icg_ba {
     int device;
     cudaStream_t stream;
     cudaStream_t stream_cam = nullptr;  // the camera-only factors are linearised concurrently with the vision chain
-    cudaStream_t stream_gram = nullptr; // pair Gram chain (H_vis) beside lin_lm -> Schur: both only consume lin_vis' records
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool own_stream;
     int nblk_vis;
     int cur_windows;
@@ -1513,7 +1508,7 @@ struct icg_ba {
     HostDev<LmState> st;
     HostDev<double> pose, mix, ext, rho, f_const, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
         marg_H0, marg_b0, marg_c0;
-    HostDev<int> f_slot, f_meta_s;
+    HostDev<int> f_slot, f_meta_s, vb_lm0;
     HostDev<double> f_const_s;
     HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
     HostDev<uint8_t> f_active;
@@ -1728,9 +1723,6 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     else
         ICG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     ICG_CUDA(cudaStreamCreateWithFlags(&h->stream_cam, cudaStreamNonBlocking));
-    ICG_CUDA(cudaStreamCreateWithFlags(&h->stream_gram, cudaStreamNonBlocking));
-    ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
-    ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->prof = getenv("ICG_BA_PROFILE") != nullptr;
@@ -1738,6 +1730,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     C.NW = max_windows, C.K = max_K, C.L = max_L, C.F = max_F, C.G = std::max(1, max_gnss), C.R = std::max(1, max_marg_r);
     C.NCV = 6 * max_K + 7, C.N = 15 * max_K + 7, C.NS = (C.N + 3) & ~3, C.NCA = 4 * ((C.NCV + 1 + 3) / 4);
     C.RJ = (2 * max_F + 31) & ~31, C.LP = (max_L + 31) & ~31;
+    C.NVB = (max_F + 127 - max_K) / (128 - max_K) + max_L / 128 + 4;  // worst case: every run is cut short by one landmark's K - 1 factors
     h->nblk_vis = (max_F + 255) / 256;
     const size_t NW = max_windows;
 #define HD(field, count)                                                       \
@@ -1750,7 +1743,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * 64 * 9)
     HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
     HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * 64) HD(marg_node, NW * 64) HD(f_active, NW * C.F)
-    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F) HD(f_meta_s, NW * C.F * 4) HD(f_const_s, NW * C.F * 14)
+    HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F) HD(f_meta_s, NW * C.F * 4) HD(vb_lm0, NW * C.NVB) HD(f_const_s, NW * C.F * 14)
     HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
 #undef HD
     BaDev &D = h->D;
@@ -1758,7 +1751,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
     D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
     D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
-    D.f_slot = h->f_slot.d, D.f_meta_s = h->f_meta_s.d, D.f_const_s = h->f_const_s.d;
+    D.f_slot = h->f_slot.d, D.f_meta_s = h->f_meta_s.d, D.vb_lm0 = h->vb_lm0.d, D.f_const_s = h->f_const_s.d;
     D.lm_off = h->lm_off.d, D.lm_fidx = h->lm_fidx.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
     D.gnss_node = h->gnss_node.d, D.gnss_blh = h->gnss_blh.d, D.gnss_std = h->gnss_std.d, D.lever = h->lever.d;
     D.pose_prior = h->pose_prior.d, D.pose_prior_sinfo = h->pose_prior_sinfo.d, D.mix_prior = h->mix_prior.d, D.mix_prior_std = h->mix_prior_std.d;
@@ -1769,7 +1762,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     DM(pose_c, NW * C.K * 7) DM(mix_c, NW * C.K * 9) DM(ext_c, NW * 8) DM(rho_c, NW * C.L)
     DM(pose_0, NW * C.K * 7) DM(mix_0, NW * C.K * 9) DM(ext_0, NW * 8) DM(rho_0, NW * C.L)
     DM(AW, NW * C.NCA * C.LP) DM(Mp, NW * (size_t) C.K * (C.K - 1) * 210) DM(CJ, NW * BA_SPLIT_J * C.NCA * C.NCA) DM(CW, NW * BA_SPLIT_W * C.NCA * C.NCA)
-    DM(jcomp, NW * C.F * 40) DM(jrho, NW * C.F * 4) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
+    DM(jcomp, NW * C.F * 40) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
     DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(Hs, NW * C.NS * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(red, NW * (2 * (size_t) C.NCA * C.NCA + 8)) DM(redmax, NW) DM(red2, NW * 4) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
 #undef DM
     if (rc != ICG_OK) return rc;
@@ -1809,14 +1802,11 @@ void icg_ba_destroy(icg_ba *h) {
     h->imu_blob.release(), h->imu_U.release(), h->gnss_blh.release(), h->gnss_std.release(), h->lever.release(), h->pose_prior.release();
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
-    h->f_slot.release(), h->f_meta_s.release(), h->f_const_s.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
+    h->f_slot.release(), h->f_meta_s.release(), h->vb_lm0.release(), h->f_const_s.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
     if (h->marg_ready) h->marg_map.release(), h->marg_oJ0.release(), h->marg_oe0.release(), h->marg_oHp.release(), h->marg_obp.release();
     for (void *p : h->dev_only) cudaFree(p);
     if (h->stream_cam) cudaStreamSynchronize(h->stream_cam), cudaStreamDestroy(h->stream_cam);
-    if (h->stream_gram) cudaStreamSynchronize(h->stream_gram), cudaStreamDestroy(h->stream_gram);
-    if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
-    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -1890,6 +1880,18 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
         {
             std::vector<int> cur(off, off + p.L);
             for (int f = 0; f < p.F; f++) fslot[f] = cur[p.f_lm[f]], fidx[cur[p.f_lm[f]]++] = f;
+            // lin_vis runs: greedy packing of whole landmarks into <= 128 record slots
+            int *vbh = h->vb_lm0.h + (size_t) w * C.NVB;
+            int nrun = 0, l0 = 0;
+            while (l0 < p.L) {
+                int l1 = l0;
+                while (l1 < p.L && off[l1 + 1] - off[l0] <= 128) l1++;
+                if (l1 == l0 || nrun >= C.NVB - 2) PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d: landmark %d has more than 128 factors or the run table overflows", w, l0);
+                vbh[nrun++] = l0;
+                l0 = l1;
+            }
+            vbh[nrun] = p.L;
+            vbh[C.NVB - 1] = nrun;
             int *meta = h->f_meta_s.h + (size_t) w * C.F * 4;
             double *fcs = h->f_const_s.h + (size_t) w * C.F * 14;
             for (int q = 0; q < p.F; q++) {
@@ -2006,7 +2008,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     ICG_CUDA(h->dims.up(s));
     ICG_CUDA(h->pose.up(s)); ICG_CUDA(h->mix.up(s)); ICG_CUDA(h->ext.up(s)); ICG_CUDA(h->rho.up(s));
     ICG_CUDA(h->f_lm.up(s)); ICG_CUDA(h->f_ref.up(s)); ICG_CUDA(h->f_obs.up(s)); ICG_CUDA(h->f_const.up(s)); ICG_CUDA(h->f_active.up(s));
-    ICG_CUDA(h->f_slot.up(s)); ICG_CUDA(h->f_meta_s.up(s)); ICG_CUDA(h->f_const_s.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
+    ICG_CUDA(h->f_slot.up(s)); ICG_CUDA(h->f_meta_s.up(s)); ICG_CUDA(h->vb_lm0.up(s)); ICG_CUDA(h->f_const_s.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
     ICG_CUDA(h->gnss_node.up(s)); ICG_CUDA(h->gnss_blh.up(s)); ICG_CUDA(h->gnss_std.up(s)); ICG_CUDA(h->lever.up(s));
     ICG_CUDA(h->pose_prior.up(s)); ICG_CUDA(h->pose_prior_sinfo.up(s)); ICG_CUDA(h->mix_prior.up(s)); ICG_CUDA(h->mix_prior_std.up(s));
     ICG_CUDA(h->marg_type.up(s)); ICG_CUDA(h->marg_node.up(s)); ICG_CUDA(h->marg_x0.up(s)); ICG_CUDA(h->marg_H0.up(s)); ICG_CUDA(h->marg_b0.up(s));
@@ -2062,7 +2064,7 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
     const BaDev &D = h->D;
     const int n = h->cur_windows;
     cudaStream_t s = h->stream;
-    const dim3 g_vis((C.F + 127) / 128, n), g_lm((C.L + 31) / 32, n), g_sw(BA_SPLIT_W, n), g_cost(h->nblk_vis, n);
+    const dim3 g_vis(C.NVB - 2, n), g_cost(h->nblk_vis, n);
     // iteration 0 linearisation + (max_iter) x [schur syrk, solve, cost, accept, re-linearise]; one extra solve call
     // performs the final termination bookkeeping.
     for (int it = 0; it <= max_num_iterations; it++) {
@@ -2074,17 +2076,16 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         prof_mark(h, 0);
         ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
         prof_mark(h, 1);
-        ICG_CUDA(cudaEventRecord(h->ev_fork2, s));
-        ICG_CUDA(cudaStreamWaitEvent(h->stream_gram, h->ev_fork2, 0));
-        ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, h->stream_gram>>>(C, D);
-        ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, h->stream_gram>>>(C, D);
-        ICG_CUDA(cudaEventRecord(h->ev_join2, h->stream_gram));
-        ba_lin_lm<<<g_lm, 256, 0, s>>>(C, D);
-        prof_mark(h, 2);
-        ba_schur_dmma<<<g_sw, 256, h->smem_schur, s>>>(C, D, h->ld_schur);
+        // (measured: one fused launch or two streams are both slower -- the Schur CTAs' shared memory throttles the latency-bound
+        //  Gram warps when they share SMs)
+        ba_schur_dmma<<<dim3(BA_SPLIT_W, n), 256, h->smem_schur, s>>>(C, D, h->ld_schur);
         prof_mark(h, 5);
-        ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join2, 0));
-        prof_mark(h, 13);
+        ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
+        prof_mark(h, 3);
+        if (h->comm) {
+            ba_pair_gram2<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
+            prof_mark(h, 4);
+        }
         ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
         prof_mark(h, 6);
         if (h->comm) {  // landmark-sharded window: one sum all-reduce of [H_vis g | Schur | cost, |rho|^2] + one max all-reduce
@@ -2095,11 +2096,11 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
             rc = nccl_allreduce(h, D.redmax, (size_t) n, 1);
             if (rc != ICG_OK) return rc;
         }
-        ba_hsum<<<dim3((C.NCV * C.NS + 255) / 256, n), 256, 0, s>>>(C, D);
+        ba_hsum<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
         prof_mark(h, 12);
         ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
         prof_mark(h, 8);
-        count_launch(h->comm ? 9 : 8);
+        count_launch(h->comm ? 8 : 6);
         if (it == max_num_iterations) break;
         ICG_CUDA(cudaEventRecord(h->ev_fork, s));
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
@@ -2377,8 +2378,7 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
     const BaDev &D = h->D;
     const size_t smem = sizeof(double) * (8 * 480 + 2 * (size_t) C.R) + sizeof(int) * (size_t) C.R + 64;
     marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 0);
-    ba_lin_vis<<<dim3((C.F + 127) / 128, n), 128, 0, s>>>(C, D);
-    ba_lin_lm<<<dim3((C.L + 31) / 32, n), 256, 0, s>>>(C, D);
+    ba_lin_vis<<<dim3(C.NVB - 2, n), 128, 0, s>>>(C, D);
     ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
     marg_assemble<<<n, 256, smem, s>>>(C, D, M);
     marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, 0);

@@ -181,11 +181,11 @@ __device__ __forceinline__ void bilinear_weights(float a, float b, int &iw00, in
 }
 
 __device__ __forceinline__ float warp_sum_exact(int v) {
-    // exact sum of 32 int32 values (two REDUX on 16-bit halves, recombined exactly in f64), rounded ONCE to f32
+    // exact sum of 32 int32 values (two REDUX on 16-bit halves, recombined exactly in int64), rounded ONCE to f32
     int lo = v & 0xFFFF, hi = v >> 16;
     int slo = __reduce_add_sync(0xffffffffu, lo);
     int shi = __reduce_add_sync(0xffffffffu, hi);
-    return (float) ((double) shi * 65536.0 + (double) slo);
+    return (float) ((long long) shi * 65536LL + (long long) slo);  // exact 64-bit integer, one rounding (int64 -> f32, RN)
 }
 
 // ---- packed-byte bilinear taps ------------------------------------------------------------------------------------------------
@@ -251,7 +251,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
 
     for (int level = maxLevel; level >= 0; level--) {
         const KltLevel &L = A.lv[level];
-        const float scale = (float) (1. / (1 << level));
+        const float scale = __int_as_float((127 - level) << 23);  // 2^-level, exact (OpenCV: (float) (1. / (1 << level)))
         float px = prev.x * scale, py = prev.y * scale;
         if (level == maxLevel) {
             if (A.use_initial_flow) {
@@ -399,7 +399,7 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         // ---- the template now lives in registers: prefetch the NEXT level's template window while this level iterates
         if (level > 0) {
             const KltLevel &Ln = A.lv[level - 1];
-            const float sn = (float) (1. / (1 << (level - 1)));
+            const float sn = __int_as_float((127 - (level - 1)) << 23);
             const int npx = __float2int_rd(prev.x * sn - half), npy = __float2int_rd(prev.y * sn - half);
             if (!(npx < -KLT_WIN || npx >= Ln.W || npy < -KLT_WIN || npy >= Ln.H)) {
                 int nx0, ny0;
@@ -482,7 +482,9 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             nextPt.x = nx + half;
             nextPt.y = ny + half;
             if ((double) dx * (double) dx + (double) dy * (double) dy <= A.eps2) break;
-            if (j > 0 && fabs((double) (dx + pdx)) < 0.01 && fabs((double) (dy + pdy)) < 0.01) {
+            // OpenCV compares the float sums with the double 0.01; for a float x, |x| < 0.01 (double) <=> |x| <= 0.01f, because
+            // 0.01f = 0.0099999997765 is the largest float below 0.01
+            if (j > 0 && fabsf(dx + pdx) <= 0.01f && fabsf(dy + pdy) <= 0.01f) {
                 nextPt.x -= dx * 0.5f;
                 nextPt.y -= dy * 0.5f;
                 break;

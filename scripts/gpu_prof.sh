@@ -9,6 +9,9 @@ timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-sharded 
 if [ -n "${NCU_K:-}" ]; then
 timeout 500 ncu --set full --clock-control none --cache-control none --import-source on -k regex:"$NCU_K" -s ${NCU_S:-5} -c ${NCU_C:-1} -f -o $O/${T}_ncu python scripts/prof_ba.py 148 1 > $O/${T}_ncu.log 2>&1
 fi
+if [ -n "${NCU_KLT:-}" ]; then
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:klt_track -s 1 -c 1 -f -o $O/${T}_klt python bench.py --steps 1 --warmup 1 --streams 148 --no-cpu-baseline --no-sharded --no-ba --no-detect > $O/${T}_ncu_klt.log 2>&1
+fi
 tail -25 $O/${T}_pytest.log; cat $O/${T}_prof1.log
 python - "$O/${T}_bench.json" <<'PY'
 import json,sys
