@@ -21,6 +21,7 @@ SOURCES = {
     "common.cu": [],
     "klt.cu": ["-fmad=false"],
     "detect.cu": ["-fmad=false"],
+    "clahe.cu": ["-fmad=false"],
     "ba.cu": [],
 }
 

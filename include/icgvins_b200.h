@@ -99,6 +99,18 @@ int icg_klt_track_batch_dev(icg_klt *h, int n_total, const int32_t *dev_slots, c
                             int mode);
 int icg_klt_sync(icg_klt *h);
 
+/* ----- pre-pass of path A: cv::CLAHE (IG/tracking/tracking.cc:62 createCLAHE(3.0, Size(21, 21)); :141 clahe_->apply(img, img)) ----- */
+typedef struct icg_clahe icg_clahe;
+int icg_clahe_create(icg_clahe **h, int width, int height, int tiles_x, int tiles_y, double clip_limit, int device, void *stream);
+void icg_clahe_destroy(icg_clahe *h);
+/* Drop-in for cv::CLAHE::apply(src, dst) on 8-bit single-channel host buffers (dst may alias src): H2D, per-tile LUTs, bilinear LUT
+ * interpolation, D2H; synchronous.  Bit-exact with OpenCV (tests/golden/clahe_golden.npz). */
+int icg_clahe_apply(icg_clahe *h, const uint8_t *src, int src_stride, uint8_t *dst, int dst_stride);
+/* Device-resident variant (asynchronous on the handle's stream): src / dst are device pointers, e.g. the level-0 plane of a KLT slot
+ * (icg_klt_slot_level0) so that upload -> CLAHE -> pyramid -> track never leaves HBM; dst may alias src. */
+int icg_clahe_apply_dev(icg_clahe *h, const uint8_t *dev_src, int src_pitch, uint8_t *dev_dst, int dst_pitch);
+int icg_clahe_sync(icg_clahe *h);
+
 /* ----- detection leg of path A: Tracking::featuresDetection (IG/tracking/tracking.cc:576-688) ----- */
 typedef struct icg_rect {
     int32_t x, y, w, h;

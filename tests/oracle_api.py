@@ -207,3 +207,14 @@ def detect_block(lib, img, mask, roi, n, quality, min_dist):
     m = np.ascontiguousarray(mask) if mask is not None else None
     cnt = lib.icgo_detect_block(_p(img), _p(m) if m is not None else None, W, H, W, x0, y0, w, h, n, quality, min_dist, _p(out))
     return out[:cnt].copy()
+
+
+# ------------------------------------------------------------------------------------------------ CLAHE oracle
+def clahe_apply(lib, img, clip, tiles_x, tiles_y, in_place=False):
+    lib.icgo_clahe_apply.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, vp, C.c_int]
+    lib.icgo_clahe_apply.restype = None
+    img = img if in_place else np.ascontiguousarray(img)
+    H, W = img.shape
+    out = img if in_place else np.zeros_like(img)
+    lib.icgo_clahe_apply(_p(img), W, H, W, float(clip), tiles_x, tiles_y, _p(out), W)
+    return out
