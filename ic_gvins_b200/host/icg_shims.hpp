@@ -142,6 +142,22 @@ private:
     icg_ba *h_ = nullptr;
 };
 
+// cv::Ptr<cv::CLAHE> clahe_ = cv::createCLAHE(3.0, cv::Size(21, 21)) (IG/tracking/tracking.cc:62); clahe_->apply(img, img) (:141)
+class Clahe {
+public:
+    Clahe(int width, int height, double clipLimit = 3.0, Size tileGridSize = Size(21, 21), int device = 0) {
+        check(icg_clahe_create(&h_, width, height, tileGridSize.width, tileGridSize.height, clipLimit, device, nullptr), "icg_clahe_create");
+    }
+    ~Clahe() { icg_clahe_destroy(h_); }
+    Clahe(const Clahe &) = delete;
+    Clahe &operator=(const Clahe &) = delete;
+    // apply(src, dst) on 8-bit single-channel images; dst may be src
+    void apply(const uint8_t *src, int src_step, uint8_t *dst, int dst_step) { check(icg_clahe_apply(h_, src, src_step, dst, dst_step), "icg_clahe_apply"); }
+
+private:
+    icg_clahe *h_ = nullptr;
+};
+
 // Tracking::featuresDetection's tbb::parallel_for body (IG/tracking/tracking.cc:627-656) for all blocks in one call.
 class BlockDetector {
 public:
