@@ -32,8 +32,8 @@ NFRAMES = 6           # distinct frames per stream (ping-pong sequence 0..5..0)
 KLT_BYTES_PER_FRAME_TRACK = 2 * 952_000 + 58 * NPTS                     # tracker kernel only (both pyramids + point I/O)
 KLT_BYTES_PER_FRAME_TOTAL = int(W * H * (1 + 5 / 16 + 21 / 64 + 2 * 85 / 64) + 58 * NPTS)  # 3 097 400
 # dram__bytes_read.sum + dram__bytes_write.sum of klt_track_kernel from the ncu --set full capture in profiles/r1_klt_v2_ncu.md
-# (266.787 MB + 5.029 MB for one launch over B = 148 frames), per frame; the bench scales it to its own B
-KLT_DRAM_BYTES_PER_FRAME_NCU = (266_787_072 + 5_028_608) / 148.0
+# (266.831 MB + 7.692 MB for one launch over B = 148 frames), per frame; the bench scales it to its own B
+KLT_DRAM_BYTES_PER_FRAME_NCU = (266_830_592 + 7_691_520) / 148.0
 
 
 def parse():
