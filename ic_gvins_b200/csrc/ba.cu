@@ -67,9 +67,8 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     int *f_lm, *f_ref, *f_obs;
     double *f_const;
     uint8_t *f_active;
-    int *lm_off, *lm_fidx;
+    int *lm_off;  // CSR offsets of the factor records by landmark
     int *vb_lm0;  // [NW][NVB] first landmark of every lin_vis run (runs hold whole landmarks, <= 128 factors); last entry = run count
-    int *f_slot;  // position of factor f in landmark-CSR order: the per-factor records are stored in that order
     int *f_meta_s;       // per record slot: (landmark, reference node, observing node, factor id)
     double *f_const_s;   // per record slot: the factor's 14 constants (copy of f_const in slot order)
     int *pair_off, *pair_ro, *pair_fidx, *npairs;  // factors grouped by (reference node, observing node)
@@ -1508,7 +1507,7 @@ struct icg_ba {
     HostDev<LmState> st;
     HostDev<double> pose, mix, ext, rho, f_const, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
         marg_H0, marg_b0, marg_c0;
-    HostDev<int> f_slot, f_meta_s, vb_lm0;
+    HostDev<int> f_slot, f_meta_s, vb_lm0;  // f_slot / lm_fidx: host-side packing helpers only (factor id <-> record slot)
     HostDev<double> f_const_s;
     HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
     HostDev<uint8_t> f_active;
@@ -1758,8 +1757,8 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
     D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
     D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
-    D.f_slot = h->f_slot.d, D.f_meta_s = h->f_meta_s.d, D.vb_lm0 = h->vb_lm0.d, D.f_const_s = h->f_const_s.d;
-    D.lm_off = h->lm_off.d, D.lm_fidx = h->lm_fidx.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
+    D.f_meta_s = h->f_meta_s.d, D.vb_lm0 = h->vb_lm0.d, D.f_const_s = h->f_const_s.d;
+    D.lm_off = h->lm_off.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
     D.gnss_node = h->gnss_node.d, D.gnss_blh = h->gnss_blh.d, D.gnss_std = h->gnss_std.d, D.lever = h->lever.d;
     D.pose_prior = h->pose_prior.d, D.pose_prior_sinfo = h->pose_prior_sinfo.d, D.mix_prior = h->mix_prior.d, D.mix_prior_std = h->mix_prior_std.d;
     D.marg_type = h->marg_type.d, D.marg_node = h->marg_node.d, D.marg_x0 = h->marg_x0.d, D.marg_H0 = h->marg_H0.d, D.marg_b0 = h->marg_b0.d, D.marg_c0 = h->marg_c0.d;
@@ -2015,7 +2014,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     ICG_CUDA(h->dims.up(s));
     ICG_CUDA(h->pose.up(s)); ICG_CUDA(h->mix.up(s)); ICG_CUDA(h->ext.up(s)); ICG_CUDA(h->rho.up(s));
     ICG_CUDA(h->f_lm.up(s)); ICG_CUDA(h->f_ref.up(s)); ICG_CUDA(h->f_obs.up(s)); ICG_CUDA(h->f_const.up(s)); ICG_CUDA(h->f_active.up(s));
-    ICG_CUDA(h->f_slot.up(s)); ICG_CUDA(h->f_meta_s.up(s)); ICG_CUDA(h->vb_lm0.up(s)); ICG_CUDA(h->f_const_s.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->lm_fidx.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
+    ICG_CUDA(h->f_meta_s.up(s)); ICG_CUDA(h->vb_lm0.up(s)); ICG_CUDA(h->f_const_s.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
     ICG_CUDA(h->gnss_node.up(s)); ICG_CUDA(h->gnss_blh.up(s)); ICG_CUDA(h->gnss_std.up(s)); ICG_CUDA(h->lever.up(s));
     ICG_CUDA(h->pose_prior.up(s)); ICG_CUDA(h->pose_prior_sinfo.up(s)); ICG_CUDA(h->mix_prior.up(s)); ICG_CUDA(h->mix_prior_std.up(s));
     ICG_CUDA(h->marg_type.up(s)); ICG_CUDA(h->marg_node.up(s)); ICG_CUDA(h->marg_x0.up(s)); ICG_CUDA(h->marg_H0.up(s)); ICG_CUDA(h->marg_b0.up(s));
