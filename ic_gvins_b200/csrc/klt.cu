@@ -6,11 +6,12 @@
 //
 // Design (B200-first, not a translation of OpenCV's row-parallel CPU code):
 //   * pyramids live in HBM as [slot][row][pitch] u8 planes per level; one 3-D TMA descriptor per level.
-//   * one warp tracks one point through all levels (forward, then backward): the 21x21 template
-//     (I, Ix, Iy) lives in registers (14 px / lane), the 32x32 search window of the second image is staged
-//     into shared memory by TMA (cp.async.bulk.tensor.3d, mbarrier completion) and re-centred only when the
-//     track leaves it; Scharr derivatives are computed in-kernel from the staged template window
-//     (no derivative image ever touches HBM); the 2x2 normal equations are reduced with REDUX (exact integer).
+//   * one warp tracks one point through all levels (forward, then backward): the 21x21 template (I, Ix, Iy) lives in registers
+//     (two 7-pixel horizontal runs per lane), the 48x32 search window of the second image is staged into shared memory by TMA
+//     (cp.async.bulk.tensor.3d, mbarrier completion) and re-centred only when the track leaves it; the template comes from ONE exact
+//     Q14 interpolation grid per level (interpolate first, differentiate second: no derivative image ever touches HBM); the bilinear
+//     taps of a run are dp2a on packed bytes (aligned 32-bit shared-memory loads + funnel shifts, not byte loads); the 2x2 normal
+//     equations are reduced with REDUX (exact integer sums, one rounding).
 //   * compile with -fmad=false: the float sequence of the reference library must not be contracted.
 #include <math.h>
 #include <string.h>

@@ -204,3 +204,30 @@ def test_prior_round_trip_through_the_solver(olib):
     for _ in range(2):
         oa.ba_solve(olib, q, 20)
     assert np.abs(q["pose"].reshape(-1, 7)[:, :3] - before.reshape(-1, 7)[:, :3]).max() < 5e-4
+
+
+def test_two_node_marginalization_is_a_marginal(olib):
+    """num_marg = 2 (a non-keyframe time node sits between the two oldest keyframes, ic_gvins.cc:1421-1424): both nodes, both
+    preintegration factors and the landmarks anchored in either node leave; the marginal property must still hold"""
+    prob = make(olib, K=7, L=70, seed=21)
+    out = oa.ba_marginalize(olib, prob, 2)
+    H, b, m, col = numpy_equation(olib, prob, 2)
+    assert out["m"] == m and out["r"] == H.shape[0] - m
+    assert ("mix", 2) in col and ("pose", 2) in col  # node 2 is touched by preintegration factor 1
+    assert not any(t == 1 and n > 0 for t, n in zip(out["block_type"], out["block_node"]))  # only mix of the new node 0 remains
+    rng = np.random.default_rng(1)
+    sc = 1.0 / np.sqrt(np.diag(H)[m:])
+
+    def full_min(dxr):
+        dxm = np.linalg.solve(H[:m, :m], b[:m] - H[:m, m:] @ dxr)
+        dx = np.concatenate([dxm, dxr])
+        return 0.5 * dx @ H @ dx - b @ dx
+
+    def prior(dxr):
+        e = out["e0"] + out["J0"] @ dxr
+        return 0.5 * e @ e
+
+    d0 = full_min(np.zeros(out["r"])) - prior(np.zeros(out["r"]))
+    for _ in range(4):
+        dxr = rng.normal(size=out["r"]) * sc
+        assert abs(full_min(dxr) - prior(dxr) - d0) <= 1e-7 * max(1.0, abs(prior(dxr)))
