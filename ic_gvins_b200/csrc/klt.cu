@@ -75,11 +75,29 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // ------------------------------------------------------------------------------------------------ pyrDown
 // cv::pyrDown: dst(y,x) = (sum_{i,j} k_i k_j src(2y+i, 2x+j) + 128) >> 8, k = [1 4 6 4 1], reflect-101.
-// One thread per output pixel: five source rows, each read as two aligned 16-bit loads + one byte (2x-2 is even); neighbouring
-// threads overlap in L1.  HBM-bound: every source byte is fetched from DRAM once (W*H bytes in, W*H/4 out per level).
-__device__ __forceinline__ int pd_row5(const uint8_t *__restrict__ r, int x0) {
-    const unsigned a = *(const unsigned short *) (r + x0), b = *(const unsigned short *) (r + x0 + 2), c = r[x0 + 4];
-    return (int) (a & 0xff) + 4 * (int) (a >> 8) + 6 * (int) (b & 0xff) + 4 * (int) (b >> 8) + (int) c;
+// One thread per FOUR horizontally adjacent output pixels: a source row contributes the 11 bytes [8t-2, 8t+8], fetched as four aligned
+// 32-bit words from 8t-4; the row filter of each output is one dp4a (weights 1 4 6 4 on a funnel-shifted 4-byte window) plus the fifth tap.
+// HBM-bound in bytes (W*H in, W*H/4 out per level); the packed form keeps it off the issue limit.
+__device__ __forceinline__ void pd_row4(const uint8_t *__restrict__ r, int t, int h[4]) {
+    const unsigned *wp = (const unsigned *) (r + 8 * t - 4);  // 4-byte aligned: row starts are 16-byte aligned
+    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+    const unsigned K = 0x04060401u;  // bytes (1, 4, 6, 4)
+    h[0] = (int) __dp4a(__funnelshift_r(w0, w1, 16), K, w1 >> 16 & 0xFFu);  // columns 8t-2 .. 8t+1, + 8t+2
+    h[1] = (int) __dp4a(w1, K, w2 & 0xFFu);                                 // 8t .. 8t+3, + 8t+4
+    h[2] = (int) __dp4a(__funnelshift_r(w1, w2, 16), K, w2 >> 16 & 0xFFu);  // 8t+2 .. 8t+5, + 8t+6
+    h[3] = (int) __dp4a(w2, K, w3 & 0xFFu);                                 // 8t+4 .. 8t+7, + 8t+8
+}
+__device__ __forceinline__ int pd_scalar(const uint8_t *__restrict__ src, int sW, int sH, int spitch, int x, int y) {
+    const int kk[5] = {1, 4, 6, 4, 1};
+    const int x0 = 2 * x - 2, y0 = 2 * y - 2;
+    int s = 0;
+    for (int j = 0; j < 5; j++) {
+        const uint8_t *r = src + (size_t) reflect101(y0 + j, sH) * spitch;
+        int rs = 0;
+        for (int i = 0; i < 5; i++) rs += kk[i] * r[reflect101(x0 + i, sW)];
+        s += kk[j] * rs;
+    }
+    return (s + 128) >> 8;
 }
 __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict__ src, int sW, int sH, int spitch, size_t s_slot,
                                                        uint8_t *__restrict__ dst, int dW, int dH, int dpitch, size_t d_slot,
@@ -87,25 +105,30 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
     const int slot = first_slot + blockIdx.z;
     src += (size_t) slot * s_slot + (size_t) KLT_PAD * spitch + KLT_PAD;  // interiors of the padded planes
     dst += (size_t) slot * d_slot + (size_t) KLT_PAD * dpitch + KLT_PAD;
-    const int x = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int t = blockIdx.x * 64 + (threadIdx.x & 63), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int x = 4 * t;
     if (x >= dW || y >= dH) return;
-    const int x0 = 2 * x - 2, y0 = 2 * y - 2;
-    int s;
-    if (x0 >= 0 && x0 + 4 < sW && y0 >= 0 && y0 + 4 < sH) {
+    const int y0 = 2 * y - 2;
+    uint8_t *drow = dst + (size_t) y * dpitch;
+    if (t >= 1 && 8 * t + 8 < sW && x + 3 < dW && y0 >= 0 && y0 + 4 < sH) {
         const uint8_t *r = src + (size_t) y0 * spitch;
-        s = pd_row5(r, x0) + 4 * pd_row5(r + spitch, x0) + 6 * pd_row5(r + 2 * (size_t) spitch, x0) + 4 * pd_row5(r + 3 * (size_t) spitch, x0) +
-            pd_row5(r + 4 * (size_t) spitch, x0);
-    } else {
-        const int kk[5] = {1, 4, 6, 4, 1};
-        s = 0;
-        for (int j = 0; j < 5; j++) {
-            const uint8_t *r = src + (size_t) reflect101(y0 + j, sH) * spitch;
-            int rs = 0;
-            for (int i = 0; i < 5; i++) rs += kk[i] * r[reflect101(x0 + i, sW)];
-            s += kk[j] * rs;
+        int h0[4], h1[4], h2[4], h3[4], h4[4];
+        pd_row4(r, t, h0);
+        pd_row4(r + spitch, t, h1);
+        pd_row4(r + 2 * (size_t) spitch, t, h2);
+        pd_row4(r + 3 * (size_t) spitch, t, h3);
+        pd_row4(r + 4 * (size_t) spitch, t, h4);
+        unsigned out = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int v = (h0[j] + 4 * h1[j] + 6 * h2[j] + 4 * h3[j] + h4[j] + 128) >> 8;
+            out |= (unsigned) v << (8 * j);
         }
+        *(unsigned *) (drow + x) = out;
+    } else {
+        for (int j = 0; j < 4; j++)
+            if (x + j < dW) drow[x + j] = (uint8_t) pd_scalar(src, sW, sH, spitch, x + j, y);
     }
-    dst[(size_t) y * dpitch + x] = (uint8_t) ((s + 128) >> 8);
 }
 
 // Fill the reflect-101 padding of all levels of a range of slots (OpenCV pads its pyramid the same way, lkpyramid.cpp).
@@ -759,7 +782,7 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
     ICG_CUDA(cudaSetDevice(h->device));
     for (int l = 1; l < KLT_LEVELS; l++) {
         const KltLevel &s = h->lv[l - 1], &d = h->lv[l];
-        dim3 grid((d.W + 63) / 64, (d.H + 3) / 4, count);
+        dim3 grid((d.W + 255) / 256, (d.H + 3) / 4, count);
         pyr_down_kernel<<<grid, 256, 0, h->stream>>>(s.base, s.W, s.H, s.pitch, s.slot_stride, h->planes[l], d.W, d.H, d.pitch,
                                                      d.slot_stride, first_slot);
         ICG_CHECK_LAUNCH();
