@@ -1,0 +1,54 @@
+"""Host-side mirror of the reference's `Camera` (IG/tracking/camera.cc): same method names and argument meaning, arithmetic in
+libicgvins_b200.so (host functions: SURVEY 8a row A6 keeps the camera model on the CPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib, vp
+
+
+class CameraStruct(C.Structure):
+    """ctypes image of `icg_camera`."""
+    _fields_ = [(k, C.c_double) for k in ("fx", "fy", "cx", "cy", "skew", "k1", "k2", "p1", "p2", "k3")]
+
+
+class Camera:
+    def __init__(self, intrinsic, distortion):
+        """Camera::createCamera (camera.cc:48-70): intrinsic = [fx, fy, cx, cy(, skew)], distortion = [k1, k2, p1, p2(, k3)]"""
+        i, d = list(map(float, intrinsic)), list(map(float, distortion))
+        self.c = CameraStruct(i[0], i[1], i[2], i[3], i[4] if len(i) == 5 else 0.0, d[0], d[1], d[2], d[3], d[4] if len(d) == 5 else 0.0)
+
+    def _pts(self, pts):
+        return np.ascontiguousarray(np.array(pts, np.float32).reshape(-1, 2))
+
+    def undistortPoints(self, pts):
+        p = self._pts(pts)
+        check(lib().icg_camera_undistort_points(C.byref(self.c), vp(p.ctypes.data), p.shape[0]), "icg_camera_undistort_points")
+        return p
+
+    def distortPoints(self, pts):
+        p = self._pts(pts)
+        check(lib().icg_camera_distort_points(C.byref(self.c), vp(p.ctypes.data), p.shape[0]), "icg_camera_distort_points")
+        return p
+
+    def distortCameraPoint(self, pc):
+        a = np.ascontiguousarray(np.array(pc, np.float64).reshape(-1, 3))
+        out = np.zeros((a.shape[0], 2), np.float32)
+        check(lib().icg_camera_distort_camera_points(C.byref(self.c), vp(a.ctypes.data), vp(out.ctypes.data), a.shape[0]), "icg_camera_distort_camera_points")
+        return out
+
+    def pixel2cam(self, pts):
+        p = self._pts(pts)
+        out = np.zeros((p.shape[0], 3))
+        check(lib().icg_camera_pixel2cam(C.byref(self.c), vp(p.ctypes.data), vp(out.ctypes.data), p.shape[0]), "icg_camera_pixel2cam")
+        return out
+
+    def world2pixel(self, world, R, t):
+        a = np.ascontiguousarray(np.array(world, np.float64).reshape(-1, 3))
+        Rm, tv = np.ascontiguousarray(np.array(R, np.float64).reshape(3, 3)), np.ascontiguousarray(np.array(t, np.float64).reshape(3))
+        out = np.zeros((a.shape[0], 2), np.float32)
+        check(lib().icg_camera_world2pixel(C.byref(self.c), vp(Rm.ctypes.data), vp(tv.ctypes.data), vp(a.ctypes.data), vp(out.ctypes.data), a.shape[0]),
+              "icg_camera_world2pixel")
+        return out

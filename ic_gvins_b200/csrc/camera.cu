@@ -1,0 +1,110 @@
+// camera.cu -- SURVEY.md 8a row A6: the radtan camera model of the front end.  HOST code by design: <= 300 points per frame, FP64,
+// called from the tracking thread between the GPU stages (SURVEY: "small; stays host").  No kernels here; compiled into the same
+// library so that the Tracking shims find every call they replace behind one C ABI.
+//
+// Replaces Camera::undistortPoints / distortPoints / distortPoint / distortCameraPoint / pixel2cam / cam2pixel / world2pixel
+// (IG/tracking/camera.cc:72-146).  undistortPoints forwards to cv::undistortPoints(pts, pts, K, D, Mat(), K) in the reference
+// (:72-74); OpenCV is un-vendored, its algorithm (calib3d/undistort: five fixed-point iterations, skew ignored when normalising, P = K
+// applied with its skew) is restated here and pinned against cv2 4.13.0 by tests/golden/camera_golden.npz -- float outputs bit-identical.
+#include <math.h>
+
+#include "common.cuh"
+
+using namespace icg;
+
+namespace {
+inline void pixel2cam(const icg_camera &c, double u, double v, double &x, double &y) {  // camera.cc:126-130
+    y = (v - c.cy) / c.fy;
+    x = (u - c.cx - c.skew * y) / c.fx;
+}
+inline void cam2pixel(const icg_camera &c, double x, double y, double z, float &u, float &v) {  // camera.cc:132-134
+    u = (float) ((c.fx * x + c.skew * y) / z + c.cx);
+    v = (float) (c.fy * y / z + c.cy);
+}
+inline void distort_xy(const icg_camera &c, double x, double y, double &xd, double &yd) {  // camera.cc:79-86
+    const double r2 = x * x + y * y;
+    const double rr = (1 + c.k1 * r2 + c.k2 * r2 * r2 + c.k3 * r2 * r2 * r2);
+    xd = x * rr + 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
+    yd = y * rr + c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
+}
+inline bool bad(const icg_camera *c, const void *p, int n, const char *who) {
+    if (!c || (!p && n > 0) || n < 0 || !(c->fx != 0.0) || !(c->fy != 0.0)) {
+        set_error("%s: bad arguments", who);
+        return true;
+    }
+    return false;
+}
+}  // namespace
+
+extern "C" {
+
+int icg_camera_undistort_points(const icg_camera *c, float *pts_xy, int n) {
+    if (bad(c, pts_xy, n, "icg_camera_undistort_points")) return ICG_EINVAL;
+    const double ifx = 1.0 / c->fx, ify = 1.0 / c->fy;
+    for (int i = 0; i < n; i++) {
+        double x = ((double) pts_xy[2 * i] - c->cx) * ifx, y = ((double) pts_xy[2 * i + 1] - c->cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {  // TermCriteria(MAX_ITER, 5, 0.01): no EPS test
+            const double r2 = x * x + y * y;
+            const double icdist = 1.0 / (1 + ((c->k3 * r2 + c->k2) * r2 + c->k1) * r2);
+            if (icdist < 0) {  // test: undistortPoints regression 14583
+                x = x0, y = y0;
+                break;
+            }
+            const double dx = 2 * c->p1 * x * y + c->p2 * (r2 + 2 * x * x), dy = c->p1 * (r2 + 2 * y * y) + 2 * c->p2 * x * y;
+            x = (x0 - dx) * icdist;
+            y = (y0 - dy) * icdist;
+        }
+        // R = identity, P = K (with its skew): [xx yy ww] = K [x y 1]
+        const double xx = c->fx * x + c->skew * y + c->cx, yy = c->fy * y + c->cy;
+        pts_xy[2 * i] = (float) xx;
+        pts_xy[2 * i + 1] = (float) yy;
+    }
+    return ICG_OK;
+}
+
+int icg_camera_distort_points(const icg_camera *c, float *pts_xy, int n) {
+    if (bad(c, pts_xy, n, "icg_camera_distort_points")) return ICG_EINVAL;
+    for (int i = 0; i < n; i++) {
+        double x, y, xd, yd;
+        pixel2cam(*c, pts_xy[2 * i], pts_xy[2 * i + 1], x, y);
+        distort_xy(*c, x, y, xd, yd);
+        cam2pixel(*c, xd, yd, 1.0, pts_xy[2 * i], pts_xy[2 * i + 1]);
+    }
+    return ICG_OK;
+}
+
+int icg_camera_distort_camera_points(const icg_camera *c, const double *pc_xyz, float *px_xy, int n) {
+    if (bad(c, pc_xyz, n, "icg_camera_distort_camera_points") || !px_xy) return ICG_EINVAL;
+    for (int i = 0; i < n; i++) {
+        const double x = pc_xyz[3 * i] / pc_xyz[3 * i + 2], y = pc_xyz[3 * i + 1] / pc_xyz[3 * i + 2];
+        double xd, yd;
+        distort_xy(*c, x, y, xd, yd);
+        // camera.cc:114-115: the distorted coordinates pass through float before cam2pixel
+        cam2pixel(*c, (double) (float) xd, (double) (float) yd, 1.0, px_xy[2 * i], px_xy[2 * i + 1]);
+    }
+    return ICG_OK;
+}
+
+int icg_camera_pixel2cam(const icg_camera *c, const float *px_xy, double *cam_xyz, int n) {
+    if (bad(c, px_xy, n, "icg_camera_pixel2cam") || !cam_xyz) return ICG_EINVAL;
+    for (int i = 0; i < n; i++) {
+        pixel2cam(*c, px_xy[2 * i], px_xy[2 * i + 1], cam_xyz[3 * i], cam_xyz[3 * i + 1]);
+        cam_xyz[3 * i + 2] = 1.0;
+    }
+    return ICG_OK;
+}
+
+int icg_camera_world2pixel(const icg_camera *c, const double *R9, const double *t3, const double *pw_xyz, float *px_xy, int n) {
+    if (bad(c, pw_xyz, n, "icg_camera_world2pixel") || !R9 || !t3 || !px_xy) return ICG_EINVAL;
+    for (int i = 0; i < n; i++) {
+        const double d[3] = {pw_xyz[3 * i] - t3[0], pw_xyz[3 * i + 1] - t3[1], pw_xyz[3 * i + 2] - t3[2]};
+        // world2cam: pose.R^T (world - pose.t)   (camera.cc:148-150); R9 row-major
+        const double x = R9[0] * d[0] + R9[3] * d[1] + R9[6] * d[2], y = R9[1] * d[0] + R9[4] * d[1] + R9[7] * d[2],
+                     z = R9[2] * d[0] + R9[5] * d[1] + R9[8] * d[2];
+        cam2pixel(*c, x, y, z, px_xy[2 * i], px_xy[2 * i + 1]);
+    }
+    return ICG_OK;
+}
+
+}  // extern "C"

@@ -142,6 +142,22 @@ private:
     icg_ba *h_ = nullptr;
 };
 
+// Camera (IG/tracking/camera.cc): the point-wise model functions Tracking calls (host code in the library)
+class CameraModel {
+public:
+    explicit CameraModel(const icg_camera &c) : c_(c) {}
+    void undistortPoints(std::vector<Point2f> &pts) const { check(icg_camera_undistort_points(&c_, reinterpret_cast<float *>(pts.data()), (int) pts.size()), "icg_camera_undistort_points"); }
+    void distortPoints(std::vector<Point2f> &pts) const { check(icg_camera_distort_points(&c_, reinterpret_cast<float *>(pts.data()), (int) pts.size()), "icg_camera_distort_points"); }
+    Point2f distortCameraPoint(const double pc[3]) const {
+        Point2f out{};
+        check(icg_camera_distort_camera_points(&c_, pc, reinterpret_cast<float *>(&out), 1), "icg_camera_distort_camera_points");
+        return out;
+    }
+
+private:
+    icg_camera c_;
+};
+
 // cv::Ptr<cv::CLAHE> clahe_ = cv::createCLAHE(3.0, cv::Size(21, 21)) (IG/tracking/tracking.cc:62); clahe_->apply(img, img) (:141)
 class Clahe {
 public:

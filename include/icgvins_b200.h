@@ -99,6 +99,22 @@ int icg_klt_track_batch_dev(icg_klt *h, int n_total, const int32_t *dev_slots, c
                             int mode);
 int icg_klt_sync(icg_klt *h);
 
+/* ----- camera model of path A: HOST functions by design (<= 300 points per frame, FP64) ----- */
+typedef struct icg_camera {
+    double fx, fy, cx, cy, skew; /* intrinsic_(0,0), (1,1), (0,2), (1,2), (0,1)   (IG/tracking/camera.cc:29-33) */
+    double k1, k2, p1, p2, k3;   /* distortion_ in OpenCV order                    (:35-39) */
+} icg_camera;
+/* Camera::undistortPoints (IG/tracking/camera.cc:72-74) == cv::undistortPoints(pts, pts, K, D, Mat(), K); in place on n (x, y) floats */
+int icg_camera_undistort_points(const icg_camera *c, float *pts_xy, int n);
+/* Camera::distortPoints / distortPoint (:76-104): pixel2cam -> radtan -> cam2pixel, in place */
+int icg_camera_distort_points(const icg_camera *c, float *pts_xy, int n);
+/* Camera::distortCameraPoint (:106-120) for n camera-frame points (x, y, z) -> distorted pixels */
+int icg_camera_distort_camera_points(const icg_camera *c, const double *pc_xyz, float *px_xy, int n);
+/* Camera::pixel2cam (:126-130): pixels -> normalised camera points (x, y, 1) */
+int icg_camera_pixel2cam(const icg_camera *c, const float *px_xy, double *cam_xyz, int n);
+/* Camera::world2pixel (:144-146) = cam2pixel(R^T (pw - t)); R9 row-major body/camera attitude, t3 its position */
+int icg_camera_world2pixel(const icg_camera *c, const double *R9, const double *t3, const double *pw_xyz, float *px_xy, int n);
+
 /* ----- pre-pass of path A: cv::CLAHE (IG/tracking/tracking.cc:62 createCLAHE(3.0, Size(21, 21)); :141 clahe_->apply(img, img)) ----- */
 typedef struct icg_clahe icg_clahe;
 int icg_clahe_create(icg_clahe **h, int width, int height, int tiles_x, int tiles_y, double clip_limit, int device, void *stream);

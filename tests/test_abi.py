@@ -33,9 +33,13 @@ def test_no_cpu_fallback_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     from ic_gvins_b200 import IcgError
+    from ic_gvins_b200.ba import WindowSolver
+    from ic_gvins_b200.clahe import Clahe
+    from ic_gvins_b200.detect import Detector
     from ic_gvins_b200.klt import KltTracker
-    with pytest.raises(IcgError):
-        KltTracker(320, 240)
+    for make in (lambda: KltTracker(320, 240), lambda: Detector(320, 240), lambda: Clahe(320, 240), lambda: WindowSolver(max_windows=1)):
+        with pytest.raises(IcgError, match="no CUDA device|no CPU fallback"):
+            make()
 
 
 def test_product_does_not_import_oracle():

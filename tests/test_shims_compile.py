@@ -28,6 +28,11 @@ int main(int argc, char **) {
         std::vector<float> err;
         k.calcOpticalFlowPyrLK(a, a, p, q, st, err, icg_b200::Size(21, 21), 3, icg_b200::TermCriteria(3, 30, 0.01), 4);
         k.trackForwardBackward(a, a, p, q, st);
+        icg_b200::CameraModel cm(icg_camera{787, 787, 640, 280, 0, 0, 0, 0, 0, 0});
+        cm.undistortPoints(p);
+        cm.distortPoints(p);
+        const double pc[3] = {0.1, 0.2, 1.0};
+        cm.distortCameraPoint(pc);
         icg_b200::Clahe c(1280, 560);
         c.apply(nullptr, 1280, nullptr, 1280);
         icg_b200::BlockDetector d(1280, 560, 18, 32, 213 * 186);
