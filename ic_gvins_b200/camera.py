@@ -52,3 +52,11 @@ class Camera:
         check(lib().icg_camera_world2pixel(C.byref(self.c), vp(Rm.ctypes.data), vp(tv.ctypes.data), vp(a.ctypes.data), vp(out.ctypes.data), a.shape[0]),
               "icg_camera_world2pixel")
         return out
+
+
+def calculate_histogram(image) -> float:
+    """Tracking::calculateHistigram (IG/tracking/tracking.cc:88-104): the brightness statistic of the histogram gate"""
+    img = np.ascontiguousarray(image, np.uint8)
+    out = C.c_double()
+    check(lib().icg_tracking_histogram(vp(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], C.byref(out)), "icg_tracking_histogram")
+    return out.value

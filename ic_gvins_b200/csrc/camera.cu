@@ -107,4 +107,25 @@ int icg_camera_world2pixel(const icg_camera *c, const double *R9, const double *
     return ICG_OK;
 }
 
+// Tracking::calculateHistigram (IG/tracking/tracking.cc:88-104): cv::calcHist (256 uniform bins, float counts) then
+// sum_k hist[k] * (float) k / 256.0 in double, divided by cols * rows -- the brightness gate of Tracking::preprocessing (:115-133).
+int icg_tracking_histogram(const uint8_t *img, int width, int height, int stride, double *out) {
+    if (!img || !out || width < 1 || height < 1 || stride < width) {
+        set_error("icg_tracking_histogram: bad arguments");
+        return ICG_EINVAL;
+    }
+    unsigned cnt[256] = {0};
+    for (int y = 0; y < height; y++) {
+        const uint8_t *r = img + (size_t) y * stride;
+        for (int x = 0; x < width; x++) cnt[r[x]]++;
+    }
+    double hist = 0;
+    for (int k = 0; k < 256; k++) {
+        const float prod = (float) cnt[k] * (float) k;  // float x float, as histogram.at<float>(k) * (float) k
+        hist += (double) prod / 256.0;
+    }
+    *out = hist / (double) (width * height);  // hist /= (image.cols * image.rows): int product
+    return ICG_OK;
+}
+
 }  // extern "C"

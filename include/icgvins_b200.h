@@ -115,6 +115,10 @@ int icg_camera_pixel2cam(const icg_camera *c, const float *px_xy, double *cam_xy
 /* Camera::world2pixel (:144-146) = cam2pixel(R^T (pw - t)); R9 row-major body/camera attitude, t3 its position */
 int icg_camera_world2pixel(const icg_camera *c, const double *R9, const double *t3, const double *pw_xyz, float *px_xy, int n);
 
+/* Tracking::calculateHistigram (IG/tracking/tracking.cc:88-104): the brightness statistic of the histogram gate in
+ * Tracking::preprocessing (:115-133).  Host function (one pass over the frame). */
+int icg_tracking_histogram(const uint8_t *img, int width, int height, int stride, double *out);
+
 /* ----- pre-pass of path A: cv::CLAHE (IG/tracking/tracking.cc:62 createCLAHE(3.0, Size(21, 21)); :141 clahe_->apply(img, img)) ----- */
 typedef struct icg_clahe icg_clahe;
 int icg_clahe_create(icg_clahe **h, int width, int height, int tiles_x, int tiles_y, double clip_limit, int device, void *stream);

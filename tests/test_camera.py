@@ -65,3 +65,17 @@ def test_camera_rejects_bad_arguments():
     p = np.zeros((4, 2), np.float32)
     assert lib().icg_camera_undistort_points(C.byref(c), C.c_void_p(p.ctypes.data), 4) != 0
     assert b"bad arguments" in lib().icg_last_error()
+
+
+def test_histogram_gate_statistic_matches_cv2():
+    """Tracking::calculateHistigram (tracking.cc:88-104) restated with cv2.calcHist + the reference's float / double sequence"""
+    cv2 = pytest.importorskip("cv2")
+    from ic_gvins_b200.camera import calculate_histogram
+    rng = np.random.default_rng(11)
+    for img in (rng.integers(0, 256, (560, 1280), dtype=np.uint8), np.full((480, 640), 200, np.uint8),
+                (rng.normal(120, 30, (217, 333)).clip(0, 255)).astype(np.uint8)):
+        h = cv2.calcHist([img], [0], None, [256], [0, 256]).reshape(-1)  # float32 counts
+        acc = 0.0
+        for k in range(256):
+            acc += float(np.float32(h[k]) * np.float32(k)) / 256.0
+        assert calculate_histogram(img) == acc / (img.shape[0] * img.shape[1])
