@@ -225,6 +225,11 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- B200 arm
 def run_b200(args):
+    # the contract is ONE JSON line on stdout: libraries that chat on fd 1 (e.g. "NCCL version ..." at communicator creation) are sent
+    # to stderr for the duration of the run; the saved descriptor is used for the final line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -595,7 +600,8 @@ def run_b200(args):
         else:
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
     if rank == 0:
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     trk.close()
     for sv in solvers:
         sv.close()
