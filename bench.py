@@ -583,6 +583,14 @@ def run_b200(args):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": int(B * KLT_DRAM_BYTES_PER_FRAME_NCU),
                      "traffic_source": "ncu --set full, one launch at B = 148 (profiles/r1_klt_v2_ncu.md), scaled to this B", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": B * KLT_BYTES_PER_FRAME_TRACK},
+        # second roofline, informative: the window solve as a whole against the FP64 rate measured on this part (scripts/fp64_probe.cu:
+        # 36.3 TFLOP/s DFMA, 37.0 DMMA).  Algorithmic flops = SURVEY 8d's 5 MFLOP per LM iteration of a cfg-3 window x the 22 linearise +
+        # solve iterations of gvinsOptimization (5 + 15 + the two bookkeeping passes) x B windows; the path is latency-bound (profiles/r1_ba_stages.md)
+        "roofline_ba": ({"kernels": "gvinsOptimization kernel sequence (ba_lin_vis .. ba_accept), whole batch", "bound": "fp64", "unit": "TFLOP/s",
+                         "achieved": 5.0e6 * 22 * B / (ba_info["ms_per_batch"] * 1e-3) / 1e12, "peak": 36.3,
+                         "peak_source": "scripts/fp64_probe.cu on the gpurun B200 (profiles/r1_ba_stages.md)",
+                         "frac": 5.0e6 * 22 * B / (ba_info["ms_per_batch"] * 1e-3) / 1e12 / 36.3,
+                         "algorithmic_flops_per_batch": 5.0e6 * 22 * B} if ba_info else None),
         "klt_only": {"value": frames_per_step * args.steps / (ms_klt / 1e3), "unit": "frames/s"},
         "ba_only": ba_info,
         "sharded_ba": sharded,
