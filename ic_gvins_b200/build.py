@@ -22,7 +22,8 @@ SOURCES = {
     "klt.cu": ["-fmad=false"],
     "detect.cu": ["-fmad=false"],
     "clahe.cu": ["-fmad=false"],
-    "camera.cu": ["-fmad=false"],  # host code only; no contraction of the reference's double sequence
+    "camera.cu": ["-fmad=false"],
+    "fundamental.cu": ["-fmad=false"],  # host code only  # host code only; no contraction of the reference's double sequence
     "ba.cu": [],
 }
 

@@ -60,3 +60,16 @@ def calculate_histogram(image) -> float:
     out = C.c_double()
     check(lib().icg_tracking_histogram(vp(img.ctypes.data), img.shape[1], img.shape[0], img.strides[0], C.byref(out)), "icg_tracking_histogram")
     return out.value
+
+
+def findFundamentalMat(points1, points2, ransacReprojThreshold=3.0, confidence=0.99, maxIters=1000):
+    """cv2.findFundamentalMat(points1, points2, cv2.FM_RANSAC, ransacReprojThreshold, confidence) -> (F, status) as
+    Tracking::trackReferenceFrame uses it (IG/tracking/tracking.cc:547)"""
+    p1 = np.ascontiguousarray(np.array(points1, np.float32).reshape(-1, 2))
+    p2 = np.ascontiguousarray(np.array(points2, np.float32).reshape(-1, 2))
+    assert p1.shape == p2.shape
+    st = np.zeros(p1.shape[0], np.uint8)
+    F = np.zeros(9)
+    check(lib().icg_find_fundamental_mat_ransac(vp(p1.ctypes.data), vp(p2.ctypes.data), p1.shape[0], float(ransacReprojThreshold), float(confidence),
+                                                int(maxIters), vp(st.ctypes.data), vp(F.ctypes.data)), "icg_find_fundamental_mat_ransac")
+    return F.reshape(3, 3), st

@@ -115,6 +115,13 @@ int icg_camera_pixel2cam(const icg_camera *c, const float *px_xy, double *cam_xy
 /* Camera::world2pixel (:144-146) = cam2pixel(R^T (pw - t)); R9 row-major body/camera attitude, t3 its position */
 int icg_camera_world2pixel(const icg_camera *c, const double *R9, const double *t3, const double *pw_xyz, float *px_xy, int n);
 
+/* Drop-in for cv::findFundamentalMat(pts1, pts2, cv::FM_RANSAC, threshold, confidence, status) as Tracking::trackReferenceFrame calls it
+ * (IG/tracking/tracking.cc:547, maxIters = 1000): status[i] = 1 for the inliers of the best 7-point model; F9 (row-major, may be NULL)
+ * receives that model.  HOST function in this round (<= 300 pairs, serially adaptive loop); the inlier mask is identical to OpenCV's
+ * (tests/golden/fundamental_golden.npz).  n >= 15 as at the call site. */
+int icg_find_fundamental_mat_ransac(const float *pts1_xy, const float *pts2_xy, int n, double threshold, double confidence, int max_iters,
+                                    uint8_t *status, double *F9);
+
 /* Tracking::calculateHistigram (IG/tracking/tracking.cc:88-104): the brightness statistic of the histogram gate in
  * Tracking::preprocessing (:115-133).  Host function (one pass over the frame). */
 int icg_tracking_histogram(const uint8_t *img, int width, int height, int stride, double *out);
