@@ -72,6 +72,7 @@ def _declare(L: C.CDLL) -> None:
     L.icg_camera_pixel2cam.argtypes = [vp, vp, vp, C.c_int]
     L.icg_camera_world2pixel.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     L.icg_tracking_histogram.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
+    L.icg_triangulate_points.argtypes = [vp, vp, vp, vp, C.c_int, vp]
     L.icg_find_fundamental_mat_ransac.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp]
     # ---- CLAHE
     L.icg_clahe_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, vp]
@@ -109,7 +110,7 @@ EXPORTS = [
     "icg_klt_upload_level0", "icg_klt_slot_level0", "icg_klt_slot_level", "icg_klt_build_pyramids",
     "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
     "icg_detect_create", "icg_detect_destroy", "icg_detect_blocks", "icg_corner_subpix",
-    "icg_camera_undistort_points", "icg_camera_distort_points", "icg_camera_distort_camera_points", "icg_camera_pixel2cam", "icg_camera_world2pixel", "icg_tracking_histogram", "icg_find_fundamental_mat_ransac",
+    "icg_camera_undistort_points", "icg_camera_distort_points", "icg_camera_distort_camera_points", "icg_camera_pixel2cam", "icg_camera_world2pixel", "icg_tracking_histogram", "icg_find_fundamental_mat_ransac", "icg_triangulate_points",
     "icg_clahe_create", "icg_clahe_destroy", "icg_clahe_apply", "icg_clahe_apply_dev", "icg_clahe_sync",
     "icg_imu_preintegrate", "icg_ba_create", "icg_ba_destroy", "icg_ba_solve", "icg_ba_upload", "icg_ba_run", "icg_ba_download",
     "icg_ba_sync", "icg_nccl_unique_id", "icg_ba_set_shard", "icg_ba_gvins_optimization", "icg_ba_run_gvins", "icg_ba_gvins_optimization_begin", "icg_ba_gvins_optimization_end", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate", "icg_ba_marginalize",

@@ -73,3 +73,15 @@ def findFundamentalMat(points1, points2, ransacReprojThreshold=3.0, confidence=0
     check(lib().icg_find_fundamental_mat_ransac(vp(p1.ctypes.data), vp(p2.ctypes.data), p1.shape[0], float(ransacReprojThreshold), float(confidence),
                                                 int(maxIters), vp(st.ctypes.data), vp(F.ctypes.data)), "icg_find_fundamental_mat_ransac")
     return F.reshape(3, 3), st
+
+
+def triangulatePoints(Tcw0, Tcw1, pc0, pc1):
+    """Tracking::triangulatePoint (IG/tracking/tracking.cc:796-808) for n pairs: Tcw0 (n, 3, 4), Tcw1 (3, 4), pc0 / pc1 (n, 2 or 3) -> pw (n, 3)"""
+    a = np.ascontiguousarray(np.array(Tcw0, np.float64).reshape(-1, 12))
+    b = np.ascontiguousarray(np.array(Tcw1, np.float64).reshape(12))
+    p0 = np.ascontiguousarray(np.array(pc0, np.float64).reshape(a.shape[0], -1)[:, :2])
+    p1 = np.ascontiguousarray(np.array(pc1, np.float64).reshape(a.shape[0], -1)[:, :2])
+    out = np.zeros((a.shape[0], 3))
+    check(lib().icg_triangulate_points(vp(a.ctypes.data), vp(b.ctypes.data), vp(p0.ctypes.data), vp(p1.ctypes.data), a.shape[0], vp(out.ctypes.data)),
+          "icg_triangulate_points")
+    return out

@@ -265,4 +265,57 @@ int icg_find_fundamental_mat_ransac(const float *pts1_xy, const float *pts2_xy, 
     return ICG_OK;
 }
 
+// Tracking::triangulatePoint (IG/tracking/tracking.cc:796-808) for n point pairs: rows of the 4 x 4 design matrix
+//   pc0.x * P0.row(2) - P0.row(0),  pc0.y * P0.row(2) - P0.row(1),  pc1.x * P1.row(2) - P1.row(0),  pc1.y * P1.row(2) - P1.row(1)
+// (P = T_c_w, 3 x 4 row-major), pw = right singular vector of the smallest singular value, dehomogenised (scale / sign invariant, so any
+// accurate SVD gives the reference's Eigen::JacobiSVD result up to rounding).  Host function: <= 300 pairs, the caller interleaves it
+// with map bookkeeping (:715-789).
+int icg_triangulate_points(const double *Tcw0 /* n x 12 */, const double *Tcw1 /* 12 */, const double *pc0_xy, const double *pc1_xy, int n,
+                           double *pw_xyz) {
+    if ((!Tcw0 || !Tcw1 || !pc0_xy || !pc1_xy || !pw_xyz) && n > 0) {
+        set_error("icg_triangulate_points: bad arguments");
+        return ICG_EINVAL;
+    }
+    for (int i = 0; i < n; i++) {
+        const double *P0 = Tcw0 + 12 * (size_t) i, *P1 = Tcw1;
+        double G[4][4], V[4][4];  // column-major columns of the design matrix / of V
+        for (int c = 0; c < 4; c++) {
+            G[c][0] = pc0_xy[2 * i] * P0[8 + c] - P0[c];
+            G[c][1] = pc0_xy[2 * i + 1] * P0[8 + c] - P0[4 + c];
+            G[c][2] = pc1_xy[2 * i] * P1[8 + c] - P1[c];
+            G[c][3] = pc1_xy[2 * i + 1] * P1[8 + c] - P1[4 + c];
+            for (int r = 0; r < 4; r++) V[c][r] = r == c ? 1.0 : 0.0;
+        }
+        for (int sweep = 0; sweep < 60; sweep++) {  // one-sided Jacobi: orthogonalise the columns
+            bool rotated = false;
+            for (int p = 0; p < 3; p++)
+                for (int q = p + 1; q < 4; q++) {
+                    double al = 0, be = 0, ga = 0;
+                    for (int r = 0; r < 4; r++) al += G[p][r] * G[p][r], be += G[q][r] * G[q][r], ga += G[p][r] * G[q][r];
+                    if (ga == 0.0 || fabs(ga) <= 1e-16 * sqrt(al * be)) continue;
+                    rotated = true;
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                    for (int r = 0; r < 4; r++) {
+                        const double x = G[p][r], y = G[q][r];
+                        G[p][r] = cs * x - sn * y, G[q][r] = sn * x + cs * y;
+                        const double vx = V[p][r], vy = V[q][r];
+                        V[p][r] = cs * vx - sn * vy, V[q][r] = sn * vx + cs * vy;
+                    }
+                }
+            if (!rotated) break;
+        }
+        int best = 0;
+        double bn = 1e300;
+        for (int c = 0; c < 4; c++) {
+            double nn = 0;
+            for (int r = 0; r < 4; r++) nn += G[c][r] * G[c][r];
+            if (nn < bn) bn = nn, best = c;
+        }
+        for (int k = 0; k < 3; k++) pw_xyz[3 * (size_t) i + k] = V[best][k] / V[best][3];
+    }
+    return ICG_OK;
+}
+
 }  // extern "C"

@@ -122,6 +122,11 @@ int icg_camera_world2pixel(const icg_camera *c, const double *R9, const double *
 int icg_find_fundamental_mat_ransac(const float *pts1_xy, const float *pts2_xy, int n, double threshold, double confidence, int max_iters,
                                     uint8_t *status, double *F9);
 
+/* Tracking::triangulatePoint (IG/tracking/tracking.cc:796-808) for n point pairs: Tcw0 = n x (3 x 4 row-major T_c_w of the reference frames),
+ * Tcw1 = the current frame's, pc0 / pc1 = normalised camera coordinates (x, y); pw = dehomogenised null vector of the 4 x 4 design matrix.
+ * Host function. */
+int icg_triangulate_points(const double *Tcw0, const double *Tcw1, const double *pc0_xy, const double *pc1_xy, int n, double *pw_xyz);
+
 /* Tracking::calculateHistigram (IG/tracking/tracking.cc:88-104): the brightness statistic of the histogram gate in
  * Tracking::preprocessing (:115-133).  Host function (one pass over the frame). */
 int icg_tracking_histogram(const uint8_t *img, int width, int height, int stride, double *out);

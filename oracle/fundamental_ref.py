@@ -121,3 +121,11 @@ def find_fm_ransac(m1,m2,thresh,conf,maxIters=1000):
                 niters=update_iters(conf,(count-good)/count,7,niters)
         it+=1
     return best
+
+
+def triangulate_point(T0, T1, pc0, pc1):
+    """Tracking::triangulatePoint (tracking.cc:796-808): T = 3 x 4 T_c_w; pw = V[:, -1] of the 4 x 4 design matrix, dehomogenised"""
+    T0, T1 = np.asarray(T0, float).reshape(3, 4), np.asarray(T1, float).reshape(3, 4)
+    D = np.stack([pc0[0] * T0[2] - T0[0], pc0[1] * T0[2] - T0[1], pc1[0] * T1[2] - T1[0], pc1[1] * T1[2] - T1[1]])
+    v = np.linalg.svd(D)[2][-1]
+    return v[:3] / v[3]

@@ -53,3 +53,27 @@ def test_degenerate_inputs():
     q = np.ones((20, 2), np.float32)
     F, st = findFundamentalMat(q, q, 1.5, 0.99)
     assert st.sum() == 0 and not F.any()
+
+
+def test_triangulation_matches_the_restatement_and_recovers_the_points():
+    """Tracking::triangulatePoint: product vs the numpy SVD restatement (1e-9 relative), and ground truth on noise-free views"""
+    from ic_gvins_b200.camera import triangulatePoints
+    rng = np.random.default_rng(8)
+    n = 200
+
+    def tcw(yaw, t):
+        R = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])  # R_w_c
+        return np.hstack([R.T, (-R.T @ np.asarray(t))[:, None]])
+
+    T1 = tcw(0.12, (0.9, 0.05, 0.2))
+    T0 = np.stack([tcw(0.01 * (k % 5), (0.1 * (k % 3), 0.0, 0.0)) for k in range(n)])
+    pw = np.stack([rng.uniform(-10, 10, n), rng.uniform(-4, 4, n), rng.uniform(8, 60, n)], 1)
+    pc0 = np.stack([(T0[k] @ np.append(pw[k], 1.0)) for k in range(n)])
+    pc1 = (T1 @ np.hstack([pw, np.ones((n, 1))]).T).T
+    pc0, pc1 = pc0[:, :2] / pc0[:, 2:], pc1[:, :2] / pc1[:, 2:]
+    got = triangulatePoints(T0, T1, pc0, pc1)
+    assert np.abs(got - pw).max() <= 1e-8 * np.abs(pw).max()
+    noisy0, noisy1 = pc0 + rng.normal(0, 1e-3, pc0.shape), pc1 + rng.normal(0, 1e-3, pc1.shape)
+    got = triangulatePoints(T0, T1, noisy0, noisy1)
+    want = np.stack([ref.triangulate_point(T0[k], T1, noisy0[k], noisy1[k]) for k in range(n)])
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
