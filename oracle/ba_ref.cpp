@@ -843,12 +843,23 @@ SolveSummary solve(WindowProblem &W, int max_num_iterations, int num_threads) {
             double h = hl[l] + D2[nc + l];
             hinv[l]  = 1.0 / h;
         }
+        // only camera columns that couple to some landmark have a non-zero row in W (the mix blocks never do): restricting the
+        // Schur update to them skips exact zeros only -- same values, as Ceres' block-sparse Schur eliminator does structurally
+        std::vector<int> nzrow;
         for (int i = 0; i < nc; i++) {
+            const double *wi = &Wm[(size_t) i * L];
+            bool any = false;
+            for (int l = 0; l < L && !any; l++) any = wi[l] != 0.0;
+            if (any) nzrow.push_back(i);
+        }
+        for (size_t ii = 0; ii < nzrow.size(); ii++) {
+            const int i = nzrow[ii];
             const double *wi = &Wm[(size_t) i * L];
             double s = 0;
             for (int l = 0; l < L; l++) s += wi[l] * hinv[l] * (-gl[l]);
             rhs[i] -= s;
-            for (int j = i; j < nc; j++) {
+            for (size_t jj = ii; jj < nzrow.size(); jj++) {
+                const int j = nzrow[jj];
                 const double *wj = &Wm[(size_t) j * L];
                 double t = 0;
                 for (int l = 0; l < L; l++) t += wi[l] * hinv[l] * wj[l];
