@@ -548,9 +548,13 @@ void evaluate_block(const Program &P, const Residual &R, bool want_jac, EvalBloc
     E.nres = nres;
     E.r.assign(nres, 0.0);
     const int nb = (int) R.blocks.size();
-    std::vector<const double *> params(nb);
-    std::vector<std::vector<double>> Jg(nb);
-    std::vector<double *> jp(nb, nullptr);
+    // scratch reused across calls (per thread): the evaluation runs ~3 000 times per LM iteration, allocation must stay out of it
+    static thread_local std::vector<const double *> params;
+    static thread_local std::vector<std::vector<double>> Jg;
+    static thread_local std::vector<double *> jp;
+    params.assign(nb, nullptr);
+    jp.assign(nb, nullptr);
+    if ((int) Jg.size() < nb) Jg.resize(nb);
     for (int i = 0; i < nb; i++) {
         const Block &B = P.blocks[R.blocks[i]];
         params[i]      = override_data ? (*override_data)[R.blocks[i]] : B.data;
@@ -598,9 +602,12 @@ void evaluate_block(const Program &P, const Residual &R, bool want_jac, EvalBloc
         for (auto &v : E.r) v *= residual_scaling;
     }
     if (want_jac) {
-        E.J.assign(nb, {});
+        E.J.resize(nb);
         for (int i = 0; i < nb; i++) {
-            if (!jp[i]) continue;
+            if (!jp[i]) {
+                E.J[i].clear();
+                continue;
+            }
             const Block &B = P.blocks[R.blocks[i]];
             // local parameterization: J_local = J_global * [I6; 0] for poses (pose_parameterization.h:51-57), identity otherwise
             E.J[i].assign((size_t) nres * B.lsize, 0.0);
