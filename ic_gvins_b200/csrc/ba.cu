@@ -41,6 +41,7 @@ using namespace bam;
 constexpr int BA_SPLIT_J = 1;   // the vision Gram matrix is produced whole by ba_pair_gram
 constexpr int BA_SPLIT_W = 4;   // row splits of the Schur SYRK (partials summed in fixed order -> deterministic)
 constexpr int BA_CHOL_NB = 8;   // Cholesky block width
+constexpr int BA_MARG_MAXB = 72;  // remained blocks of a prior: <= 2 max_K + 2 = 66 at max_K = 32 (table stride)
 
 struct BaCaps {
     int NW, K, L, F, G, R;     // capacities
@@ -64,6 +65,8 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     double *pose, *mix, *ext, *rho;          // current parameters
     double *pose_c, *mix_c, *ext_c, *rho_c;  // candidate
     double *pose_0, *mix_0, *ext_0, *rho_0;  // initial copy (for re-running the same problem: bench)
+    uint8_t *f_active_0;                     // pristine copies of what the two-pass protocol mutates (restart re-solves the UPLOADED problem)
+    double *gnss_std_0;
     int *f_lm, *f_ref, *f_obs;
     double *f_const;
     uint8_t *f_active;
@@ -507,8 +510,8 @@ __device__ void imu_factor_warp(const double *blob, const double *U, const doubl
 // marginalization prior (IG/factors/marginalization_factor.h:47-101): dx of every remained block
 __device__ void marg_dx(const BaCaps &C, const BaDev &D, int w, const WinDims &dm, const double *pose, const double *mix, const double *ext, double *dx,
                         int *colmap, int tid, int nthreads) {
-    const int *type = D.marg_type + (size_t) w * 64, *node = D.marg_node + (size_t) w * 64;
-    const double *x0 = D.marg_x0 + (size_t) w * 64 * 9;
+    const int *type = D.marg_type + (size_t) w * BA_MARG_MAXB, *node = D.marg_node + (size_t) w * BA_MARG_MAXB;
+    const double *x0 = D.marg_x0 + (size_t) w * BA_MARG_MAXB * 9;
     if (tid == 0) {
         int col = 0, xo = 0;
         for (int b = 0; b < dm.marg_nb; b++) {
@@ -1493,13 +1496,13 @@ struct HostDev {  // pinned host staging + device array
 struct icg_ba {
     BaCaps C;
     BaDev D;
-    int device;
-    cudaStream_t stream;
+    int device = 0;
+    cudaStream_t stream = nullptr;
     cudaStream_t stream_cam = nullptr;  // the camera-only factors are linearised concurrently with the vision chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool own_stream;
-    int nblk_vis;
-    int cur_windows;
+    bool own_stream = false;
+    int nblk_vis = 0;
+    int cur_windows = 0;
     size_t smem_cam, smem_solve, smem_schur;
     int ld_schur;
     int use_global_S;
@@ -1694,8 +1697,10 @@ int icg_imu_preintegrate(const double *state16, const double *iewn3, const doubl
     return ICG_OK;
 }
 
+static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int max_F, int max_gnss, int max_marg_r, void *stream);
+
 int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F, int max_gnss, int max_marg_r, int device, void *stream) {
-    if (!out || max_windows < 1 || max_K < 2 || max_K > 32 || max_L < 1 || max_F < 1 || max_gnss < 0 || max_marg_r < 0) {
+    if (!out || max_windows < 1 || max_K < 2 || max_K > 32 || max_L < 0 || max_F < 0 || max_gnss < 0 || max_marg_r < 0) {
         set_error("icg_ba_create: bad arguments");
         return ICG_EINVAL;
     }
@@ -1717,11 +1722,22 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     }
     icg_ba *h = new icg_ba();
     h->device = device;
-    h->own_stream = stream == nullptr;
-    if (stream)
+    const int rc_init = ba_create_body(h, max_windows, max_K, max_L, max_F, max_gnss, max_marg_r, stream);
+    if (rc_init != ICG_OK) {  // every failure path releases what was already allocated (streams, events, pinned + device memory)
+        icg_ba_destroy(h);
+        return rc_init;
+    }
+    *out = h;
+    return ICG_OK;
+}
+
+static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int max_F, int max_gnss, int max_marg_r, void *stream) {
+    if (stream) {
         h->stream = (cudaStream_t) stream;
-    else
+    } else {
         ICG_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+    }
     {   // the forked camera-factor kernels are one latency-bound CTA per window: give them priority so that they are placed before the
         // wide vision kernels fill the SMs (otherwise they start late and then contend with the Schur / Gram kernels)
         int prio_lo = 0, prio_hi = 0;
@@ -1733,6 +1749,7 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     h->prof = getenv("ICG_BA_PROFILE") != nullptr;
     if (getenv("ICG_BA_PROFILE_SKIP")) h->prof_skip = atoi(getenv("ICG_BA_PROFILE_SKIP"));
     BaCaps &C = h->C;
+    max_L = std::max(1, max_L), max_F = std::max(1, max_F);  // capacities stay >= 1; windows without landmarks (first keyframes, IG/ic_gvins.cc:1698) are accepted
     C.NW = max_windows, C.K = max_K, C.L = max_L, C.F = max_F, C.G = std::max(1, max_gnss), C.R = std::max(1, max_marg_r);
     C.NCV = 6 * max_K + 7, C.N = 15 * max_K + 7, C.NS = (C.N + 3) & ~3, C.NCA = 4 * ((C.NCV + 1 + 3) / 4);
     C.RJ = (2 * max_F + 31) & ~31, C.LP = (max_L + 31) & ~31;
@@ -1746,9 +1763,9 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     }
     HD(dims, NW) HD(st, NW) HD(pose, NW * C.K * 7) HD(mix, NW * C.K * 9) HD(ext, NW * 8) HD(rho, NW * C.L) HD(f_const, NW * C.F * 14)
     HD(imu_blob, NW * C.K * ICG_IMU_BLOB_DOUBLES) HD(imu_U, NW * C.K * 225) HD(gnss_blh, NW * C.G * 3) HD(gnss_std, NW * C.G * 3) HD(lever, NW * 3)
-    HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * 64 * 9)
+    HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * BA_MARG_MAXB * 9)
     HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
-    HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * 64) HD(marg_node, NW * 64) HD(f_active, NW * C.F)
+    HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * BA_MARG_MAXB) HD(marg_node, NW * BA_MARG_MAXB) HD(f_active, NW * C.F)
     HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F) HD(f_meta_s, NW * C.F * 4) HD(vb_lm0, NW * C.NVB) HD(f_const_s, NW * C.F * 14)
     HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
 #undef HD
@@ -1771,6 +1788,12 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     DM(jcomp, NW * C.F * 40) DM(costf, NW * C.F) DM(hl, NW * C.L) DM(gl, NW * C.L) DM(scale_l, NW * C.L) DM(scale_c, NW * C.NS)
     DM(Hc, NW * C.NS * C.NS) DM(gc, NW * C.NS) DM(Hs, NW * C.NS * C.NS) DM(cost_part, NW * (h->nblk_vis + 1)) DM(red, NW * (2 * (size_t) C.NCA * C.NCA + 8)) DM(redmax, NW) DM(red2, NW * 4) DM(step_c, NW * C.NS) DM(step_l, NW * C.L)
 #undef DM
+    if (rc == ICG_OK) rc = dmalloc(h, &D.gnss_std_0, NW * C.G * 3);
+    if (rc == ICG_OK) {
+        double *fa0 = nullptr;
+        rc = dmalloc(h, &fa0, (NW * C.F + 7) / 8 + 1);
+        D.f_active_0 = (uint8_t *) fa0;
+    }
     if (rc != ICG_OK) return rc;
     // shared-memory budgets
     h->smem_cam = sizeof(double) * ((size_t) C.K * 480 + (size_t) C.G * 24 + 48 + 16 + 2 * (size_t) C.R + 8) + sizeof(int) * (size_t) C.R + 64;
@@ -1793,14 +1816,13 @@ int icg_ba_create(icg_ba **out, int max_windows, int max_K, int max_L, int max_F
     ICG_CUDA(cudaFuncSetAttribute(ba_cost_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
     ICG_CUDA(cudaStreamSynchronize(h->stream));
     h->cur_windows = 0;
-    *out = h;
     return ICG_OK;
 }
 
 void icg_ba_destroy(icg_ba *h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     prof_collect(h);
     prof_print(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
@@ -1815,7 +1837,7 @@ void icg_ba_destroy(icg_ba *h) {
     if (h->stream_cam) cudaStreamSynchronize(h->stream_cam), cudaStreamDestroy(h->stream_cam);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -1838,8 +1860,8 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     } while (0)
     auto pack_one = [&](int w, std::string &err) -> int {
         const icg_ba_problem &p = P[w];
-        if (p.K < 2 || p.K > C.K || p.L < 1 || p.L > C.L || p.F < 0 || p.F > C.F || p.n_imu < 0 || p.n_imu > p.K - 1 || p.n_gnss < 0 || p.n_gnss > C.G ||
-            p.marg_r < 0 || p.marg_r > C.R || p.marg_nblocks < 0 || p.marg_nblocks > 64 || !p.pose || !p.mix || !p.ext || !p.invdepth) {
+        if (p.K < 2 || p.K > C.K || p.L < 0 || p.L > C.L || p.F < 0 || p.F > C.F || p.n_imu < 0 || p.n_imu > p.K - 1 || p.n_gnss < 0 || p.n_gnss > C.G ||
+            p.marg_r < 0 || p.marg_r > C.R || p.marg_nblocks < 0 || p.marg_nblocks > 2 * C.K + 2 || !p.pose || !p.mix || !p.ext || !p.invdepth) {
             PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d exceeds the handle's capacity or has null parameter arrays (K=%d L=%d F=%d gnss=%d marg_r=%d)", w, p.K, p.L, p.F,
                       p.n_gnss, p.marg_r);
         }
@@ -1962,13 +1984,13 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
                 }
                 tot += (t == 0 || t == 2) ? 7 : t == 1 ? 9 : 1;
                 cols += (t == 0 || t == 2) ? 6 : t == 1 ? 9 : 1;
-                h->marg_type.h[(size_t) w * 64 + b] = t;
-                h->marg_node.h[(size_t) w * 64 + b] = p.marg_block_node[b];
+                h->marg_type.h[(size_t) w * BA_MARG_MAXB + b] = t;
+                h->marg_node.h[(size_t) w * BA_MARG_MAXB + b] = p.marg_block_node[b];
             }
-            if (cols != r || tot > 64 * 9) {
+            if (cols != r || tot > BA_MARG_MAXB * 9) {
                 PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d marginalization prior size mismatch (blocks give %d columns, marg_r=%d)", w, cols, r);
             }
-            memcpy(h->marg_x0.h + (size_t) w * 64 * 9, p.marg_x0, sizeof(double) * tot);
+            memcpy(h->marg_x0.h + (size_t) w * BA_MARG_MAXB * 9, p.marg_x0, sizeof(double) * tot);
             double *H0 = h->marg_H0.h + (size_t) w * C.R * C.R, *b0 = h->marg_b0.h + (size_t) w * C.R;
             for (int i = 0; i < r; i++) {
                 for (int j = i; j < r; j++) {
@@ -2025,6 +2047,8 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     ICG_CUDA(cudaMemcpyAsync(D.mix_0, D.mix, sizeof(double) * (size_t) C.NW * C.K * 9, cudaMemcpyDeviceToDevice, s));
     ICG_CUDA(cudaMemcpyAsync(D.ext_0, D.ext, sizeof(double) * (size_t) C.NW * 8, cudaMemcpyDeviceToDevice, s));
     ICG_CUDA(cudaMemcpyAsync(D.rho_0, D.rho, sizeof(double) * (size_t) C.NW * C.L, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.f_active_0, D.f_active, (size_t) C.NW * C.F, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.gnss_std_0, D.gnss_std, sizeof(double) * (size_t) C.NW * C.G * 3, cudaMemcpyDeviceToDevice, s));
     // the dense SYRK operands keep a fixed sparsity pattern per problem: zero them once here
     h->cur_windows = n;
     return ICG_OK;
@@ -2143,9 +2167,10 @@ static int restore_params(icg_ba *h) {
     ICG_CUDA(cudaMemcpyAsync(D.mix, D.mix_0, sizeof(double) * (size_t) n * C.K * 9, cudaMemcpyDeviceToDevice, s));
     ICG_CUDA(cudaMemcpyAsync(D.ext, D.ext_0, sizeof(double) * (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
     ICG_CUDA(cudaMemcpyAsync(D.rho, D.rho_0, sizeof(double) * (size_t) n * C.L, cudaMemcpyDeviceToDevice, s));
-    // problem data the two-pass protocol mutates: factor activity, GNSS std, GNSS loss flag
-    ICG_CUDA(h->f_active.up(s, (size_t) n * C.F));
-    ICG_CUDA(h->gnss_std.up(s, (size_t) n * C.G * 3));
+    // problem data the two-pass protocol mutates: factor activity, GNSS std (device-side pristine copies: the pinned staging buffers
+    // receive the culled / re-weighted results in icg_ba_gvins_optimization_end), GNSS loss flag
+    ICG_CUDA(cudaMemcpyAsync(D.f_active, D.f_active_0, (size_t) n * C.F, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.gnss_std, D.gnss_std_0, sizeof(double) * (size_t) n * C.G * 3, cudaMemcpyDeviceToDevice, s));
     ICG_CUDA(h->dims.up(s, n));
     return ICG_OK;
 }
@@ -2354,8 +2379,15 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
             tl[p.f_lm[f]] = 1, tp[p.f_obs[f]] = 1, any_vis = true;
         }
         bool has_ext = any_vis, has_td = any_vis;
-        for (int k = 0; k < nm; k++) tp[k] = tm[k] = 1;
-        if (p.n_imu >= nm) tp[nm] = tm[nm] = 1;  // factor nm-1 joins node nm-1 and node nm
+        // a block exists in the marginalization problem only if some factor touches it (MarginalizationInfo::addResidualBlockInfo,
+        // marginalization_info.h:103-121): removed nodes without any factor get no columns
+        for (int f = 0; f < p.F; f++)
+            if (!(p.f_active && !p.f_active[f]) && p.f_ref[f] < nm) tp[p.f_ref[f]] = 1;
+        for (int k = 0; k < nm && k < p.n_imu; k++) tp[k] = tm[k] = tp[k + 1] = tm[k + 1] = 1;  // factor k joins node k and node k + 1
+        for (int g = 0; g < p.n_gnss; g++)
+            if (p.gnss_node[g] < nm) tp[p.gnss_node[g]] = 1;
+        if (p.has_pose_prior) tp[0] = 1;
+        if (p.has_mix_prior) tm[0] = 1;
         for (int b = 0; b < p.marg_nblocks && p.marg_r > 0; b++) {
             const int t = p.marg_block_type[b], nd = p.marg_block_node[b];
             if (t == 0) tp[nd] = 1;
@@ -2365,7 +2397,10 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
         }
         int idx = 0;
         for (int k = 0; k < C.K; k++) pose_col[k] = mix_col[k] = -1;
-        for (int k = 0; k < nm; k++) pose_col[k] = idx, idx += 6, mix_col[k] = idx, idx += 9;
+        for (int k = 0; k < nm; k++) {
+            if (tp[k]) pose_col[k] = idx, idx += 6;
+            if (tm[k]) mix_col[k] = idx, idx += 9;
+        }
         for (int l = 0; l < C.L; l++) lm_col[l] = -1;
         for (int l = 0; l < p.L; l++)
             if (tl[l]) lm_col[l] = idx++;

@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(256) marg_assemble(BaCaps C, BaDev D, MargDev 
     if (dm.marg_r > 0) {
         const int r = dm.marg_r;
         if (tid == 0) {
-            const int *type = D.marg_type + (size_t) w * 64, *node = D.marg_node + (size_t) w * 64;
-            const double *x0 = D.marg_x0 + (size_t) w * 64 * 9;
+            const int *type = D.marg_type + (size_t) w * BA_MARG_MAXB, *node = D.marg_node + (size_t) w * BA_MARG_MAXB;
+            const double *x0 = D.marg_x0 + (size_t) w * BA_MARG_MAXB * 9;
             int col = 0, xo = 0;
             for (int b = 0; b < dm.marg_nb; b++) {
                 const int t = type[b], nd = node[b];
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) marg_assemble(BaCaps C, BaDev D, MargDev 
     // ---- GNSS at the removed nodes (:1505-1516), first-window priors (:1542-1554): pose / mix diagonal blocks, thread per entry
     for (int e = tid; e < nm * 42; e += blockDim.x) {
         const int k = e / 42, q = e % 42;
-        if (k >= K) continue;
+        if (k >= K || pose_col[k] < 0) continue;  // a removed node no factor touches has no columns
         double s = 0;
         const int a = q < 36 ? q / 6 : q - 36, b = q % 6;
         for (int g = 0; g < dm.n_gnss; g++) {

@@ -780,6 +780,8 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
         return ICG_EINVAL;
     }
     ICG_CUDA(cudaSetDevice(h->device));
+    // a producer may have written these level-0 planes in place (icg_klt_slot_level0): the host API's content cache must not hit on them
+    for (int sl = first_slot; sl < first_slot + count; sl++) h->slot_hash[sl] = 0;
     for (int l = 1; l < KLT_LEVELS; l++) {
         const KltLevel &s = h->lv[l - 1], &d = h->lv[l];
         dim3 grid((d.W + 255) / 256, (d.H + 3) / 4, count);
