@@ -82,7 +82,8 @@ def imu_samples(t0, t1, rate, rng, bg, ba, yaw_rate=5.0 * D2R):
 
 
 # ---------------------------------------------------------------------------------------------- problem
-def make_window(preintegrate, K=10, L=300, seed=2024, full_visibility=False, perturb=True, with_marg=False, pixel_noise=0.5):
+def make_window(preintegrate, K=10, L=300, seed=2024, full_visibility=False, perturb=True, with_marg=False, pixel_noise=0.5, with_priors=False,
+                gnss_every=2):
     rng = np.random.Generator(np.random.PCG64(seed))
     dtk, rate = 0.5, 200.0
     times = np.arange(K) * dtk
@@ -142,7 +143,7 @@ def make_window(preintegrate, K=10, L=300, seed=2024, full_visibility=False, per
     pn_all = np.concatenate(pn_all, axis=0)
 
     # ---- GNSS on every 2nd node
-    gnss_node = np.arange(0, K, 2, dtype=np.int32)
+    gnss_node = np.arange(0, K, gnss_every, dtype=np.int32)
     gnss_std = np.tile(np.array([0.05, 0.05, 0.1]), (len(gnss_node), 1))
     gnss_blh = np.zeros((len(gnss_node), 3))
     for i, k in enumerate(gnss_node):
@@ -192,5 +193,16 @@ def make_window(preintegrate, K=10, L=300, seed=2024, full_visibility=False, per
         x0 = np.concatenate([pose_t[0], mix_t[0], pose_t[1], mix_t[1], ext_t[:7], [0.0]])
         prob.update(marg_r=r, marg_nblocks=len(types), marg_block_type=types, marg_block_node=nodes, marg_x0=x0,
                     marg_J0=J0.reshape(-1).copy(), marg_e0=rng.normal(0, 0.1, r))
+    if with_priors:
+        # first-window priors as GVINS::constructPrior builds them (IG/ic_gvins.cc:720-760): the initial pose / mix of node 0 with their stds
+        pp = pose_t[0].copy()
+        pp[:3] += rng.normal(0, 0.05, 3)
+        q = q_mul(pp[3:], q_from_rotvec(rng.normal(0, 0.2 * D2R, 3)))
+        pp[3:] = q / np.linalg.norm(q)
+        mp = mix_t[0].copy()
+        mp[:3] += rng.normal(0, 0.05, 3)
+        prob.update(has_pose_prior=1, pose_prior=pp, pose_prior_std=np.array([0.1, 0.1, 0.2, 0.5 * D2R, 0.5 * D2R, 1.0 * D2R]),
+                    has_mix_prior=1, mix_prior=mp,
+                    mix_prior_std=np.array([0.1, 0.1, 0.1] + [100.0 * D2R / 3600.0] * 3 + [100.0 * 1e-5] * 3))
     truth = dict(pose=pose_t, mix=mix_t, ext=ext_t, invdepth=invdepth_t)
     return prob, truth

@@ -97,6 +97,23 @@ def merge_shard(prob: dict, shard: dict) -> None:
         prob[k][...] = shard[k]
 
 
+def connect_shards(solver: "WindowSolver", rank: int, world: int, transport: str, dist) -> None:
+    """Join `solver` to the landmark-shard group of `world` processes (one per GPU).  `dist` is an initialised torch.distributed module
+    (any backend): it only carries the rendezvous blobs -- the ncclUniqueId for transport "nccl", the CUDA IPC handles of the exchange
+    buffers for transport "p2p" (peer-memory stores over NVLink, no NCCL on the data path)."""
+    if transport == "nccl":
+        ids = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        solver.set_shard(rank, world, ids[0])
+    elif transport == "p2p":
+        mine = solver.shard_export()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, mine)
+        solver.shard_connect(rank, world, blobs)
+    else:
+        raise ValueError(transport)
+
+
 def nccl_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     check(lib().icg_nccl_unique_id(buf), "icg_nccl_unique_id")
