@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=296, help="independent streams (frames in flight) per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames (LK pairs + window solves) per host process per CPU-arm repetition")
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--ba-handles", type=int, default=2, help="solver handles (CUDA streams) the B windows are split over")
     ap.add_argument("--no-sharded", action="store_true", help="skip the cfg-4 landmark-sharded BA section")
@@ -114,59 +114,29 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_klt_frames_per_sec(frames, pts, seconds: float, threads: int):
-    """The reference front end on host cores: cv2 (the OpenCV the reference links) called as tracking.cc:385-403 does.
-    Falls back to the C oracle port when cv2 is not importable.  Returns (frames/s, kind, cores, sample)."""
-    seq = frame_sequence(1000)
-    try:
-        import cv2
-        cv2.setNumThreads(threads)
-        crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 0.01)
+def cpu_arm_inputs(frames, pts, n_probs=4):
+    """Inputs of oracle/cpu_arm.py: the 10 adjacent frame pairs of the ping-pong sequence with their points, a few cfg-3 windows."""
+    import ctypes as C
+    import oracle
+    from tests import oracle_api as oa
+    seq = frame_sequence(10)
+    pairs = []
+    for k in range(10):
+        prev, init = pair_points(pts, seq[k], seq[k + 1], 99 + k)
+        pairs.append((seq[k], seq[k + 1], prev, init))
+    olib = C.CDLL(oracle.build())
+    oa.declare(olib)
+    oa.declare_ba(olib)
+    probs = make_windows(n_probs, lambda *a: oa.preintegrate(olib, *a))
+    return pairs, probs
 
-        def one(fa, fb, k):
-            prev, init = pair_points(pts, fa, fb, 99 + k)
-            fwd, st, _ = cv2.calcOpticalFlowPyrLK(frames[fa], frames[fb], prev.reshape(-1, 1, 2), init.reshape(-1, 1, 2).copy(),
-                                                  winSize=(21, 21), maxLevel=3, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
-            bwd, st2, _ = cv2.calcOpticalFlowPyrLK(frames[fb], frames[fa], fwd, prev.reshape(-1, 1, 2).copy(), winSize=(21, 21),
-                                                   maxLevel=3, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
-            return int(st.sum())
-        kind, cores = "reference", cv2.getNumThreads()
-        label = f"cv2 {cv2.__version__} calcOpticalFlowPyrLK fwd+bwd"
-    except Exception:
-        import ctypes as C
-        import oracle
-        from tests import oracle_api as oa
-        olib = C.CDLL(oracle.build())
-        oa.declare(olib)
 
-        def one(fa, fb, k):
-            prev, init = pair_points(pts, fa, fb, 99 + k)
-            return int(oa.track_fb(olib, frames[fa], frames[fb], prev, init)[2].sum())
-        kind, cores, label = "port", 1, "oracle/klt_ref.c fwd+bwd"
-    one(seq[0], seq[1], 0)
-    # throughput mode, like the GPU arm: `streams` independent streams in parallel host threads (cv2 / ctypes release the GIL), each
-    # call single-threaded inside -- the reference's own per-stream threading gains nothing at 300 points
-    streams = max(1, threads)
-    if kind == "reference":
-        import cv2
-        cv2.setNumThreads(1)
-    counts = [0] * streams
-    t0 = time.perf_counter()
-
-    def worker(t):
-        k = t
-        while time.perf_counter() - t0 < seconds:
-            one(seq[k % 10], seq[k % 10 + 1], k)
-            k += streams
-            counts[t] += 1
-    th = [threading.Thread(target=worker, args=(t,)) for t in range(streams)]
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
-    dt = time.perf_counter() - t0
-    k = sum(counts)
-    return k / dt, kind, streams, f"{k} frames over {streams} parallel streams (one host thread each) in {dt:.1f}s: {label}, 300 pts, 1280x560"
+def cpu_throughput(frames, pts, reps, n_frames, do_ba=True):
+    """The reference's CPU path in throughput mode on every usable host core (one pinned process per core, fixed work, median of `reps`):
+    oracle/cpu_arm.py.  Returns its result dict."""
+    from oracle import cpu_arm
+    pairs, probs = cpu_arm_inputs(frames, pts)
+    return cpu_arm.measure(frames, pairs, probs, reps=reps, n_frames=n_frames, do_ba=do_ba)
 
 
 def cpu_single_stream(frames, pts, seconds: float = 1.5):
@@ -212,78 +182,25 @@ def make_windows(n, preintegrate, seed0=2024):
     return [synth_ba.make_window(preintegrate, K=10, L=300, seed=seed0 + b)[0] for b in range(n)]
 
 
-def cpu_ba_solves_per_sec(seconds: float, threads: int = 1):
-    """The reference's window solve on host cores.  Ceres is not installed (and cannot be: no network), so this is the
-    oracle PORT of GVINS::gvinsOptimization (5 + chi2 culling + 15 LM iterations, DENSE_SCHUR), in throughput mode like the GPU
-    arm: one independent window per host thread.  Returns (solves/s, sample)."""
-    import copy
-    import ctypes as C
-    import oracle
-    from tests import oracle_api as oa
-    olib = C.CDLL(oracle.build())
-    oa.declare(olib)
-    oa.declare_ba(olib)
-    probs = make_windows(2, lambda *a: oa.preintegrate(olib, *a))
-
-    def one(p):
-        p = copy.deepcopy(p)
-        p["gnss_huber"] = 1
-        oa.ba_solve(olib, p, 5, threads)
-        rc, gc = oa.ba_residual_costs(olib, p)
-        std = p["gnss_std"].reshape(-1, 3)
-        for g in range(p["n_gnss"]):
-            if 2 * gc[g] > 7.815:
-                std[g] *= np.sqrt(2 * gc[g] / 7.815)
-        p["gnss_std"] = std.reshape(-1)
-        p["f_active"][2 * rc > 5.991] = 0
-        p["gnss_huber"] = 0
-        oa.ba_solve(olib, p, 15, threads)
-    one(probs[0])
-    # throughput mode: independent windows in parallel host threads, one solver thread each (the port does not speed up with
-    # num_threads = 4; Ceres' own threading is irrelevant once every core has a window of its own)
-    streams = max(1, os.cpu_count() or 1)
-    counts = [0] * streams
-    t0 = time.perf_counter()
-
-    def worker(t):
-        while time.perf_counter() - t0 < seconds:
-            one(probs[(t + counts[t]) % 2])
-            counts[t] += 1
-    th = [threading.Thread(target=worker, args=(t,)) for t in range(streams)]
-    for x in th:
-        x.start()
-    for x in th:
-        x.join()
-    dt = time.perf_counter() - t0
-    k = sum(counts)
-    return k / dt, f"{k} window solves over {streams} parallel host threads in {dt:.1f}s: oracle port of gvinsOptimization (K=10, L=300, 5+15 LM its)"
-
-
 def run_reference(args):
+    """`--impl reference`: the reference's CPU path on the box's host cores (rank 0 only).  Each of the W + K steps is one fixed-work
+    repetition of oracle/cpu_arm.py (every usable core: one pinned process, 8 frames each); value = median over the K timed steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     frames, pts = make_stream(1234)
-    threads = os.cpu_count() or 1
-    per_step = max(1.0, min(10.0, 120.0 / max(1, args.steps + args.warmup)))
-    vals = []
-    info = None
-    for i in range(args.warmup + args.steps):
-        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, per_step * (0.5 if not args.no_ba else 1.0), threads)
-        if not args.no_ba:
-            sps, bsample = cpu_ba_solves_per_sec(per_step * 0.5)
-            fps = 1.0 / (1.0 / fps + 1.0 / sps)  # one window solve per frame (conservative: every frame a keyframe)
-            sample = sample + " + " + bsample
-            kind = "reference(cv2 KLT) + port(BA oracle), throughput mode: one independent stream per host thread"
-        info = (kind, cores, sample)
-        if i >= args.warmup:
-            vals.append(fps)
-    v = float(np.mean(vals))
+    reps = max(1, args.steps + args.warmup)
+    res = cpu_throughput(frames, pts, reps=reps, n_frames=args.cpu_frames, do_ba=not args.no_ba)
+    timed = res["per_repetition"][args.warmup:] or res["per_repetition"]
+    v = float(np.median(timed))
+    res = dict(res, value=v, per_repetition_timed=timed)
     line = {"impl": "reference", "metric": "frames/sec (KLT+BA) 1280x560 300-feat 10-KF window", "value": v, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT)", "data": "synthetic",
-            "config": {"workload": WORKLOAD if not args.no_ba else WORKLOAD_KLT, "streams_per_gpu": 1},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": info[1], "kind": info[0], "sample": info[2]},
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * res["cores"] * args.cpu_frames / v,
+            "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT), f64 (BA)", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not args.no_ba else WORKLOAD_KLT, "streams_per_gpu": res["cores"],
+                       "note": "CPU arm: one independent stream per host core (streams_per_gpu = host processes here)"},
+            "cpu_baseline": res,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -665,16 +582,12 @@ def run_b200(args):
         "tracked_fraction": good / float(n_total),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, kind, cores, sample = cpu_klt_frames_per_sec(frames, pts, args.cpu_seconds * (0.5 if use_ba else 1.0), os.cpu_count() or 1)
+        res = cpu_throughput(frames, pts, reps=5, n_frames=args.cpu_frames, do_ba=use_ba)
         if use_ba:
-            sps, bsample = cpu_ba_solves_per_sec(args.cpu_seconds * 0.5)
             ss_klt, ss_ba = cpu_single_stream(frames, pts)
-            line["cpu_baseline"] = {"value": 1.0 / (1.0 / fps + 1.0 / sps), "unit": "frames/s", "cores": cores,
-                                    "single_stream": {"klt_frames_per_s": ss_klt, "ba_solves_per_s": ss_ba,
-                                                      "note": "one stream as the reference runs it: cv2 LK with all threads, one 4-thread solve at a time"}, "kind": "reference(cv2 KLT) + port(BA oracle), throughput mode: one independent stream per host thread",
-                                    "sample": sample + " + " + bsample, "klt_frames_per_s": fps, "ba_solves_per_s": sps}
-        else:
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+            res["single_stream"] = {"klt_frames_per_s": ss_klt, "ba_solves_per_s": ss_ba,
+                                    "note": "context: ONE stream as the reference runs it (cv2 LK with all threads, one 4-thread solve at a time)"}
+        line["cpu_baseline"] = res
     if rank == 0:
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
