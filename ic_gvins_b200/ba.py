@@ -106,10 +106,11 @@ def connect_shards(solver: "WindowSolver", rank: int, world: int, transport: str
         dist.broadcast_object_list(ids, src=0)
         solver.set_shard(rank, world, ids[0])
     elif transport == "p2p":
-        mine = solver.shard_export()
+        mine = solver.shard_export(rank, world)
         blobs = [None] * world
         dist.all_gather_object(blobs, mine)
-        solver.shard_connect(rank, world, blobs)
+        solver.shard_connect(blobs)
+        dist.barrier()
     else:
         raise ValueError(transport)
 
@@ -155,6 +156,18 @@ class WindowSolver:
         """Make this handle solve landmark shard `rank` of `world` (one process per GPU; NCCL all-reduce per LM attempt)."""
         buf = (C.c_uint8 * 128)(*unique_id) if unique_id else None
         check(lib().icg_ba_set_shard(self._h, rank, world, buf), "icg_ba_set_shard")
+
+    def shard_export(self, rank: int, world: int) -> bytes:
+        """Allocate this rank's peer-memory exchange buffer for a group of `world` ranks; returns the blob the other ranks need."""
+        buf = (C.c_uint8 * 128)()
+        check(lib().icg_ba_shard_export(self._h, rank, world, buf), "icg_ba_shard_export")
+        return bytes(buf)
+
+    def shard_connect(self, blobs) -> None:
+        """blobs: the `world` export blobs in rank order."""
+        raw = b"".join(blobs)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        check(lib().icg_ba_shard_connect(self._h, buf), "icg_ba_shard_connect")
 
     def solve(self, problems, max_num_iterations: int):
         """ceres::Solver::Solve on a list of problem dicts (updated in place).  Returns a list of summaries."""

@@ -22,6 +22,7 @@
 //   cost       : candidate cost (all factors, residuals only);   accept : Ceres step acceptance + radius update
 //   ba_marg.cuh: sliding-window marginalization (MarginalizationInfo) on the same device-resident linearisation
 #include <dlfcn.h>
+#include <unistd.h>
 #include <math.h>
 #include <nccl.h>
 #include <stdlib.h>
@@ -59,7 +60,19 @@ struct LmState {
     int iter, n_success, n_invalid, done, need_lin, last_success, first, step_valid, fresh_lin, max_iter, chol_ok;
 };
 
+// Exchange state of the split pipeline (ba_split.cuh): one buffer per rank holding the inbox of reduction operands, the step broadcast, the
+// scalar exchange and the epoch flags; `peer[r]` is rank r's buffer as mapped into this process (peer memory, CUDA IPC or same process)
+struct ShardDev {
+    int split;                 // 1: the split pipeline drives this handle (large systems and / or landmark shards)
+    int PK, BS, RV;            // packed partial length, step-broadcast stride, reduced-vector stride (doubles)
+    double *peer[8];
+    size_t off_inbox, off_bcast, off_scal, off_flagA, off_flagB, off_flagC;  // offsets in doubles, identical on every rank
+    double *redv;              // [NW][RV] owner-side reduced vectors: diag H_vis | g_vis | W phi g_l | cost, sum rho^2, max |g_l|
+    int *err;                  // device error word (flag wait timed out)
+};
+
 struct BaDev {  // device pointers (flat, capacity-strided by window)
+    ShardDev S;
     WinDims *dims;
     LmState *st;
     double *pose, *mix, *ext, *rho;          // current parameters
@@ -709,6 +722,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_lin_cam(BaCaps C, BaDev D) {
     const int w = blockIdx.x;
     LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
+    if (D.S.split && (w % D.world) != D.rank) return;  // split pipeline: the window's owner handles the camera-only factors
     const WinDims dm = D.dims[w];
     double c = cam_factors(C, D, w, dm, D.pose + (size_t) w * C.K * 7, D.mix + (size_t) w * C.K * 9, D.ext + (size_t) w * 8, true, smem);
     if (threadIdx.x == 0) st.cost_cam = c;
@@ -1212,6 +1226,7 @@ __global__ void __launch_bounds__(CAM_THREADS) ba_cost_cam(BaCaps C, BaDev D, in
     const int w = blockIdx.x;
     const LmState &st = D.st[w];
     if (st.done || !st.step_valid) return;
+    if (D.S.split && (w % D.world) != D.rank) return;
     const WinDims dm = D.dims[w];
     double c = cam_factors(C, D, w, dm, D.pose_c + (size_t) w * C.K * 7, D.mix_c + (size_t) w * C.K * 9, D.ext_c + (size_t) w * 8, false, smem);
     if (threadIdx.x == 0) D.cost_part[(size_t) w * (nblk_vis + 1) + nblk_vis] = c;
@@ -1421,6 +1436,7 @@ __global__ void ba_imu_eval_kernel(const double *blob, const double *U, const do
 
 }  // namespace icg
 
+#include "ba_split.cuh"
 #include "ba_marg.cuh"
 
 // ======================================================================================================= host side
@@ -1518,7 +1534,14 @@ struct icg_ba {
     HostDev<double> scratch;  // single-factor evaluation
     HostDev<LmState> st_save;   // pass-1 LM state of the two-pass protocol
     HostDev<int> cull_counters; // per window: reprojection factors removed, GNSS fixes re-weighted
-    void *comm = nullptr;       // ncclComm_t when this handle solves a landmark shard
+    void *comm = nullptr;       // ncclComm_t when this handle solves a landmark shard (transport "nccl")
+    // split pipeline (ba_split.cuh): exchange buffer of this rank, peers' buffers opened through CUDA IPC, epoch counter of the flags
+    double *xbuf = nullptr;
+    size_t xbuf_doubles = 0;
+    int x_world = 0;
+    void *ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long epoch = 0;
+    size_t smem_solve_cam = 0, smem_step_lm = 0;
     // in-situ stage timing (ICG_BA_PROFILE=1): events between the kernels of the LM sequence on the main stream, read back in
     // icg_ba_sync / icg_ba_download and printed by icg_ba_destroy (warm caches, real launch gaps -- unlike an ncu replay)
     bool prof = false;
@@ -1588,6 +1611,8 @@ static int nccl_allreduce(icg_ba *h, double *buf, size_t count, int op_max) {
 
 
 extern "C" {
+static int split_setup(icg_ba *h, int rank, int world);
+static void split_release(icg_ba *h);
 
 int icg_imu_preintegrate(const double *state16, const double *iewn3, const double *gravity3, const double *noise5, const double *imu, int n, double *blob,
                          double *end_state10) {
@@ -1801,13 +1826,14 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     size_t packed = sizeof(double) * ((size_t) (C.N + 1) * (C.N + 2) / 2);
     h->use_global_S = (vec + packed > 220 * 1024) ? 1 : 0;
     h->smem_solve = vec + (h->use_global_S ? 0 : packed);
-    if (h->use_global_S) {
-        rc = dmalloc(h, &D.Sglobal, NW * ((size_t) (C.N + 1) * (C.N + 2) / 2));
+    D.Sglobal = nullptr;
+    memset(&D.S, 0, sizeof(D.S));
+    if (h->use_global_S) {  // the reduced system does not fit one CTA: the split pipeline (cluster solve, S in L2) drives this handle
+        rc = split_setup(h, 0, 1);
         if (rc != ICG_OK) return rc;
     } else {
-        D.Sglobal = nullptr;
+        ICG_CUDA(cudaFuncSetAttribute(ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve));
     }
-    ICG_CUDA(cudaFuncSetAttribute(ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve));
     h->ld_schur = 16 * ((C.NCA + 15) / 16) + 8;  // = 8 mod 16 doubles: conflict-free fragment reads
     h->smem_schur = sizeof(double) * ((size_t) SCHUR_RCH * h->ld_schur + SCHUR_RCH);
     ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_schur));
@@ -1832,6 +1858,7 @@ void icg_ba_destroy(icg_ba *h) {
     h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
     h->f_slot.release(), h->f_meta_s.release(), h->vb_lm0.release(), h->f_const_s.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
+    split_release(h);
     if (h->marg_ready) h->marg_map.release(), h->marg_oJ0.release(), h->marg_oe0.release(), h->marg_oHp.release(), h->marg_obp.release();
     for (void *p : h->dev_only) cudaFree(p);
     if (h->stream_cam) cudaStreamSynchronize(h->stream_cam), cudaStreamDestroy(h->stream_cam);
@@ -2056,7 +2083,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
 
 // ---- in-situ stage timing
 static const char *PROF_NAMES[16] = {"(gap/other)", "lin_vis", "lin_lm", "pair_gram1", "pair_gram2", "schur_dmma", "join lin_cam + lin_done",
-                                     "pack1", "solve", "cost (+cost_cam)", "pack2", "accept", "hsum", "join gram chain", "", ""};
+                                     "pack1 / export + signal", "solve", "cost (+cost_cam)", "pack2 / exchange", "accept", "hsum / reduce", "join gram chain", "step_lm", ""};
 static void prof_mark(icg_ba *h, int tag) {
     if (!h->prof) return;
     if (h->prof_used == h->prof_ev.size()) {
@@ -2094,7 +2121,10 @@ static void prof_print(icg_ba *h) {
             fprintf(stderr, "  %-28s %9.3f ms  %8.1f us  %5.1f %%\n", PROF_NAMES[t], h->prof_ms[t], 1e3 * h->prof_ms[t] / h->prof_cnt[t], 100.0 * h->prof_ms[t] / tot);
 }
 
+static int enqueue_lm_split(icg_ba *h, int max_num_iterations);
+
 static int enqueue_lm(icg_ba *h, int max_num_iterations) {
+    if (h->D.S.split) return enqueue_lm_split(h, max_num_iterations);
     const BaCaps &C = h->C;
     const BaDev &D = h->D;
     const int n = h->cur_windows;
@@ -2153,6 +2183,136 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         ba_accept<<<n, 128, 0, s>>>(C, D, h->nblk_vis);
         prof_mark(h, 11);
         count_launch(h->comm ? 4 : 3);
+    }
+    ICG_CHECK_LAUNCH();
+    return ICG_OK;
+}
+
+// ---- split pipeline: host side
+static void split_release(icg_ba *h) {
+    for (int r = 0; r < 8; r++)
+        if (h->ipc_opened[r]) cudaIpcCloseMemHandle(h->ipc_opened[r]), h->ipc_opened[r] = nullptr;
+    if (h->xbuf) cudaFree(h->xbuf), h->xbuf = nullptr;
+    if (h->D.S.redv) cudaFree(h->D.S.redv), h->D.S.redv = nullptr;
+    if (h->D.S.err) cudaFree(h->D.S.err), h->D.S.err = nullptr;
+    if (h->D.Sglobal) cudaFree(h->D.Sglobal), h->D.Sglobal = nullptr;
+    h->D.S.split = 0;
+}
+
+// (re)allocate the exchange buffer of this rank for a group of `world` ranks and switch the handle to the split pipeline.  The layout
+// depends only on (max_windows, max_K, world), so every rank computes the same offsets.
+static int split_setup(icg_ba *h, int rank, int world) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) {
+        set_error("split pipeline: rank %d / world %d out of range (<= 8 GPUs of one box)", rank, world);
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    split_release(h);
+    const BaCaps &C = h->C;
+    ShardDev &S = h->D.S;
+    const size_t NW = C.NW, G = world;
+    const size_t TRI = (size_t) C.NCV * (C.NCV + 1) / 2;
+    S.PK = (int) ((TRI + 3 * (size_t) C.NCV + 4 + 3) & ~(size_t) 3);
+    S.BS = (SPLIT_HDR + C.NS + 3) & ~3;
+    S.RV = (3 * C.NCV + 4 + 3) & ~3;
+    const size_t NWo = (NW + G - 1) / G;
+    size_t off = 0;
+    S.off_inbox = off, off += NWo * G * S.PK;
+    S.off_bcast = off, off += NW * S.BS;
+    S.off_scal = off, off += NW * G * SPLIT_SCAL;
+    S.off_flagA = off, off += 8;
+    S.off_flagB = off, off += (NW + 3) & ~(size_t) 3;
+    S.off_flagC = off, off += (NW * G + 3) & ~(size_t) 3;
+    h->xbuf_doubles = off;
+    if (cudaMalloc(&h->xbuf, sizeof(double) * off) != cudaSuccess || cudaMalloc(&S.redv, sizeof(double) * NW * S.RV) != cudaSuccess ||
+        cudaMalloc(&S.err, sizeof(int) * 4) != cudaSuccess ||
+        cudaMalloc(&h->D.Sglobal, sizeof(double) * NWo * ((size_t) (C.N + 1) * (C.N + 2) / 2)) != cudaSuccess) {
+        set_error("split pipeline: allocation of the exchange buffers failed (%zu doubles)", off);
+        return ICG_ENOMEM;
+    }
+    ICG_CUDA(cudaMemset(h->xbuf, 0, sizeof(double) * off));
+    ICG_CUDA(cudaMemset(S.redv, 0, sizeof(double) * NW * S.RV));
+    ICG_CUDA(cudaMemset(S.err, 0, sizeof(int) * 4));
+    for (int r = 0; r < 8; r++) S.peer[r] = nullptr;
+    S.peer[rank] = h->xbuf;
+    S.split = 1;
+    h->D.rank = rank, h->D.world = world;
+    h->x_world = world;
+    h->epoch = 0;
+    h->smem_solve_cam = sizeof(double) * (40 + 4 * (size_t) C.NS + (size_t) SPLIT_BS_ROWS * (C.NS + 1));
+    h->smem_step_lm = sizeof(double) * (40 + (size_t) C.NS);
+    ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve_cam));
+    ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+    ICG_CUDA(cudaFuncSetAttribute(ba_step_lm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_step_lm));
+    return ICG_OK;
+}
+
+static int launch_solve_cam(icg_ba *h, int n, unsigned long long epoch) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned) (n * SPLIT_CLUSTER)), cfg.blockDim = dim3(SOLVE_THREADS);
+    cfg.dynamicSmemBytes = h->smem_solve_cam, cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SPLIT_CLUSTER, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at, cfg.numAttrs = 1;
+    ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam, h->C, h->D, epoch));
+    return ICG_OK;
+}
+
+// One LM sequence of the split pipeline (see ba_split.cuh).  Window w of a sharded group is solved by rank w mod world; the solve kernel
+// is launched over all windows and the clusters of windows owned elsewhere return at once.
+static int enqueue_lm_split(icg_ba *h, int max_num_iterations) {
+    const BaCaps &C = h->C;
+    const BaDev &D = h->D;
+    const int n = h->cur_windows;
+    cudaStream_t s = h->stream;
+    for (int r = 0; r < D.world; r++)
+        if (!D.S.peer[r]) {
+            set_error("landmark-sharded solve: peer %d is not connected (icg_ba_shard_connect)", r);
+            return ICG_EINVAL;
+        }
+    const dim3 g_vis(C.NVB - 2, n), g_cost(h->nblk_vis, n), g_nn(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n);
+    for (int it = 0; it <= max_num_iterations; it++) {
+        const unsigned long long epoch = ++h->epoch;
+        ICG_CUDA(cudaEventRecord(h->ev_fork, s));
+        ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
+        ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+        ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        prof_mark(h, 0);
+        ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
+        prof_mark(h, 1);
+        ba_schur_dmma<<<dim3(BA_SPLIT_W, n), 256, h->smem_schur, s>>>(C, D, h->ld_schur);
+        prof_mark(h, 5);
+        ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
+        prof_mark(h, 3);
+        ba_export<<<g_nn, 256, 0, s>>>(C, D);
+        ba_signal<<<1, 32, 0, s>>>(D, epoch);
+        prof_mark(h, 7);
+        ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+        prof_mark(h, 6);
+        ba_reduce<<<g_nn, 256, 0, s>>>(C, D, epoch);
+        prof_mark(h, 12);
+        int rc = launch_solve_cam(h, n, epoch);
+        if (rc != ICG_OK) return rc;
+        prof_mark(h, 8);
+        ba_step_lm<<<n, SOLVE_THREADS, h->smem_step_lm, s>>>(C, D, epoch);
+        prof_mark(h, 14);
+        count_launch(9);
+        if (it == max_num_iterations) break;
+        ICG_CUDA(cudaEventRecord(h->ev_fork, s));
+        ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
+        ba_cost_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D, h->nblk_vis);
+        ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        ba_cost<<<g_cost, 256, 0, s>>>(C, D, h->nblk_vis);
+        ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+        prof_mark(h, 9);
+        ba_exchange<<<(n + 63) / 64, 64, 0, s>>>(C, D, n, h->nblk_vis, epoch);
+        prof_mark(h, 10);
+        ba_accept_split<<<n, 128, 0, s>>>(C, D, epoch);
+        prof_mark(h, 11);
+        count_launch(4);
     }
     ICG_CHECK_LAUNCH();
     return ICG_OK;
@@ -2232,6 +2392,10 @@ int icg_ba_download(icg_ba *h, int n, const icg_ba_problem *P, icg_ba_summary *s
     cudaStream_t s = h->stream;
     ICG_CUDA(h->pose.down(s)); ICG_CUDA(h->mix.down(s)); ICG_CUDA(h->ext.down(s)); ICG_CUDA(h->rho.down(s)); ICG_CUDA(h->st.down(s, n));
     ICG_CUDA(cudaStreamSynchronize(s));
+    if (h->D.S.split && icg_ba_shard_error(h) != 0) {
+        set_error("icg_ba_download: a peer exchange of the split pipeline timed out (a rank of the shard group did not run the same sequence)");
+        return ICG_ECUDA;
+    }
     for (int w = 0; w < n; w++) {
         if (P) {
             const icg_ba_problem &p = P[w];
@@ -2348,7 +2512,7 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
         set_error("icg_ba_marginalize: bad arguments");
         return ICG_EINVAL;
     }
-    if (h->comm) {
+    if (h->comm || h->D.world > 1) {
         set_error("icg_ba_marginalize: not available on a landmark-sharded handle (icg_ba_set_shard(world = 1) first)");
         return ICG_EUNSUPPORTED;
     }
@@ -2489,6 +2653,14 @@ int icg_ba_set_shard(icg_ba *h, int rank, int world, const uint8_t *id128) {
         a.CommDestroy((ncclComm_t) h->comm);
         h->comm = nullptr;
     }
+    if (h->D.S.split && h->x_world > 1) {  // leaving a peer-memory shard group
+        int rc = h->use_global_S ? split_setup(h, 0, 1) : (split_release(h), ICG_OK);
+        if (rc != ICG_OK) return rc;
+    }
+    if (world > 1 && h->use_global_S) {
+        set_error("icg_ba_set_shard: windows of this size (max_K = %d) are solved by the split pipeline; use icg_ba_shard_export / icg_ba_shard_connect (transport p2p)", h->C.K);
+        return ICG_EUNSUPPORTED;
+    }
     h->D.rank = rank, h->D.world = world;
     if (world == 1) return ICG_OK;
     if (!id128 || !a.lib || !a.CommInitRank) {
@@ -2505,6 +2677,81 @@ int icg_ba_set_shard(icg_ba *h, int rank, int world, const uint8_t *id128) {
     }
     h->comm = comm;
     return ICG_OK;
+}
+
+// ---- landmark shards over peer memory (transport "p2p")
+struct ShardBlob {  // what a rank publishes to the others (ICG_SHARD_BLOB_BYTES)
+    uint64_t magic, pid, ptr, doubles;
+    int32_t rank, world, device, pad;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(ShardBlob) <= ICG_SHARD_BLOB_BYTES, "ShardBlob size");
+
+int icg_ba_shard_export(icg_ba *h, int rank, int world, uint8_t *blob) {
+    if (!h || !blob) {
+        set_error("icg_ba_shard_export: bad arguments");
+        return ICG_EINVAL;
+    }
+    if (h->comm) {
+        nccl_api().CommDestroy((ncclComm_t) h->comm);
+        h->comm = nullptr;
+    }
+    int rc = split_setup(h, rank, world);
+    if (rc != ICG_OK) return rc;
+    ShardBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = 0x49434753484152ull, b.pid = (uint64_t) getpid(), b.ptr = (uint64_t) (uintptr_t) h->xbuf, b.doubles = h->xbuf_doubles;
+    b.rank = rank, b.world = world, b.device = h->device;
+    if (world > 1) ICG_CUDA(cudaIpcGetMemHandle(&b.ipc, h->xbuf));
+    memset(blob, 0, ICG_SHARD_BLOB_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return ICG_OK;
+}
+
+int icg_ba_shard_connect(icg_ba *h, const uint8_t *blobs) {
+    if (!h || !blobs || !h->D.S.split) {
+        set_error("icg_ba_shard_connect: call icg_ba_shard_export first");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    const int world = h->D.world, rank = h->D.rank;
+    for (int r = 0; r < world; r++) {
+        ShardBlob b;
+        memcpy(&b, blobs + (size_t) r * ICG_SHARD_BLOB_BYTES, sizeof(b));
+        if (b.magic != 0x49434753484152ull || b.rank != r || b.world != world || b.doubles != h->xbuf_doubles) {
+            set_error("icg_ba_shard_connect: blob %d does not describe rank %d of %d with the same window capacity", r, r, world);
+            return ICG_EINVAL;
+        }
+        if (r == rank) continue;
+        if (b.pid == (uint64_t) getpid()) {  // same process (several handles driven by one host process): plain device pointers
+            if (b.device != h->device) {
+                int can = 0;
+                ICG_CUDA(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+                if (!can) {
+                    set_error("icg_ba_shard_connect: device %d cannot access device %d", h->device, b.device);
+                    return ICG_EUNSUPPORTED;
+                }
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ICG_CUDA(e);
+                cudaGetLastError();
+            }
+            h->D.S.peer[r] = (double *) (uintptr_t) b.ptr;
+        } else {  // one process per GPU: map the peer's buffer through CUDA IPC (NVLink peer memory)
+            void *p = nullptr;
+            ICG_CUDA(cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->ipc_opened[r] = p;
+            h->D.S.peer[r] = (double *) p;
+        }
+    }
+    return ICG_OK;
+}
+
+int icg_ba_shard_error(icg_ba *h) {
+    if (!h || !h->D.S.split) return 0;
+    int e = 0;
+    cudaSetDevice(h->device);
+    if (cudaMemcpy(&e, h->D.S.err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e;
 }
 
 int icg_ba_sync(icg_ba *h) {

@@ -1,0 +1,634 @@
+// ba_split.cuh -- the "split" LM pipeline of the window solve: large reduced systems (n = 15K + 7 beyond one CTA's shared memory, cfg 4)
+// and landmark-sharded solves over the GPUs of one box.  Included by ba.cu.
+//
+// One LM attempt, rank g of G (G = 1: everything is local), windows w = 0 .. W-1, owner(w) = w mod G:
+//
+//   every rank   ba_lin_vis / ba_schur_dmma / ba_pair_gram1     its landmark shard of every window (the kernels of the fused pipeline)
+//   every rank   ba_export        packs [tri(H_vis - Schur) | diag H_vis | g_vis | W phi g_l | cost, sum rho^2, max |g_l|] of window w and
+//                                 STORES it into the inbox of owner(w) -- peer memory over NVLink (P2P stores), slot [w / G][g]
+//                ba_signal        release-flag "my partials of this epoch have landed" on every peer
+//   owner        ba_reduce        waits for the G flags, sums the G slots in rank order (deterministic, identical regardless of arrival
+//                                 order) into Hs = H_c + sum; the reduction is fused into the assembly of the solve's operand
+//   owner        ba_solve_cam     thread-block CLUSTER per window: Jacobi scaling, LM diagonal, packed S in global memory (L2), blocked
+//                                 Cholesky (DMMA panel updates spread over the cluster's CTAs, cluster barriers), blocked back-substitution;
+//                                 broadcasts [header | camera step] into every rank's step buffer (P2P stores + per-window release flag)
+//   every rank   ba_step_lm       waits for the window's flag; candidate camera blocks x (+) delta (redundantly, bit-identical), landmark
+//                                 back-substitution + candidates of its own landmarks, its parts of the model cost change and step norm
+//   every rank   ba_cost (+ ba_cost_cam on the owner)
+//   every rank   ba_exchange      [model cost change, |step|^2, non-finite, candidate cost, sum rho^2] of its shard -> slot [w][g] of EVERY rank
+//   every rank   ba_accept_split  waits for the G slots, sums them in rank order: identical inputs -> identical accept / reject, radius and
+//                                 termination decisions on every rank, no broadcast of the LM state
+//
+// Three flag synchronisations per attempt, no NCCL on the data path, no host round trip.  The flags are monotonically increasing epoch
+// counters (one per LM attempt over the life of the handle); a consumer that does not see its flag within ~2 s raises the handle's
+// device-side error word instead of hanging the GPU.
+#pragma once
+#include <cooperative_groups.h>
+
+namespace icg {
+namespace cg = cooperative_groups;
+
+constexpr int SPLIT_CLUSTER = 4;      // CTAs per window in ba_solve_cam
+constexpr int SPLIT_HDR = 16;         // header doubles of the step broadcast
+constexpr int SPLIT_SCAL = 8;         // doubles per (window, rank) slot of the scalar exchange
+constexpr int SPLIT_BS_ROWS = 32;     // rows per block of the blocked back-substitution
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// spin until *f >= epoch (flags only grow); ~2 s budget, then the error word is raised and the caller proceeds (results are discarded by
+// the host, which reports ICG_ECUDA): a lost peer must not hang the GPU
+__device__ __forceinline__ void wait_flag(const unsigned long long *f, unsigned long long epoch, int *err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch) {
+        if (clock64() - t0 > 4000000000ll) {
+            atomicExch(err, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
+__device__ __forceinline__ double *x_inbox(const BaDev &D, int peer, int w, int from) {
+    const ShardDev &S = D.S;
+    return S.peer[peer] + S.off_inbox + ((size_t) (w / D.world) * D.world + from) * S.PK;
+}
+__device__ __forceinline__ double *x_bcast(const BaDev &D, int peer, int w) { return D.S.peer[peer] + D.S.off_bcast + (size_t) w * D.S.BS; }
+__device__ __forceinline__ double *x_scal(const BaDev &D, int peer, int w, int from) {
+    return D.S.peer[peer] + D.S.off_scal + ((size_t) w * D.world + from) * SPLIT_SCAL;
+}
+__device__ __forceinline__ unsigned long long *x_flagA(const BaDev &D, int peer, int from) {
+    return (unsigned long long *) (D.S.peer[peer] + D.S.off_flagA) + from;
+}
+__device__ __forceinline__ unsigned long long *x_flagB(const BaDev &D, int peer, int w) {
+    return (unsigned long long *) (D.S.peer[peer] + D.S.off_flagB) + w;
+}
+__device__ __forceinline__ unsigned long long *x_flagC(const BaDev &D, int peer, int w, int from) {
+    return (unsigned long long *) (D.S.peer[peer] + D.S.off_flagC) + (size_t) w * D.world + from;
+}
+__device__ __forceinline__ int tri_idx(int A, int B, int ncv) { return A * ncv - A * (A - 1) / 2 + (B - A); }  // A <= B < ncv
+
+// ------------------------------------------------------------------------------------------------ export (every rank)
+// thread per entry (A <= B) of the symmetric (NCV+1)^2 matrix [H_vis g_vis; g_vis^T .]: gathers the per-pair Gram matrices (ba_hsum's job in the
+// fused pipeline), subtracts the Schur partials and stores into the owner's inbox.  Block 0 of a window also reduces the scalars.
+__global__ void __launch_bounds__(256) ba_export(BaCaps C, BaDev D) {
+    __shared__ short s_slot[32 * 32];
+    __shared__ double s_red[40];
+    const int w = blockIdx.y, tid = threadIdx.x;
+    const LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    const int K = dm.K, NCV = 6 * K + 7, nn = NCV + 1;
+    if ((int) blockIdx.x * 256 >= nn * nn) return;
+    const int owner = w % D.world;
+    double *P = x_inbox(D, owner, w, D.rank);
+    const int TRI = NCV * (NCV + 1) / 2;
+    gram2_slots(C, D, w, K, s_slot);
+    const int t = blockIdx.x * 256 + tid;
+    if (t < nn * nn) {
+        const int A = t / nn, B = t - A * nn;
+        if (B >= A && A < NCV) {
+            const double cj = gram2_entry(C, D, w, K, s_slot, A, B);
+            const double *CWp = D.CW + (size_t) w * BA_SPLIT_W * C.NCA * C.NCA;
+            double cw = 0;
+#pragma unroll
+            for (int k = 0; k < BA_SPLIT_W; k++) cw += CWp[(size_t) k * C.NCA * C.NCA + (size_t) B * C.NCA + A];
+            if (B < NCV) {
+                P[tri_idx(A, B, NCV)] = cj - cw;
+                if (A == B) P[TRI + A] = cj;
+            } else {
+                P[TRI + NCV + A] = cj;       // g_vis
+                P[TRI + 2 * NCV + A] = cw;   // W phi g_l
+            }
+        }
+    }
+    if (blockIdx.x != 0) return;
+    double c = 0, q = 0, gm = 0;
+    for (int f = tid; f < dm.F; f += 256) c += D.costf[(size_t) w * C.F + f];
+    for (int l = tid; l < dm.L; l += 256) {
+        const double r = D.rho[(size_t) w * C.L + l];
+        q += r * r;
+        gm = fmax(gm, fabs(D.gl[(size_t) w * C.L + l]));
+    }
+    c = block_sum(c, s_red);
+    q = block_sum(q, s_red);
+    gm = block_max(gm, s_red);
+    if (tid == 0) P[TRI + 3 * NCV] = c, P[TRI + 3 * NCV + 1] = q, P[TRI + 3 * NCV + 2] = gm;
+}
+
+// everything this rank stored for `epoch` has been issued by earlier kernels of the stream: publish (one thread per peer)
+__global__ void ba_signal(BaDev D, unsigned long long epoch) {
+    const int q = threadIdx.x;
+    if (q >= D.world) return;
+    __threadfence_system();
+    st_release_sys(x_flagA(D, q, D.rank), epoch);
+}
+
+// ------------------------------------------------------------------------------------------------ reduce (owner)
+__global__ void __launch_bounds__(256) ba_reduce(BaCaps C, BaDev D, unsigned long long epoch) {
+    const int w = blockIdx.y, tid = threadIdx.x;
+    if (w % D.world != D.rank) return;
+    if (D.st[w].done) return;
+    const int K = D.dims[w].K, NCV = 6 * K + 7, nn = NCV + 1, TRI = NCV * (NCV + 1) / 2;
+    if ((int) blockIdx.x * 256 >= nn * nn) return;
+    if (tid < D.world) wait_flag(x_flagA(D, D.rank, tid), epoch, D.S.err);
+    __syncthreads();
+    const int t = blockIdx.x * 256 + tid;
+    if (t >= nn * nn) return;
+    const int A = t / nn, B = t - A * nn;  // same thread -> entry map as ba_export
+    if (B < A) return;
+    const double *P0 = x_inbox(D, D.rank, w, 0);
+    const size_t PK = D.S.PK;
+    auto rsum = [&](int e) {  // fixed rank order: identical on every run and on every rank count
+        double s = 0;
+        for (int r = 0; r < D.world; r++) s += __ldcg(P0 + (size_t) r * PK + e);
+        return s;
+    };
+    double *rv = D.S.redv + (size_t) w * D.S.RV;
+    if (A < NCV && B < NCV) {
+        D.Hs[(size_t) w * C.NS * C.NS + (size_t) B * C.NS + A] = D.Hc[(size_t) w * C.NS * C.NS + (size_t) B * C.NS + A] + rsum(tri_idx(A, B, NCV));
+        if (A == B) rv[A] = rsum(TRI + A);
+    } else if (A < NCV) {  // B == NCV: the gradient column
+        rv[NCV + A] = rsum(TRI + NCV + A);
+        rv[2 * NCV + A] = rsum(TRI + 2 * NCV + A);
+    } else {               // A == B == NCV: the scalars
+        rv[3 * NCV] = rsum(TRI + 3 * NCV);
+        rv[3 * NCV + 1] = rsum(TRI + 3 * NCV + 1);
+        double m = 0;
+        for (int r = 0; r < D.world; r++) m = fmax(m, __ldcg(P0 + (size_t) r * PK + TRI + 3 * NCV + 2));
+        rv[3 * NCV + 2] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ solve_cam (owner, cluster per window)
+// The camera-side half of ba_solve for systems that do not fit one CTA: S lives packed in global memory (L2-resident, written and read by all
+// CTAs of the cluster between cluster barriers -- cluster.sync orders the global accesses at cluster scope and invalidates L1).
+// Row i of the packed lower triangle starts at i (i + 1) / 2; the augmented row N carries the right-hand side.
+__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D, unsigned long long epoch) {
+    extern __shared__ double sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int) cluster.num_blocks(), cr = (int) cluster.block_rank();
+    const int w = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (w % D.world != D.rank) return;   // uniform over the cluster
+    LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    const int K = dm.K, NCV = 6 * K + 7, N = 15 * K + 7, NR = N + 1;
+    const int CT = CL * SOLVE_THREADS, ctid = cr * SOLVE_THREADS + tid, cwarp = ctid >> 5, ncwarps = CT / 32;
+    // snapshot of the LM state (CTA 0 updates it after the first cluster barrier)
+    const int f_first = st.first, f_fresh = st.fresh_lin, f_last = st.last_success, f_iter = st.iter, f_maxit = st.max_iter;
+    const double radius = st.radius, cost_cam = st.cost_cam, gmax_old = st.gmax, xcost_old = st.x_cost, init_old = st.initial_cost;
+    double *s_red = sm;                  // 40
+    double *s_scale = s_red + 40;        // N
+    double *s_g = s_scale + C.NS;        // N
+    double *s_rhs = s_g + C.NS;          // N   rhs' then step'
+    double *s_d2 = s_rhs + C.NS;         // N
+    double *s_blk = s_d2 + C.NS;         // SPLIT_BS_ROWS x (NS + 1): row block of L for the back-substitution (CTA 0)
+    double *S = D.Sglobal + (size_t) (w / D.world) * ((size_t) (C.N + 1) * (C.N + 2) / 2);  // one workspace per OWNED window
+    const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS, *Hs = D.Hs + (size_t) w * C.NS * C.NS;
+    const double *rv = D.S.redv + (size_t) w * D.S.RV;   // [diag H_vis | g_vis | W phi g_l | cost, sum rho^2, max |g_l|]
+    double *scale_c = D.scale_c + (size_t) w * C.NS;
+    // ---- gradient, Jacobi scaling (first linearisation), LM diagonal, rhs: every CTA keeps its own copy (no DSMEM traffic)
+    for (int a = tid; a < N; a += SOLVE_THREADS) {
+        const double g = gcam[a] + (a < NCV ? rv[NCV + a] : 0.0);
+        s_g[a] = g;
+        const double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? rv[a] : 0.0);
+        const double sc = f_first ? 1.0 / (1.0 + sqrt(h)) : scale_c[a];
+        s_scale[a] = sc;
+        const double hs = sc * sc * h;
+        s_d2[a] = fmin(fmax(hs, 1e-6), 1e32) / radius;
+        s_rhs[a] = -sc * (g - (a < NCV ? rv[2 * NCV + a] : 0.0));
+    }
+    __syncthreads();
+    double gmax_now = gmax_old, x_cost = xcost_old;
+    if (f_fresh) {
+        double gm = 0;
+        for (int a = tid; a < N; a += SOLVE_THREADS) gm = fmax(gm, fabs(s_g[a]));
+        gm = fmax(block_max(gm, s_red), rv[3 * NCV + 2]);
+        gmax_now = gm;
+        x_cost = rv[3 * NCV] + cost_cam;
+    }
+    int term = 0;
+    if (f_iter >= f_maxit) term = 1;                               // NO_CONVERGENCE
+    else if (f_last && gmax_now <= 1e-10) term = 2;                // gradient tolerance
+    else if (f_last && radius <= 1e-32) term = 2;                  // min trust region radius
+    cluster.sync();  // every CTA has read the state it needs
+    if (cr == 0 && tid == 0) {
+        st.x_cost = x_cost, st.gmax = gmax_now;
+        if (f_first) st.initial_cost = x_cost;
+        st.fresh_lin = 0, st.first = 0, st.need_lin = 0;
+        if (term) st.done = term, st.step_valid = 0;
+        else st.iter = f_iter + 1;
+    }
+    if (cr == 0 && f_first)
+        for (int a = tid; a < N; a += SOLVE_THREADS) scale_c[a] = s_scale[a];
+    double *BC = nullptr;
+    if (term) {
+        // broadcast the termination (header only) and leave
+        if (cr == 0) {
+            __syncthreads();
+            for (int q = tid; q < D.world; q += SOLVE_THREADS) {
+                BC = x_bcast(D, q, w);
+                BC[0] = (double) term, BC[1] = 0.0, BC[2] = x_cost, BC[3] = gmax_now, BC[4] = f_first ? x_cost : init_old, BC[5] = 0.0;
+                __threadfence_system();
+                st_release_sys(x_flagB(D, q, w), epoch);
+            }
+        }
+        return;
+    }
+    // ---- assemble S' = s H s + D^2 (packed lower, global), warp per row over the whole cluster
+    for (int i = cwarp; i < N; i += ncwarps) {
+        const double *src = (i < NCV ? Hs : Hc) + (size_t) i * C.NS;
+        double *dst = S + (size_t) i * (i + 1) / 2;
+        const double si = s_scale[i];
+        for (int j = lane; j <= i; j += 32) {
+            double v = si * s_scale[j] * src[j];
+            if (i == j) v += s_d2[i];
+            dst[j] = v;
+        }
+    }
+    for (int a = ctid; a < N; a += CT) S[(size_t) N * (N + 1) / 2 + a] = s_rhs[a];
+    cluster.sync();
+    // ---- blocked left-looking Cholesky, 8 columns per step; panel update (DMMA) and row solves spread over the cluster
+    int fail = 0;
+    for (int J0 = 0; J0 < N; J0 += BA_CHOL_NB) {
+        const int nb = min(BA_CHOL_NB, N - J0);
+        if (J0 > 0) {
+            const int g = lane >> 2, kk = lane & 3;
+            const int ntile = (NR - J0 + 7) / 8;
+            const int cb = J0 + g;
+            const bool okb = cb < NR;
+            const double *rb = S + (okb ? (size_t) cb * (cb + 1) / 2 : 0);
+            for (int tI = cwarp; tI < ntile; tI += ncwarps) {
+                const int ia = J0 + 8 * tI + g;
+                const bool oka = ia < NR;
+                const double *ra = S + (oka ? (size_t) ia * (ia + 1) / 2 : 0);
+                double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+                int k0 = 0;
+                for (; k0 + 16 <= J0; k0 += 16) {  // four independent accumulator pairs: the operands come from L2
+                    const double a0 = oka ? ra[k0 + kk] : 0.0, b0 = okb ? rb[k0 + kk] : 0.0;
+                    const double a1 = oka ? ra[k0 + 4 + kk] : 0.0, b1 = okb ? rb[k0 + 4 + kk] : 0.0;
+                    const double a2 = oka ? ra[k0 + 8 + kk] : 0.0, b2 = okb ? rb[k0 + 8 + kk] : 0.0;
+                    const double a3 = oka ? ra[k0 + 12 + kk] : 0.0, b3 = okb ? rb[k0 + 12 + kk] : 0.0;
+                    dmma884(c0, c1, a0, b0);
+                    dmma884(d0, d1, a1, b1);
+                    dmma884(e0, e1, a2, b2);
+                    dmma884(f0, f1, a3, b3);
+                }
+                for (; k0 + 4 <= J0; k0 += 4) {
+                    const double a0 = oka ? ra[k0 + kk] : 0.0, b0 = okb ? rb[k0 + kk] : 0.0;
+                    dmma884(c0, c1, a0, b0);
+                }
+                c0 += d0 + (e0 + f0), c1 += d1 + (e1 + f1);
+                const int i = J0 + 8 * tI + g;
+                if (i < NR) {
+                    const int ca = J0 + 2 * kk;
+                    double *ri = S + (size_t) i * (i + 1) / 2;
+                    if (ca < J0 + nb && ca <= i) ri[ca] -= c0;
+                    if (ca + 1 < J0 + nb && ca + 1 <= i) ri[ca + 1] -= c1;
+                }
+            }
+            cluster.sync();
+        }
+        {
+            // every thread factors the nb x nb diagonal block redundantly (identical verdict everywhere), row owners solve / write back
+            double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
+            bool bad = false;
+#pragma unroll
+            for (int a = 0; a < BA_CHOL_NB; a++)
+#pragma unroll
+                for (int b = 0; b < BA_CHOL_NB; b++) Ld[a][b] = (a < nb && b <= a) ? S[(size_t) (J0 + a) * (J0 + a + 1) / 2 + J0 + b] : (a == b ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < BA_CHOL_NB; j++) {
+                double d = Ld[j][j];
+#pragma unroll
+                for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
+                if (!(d > 0.0) || !isfinite(d)) bad = true;
+                const double di = rsqrt(d);
+                dinv[j] = di;
+                Ld[j][j] = d * di;
+#pragma unroll
+                for (int a = j + 1; a < BA_CHOL_NB; a++) {
+                    double sum = Ld[a][j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
+                    Ld[a][j] = sum * di;
+                }
+            }
+            if (bad) fail = 1;
+            // rows below the block: solve against the factored diagonal block (each thread touches its own row only)
+            const int i = J0 + ctid;
+            if (i >= J0 + nb && i < NR && !fail) {
+                double *ri = S + (size_t) i * (i + 1) / 2 + J0;
+                double x[BA_CHOL_NB];
+#pragma unroll
+                for (int c = 0; c < BA_CHOL_NB; c++) x[c] = c < nb ? ri[c] : 0.0;
+#pragma unroll
+                for (int c = 0; c < BA_CHOL_NB; c++) {
+                    double sum = x[c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) sum -= x[k] * Ld[c][k];
+                    x[c] = sum * dinv[c];
+                }
+#pragma unroll
+                for (int c = 0; c < BA_CHOL_NB; c++)
+                    if (c < nb) ri[c] = x[c];
+            }
+            cluster.sync();
+            // the block's own rows are written back only now: every thread of the cluster has read the unfactored block above, and no
+            // later step of the factorisation reads these entries again (the back-substitution does)
+            if (i < J0 + nb && !fail) {
+                double *ri = S + (size_t) i * (i + 1) / 2 + J0;
+                const int a = i - J0;
+#pragma unroll
+                for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {
+                    if (a2 != a) continue;
+#pragma unroll
+                    for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
+                }
+            }
+        }
+        if (fail) break;  // identical on every thread of the cluster
+    }
+    if (cr != 0) return;
+    // ---- CTA 0: blocked backward substitution L^T x = y.  Blocks of SPLIT_BS_ROWS rows, last block first: the block's rows (all columns
+    //      up to the diagonal) are staged in shared memory with one coalesced sweep; one warp solves the triangle, every thread then
+    //      subtracts the block's contribution from the y entries above it.
+    const bool valid = !fail;
+    double *y = s_rhs;  // y = L^-1 rhs' sits in the augmented row
+    __syncthreads();
+    if (valid) {
+        for (int a = tid; a < N; a += SOLVE_THREADS) y[a] = S[(size_t) N * (N + 1) / 2 + a];
+        __syncthreads();
+        const int ldb = C.NS + 1;
+        for (int j1 = N; j1 > 0; j1 -= SPLIT_BS_ROWS) {
+            const int j0 = max(0, j1 - SPLIT_BS_ROWS), nr = j1 - j0;
+            for (int e = tid; e < nr * j1; e += SOLVE_THREADS) {
+                const int r = e / j1, c = e - r * j1;
+                const int row = j0 + r;
+                s_blk[r * ldb + c] = c <= row ? S[(size_t) row * (row + 1) / 2 + c] : 0.0;
+            }
+            __syncthreads();
+            if (warp == 0) {  // triangle: x_j = (y_j - sum_{i > j in block} L_ij x_i) / L_jj, j descending
+                double xv = lane < nr ? y[j0 + lane] : 0.0;
+                for (int r = nr - 1; r >= 0; r--) {
+                    const double xj = __shfl_sync(0xffffffffu, xv, r) / s_blk[r * ldb + j0 + r];
+                    if (lane == r) xv = xj;
+                    if (lane < r) xv -= s_blk[r * ldb + j0 + lane] * xj;
+                }
+                if (lane < nr) y[j0 + lane] = xv;
+            }
+            __syncthreads();
+            for (int c = tid; c < j0; c += SOLVE_THREADS) {
+                double acc = y[c];
+                for (int r = 0; r < nr; r++) acc -= s_blk[r * ldb + c] * y[j0 + r];
+                y[c] = acc;
+            }
+            __syncthreads();
+        }
+    }
+    // ---- camera part of the model cost change, broadcast of [header | delta = step' * scale]
+    double part = 0;
+    bool finite = true;
+    if (valid)
+        for (int a = tid; a < N; a += SOLVE_THREADS) {
+            const double sp = y[a];
+            finite = finite && isfinite(sp);
+            part += -0.5 * sp * (s_scale[a] * s_g[a]) + 0.5 * s_d2[a] * sp * sp;
+        }
+    const double mcc = block_sum(part, s_red);
+    const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
+    for (int q = 0; q < D.world; q++) {
+        BC = x_bcast(D, q, w);
+        if (valid)
+            for (int a = tid; a < N; a += SOLVE_THREADS) BC[SPLIT_HDR + a] = y[a] * s_scale[a];
+        if (tid == 0) {
+            BC[0] = 0.0, BC[1] = (valid && nfin == 0.0) ? 1.0 : 0.0, BC[2] = x_cost, BC[3] = gmax_now, BC[4] = f_first ? x_cost : init_old, BC[5] = mcc;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int q = tid; q < D.world; q += SOLVE_THREADS) st_release_sys(x_flagB(D, q, w), epoch);
+}
+
+// ------------------------------------------------------------------------------------------------ step_lm (every rank, CTA per window)
+__global__ void __launch_bounds__(SOLVE_THREADS) ba_step_lm(BaCaps C, BaDev D, unsigned long long epoch) {
+    extern __shared__ double sm[];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    const int K = dm.K, L = dm.L, NCV = 6 * K + 7, N = 15 * K + 7;
+    const bool owner = (w % D.world) == D.rank;
+    double *s_red = sm, *s_dl = s_red + 40;  // delta (N)
+    if (tid == 0) wait_flag(x_flagB(D, D.rank, w), epoch, D.S.err);
+    __syncthreads();
+    const double *BC = x_bcast(D, D.rank, w);
+    const int term = (int) __ldcg(BC + 0), valid = (int) __ldcg(BC + 1);
+    double *R3 = D.red2 + (size_t) w * 4;
+    if (!owner && tid == 0) {  // mirror what the owner's solve did to the LM state
+        st.x_cost = __ldcg(BC + 2), st.gmax = __ldcg(BC + 3), st.initial_cost = __ldcg(BC + 4);
+        st.fresh_lin = 0, st.first = 0, st.need_lin = 0;
+        if (term) st.done = term, st.step_valid = 0;
+        else st.iter = st.iter + 1;
+    }
+    if (term) return;
+    if (!valid) {
+        if (tid == 0) {
+            st.chol_ok = 0, st.step_valid = 0;
+            R3[0] = 0, R3[1] = 0, R3[2] = 1, R3[3] = 0;
+        }
+        return;
+    }
+    for (int a = tid; a < N; a += SOLVE_THREADS) s_dl[a] = __ldcg(BC + SPLIT_HDR + a);
+    __syncthreads();
+    const double radius = st.radius;
+    const double *hl = D.hl + (size_t) w * C.L, *gl = D.gl + (size_t) w * C.L, *scale_l = D.scale_l + (size_t) w * C.L;
+    double *step_l = D.step_l + (size_t) w * C.L;
+    const double *AW = D.AW + (size_t) w * C.LP * C.NCA;
+    double part = 0;
+    bool finite = true;
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        constexpr int LB = 4;
+        for (int l0 = LB * warp; l0 < L; l0 += LB * (SOLVE_THREADS / 32)) {
+            double d[LB];
+#pragma unroll
+            for (int u = 0; u < LB; u++) d[u] = 0;
+            for (int c = lane; c < NCV; c += 32) {
+                const double sx = s_dl[c];
+#pragma unroll
+                for (int u = 0; u < LB; u++) d[u] += (l0 + u < L ? AW[(size_t) (l0 + u) * C.NCA + c] : 0.0) * sx;
+            }
+            double mine = 0;
+#pragma unroll
+            for (int u = 0; u < LB; u++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+                if (lane == u) mine = d[u];
+            }
+            if (lane < LB && l0 + lane < L) {
+                const int l = l0 + lane;
+                const double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
+                const double sp = (-sl * gl[l] - sl * mine) / (hs + d2);
+                finite = finite && isfinite(sp);
+                step_l[l] = sp;
+                part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
+            }
+        }
+    }
+    __syncthreads();
+    const double mcc_l = block_sum(part, s_red);
+    const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
+    // candidate point: camera blocks on every rank (bit-identical), the rank's own landmarks
+    const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
+    double *pose_c = D.pose_c + (size_t) w * C.K * 7, *mix_c = D.mix_c + (size_t) w * C.K * 9, *ext_c = D.ext_c + (size_t) w * 8, *rho_c = D.rho_c + (size_t) w * C.L;
+    double sn_cam = 0, sn_l = 0;
+    for (int k = tid; k <= K; k += SOLVE_THREADS) {
+        const bool is_ext = (k == K);
+        const double *x = is_ext ? ext : pose + k * 7;
+        double *xc = is_ext ? ext_c : pose_c + k * 7;
+        if (is_ext && dm.ext_const) {
+            for (int e = 0; e < 7; e++) xc[e] = x[e];
+        } else {
+            const int c0 = is_ext ? col_ext(K) : col_pose(k);
+            double d[6];
+            for (int e = 0; e < 6; e++) d[e] = s_dl[c0 + e];
+            pose_plus(x, d, xc);
+            for (int e = 0; e < 7; e++) sn_cam += (x[e] - xc[e]) * (x[e] - xc[e]);
+        }
+    }
+    for (int e = tid; e < K * 9; e += SOLVE_THREADS) {
+        const int k = e / 9, q = e - 9 * k;
+        const double v = mix[e] + s_dl[col_mix(K, k) + q];
+        mix_c[e] = v;
+        sn_cam += (mix[e] - v) * (mix[e] - v);
+    }
+    if (tid == 0) {
+        if (dm.td_const) {
+            ext_c[7] = ext[7];
+        } else {
+            const double v = ext[7] + s_dl[col_td(K)];
+            ext_c[7] = v;
+            sn_cam += (ext[7] - v) * (ext[7] - v);
+        }
+    }
+    for (int l = tid; l < L; l += SOLVE_THREADS) {
+        const double v = rho[l] + step_l[l] * scale_l[l];
+        rho_c[l] = v;
+        sn_l += (rho[l] - v) * (rho[l] - v);
+    }
+    double rho2 = 0;  // |rho|^2 of the CURRENT point (x_norm of the parameter tolerance test)
+    for (int l = tid; l < L; l += SOLVE_THREADS) rho2 += rho[l] * rho[l];
+    sn_cam = block_sum(sn_cam, s_red);
+    sn_l = block_sum(sn_l, s_red);
+    rho2 = block_sum(rho2, s_red);
+    if (tid == 0) {
+        st.chol_ok = 1, st.step_valid = 1;
+        R3[0] = mcc_l + (owner ? __ldcg(BC + 5) : 0.0), R3[1] = sn_l + (owner ? sn_cam : 0.0), R3[2] = nfin, R3[3] = rho2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ exchange + accept (every rank)
+__global__ void ba_exchange(BaCaps C, BaDev D, int n, int nblk_vis, unsigned long long epoch) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n) return;
+    const LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    const bool owner = (w % D.world) == D.rank;
+    double cand = 0;
+    if (st.step_valid) {
+        const double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
+        const int nb = (dm.F + 255) / 256;
+        for (int b = 0; b < nb; b++) cand += part[b];
+        if (owner) cand += part[nblk_vis];
+    }
+    const double *R3 = D.red2 + (size_t) w * 4;
+    for (int q = 0; q < D.world; q++) {
+        double *s = x_scal(D, q, w, D.rank);
+        s[0] = R3[0], s[1] = R3[1], s[2] = R3[2], s[3] = cand, s[4] = R3[3];
+        __threadfence_system();
+        st_release_sys(x_flagC(D, q, w, D.rank), epoch);
+    }
+}
+
+__global__ void __launch_bounds__(128) ba_accept_split(BaCaps C, BaDev D, unsigned long long epoch) {
+    __shared__ int s_accept;
+    __shared__ double s_camsq;
+    __shared__ double s_red[40];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    if (tid < D.world) wait_flag(x_flagC(D, D.rank, w, tid), epoch, D.S.err);
+    {
+        const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8;
+        double s = 0;
+        for (int e = tid; e < dm.K * 7; e += 128) s += pose[e] * pose[e];
+        for (int e = tid; e < dm.K * 9; e += 128) s += mix[e] * mix[e];
+        if (tid < 7 && !dm.ext_const) s += ext[tid] * ext[tid];
+        if (tid == 7 && !dm.td_const) s += ext[7] * ext[7];
+        s = block_sum(s, s_red);
+        if (tid == 0) s_camsq = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s_accept = 0;
+        double mcc = 0, sn = 0, nfin = 0, cand = 0, rho2 = 0;
+        for (int r = 0; r < D.world; r++) {  // fixed rank order on every rank
+            const double *s = x_scal(D, D.rank, w, r);
+            mcc += __ldcg(s + 0), sn += __ldcg(s + 1), nfin += __ldcg(s + 2), cand += __ldcg(s + 3), rho2 += __ldcg(s + 4);
+        }
+        if (!st.chol_ok || nfin != 0.0 || !(mcc > 0.0)) {
+            st.step_valid = 0;
+            st.n_invalid++;
+            if (st.n_invalid >= 5) st.done = 3;
+            st.radius *= 0.5;
+            st.last_success = 0;
+        } else {
+            st.n_invalid = 0;
+            st.model_cost_change = mcc;
+            st.step_norm = sqrt(sn);
+            st.x_norm = sqrt(s_camsq + rho2);
+            st.cand_cost = cand;
+            if (st.step_norm <= 1e-8 * (st.x_norm + 1e-8)) {
+                st.done = 2;
+            } else if (fabs(st.x_cost - cand) <= 1e-6 * st.x_cost) {
+                st.done = 2;
+            } else {
+                const double rel = (st.x_cost - cand) / mcc;
+                if (rel > 1e-3) {
+                    s_accept = 1;
+                    st.n_success++;
+                    const double t = 2.0 * rel - 1.0;
+                    st.radius = fmin(1e16, st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t));
+                    st.decrease_factor = 2.0;
+                    st.last_success = 1;
+                    st.need_lin = 1;
+                    st.fresh_lin = 1;
+                } else {
+                    st.radius = st.radius / st.decrease_factor;
+                    st.decrease_factor *= 2.0;
+                    st.last_success = 0;
+                    st.need_lin = 0;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (!s_accept) return;
+    double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
+    const double *pose_c = D.pose_c + (size_t) w * C.K * 7, *mix_c = D.mix_c + (size_t) w * C.K * 9, *ext_c = D.ext_c + (size_t) w * 8, *rho_c = D.rho_c + (size_t) w * C.L;
+    for (int e = tid; e < dm.K * 7; e += 128) pose[e] = pose_c[e];
+    for (int e = tid; e < dm.K * 9; e += 128) mix[e] = mix_c[e];
+    if (tid < 8) ext[tid] = ext_c[tid];
+    for (int e = tid; e < dm.L; e += 128) rho[e] = rho_c[e];
+}
+
+}  // namespace icg

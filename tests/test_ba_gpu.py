@@ -303,3 +303,94 @@ def test_restart_resolves_the_uploaded_problem(olib, solver):
         assert np.array_equal(first[k], again[k]) and np.array_equal(first[k], ref[k]), k
     assert a[0]["iterations"] == b[0]["iterations"] == info0["pass2"]["iterations"]
     assert abs(a[0]["final_cost"] - b[0]["final_cost"]) == 0.0
+
+
+def _solve_sharded_in_process(probs, world, iters, K, two_pass=False):
+    """`world` solver handles in THIS process (all on cuda:0), connected over the peer-memory transport, each driven by its own host
+    thread -- the code path of one-process-per-GPU landmark sharding (ba_split.cuh), runnable on a single GPU."""
+    import threading
+    from ic_gvins_b200.ba import WindowSolver, shard_window
+    n = len(probs)
+    shards = [[shard_window(p, r, world) for p in probs] for r in range(world)]
+    solvers = [WindowSolver(max_windows=n, max_K=K, max_L=max(1, max(s["L"] for s in shards[r])), max_F=max(1, max(s["F"] for s in shards[r])),
+                            max_gnss=16, max_marg_r=64) for r in range(world)]
+    try:
+        blobs = [solvers[r].shard_export(r, world) for r in range(world)]
+        for sv in solvers:
+            sv.shard_connect(blobs)
+        out, errs = [None] * world, []
+
+        def run(r):
+            try:
+                out[r] = solvers[r].gvins_optimization_batch(shards[r], iters) if two_pass else solvers[r].solve(shards[r], iters)
+            except Exception as e:  # noqa: BLE001
+                errs.append((r, repr(e)))
+        th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(300)
+        assert not errs, errs
+    finally:
+        for sv in solvers:
+            sv.close()
+    merged = []
+    for w, p in enumerate(probs):
+        full = copy.deepcopy(p)
+        for r in range(world):
+            sh = shards[r][w]
+            full["invdepth"][sh["lm_lo"]:sh["lm_hi"]] = sh["invdepth"]
+            full["f_active"][sh["f_index"]] = sh["f_active"]
+            for key in ("pose", "mix", "ext", "gnss_std"):
+                assert np.array_equal(sh[key], shards[0][w][key]), (w, r, key, "camera-side blocks differ between shards")
+        for key in ("pose", "mix", "ext", "gnss_std"):
+            full[key] = shards[0][w][key]
+        merged.append(full)
+    return merged, out
+
+
+@pytest.mark.parametrize("world,K,L,nwin", [(2, 10, 300, 3), (3, 10, 300, 4), (2, 20, 2000, 2)])
+def test_landmark_sharded_p2p_in_process_matches_oracle(olib, world, K, L, nwin):
+    """Landmark shards over the peer-memory transport (window w owned by rank w mod world) == the oracle's solve of the whole window:
+    same LM trajectory, solution within 1e-6.  Every rank ends with bit-identical camera-side blocks."""
+    probs = []
+    for w in range(nwin):
+        p, _ = make(olib, K=K, L=L, seed=3000 + 10 * K + w, with_marg=(w % 2 == 1), with_priors=(w == 2))
+        if w % 3 == 1:
+            p["ext_const"], p["td_const"] = 1, 1
+        probs.append(p)
+    merged, out = _solve_sharded_in_process(probs, world, 20, K)
+    for w, p in enumerate(probs):
+        po = copy.deepcopy(p)
+        so = oa.ba_solve(olib, po, 20)
+        for r in range(world):
+            sg = out[r][w]
+            assert sg["iterations"] == so["iterations"] and sg["num_successful_steps"] == so["num_successful_steps"], (w, r, sg, so)
+            assert sg["termination"] == so["termination"]
+            assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-7 * so["final_cost"]
+        _compare_solution(merged[w], po)
+
+
+def test_landmark_sharded_two_pass_in_process(olib):
+    """gvinsOptimization (5 + chi2 culling + 15) on landmark shards: culling is local to the shard that owns the factor, GNSS re-weighting
+    is replicated; merged result == the single-handle two-pass result (bitwise identical LM decisions, solution within 1e-9)."""
+    from ic_gvins_b200.ba import WindowSolver
+    probs = []
+    for w in range(2):
+        p, _ = make(olib, K=10, L=300, seed=3100 + w)
+        p["f_const"].reshape(-1, 14)[10 + w, 3] += 0.2
+        p["gnss_blh"][3:6] += np.array([1.0, -0.8, 0.5])
+        probs.append(p)
+    merged, out = _solve_sharded_in_process(probs, 2, 20, 10, two_pass=True)
+    single = copy.deepcopy(probs)
+    s = WindowSolver(max_windows=2, max_K=10, max_L=300, max_F=2700, max_gnss=16, max_marg_r=64)
+    try:
+        info = s.gvins_optimization_batch(single, 20)
+    finally:
+        s.close()
+    for w in range(2):
+        assert sum(out[r][w]["reproj_removed"] for r in range(2)) == info[w]["reproj_removed"] >= 1
+        assert out[0][w]["gnss_reweighted"] == info[w]["gnss_reweighted"] >= 1
+        assert out[0][w]["pass2"]["iterations"] == info[w]["pass2"]["iterations"]
+        assert np.array_equal(merged[w]["f_active"], single[w]["f_active"])
+        _compare_solution(merged[w], single[w], rel=1e-9)
