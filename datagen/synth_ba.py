@@ -63,7 +63,7 @@ def trajectory(t, speed=5.0, yaw_rate=5.0 * D2R):
     return p, v, a, psi
 
 
-def imu_samples(t0, t1, rate, rng, bg, ba, yaw_rate=5.0 * D2R):
+def imu_samples(t0, t1, rate, rng, bg, ba, yaw_rate=5.0 * D2R, earth=True):
     """(n, 7) rows: dt, dtheta[3], dvel[3]; row 0 is the sample AT t0 (imu0 of the preintegration)."""
     n = int(round((t1 - t0) * rate))
     dt = 1.0 / rate
@@ -73,8 +73,9 @@ def imu_samples(t0, t1, rate, rng, bg, ba, yaw_rate=5.0 * D2R):
         tm = t0 + (i - 0.5) * dt  # mid-point of the sampling interval ending at t0 + i dt
         p, v, a, psi = trajectory(tm)
         R = q_mat(q_yaw(psi))
-        w_b = np.array([0.0, 0.0, yaw_rate]) + R.T @ IEWN
-        f_b = R.T @ (a - GRAVITY + 2.0 * np.cross(IEWN, v))
+        iewn = IEWN if earth else np.zeros(3)  # earth = False: the PreintegrationNormal world (no Earth rotation / Coriolis)
+        w_b = np.array([0.0, 0.0, yaw_rate]) + R.T @ iewn
+        f_b = R.T @ (a - GRAVITY + 2.0 * np.cross(iewn, v))
         out[i, 0] = dt
         out[i, 1:4] = (w_b + bg) * dt + rng.normal(0, arw * math.sqrt(dt), 3)
         out[i, 4:7] = (f_b + ba) * dt + rng.normal(0, vrw * math.sqrt(dt), 3)
@@ -83,7 +84,7 @@ def imu_samples(t0, t1, rate, rng, bg, ba, yaw_rate=5.0 * D2R):
 
 # ---------------------------------------------------------------------------------------------- problem
 def make_window(preintegrate, K=10, L=300, seed=2024, full_visibility=False, perturb=True, with_marg=False, pixel_noise=0.5, with_priors=False,
-                gnss_every=2):
+                gnss_every=2, earth=True):
     rng = np.random.Generator(np.random.PCG64(seed))
     dtk, rate = 0.5, 200.0
     times = np.arange(K) * dtk
@@ -134,13 +135,13 @@ def make_window(preintegrate, K=10, L=300, seed=2024, full_visibility=False, per
     bg_lin = bg_true + rng.normal(0, 5.0 * D2R / 3600.0, 3)
     ba_lin = ba_true + rng.normal(0, 5.0 * 1e-5, 3)
     for k in range(K - 1):
-        imu = imu_samples(times[k], times[k + 1], rate, rng, bg_true, ba_true)
+        imu = imu_samples(times[k], times[k + 1], rate, rng, bg_true, ba_true, earth=earth)
         state16 = np.concatenate([pose_t[k], mix_t[k, :3], bg_lin, ba_lin])
-        blob, pn, _ = preintegrate(state16, IEWN, GRAVITY, NOISE5, imu)
+        blob, pn, _ = preintegrate(state16, IEWN if earth else None, GRAVITY, NOISE5, imu)
         blobs[k] = blob
         pn_all.append(pn)
         pn_off.append(pn_off[-1] + pn.shape[0])
-    pn_all = np.concatenate(pn_all, axis=0)
+    pn_all = np.concatenate(pn_all, axis=0) if len(pn_all) else np.zeros((0, 4))
 
     # ---- GNSS on every 2nd node
     gnss_node = np.arange(0, K, gnss_every, dtype=np.int32)

@@ -127,9 +127,10 @@ def imu_preintegrate(state16, iewn, gravity, noise5, imu):
     n = imu.shape[0]
     blob = np.zeros(IMU_BLOB)
     end = np.zeros(10)
-    st, iw, g, nz = (np.ascontiguousarray(x, np.float64) for x in (state16, iewn, gravity, noise5))
-    check(lib().icg_imu_preintegrate(vp(st.ctypes.data), vp(iw.ctypes.data), vp(g.ctypes.data), vp(nz.ctypes.data), vp(imu.ctypes.data),
-                                     n, vp(blob.ctypes.data), vp(end.ctypes.data)), "icg_imu_preintegrate")
+    st, g, nz = (np.ascontiguousarray(x, np.float64) for x in (state16, gravity, noise5))
+    iw = np.ascontiguousarray(iewn, np.float64) if iewn is not None else None  # None: PreintegrationNormal (iswithearth false)
+    check(lib().icg_imu_preintegrate(vp(st.ctypes.data), vp(iw.ctypes.data) if iw is not None else None, vp(g.ctypes.data), vp(nz.ctypes.data),
+                                     vp(imu.ctypes.data), n, vp(blob.ctypes.data), vp(end.ctypes.data)), "icg_imu_preintegrate")
     return blob, end
 
 
@@ -289,6 +290,49 @@ class WindowSolver:
         check(lib().icg_ba_reproj_evaluate(self._h, *[vp(x.ctypes.data) for x in a], float(std), vp(r.ctypes.data),
                                            jp if want_jac else None), "icg_ba_reproj_evaluate")
         return r, Js
+
+    def gnss_evaluate(self, pose, blh, std3, lever):
+        a = [np.ascontiguousarray(x, np.float64) for x in (pose, blh, std3, lever)]
+        r, J = np.zeros(3), np.zeros((3, 7))
+        jp = (vp * 1)(vp(J.ctypes.data))
+        check(lib().icg_ba_gnss_evaluate(self._h, *[vp(x.ctypes.data) for x in a], vp(r.ctypes.data), jp), "icg_ba_gnss_evaluate")
+        return r, J
+
+    def pose_prior_evaluate(self, pose, prior7, std6):
+        a = [np.ascontiguousarray(x, np.float64) for x in (pose, prior7, std6)]
+        r, J = np.zeros(6), np.zeros((6, 7))
+        jp = (vp * 1)(vp(J.ctypes.data))
+        check(lib().icg_ba_pose_prior_evaluate(self._h, *[vp(x.ctypes.data) for x in a], vp(r.ctypes.data), jp), "icg_ba_pose_prior_evaluate")
+        return r, J
+
+    def mix_prior_evaluate(self, mix, prior9, std9):
+        a = [np.ascontiguousarray(x, np.float64) for x in (mix, prior9, std9)]
+        r, J = np.zeros(9), np.zeros((9, 9))
+        jp = (vp * 1)(vp(J.ctypes.data))
+        check(lib().icg_ba_mix_prior_evaluate(self._h, *[vp(x.ctypes.data) for x in a], vp(r.ctypes.data), jp), "icg_ba_mix_prior_evaluate")
+        return r, J
+
+    def imu_error_evaluate(self, mix):
+        m = np.ascontiguousarray(mix, np.float64)
+        r, J = np.zeros(6), np.zeros((6, 9))
+        jp = (vp * 1)(vp(J.ctypes.data))
+        check(lib().icg_ba_imu_error_evaluate(self._h, vp(m.ctypes.data), vp(r.ctypes.data), jp), "icg_ba_imu_error_evaluate")
+        return r, J
+
+    def marg_factor_evaluate(self, block_type, params, x0, J0, e0):
+        """MarginalizationFactor::Evaluate: params = list of the remained blocks' current values (global sizes)."""
+        bt = np.ascontiguousarray(block_type, np.int32)
+        ps = [np.ascontiguousarray(x, np.float64) for x in params]
+        x0, J0, e0 = (np.ascontiguousarray(x, np.float64) for x in (x0, J0, e0))
+        r = len(e0)
+        gs = {0: 7, 1: 9, 2: 7, 3: 1}
+        res = np.zeros(r)
+        Js = [np.zeros((r, gs[int(t)])) for t in bt]
+        pp = (vp * len(ps))(*[vp(x.ctypes.data) for x in ps])
+        jp = (vp * len(Js))(*[vp(x.ctypes.data) for x in Js])
+        check(lib().icg_ba_marg_factor_evaluate(self._h, r, len(bt), vp(bt.ctypes.data), pp, vp(x0.ctypes.data), vp(J0.ctypes.data), vp(e0.ctypes.data),
+                                                vp(res.ctypes.data), jp), "icg_ba_marg_factor_evaluate")
+        return res, Js
 
     def imu_evaluate(self, blob, pose0, mix0, pose1, mix1, want_jac=True):
         a = [np.ascontiguousarray(x, np.float64) for x in (blob, pose0, mix0, pose1, mix1)]

@@ -1434,6 +1434,58 @@ __global__ void ba_imu_eval_kernel(const double *blob, const double *U, const do
     for (int e = threadIdx.x; e < 450; e += 32) out[15 + e] = s_buf[30 + e];
 }
 
+// GnssFactor / ImuPosePriorFactor / ImuMixPriorFactor / ImuErrorFactor (kind 0..3), one thread; in / out layouts in the callers below
+__global__ void ba_small_factor_eval_kernel(int kind, const double *in, double *out) {
+    if (kind == 0) {         // in: pose7 blh3 std3 lever3 -> r[3], J local 3x6
+        gnss_eval(in, in + 7, in + 10, in + 13, true, out, out + 3);
+    } else if (kind == 1) {  // in: pose7 prior7 sinfo6 -> r[6], J local 6x6
+        pose_prior_eval(in, in + 7, in + 14, true, out, out + 6);
+    } else if (kind == 2) {  // in: mix9 prior9 std9 -> r[9], diag J[9]   (ImuMixPriorFactor, imu_mix_prior_factor.h:40-75)
+        for (int k = 0; k < 9; k++) out[k] = (in[k] - in[9 + k]) / in[18 + k], out[9 + k] = 1.0 / in[18 + k];
+    } else {                 // in: mix9 -> r[6], diag J[6]                (ImuErrorFactor, imu_error_factor.h:45-91)
+        for (int k = 0; k < 3; k++) {
+            out[k] = in[3 + k] / IMU_GB_STD, out[3 + k] = in[6 + k] / IMU_AB_STD;
+            out[6 + k] = 1.0 / IMU_GB_STD, out[9 + k] = 1.0 / IMU_AB_STD;
+        }
+    }
+}
+
+// MarginalizationFactor::Evaluate (IG/factors/marginalization_factor.h:47-101): e = e0 + J0 dx with dx the local difference of every
+// remained block to its linearisation point (quaternion blocks: 2 vec(q0^-1 q), sign-fixed).  One CTA; thread per residual row.
+// in: [r, nb, types[nb], x (global sizes, concatenated), x0 (same), e0[r], J0[r*r]] as doubles; out: residuals[r]
+__global__ void ba_marg_factor_eval_kernel(const double *in, double *out) {
+    extern __shared__ double s_dx[];
+    const int r = (int) in[0], nb = (int) in[1];
+    const double *types = in + 2;
+    int tot = 0;
+    for (int b = 0; b < nb; b++) tot += ((int) types[b] == 1) ? 9 : ((int) types[b] == 3) ? 1 : 7;
+    const double *x = types + nb, *x0 = x + tot, *e0 = x0 + tot, *J0 = e0 + r;
+    if (threadIdx.x == 0) {
+        int col = 0, xo = 0;
+        for (int b = 0; b < nb; b++) {
+            const int t = (int) types[b];
+            if (t == 0 || t == 2) {
+                Q dq = qmul(qinv(pose_q(x0 + xo)), pose_q(x + xo));
+                V3 a = 2.0 * qv(dq);
+                if (dq.w < 0) a = -a;
+                for (int k = 0; k < 3; k++) s_dx[col + k] = x[xo + k] - x0[xo + k];
+                s_dx[col + 3] = a.x, s_dx[col + 4] = a.y, s_dx[col + 5] = a.z;
+                col += 6, xo += 7;
+            } else {
+                const int g = t == 1 ? 9 : 1;
+                for (int k = 0; k < g; k++) s_dx[col + k] = x[xo + k] - x0[xo + k];
+                col += g, xo += g;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < r; i += blockDim.x) {
+        double sum = e0[i];
+        for (int k = 0; k < r; k++) sum += J0[(size_t) i * r + k] * s_dx[k];
+        out[i] = sum;
+    }
+}
+
 }  // namespace icg
 
 #include "ba_split.cuh"
@@ -1618,10 +1670,16 @@ int icg_imu_preintegrate(const double *state16, const double *iewn3, const doubl
                          double *end_state10) {
     // PreintegrationEarth: resetState (:305-324), setNoiseMatrix (:326-334), integrationProcess (:205-260),
     // updateJacobianAndCovariance (:266-303) of IG/preintegration/preintegration_earth.cc.  Host code (sequential recurrence).
-    if (!state16 || !iewn3 || !gravity3 || !noise5 || !imu || !blob || n < 1) {
+    // iewn3 == NULL selects PreintegrationNormal (`iswithearth: false`, IG/preintegration/preintegration_normal.cc:155-232 +
+    // PreintegrationBase::integration, preintegration_base.cc:39-70): no Earth-rotation / Coriolis terms; the blob is tagged (blob[477] = 1)
+    // so that the factor evaluates PreintegrationNormal::evaluate.
+    if (!state16 || !gravity3 || !noise5 || !imu || !blob || n < 1) {
         set_error("icg_imu_preintegrate: bad arguments");
         return ICG_EINVAL;
     }
+    const bool normal = iewn3 == nullptr;
+    const double zero3[3] = {0, 0, 0};
+    if (normal) iewn3 = zero3;
     V3 cur_p = mk(state16[0], state16[1], state16[2]), cur_v = mk(state16[7], state16[8], state16[9]);
     Q cur_q = mkq(state16[6], state16[3], state16[4], state16[5]);
     const Q q0 = cur_q;
@@ -1647,23 +1705,39 @@ int icg_imu_preintegrate(const double *state16, const double *iewn3, const doubl
         V3 cth = mk(cu[1], cu[2], cu[3]) - dt * bg, cvl = mk(cu[4], cu[5], cu[6]) - dt * ba;
         delta_time += dt;
         V3 dvfb = cvl + 0.5 * cross(cth, cvl) + (1.0 / 12.0) * (cross(pth, cvl) + cross(pvl, cth));
-        V3 dv_cor_g = dt * (grav - 2.0 * cross(iewn, cur_v));
-        Q qnn = rotvec2q(-(dt * iewn));
-        V3 dvel = mul(scale(0.5, add(ident(), qmat(qnn))), mul(qmat(cur_q), dvfb)) + dv_cor_g;
-        cur_p = cur_p + dt * cur_v + (0.5 * dt) * dvel;
-        cur_v = cur_v + dvel;
-        s0 += dt;
-        s1 = s1 + dt * cur_p;
         V3 dtheta = cth + (1.0 / 12.0) * cross(pth, cth);
-        cur_q = qnormalized(qmul(qmul(qnn, cur_q), rotvec2q(dtheta)));
-        V3 dnn = -((delta_time - 0.5 * dt) * iewn);
-        dvel = mul(qmat(qmul(qmul(qmul(qinv(q0), rotvec2q(dnn)), q0), dq)), dvfb);
-        dp = dp + dt * dv + (0.5 * dt) * dvel;
-        dv = dv + dvel;
-        dq = qnormalized(qmul(dq, rotvec2q(dtheta)));
+        M3 cbb0;
+        if (!normal) {
+            V3 dv_cor_g = dt * (grav - 2.0 * cross(iewn, cur_v));
+            Q qnn = rotvec2q(-(dt * iewn));
+            V3 dvel = mul(scale(0.5, add(ident(), qmat(qnn))), mul(qmat(cur_q), dvfb)) + dv_cor_g;
+            cur_p = cur_p + dt * cur_v + (0.5 * dt) * dvel;
+            cur_v = cur_v + dvel;
+            s0 += dt;
+            s1 = s1 + dt * cur_p;
+            cur_q = qnormalized(qmul(qmul(qnn, cur_q), rotvec2q(dtheta)));
+            V3 dnn = -((delta_time - 0.5 * dt) * iewn);
+            dvel = mul(qmat(qmul(qmul(qmul(qinv(q0), rotvec2q(dnn)), q0), dq)), dvfb);
+            dp = dp + dt * dv + (0.5 * dt) * dvel;
+            dv = dv + dvel;
+            dq = qnormalized(qmul(dq, rotvec2q(dtheta)));
+            cbb0 = neg(qmat(qmul(qmul(qmul(qinv(q0), rotvec2q(-(delta_time * iewn))), q0), dq)));
+        } else {
+            V3 dvel = mul(qmat(cur_q), dvfb) + dt * grav;
+            cur_p = cur_p + dt * cur_v + (0.5 * dt) * dvel;
+            cur_v = cur_v + dvel;
+            cur_q = qnormalized(qmul(cur_q, rotvec2q(dtheta)));
+            dvel = mul(qmat(dq), dvfb);
+            dp = dp + dt * dv + (0.5 * dt) * dvel;
+            dv = dv + dvel;
+            dq = qnormalized(qmul(dq, rotvec2q(dtheta)));
+            // phi(3,6) = -R(dq) [dvel]x, phi(3,12) = -R(dq) dt; gt(3,3) = R(dq), gt(6,0) = +I (preintegration_normal.cc:207-225): with a
+            // diagonal noise matrix G = gt noise gt^T does not see the sign of a column block of gt, so the Earth form below with
+            // cbb0 = -R(dq) is the same arithmetic
+            cbb0 = neg(qmat(dq));
+        }
         // updateJacobianAndCovariance
         double phi[225] = {0}, gt[180] = {0};
-        M3 cbb0 = neg(qmat(qmul(qmul(qmul(qinv(q0), rotvec2q(-(delta_time * iewn))), q0), dq)));
         put(phi, 15, 0, 0, ident());
         put(phi, 15, 0, 3, scale(dt, ident()));
         put(phi, 15, 3, 3, ident());
@@ -1714,6 +1788,7 @@ int icg_imu_preintegrate(const double *state16, const double *iewn3, const doubl
     blob[23] = s0, blob[24] = s1.x, blob[25] = s1.y, blob[26] = s1.z;
     memcpy(blob + 27, jac, sizeof(jac));
     memcpy(blob + 252, cov, sizeof(cov));
+    blob[477] = normal ? 1.0 : 0.0;
     if (end_state10) {
         end_state10[0] = cur_p.x, end_state10[1] = cur_p.y, end_state10[2] = cur_p.z;
         end_state10[3] = cur_q.x, end_state10[4] = cur_q.y, end_state10[5] = cur_q.z, end_state10[6] = cur_q.w;
@@ -2846,6 +2921,140 @@ int icg_ba_imu_evaluate(icg_ba *h, const double *blob, const double *pose0, cons
             if (!jacobians[b]) continue;
             for (int r = 0; r < 15; r++)
                 for (int c = 0; c < gs[b]; c++) jacobians[b][r * gs[b] + c] = c < ls[b] ? J[r * 30 + c0[b] + c] : 0.0;
+        }
+    }
+    return ICG_OK;
+}
+
+// host helper of the small single-factor seams: upload `nin` doubles, run, download `nout` doubles (through the handle's scratch buffers)
+static int small_factor_eval(icg_ba *h, int kind, const double *in, int nin, double *out, int nout) {
+    ICG_CUDA(cudaSetDevice(h->device));
+    memcpy(h->scratch.h, in, sizeof(double) * nin);
+    ICG_CUDA(cudaMemcpyAsync(h->scratch.d, h->scratch.h, sizeof(double) * nin, cudaMemcpyHostToDevice, h->stream));
+    ba_small_factor_eval_kernel<<<1, 1, 0, h->stream>>>(kind, h->scratch.d, h->scratch.d + 128);
+    count_launch();
+    ICG_CUDA(cudaMemcpyAsync(h->scratch.h + 128, h->scratch.d + 128, sizeof(double) * nout, cudaMemcpyDeviceToHost, h->stream));
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(out, h->scratch.h + 128, sizeof(double) * nout);
+    return ICG_OK;
+}
+
+int icg_ba_gnss_evaluate(icg_ba *h, const double *pose, const double *blh, const double *std3, const double *lever, double *residuals, double **jacobians) {
+    if (!h || !pose || !blh || !std3 || !lever || !residuals) {
+        set_error("icg_ba_gnss_evaluate: bad arguments");
+        return ICG_EINVAL;
+    }
+    double in[16], out[21];
+    memcpy(in, pose, 56), memcpy(in + 7, blh, 24), memcpy(in + 10, std3, 24), memcpy(in + 13, lever, 24);
+    int rc = small_factor_eval(h, 0, in, 16, out, 21);
+    if (rc != ICG_OK) return rc;
+    memcpy(residuals, out, 24);
+    if (jacobians && jacobians[0])  // global 3x7 row-major; the quaternion-w column is zero (gnss_factor.h:60-68)
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 7; c++) jacobians[0][r * 7 + c] = c < 6 ? out[3 + r * 6 + c] : 0.0;
+    return ICG_OK;
+}
+
+int icg_ba_pose_prior_evaluate(icg_ba *h, const double *pose, const double *prior7, const double *std6, double *residuals, double **jacobians) {
+    if (!h || !pose || !prior7 || !std6 || !residuals) {
+        set_error("icg_ba_pose_prior_evaluate: bad arguments");
+        return ICG_EINVAL;
+    }
+    double in[20], out[42];
+    memcpy(in, pose, 56), memcpy(in + 7, prior7, 56);
+    for (int k = 0; k < 6; k++) in[14 + k] = 1.0 / std6[k];
+    int rc = small_factor_eval(h, 1, in, 20, out, 42);
+    if (rc != ICG_OK) return rc;
+    memcpy(residuals, out, 48);
+    if (jacobians && jacobians[0])
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c < 7; c++) jacobians[0][r * 7 + c] = c < 6 ? out[6 + r * 6 + c] : 0.0;
+    return ICG_OK;
+}
+
+int icg_ba_mix_prior_evaluate(icg_ba *h, const double *mix, const double *prior9, const double *std9, double *residuals, double **jacobians) {
+    if (!h || !mix || !prior9 || !std9 || !residuals) {
+        set_error("icg_ba_mix_prior_evaluate: bad arguments");
+        return ICG_EINVAL;
+    }
+    double in[27], out[18];
+    memcpy(in, mix, 72), memcpy(in + 9, prior9, 72), memcpy(in + 18, std9, 72);
+    int rc = small_factor_eval(h, 2, in, 27, out, 18);
+    if (rc != ICG_OK) return rc;
+    memcpy(residuals, out, 72);
+    if (jacobians && jacobians[0]) {
+        memset(jacobians[0], 0, sizeof(double) * 81);
+        for (int k = 0; k < 9; k++) jacobians[0][k * 9 + k] = out[9 + k];
+    }
+    return ICG_OK;
+}
+
+int icg_ba_imu_error_evaluate(icg_ba *h, const double *mix, double *residuals, double **jacobians) {
+    if (!h || !mix || !residuals) {
+        set_error("icg_ba_imu_error_evaluate: bad arguments");
+        return ICG_EINVAL;
+    }
+    double out[12];
+    int rc = small_factor_eval(h, 3, mix, 9, out, 12);
+    if (rc != ICG_OK) return rc;
+    memcpy(residuals, out, 48);
+    if (jacobians && jacobians[0]) {  // 6x9: rows 0..2 on bg (columns 3..5), rows 3..5 on ba (columns 6..8)
+        memset(jacobians[0], 0, sizeof(double) * 54);
+        for (int k = 0; k < 3; k++) jacobians[0][k * 9 + 3 + k] = out[6 + k], jacobians[0][(3 + k) * 9 + 6 + k] = out[9 + k];
+    }
+    return ICG_OK;
+}
+
+int icg_ba_marg_factor_evaluate(icg_ba *h, int r, int nblocks, const int32_t *block_type, const double *const *parameters, const double *x0,
+                                const double *J0, const double *e0, double *residuals, double **jacobians) {
+    if (!h || r < 1 || nblocks < 1 || !block_type || !parameters || !x0 || !J0 || !e0 || !residuals) {
+        set_error("icg_ba_marg_factor_evaluate: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    int tot = 0, cols = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const int t = block_type[b];
+        if (t < 0 || t > 3 || !parameters[b]) {
+            set_error("icg_ba_marg_factor_evaluate: block %d invalid", b);
+            return ICG_EINVAL;
+        }
+        tot += t == 1 ? 9 : t == 3 ? 1 : 7, cols += t == 1 ? 9 : t == 3 ? 1 : 6;
+    }
+    if (cols != r) {
+        set_error("icg_ba_marg_factor_evaluate: the blocks give %d local columns, r = %d", cols, r);
+        return ICG_EINVAL;
+    }
+    const size_t nin = 2 + (size_t) nblocks + 2 * (size_t) tot + r + (size_t) r * r;
+    std::vector<double> in(nin);
+    in[0] = r, in[1] = nblocks;
+    for (int b = 0; b < nblocks; b++) in[2 + b] = block_type[b];
+    double *px = in.data() + 2 + nblocks;
+    int xo = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const int g = block_type[b] == 1 ? 9 : block_type[b] == 3 ? 1 : 7;
+        memcpy(px + xo, parameters[b], sizeof(double) * g);
+        xo += g;
+    }
+    memcpy(px + tot, x0, sizeof(double) * tot);
+    memcpy(px + 2 * tot, e0, sizeof(double) * r);
+    memcpy(px + 2 * tot + r, J0, sizeof(double) * (size_t) r * r);
+    double *d = nullptr;
+    ICG_CUDA(cudaMalloc(&d, sizeof(double) * (nin + r)));
+    ICG_CUDA(cudaMemcpyAsync(d, in.data(), sizeof(double) * nin, cudaMemcpyHostToDevice, h->stream));
+    ba_marg_factor_eval_kernel<<<1, 256, sizeof(double) * r, h->stream>>>(d, d + nin);
+    count_launch();
+    ICG_CUDA(cudaMemcpyAsync(residuals, d + nin, sizeof(double) * r, cudaMemcpyDeviceToHost, h->stream));
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    if (jacobians) {  // the factor is linear: d e / d (block b) = J0[:, columns of b], quaternion-w column zero (marginalization_factor.h:84-97)
+        int col = 0;
+        for (int b = 0; b < nblocks; b++) {
+            const int t = block_type[b], g = t == 1 ? 9 : t == 3 ? 1 : 7, l = t == 1 ? 9 : t == 3 ? 1 : 6;
+            if (jacobians[b])
+                for (int i = 0; i < r; i++)
+                    for (int c = 0; c < g; c++) jacobians[b][(size_t) i * g + c] = c < l ? J0[(size_t) i * r + col + c] : 0.0;
+            col += l;
         }
     }
     return ICG_OK;

@@ -222,7 +222,7 @@ BAM_HD void pose_prior_eval(const double *pose, const double *prior, const doubl
 
 // IMU blob layout (include/icgvins_b200.h)
 constexpr int IB_DT = 0, IB_DP = 1, IB_DV = 4, IB_DQ = 7, IB_BG = 11, IB_BA = 14, IB_G = 17, IB_IEWN = 20, IB_S0 = 23, IB_S1 = 24, IB_JAC = 27,
-              IB_COV = 252;
+              IB_COV = 252, IB_MODE = 477;  // mode 0: PreintegrationEarth, 1: PreintegrationNormal
 
 // PreintegrationEarth::evaluate (IG/preintegration/preintegration_earth.cc:37-90): UNWHITENED residual (15) and the
 // intermediates the Jacobian methods read (dpn, dvn, qb0b1, corrected_q: `:61-72`).
@@ -262,6 +262,11 @@ BAM_HD void imu_residual_raw(const double *b, const double *pose0, const double 
     M.cnb0 = qmat(qinv(q0));
     M.qb0b1 = qmul(qmul(qinv(q1), qnn), q0);
     V3 rp = mul(M.cnb0, M.dpn) - corrected_p, rv = mul(M.cnb0, M.dvn) - corrected_v, rq = 2.0 * qv(qmul(M.qb0b1, M.corrected_q));
+    if (b[IB_MODE] != 0.0) {
+        // PreintegrationNormal::evaluate (IG/preintegration/preintegration_normal.cc:38-75): iewn = 0 in the blob, so dpn / dvn / cnb0 above
+        // are already its terms; the attitude residual is 2 (corrected_q^-1 q0^-1 q1).vec().  M.qb0b1 carries q1^-1 q0 for the Jacobians.
+        rq = 2.0 * qv(qmul(qmul(qinv(M.corrected_q), qinv(q0)), q1));
+    }
     V3 rbg = bg1 - bg0, rba = ba1 - ba0;
     r[0] = rp.x, r[1] = rp.y, r[2] = rp.z, r[3] = rv.x, r[4] = rv.y, r[5] = rv.z, r[6] = rq.x, r[7] = rq.y, r[8] = rq.z;
     r[9] = rbg.x, r[10] = rbg.y, r[11] = rbg.z, r[12] = rba.x, r[13] = rba.y, r[14] = rba.z;
@@ -318,6 +323,17 @@ BAM_HD void imu_jacobian_raw(const double *b, const ImuMid &M, double *J /* 450,
     put(3, 21, M.cnb0);
     put(9, 24, ident());
     put(12, 27, ident());
+    if (b[IB_MODE] != 0.0) {
+        // PreintegrationNormal::residualJacobianPose0/Pose1/Mix0 (preintegration_normal.cc:77-140): only the attitude rows differ from the
+        // Earth form evaluated with iewn = 0 (M.qb0b1 = q1^-1 q0):
+        //   pose0 (6,3) = -(quaternionleft(q1^-1 q0) quaternionright(corrected_q)).bottomRight
+        //   pose1 (6,3) =  quaternionleft(corrected_q^-1 q0^-1 q1).bottomRight
+        //   mix0  (6,3) = -quaternionleft(q1^-1 q0 dq).bottomRight dq_dbg
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) J[(6 + i) * 30 + 3 + j] = -J[(6 + i) * 30 + 3 + j];
+        put(6, 18, qleft_br(qmul(qinv(M.corrected_q), qinv(M.qb0b1))));
+        put(6, 9, neg(mul(qleft_br(qmul(M.qb0b1, dq)), dq_dbg)));
+    }
 }
 
 }  // namespace bam

@@ -187,7 +187,9 @@ int icg_corner_subpix(icg_detect *h, const uint8_t *img, int stride, float *corn
  * [11..13] bg, [14..16] ba (linearisation biases), [17..19] gravity, [20..22] iewn,
  * [23] S0 = sum_i dt_i, [24..26] S1 = sum_i dt_i * pn_i   (the two moments of pn_ that
  *      PreintegrationEarth::evaluate's position-compensation loop needs, IG/preintegration/preintegration_earth.cc:55-59),
- * [27..251] jacobian_ 15x15 row-major, [252..476] covariance_ 15x15 row-major, [477..479] reserved. */
+ * [27..251] jacobian_ 15x15 row-major, [252..476] covariance_ 15x15 row-major,
+ * [477] factor form: 0 = PreintegrationEarth (IG/preintegration/preintegration_earth.cc), 1 = PreintegrationNormal
+ *       (preintegration_normal.cc, `iswithearth: false`: iewn = 0, S0 = S1 = 0), [478..479] reserved. */
 typedef struct icg_ba_problem {
     int32_t K, L, F;
     double *pose;     /* K*7 in/out */
@@ -229,7 +231,9 @@ typedef struct icg_ba_summary {
  * PreintegrationEarth::resetState/integrationProcess/updateJacobianAndCovariance (IG/preintegration/preintegration_earth.cc:205-338).
  * state16 = p[3] q_xyzw[4] v[3] bg[3] ba[3] at the interval start; noise5 = gyr_arw, acc_vrw, gyr_bias_std, acc_bias_std, corr_time;
  * imu = n rows of (dt, dtheta[3], dvel[3]), row 0 being the sample at the interval start.  Writes the factor blob and the
- * mechanised end state (p, q_xyzw, v).  Sequential recurrence; runs on the calling host thread. */
+ * mechanised end state (p, q_xyzw, v).  Sequential recurrence; runs on the calling host thread.
+ * iewn3 == NULL selects PreintegrationNormal (PreintegrationBase::integration + PreintegrationNormal::updateJacobianAndCovariance,
+ * IG/preintegration/preintegration_base.cc:39-70, preintegration_normal.cc:195-232). */
 int icg_imu_preintegrate(const double *state16, const double *iewn3, const double *gravity3, const double *noise5, const double *imu,
                          int n, double *blob_out, double *end_state10);
 
@@ -335,6 +339,22 @@ int icg_ba_reproj_evaluate(icg_ba *h, const double *pose0, const double *pose1, 
 /* PreintegrationFactor::Evaluate (IG/preintegration/preintegration_factor.h:45): residuals[15], jacobians 15x7,15x9,15x7,15x9 */
 int icg_ba_imu_evaluate(icg_ba *h, const double *imu_blob, const double *pose0, const double *mix0, const double *pose1,
                         const double *mix1, double *residuals, double **jacobians);
+
+/* The remaining CostFunction::Evaluate seams of the window graph (same contract: residuals, then one row-major Jacobian per parameter
+ * block with its GLOBAL size, any may be NULL; computed on the device):
+ *   GnssFactor::Evaluate            (IG/factors/gnss_factor.h:43-71)                 residuals[3], jacobians[0] 3x7
+ *   ImuPosePriorFactor::Evaluate    (IG/preintegration/imu_pose_prior_factor.h:42-68) residuals[6], jacobians[0] 6x7
+ *   ImuMixPriorFactor::Evaluate     (IG/preintegration/imu_mix_prior_factor.h:40-75)  residuals[9], jacobians[0] 9x9
+ *   ImuErrorFactor::Evaluate        (IG/preintegration/imu_error_factor.h:45-91)      residuals[6], jacobians[0] 6x9
+ *   MarginalizationFactor::Evaluate (IG/factors/marginalization_factor.h:47-101)      residuals[r], jacobians[b] r x (7 | 9 | 7 | 1);
+ *       parameters[b] = the current value of remained block b (block_type as in icg_ba_problem.marg_block_type), x0 / J0 / e0 the prior. */
+int icg_ba_gnss_evaluate(icg_ba *h, const double *pose, const double *blh, const double *std3, const double *lever, double *residuals,
+                         double **jacobians);
+int icg_ba_pose_prior_evaluate(icg_ba *h, const double *pose, const double *prior7, const double *std6, double *residuals, double **jacobians);
+int icg_ba_mix_prior_evaluate(icg_ba *h, const double *mix, const double *prior9, const double *std9, double *residuals, double **jacobians);
+int icg_ba_imu_error_evaluate(icg_ba *h, const double *mix, double *residuals, double **jacobians);
+int icg_ba_marg_factor_evaluate(icg_ba *h, int r, int nblocks, const int32_t *block_type, const double *const *parameters, const double *x0,
+                                const double *J0, const double *e0, double *residuals, double **jacobians);
 
 #ifdef __cplusplus
 }

@@ -190,6 +190,100 @@ void imu_sqrt_information(const double *cov, double *U /*15x15 row-major*/) {
 }
 
 // ===================================================================================== PreintegrationFactor
+// PreintegrationNormal::evaluate + residualJacobianPose0/Pose1/Mix0/Mix1 (preintegration/preintegration_normal.cc:38-142): no Earth
+// rotation terms, and the attitude residual is 2 (corrected_q^-1 q0^-1 q1).vec() (the inverse ordering of the Earth form)
+static bool evaluate_normal(const Preintegration &P, double const *const *parameters, double *residuals, double **jacobians) {
+    V3 p0 = pose_p(parameters[0]);
+    Q q0  = pose_q(parameters[0]);
+    V3 v0{parameters[1][0], parameters[1][1], parameters[1][2]}, bg0{parameters[1][3], parameters[1][4], parameters[1][5]},
+        ba0{parameters[1][6], parameters[1][7], parameters[1][8]};
+    V3 p1 = pose_p(parameters[2]);
+    Q q1  = pose_q(parameters[2]);
+    V3 v1{parameters[3][0], parameters[3][1], parameters[3][2]}, bg1{parameters[3][3], parameters[3][4], parameters[3][5]},
+        ba1{parameters[3][6], parameters[3][7], parameters[3][8]};
+    double U[225];
+    imu_sqrt_information(P.covariance, U);
+    auto blk = [&](int r, int c) {
+        M3 m;
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) m(i, j) = P.jacobian[(r + i) * 15 + c + j];
+        return m;
+    };
+    M3 dp_dbg = blk(0, 9), dp_dba = blk(0, 12), dv_dbg = blk(3, 9), dv_dba = blk(3, 12), dq_dbg = blk(6, 9);
+    V3 dbg = bg0 - P.bg, dba = ba0 - P.ba;
+    const double dt = P.delta_time;
+    V3 corrected_p = P.dp + dp_dba * dba + dp_dbg * dbg;
+    V3 corrected_v = P.dv + dv_dba * dba + dv_dbg * dbg;
+    Q corrected_q  = P.dq * rotvec2quaternion(dq_dbg * dbg);
+    Q q0i = q_inverse(q0);
+    M3 c0 = q_matrix(q0i);
+    V3 dpn = p1 - p0 - v0 * dt - 0.5 * P.gravity * dt * dt;
+    V3 dvn = v1 - v0 - P.gravity * dt;
+    double r[15];
+    V3 rp = q_rotate(q0i, dpn) - corrected_p, rv = q_rotate(q0i, dvn) - corrected_v;
+    V3 rq = 2.0 * vec(q_inverse(corrected_q) * q0i * q1), rbg = bg1 - bg0, rba = ba1 - ba0;
+    r[0] = rp.x, r[1] = rp.y, r[2] = rp.z, r[3] = rv.x, r[4] = rv.y, r[5] = rv.z, r[6] = rq.x, r[7] = rq.y, r[8] = rq.z;
+    r[9] = rbg.x, r[10] = rbg.y, r[11] = rbg.z, r[12] = rba.x, r[13] = rba.y, r[14] = rba.z;
+    for (int i = 0; i < 15; i++) {
+        double s = 0;
+        for (int k = 0; k < 15; k++) s += U[i * 15 + k] * r[k];
+        residuals[i] = s;
+    }
+    if (!jacobians) return true;
+    auto whiten = [&](const double *Jraw, int ncols, double *out) {
+        for (int i = 0; i < 15; i++)
+            for (int c = 0; c < ncols; c++) {
+                double s = 0;
+                for (int k = 0; k < 15; k++) s += U[i * 15 + k] * Jraw[k * ncols + c];
+                out[i * ncols + c] = s;
+            }
+    };
+    // bottom-right 3x3 of quaternionleft(a) * quaternionright(b) (rotation.h:103-119): -a_v b_v^T + L_br(a) R_br(b)
+    auto lr_br = [&](Q a, Q b) {
+        V3 av = vec(a), bv = vec(b);
+        M3 lr = qleft_br(a) * qright_br(b), m;
+        const double x[3] = {av.x, av.y, av.z}, y[3] = {bv.x, bv.y, bv.z};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) m(i, j) = -x[i] * y[j] + lr(i, j);
+        return m;
+    };
+    if (jacobians[0]) {  // residualJacobianPose0 (:77-97)
+        double J[15 * 7] = {0};
+        set_block(J, 7, 0, 0, -c0);
+        set_block(J, 7, 0, 3, skew(q_rotate(q0i, dpn)));
+        set_block(J, 7, 3, 3, skew(q_rotate(q0i, dvn)));
+        set_block(J, 7, 6, 3, -lr_br(q_inverse(q1) * q0, corrected_q));
+        whiten(J, 7, jacobians[0]);
+    }
+    if (jacobians[1]) {  // residualJacobianMix0 (:113-140)
+        double J[15 * 9] = {0};
+        set_block(J, 9, 0, 0, -dt * c0);
+        set_block(J, 9, 0, 3, -dp_dbg);
+        set_block(J, 9, 0, 6, -dp_dba);
+        set_block(J, 9, 3, 0, -c0);
+        set_block(J, 9, 3, 3, -dv_dbg);
+        set_block(J, 9, 3, 6, -dv_dba);
+        set_block(J, 9, 6, 3, -(qleft_br(q_inverse(q1) * q0 * P.dq) * dq_dbg));
+        set_block(J, 9, 9, 3, -m3_identity());
+        set_block(J, 9, 12, 6, -m3_identity());
+        whiten(J, 9, jacobians[1]);
+    }
+    if (jacobians[2]) {  // residualJacobianPose1 (:99-111)
+        double J[15 * 7] = {0};
+        set_block(J, 7, 0, 0, c0);
+        set_block(J, 7, 6, 3, qleft_br(q_inverse(corrected_q) * q0i * q1));
+        whiten(J, 7, jacobians[2]);
+    }
+    if (jacobians[3]) {  // residualJacobianMix1 (:142-153)
+        double J[15 * 9] = {0};
+        set_block(J, 9, 3, 0, c0);
+        set_block(J, 9, 9, 3, m3_identity());
+        set_block(J, 9, 12, 6, m3_identity());
+        whiten(J, 9, jacobians[3]);
+    }
+    return true;
+}
+
 bool PreintegrationFactor::Evaluate(double const *const *parameters, double *residuals, double **jacobians) const {
     const Preintegration &P = *pre;
     // constructState (preintegration_earth.cc:186-203)
@@ -202,6 +296,7 @@ bool PreintegrationFactor::Evaluate(double const *const *parameters, double *res
     V3 v1{parameters[3][0], parameters[3][1], parameters[3][2]}, bg1{parameters[3][3], parameters[3][4], parameters[3][5]},
         ba1{parameters[3][6], parameters[3][7], parameters[3][8]};
 
+    if (P.normal) return evaluate_normal(P, parameters, residuals, jacobians);
     // evaluate (preintegration_earth.cc:37-90)
     double U[225];
     imu_sqrt_information(P.covariance, U);
@@ -389,6 +484,37 @@ static void mat15_mul(const double *A, const double *B, double *C) {
         }
 }
 
+// covariance_ = phi covariance_ phi^T + 0.5 dt (phi G + G phi^T), G = gt noise_ gt^T  (preintegration_earth.cc:296-302, _normal.cc:226-231)
+static void propagate_covariance(Preintegration &P, const double *phi, const double *gt, double dt) {
+    // G = gt * noise * gt^T (15x15)
+    double gn[15 * 12], G[225];
+    for (int i = 0; i < 15; i++)
+        for (int j = 0; j < 12; j++) {
+            double s = 0;
+            for (int k = 0; k < 12; k++) s += gt[i * 12 + k] * P.noise[k * 12 + j];
+            gn[i * 12 + j] = s;
+        }
+    for (int i = 0; i < 15; i++)
+        for (int j = 0; j < 15; j++) {
+            double s = 0;
+            for (int k = 0; k < 12; k++) s += gn[i * 12 + k] * gt[j * 12 + k];
+            G[i * 15 + j] = s;
+        }
+    double pg[225], cov2[225], pc[225];
+    mat15_mul(phi, G, pg);  // phi * G
+    // Qk = 0.5 dt (phi G + G phi^T)
+    mat15_mul(phi, P.covariance, pc);
+    for (int i = 0; i < 15; i++)
+        for (int j = 0; j < 15; j++) {
+            double s = 0;
+            for (int k = 0; k < 15; k++) s += pc[i * 15 + k] * phi[j * 15 + k];
+            double gpt = 0;
+            for (int k = 0; k < 15; k++) gpt += G[i * 15 + k] * phi[j * 15 + k];
+            cov2[i * 15 + j] = s + 0.5 * dt * (pg[i * 15 + j] + gpt);
+        }
+    std::memcpy(P.covariance, cov2, sizeof(cov2));
+}
+
 void preint_reset(Preintegration &P, V3 p, Q q, V3 v, V3 bg, V3 ba, V3 iewn, V3 gravity, double gyr_arw, double acc_vrw, double gyr_bias_std,
                   double acc_bias_std, double corr_time) {
     // resetState (preintegration_earth.cc:305-324) + setNoiseMatrix (:326-334)
@@ -426,6 +552,42 @@ void preint_add_imu(Preintegration &P, const double *pre_raw, const double *cur_
     V3 pth, pvl, cth, cvl;
     comp(pre_raw, dtp, pth, pvl);
     comp(cur_raw, dt, cth, cvl);
+    if (P.normal) {
+        // PreintegrationBase::integration (preintegration_base.cc:39-70) + PreintegrationNormal::updateJacobianAndCovariance
+        // (preintegration_normal.cc:195-232)
+        P.delta_time += dt;
+        V3 dvfb = cvl + 0.5 * cross(cth, cvl) + (1.0 / 12.0) * (cross(pth, cvl) + cross(pvl, cth));
+        V3 dvel = q_matrix(P.cur_q) * dvfb + P.gravity * dt;
+        P.cur_p = P.cur_p + dt * P.cur_v + 0.5 * dt * dvel;
+        P.cur_v = P.cur_v + dvel;
+        V3 dtheta = cth + (1.0 / 12.0) * cross(pth, cth);
+        P.cur_q = q_normalized(P.cur_q * rotvec2quaternion(dtheta));
+        dvel = q_matrix(P.dq) * dvfb;
+        P.dp = P.dp + dt * P.dv + 0.5 * dt * dvel;
+        P.dv = P.dv + dvel;
+        P.dq = q_normalized(P.dq * rotvec2quaternion(dtheta));
+        double phi[225] = {0};
+        M3 Rdq = q_matrix(P.dq);
+        set_block(phi, 15, 0, 0, m3_identity());
+        set_block(phi, 15, 0, 3, dt * m3_identity());
+        set_block(phi, 15, 3, 3, m3_identity());
+        set_block(phi, 15, 3, 6, -(Rdq * skew(cvl)));
+        set_block(phi, 15, 3, 12, -dt * Rdq);
+        set_block(phi, 15, 6, 6, m3_identity() - skew(cth));
+        set_block(phi, 15, 6, 9, -dt * m3_identity());
+        set_block(phi, 15, 9, 9, (1 - dt / P.corr_time) * m3_identity());
+        set_block(phi, 15, 12, 12, (1 - dt / P.corr_time) * m3_identity());
+        double tmp[225];
+        mat15_mul(phi, P.jacobian, tmp);
+        std::memcpy(P.jacobian, tmp, sizeof(tmp));
+        double gt[15 * 12] = {0};
+        set_block(gt, 12, 3, 3, Rdq);
+        set_block(gt, 12, 6, 0, m3_identity());
+        set_block(gt, 12, 9, 6, m3_identity());
+        set_block(gt, 12, 12, 9, m3_identity());
+        propagate_covariance(P, phi, gt, dt);
+        return;
+    }
     // integrationProcess (preintegration_earth.cc:205-260)
     P.delta_time += dt;
     V3 dvfb     = cvl + 0.5 * cross(cth, cvl) + (1.0 / 12.0) * (cross(pth, cvl) + cross(pvl, cth));
@@ -468,33 +630,7 @@ void preint_add_imu(Preintegration &P, const double *pre_raw, const double *cur_
     setb(gt, 12, 6, 0, -m3_identity());
     setb(gt, 12, 9, 6, m3_identity());
     setb(gt, 12, 12, 9, m3_identity());
-    // G = gt * noise * gt^T (15x15)
-    double gn[15 * 12], G[225];
-    for (int i = 0; i < 15; i++)
-        for (int j = 0; j < 12; j++) {
-            double s = 0;
-            for (int k = 0; k < 12; k++) s += gt[i * 12 + k] * P.noise[k * 12 + j];
-            gn[i * 12 + j] = s;
-        }
-    for (int i = 0; i < 15; i++)
-        for (int j = 0; j < 15; j++) {
-            double s = 0;
-            for (int k = 0; k < 12; k++) s += gn[i * 12 + k] * gt[j * 12 + k];
-            G[i * 15 + j] = s;
-        }
-    double pg[225], cov2[225], pc[225];
-    mat15_mul(phi, G, pg);  // phi * G
-    // Qk = 0.5 dt (phi G + G phi^T)
-    mat15_mul(phi, P.covariance, pc);
-    for (int i = 0; i < 15; i++)
-        for (int j = 0; j < 15; j++) {
-            double s = 0;
-            for (int k = 0; k < 15; k++) s += pc[i * 15 + k] * phi[j * 15 + k];
-            double gpt = 0;
-            for (int k = 0; k < 15; k++) gpt += G[i * 15 + k] * phi[j * 15 + k];
-            cov2[i * 15 + j] = s + 0.5 * dt * (pg[i * 15 + j] + gpt);
-        }
-    std::memcpy(P.covariance, cov2, sizeof(cov2));
+    propagate_covariance(P, phi, gt, dt);
 }
 
 // ===================================================================================== residual blocks + Ceres-style evaluation
@@ -1225,6 +1361,7 @@ static void blob_to_preint(const double *b, const double *pn, int npn, Preintegr
     P.iewn    = {b[20], b[21], b[22]};
     std::memcpy(P.jacobian, b + 27, sizeof(double) * 225);
     std::memcpy(P.covariance, b + 252, sizeof(double) * 225);
+    P.normal = b[477] != 0.0;
     P.pn.assign(pn, pn + 4 * (size_t) npn);
 }
 
@@ -1243,6 +1380,7 @@ static void preint_to_blob(const Preintegration &P, double *b) {
     b[23] = s0, b[24] = s1[0], b[25] = s1[1], b[26] = s1[2];
     std::memcpy(b + 27, P.jacobian, sizeof(double) * 225);
     std::memcpy(b + 252, P.covariance, sizeof(double) * 225);
+    b[477] = P.normal ? 1.0 : 0.0;
 }
 
 static void to_window(const icg_ba_problem *p, const double *pn, const int32_t *pn_off, WindowProblem &W) {
@@ -1339,9 +1477,11 @@ int icgo_ba_residual_costs(const icg_ba_problem *p, double *reproj_cost, double 
 int icgo_preintegrate(const double *state16, const double *iewn, const double *gravity, const double *noise5, const double *imu, int n,
                       double *blob, double *pn_out, double *end_state10) {
     Preintegration P;
+    const V3 iw = iewn ? V3{iewn[0], iewn[1], iewn[2]} : V3{0, 0, 0};
     preint_reset(P, {state16[0], state16[1], state16[2]}, {state16[6], state16[3], state16[4], state16[5]}, {state16[7], state16[8], state16[9]},
-                 {state16[10], state16[11], state16[12]}, {state16[13], state16[14], state16[15]}, {iewn[0], iewn[1], iewn[2]},
+                 {state16[10], state16[11], state16[12]}, {state16[13], state16[14], state16[15]}, iw,
                  {gravity[0], gravity[1], gravity[2]}, noise5[0], noise5[1], noise5[2], noise5[3], noise5[4]);
+    P.normal = iewn == nullptr;  // iswithearth: false -> PreintegrationNormal (preintegration.h factory)
     for (int i = 1; i < n; i++) preint_add_imu(P, imu + 7 * (size_t) (i - 1), imu + 7 * (size_t) i);
     preint_to_blob(P, blob);
     if (pn_out) std::memcpy(pn_out, P.pn.data(), sizeof(double) * P.pn.size());

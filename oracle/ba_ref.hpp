@@ -136,6 +136,7 @@ struct GnssFactor : CostFunction {
 
 // Preintegration result consumed by PreintegrationFactor (preintegration/preintegration_earth.cc:37-164).
 struct Preintegration {
+    bool normal = false;  // PreintegrationNormal (iswithearth: false, preintegration/preintegration_normal.cc) instead of PreintegrationEarth
     double delta_time = 0;
     V3 dp{0, 0, 0}, dv{0, 0, 0};
     Q dq{1, 0, 0, 0};

@@ -77,8 +77,11 @@ def preintegrate(lib, state16, iewn, gravity, noise5, imu):
     blob = np.zeros(480)
     pn = np.zeros((n - 1, 4))
     end = np.zeros(10)
-    a = [np.ascontiguousarray(x, np.float64) for x in (state16, iewn, gravity, noise5)]
-    lib.icgo_preintegrate(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), _p(imu), n, _p(blob), _p(pn), _p(end))
+    a = [np.ascontiguousarray(x, np.float64) if x is not None else None for x in (state16, iewn, gravity, noise5)]
+    # iewn None: PreintegrationNormal (iswithearth false); pn stays empty in that form
+    lib.icgo_preintegrate(_p(a[0]), _p(a[1]) if a[1] is not None else None, _p(a[2]), _p(a[3]), _p(imu), n, _p(blob), _p(pn), _p(end))
+    if iewn is None:
+        pn = np.zeros((0, 4))
     return blob, pn, end
 
 

@@ -394,3 +394,95 @@ def test_landmark_sharded_two_pass_in_process(olib):
         assert out[0][w]["pass2"]["iterations"] == info[w]["pass2"]["iterations"]
         assert np.array_equal(merged[w]["f_active"], single[w]["f_active"])
         _compare_solution(merged[w], single[w], rel=1e-9)
+
+
+def test_preintegration_normal_matches_oracle(olib, solver):
+    """PreintegrationNormal (`iswithearth: false`, preintegration_normal.cc): host propagation, device factor evaluation and a window solve."""
+    from ic_gvins_b200.ba import imu_preintegrate
+    rng = np.random.default_rng(6)
+    imu = synth_ba.imu_samples(0.0, 0.5, 200.0, rng, np.zeros(3), np.zeros(3), earth=False)
+    p, v, _, psi = synth_ba.trajectory(0.0)
+    st = np.concatenate([p, synth_ba.q_yaw(psi), v, [1e-4, -2e-4, 3e-4], [1e-3, 2e-3, -1e-3]])
+    blob_o, _, end_o = oa.preintegrate(olib, st, None, synth_ba.GRAVITY, synth_ba.NOISE5, imu)
+    blob_g, end_g = imu_preintegrate(st, None, synth_ba.GRAVITY, synth_ba.NOISE5, imu)
+    assert blob_g[477] == blob_o[477] == 1.0
+    assert np.abs(blob_g[:27] - blob_o[:27]).max() <= 1e-12 * max(1.0, np.abs(blob_o[:27]).max())
+    assert rel_err(blob_g[27:252], blob_o[27:252]) <= 1e-12 and rel_err(blob_g[252:477], blob_o[252:477]) <= 1e-10
+    assert rel_err(end_g, end_o) <= 1e-13
+    prob, _ = make(olib, K=6, L=60, seed=77, earth=False)
+    pose, mix = prob["pose"].reshape(-1, 7), prob["mix"].reshape(-1, 9)
+    for k in (0, 3):
+        blob = prob["imu_blob"][480 * k:480 * (k + 1)]
+        r_o, J_o = oa.imu_eval(olib, blob, np.zeros((0, 4)), pose[k], mix[k], pose[k + 1], mix[k + 1])
+        r_g, J_g = solver.imu_evaluate(blob, pose[k], mix[k], pose[k + 1], mix[k + 1])
+        assert np.abs(r_g - r_o).max() <= 1e-7 * max(1.0, np.abs(r_o).max())
+        for a, b in zip(J_g, J_o):
+            assert np.abs(a - b).max() <= 1e-7 * max(1.0, np.abs(b).max())
+    po, pg = copy.deepcopy(prob), copy.deepcopy(prob)
+    so = oa.ba_solve(olib, po, 20)
+    sg = solver.solve(pg, 20)[0]
+    assert sg["iterations"] == so["iterations"] and sg["num_successful_steps"] == so["num_successful_steps"]
+    assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-7 * so["final_cost"]
+    _compare_solution(pg, po)
+
+
+def test_small_factor_seams_match_oracle(olib, solver):
+    """CostFunction::Evaluate seams for GnssFactor, ImuPosePriorFactor, ImuMixPriorFactor, ImuErrorFactor, MarginalizationFactor."""
+    import math
+    prob, _ = make(olib, K=6, L=60, seed=41, with_priors=True, with_marg=True)
+    pose, mix = prob["pose"].reshape(-1, 7), prob["mix"].reshape(-1, 9)
+    # GNSS
+    g = 1
+    nd = int(prob["gnss_node"][g])
+    r_o, J_o = np.zeros(3), np.zeros((3, 7))
+    a = [pose[nd].copy(), prob["gnss_blh"][3 * g:3 * g + 3].copy(), prob["gnss_std"][3 * g:3 * g + 3].copy(), np.array(prob["lever"], np.float64)]
+    olib.icgo_gnss_eval(oa._p(a[0]), oa._p(a[1]), oa._p(a[2]), oa._p(a[3]), oa._p(r_o), oa._p(J_o))
+    r_g, J_g = solver.gnss_evaluate(*a)
+    assert np.abs(r_g - r_o).max() <= 1e-12 * max(1.0, np.abs(r_o).max()) and np.abs(J_g - J_o).max() <= 1e-12 * np.abs(J_o).max()
+    # pose prior
+    r_o, J_o = np.zeros(6), np.zeros((6, 7))
+    a = [pose[0].copy(), np.asarray(prob["pose_prior"], float).copy(), np.asarray(prob["pose_prior_std"], float).copy()]
+    olib.icgo_pose_prior_eval(oa._p(a[0]), oa._p(a[1]), oa._p(a[2]), oa._p(r_o), oa._p(J_o))
+    r_g, J_g = solver.pose_prior_evaluate(*a)
+    assert np.abs(r_g - r_o).max() <= 1e-11 * max(1.0, np.abs(r_o).max()) and np.abs(J_g - J_o).max() <= 1e-11 * np.abs(J_o).max()
+    # mix prior / bias-magnitude factor: closed forms (imu_mix_prior_factor.h:40-75, imu_error_factor.h:45-91)
+    sd = np.asarray(prob["mix_prior_std"], float)
+    r_g, J_g = solver.mix_prior_evaluate(mix[0], prob["mix_prior"], sd)
+    assert np.allclose(r_g, (mix[0] - prob["mix_prior"]) / sd, rtol=1e-14) and np.allclose(J_g, np.diag(1.0 / sd), rtol=1e-14)
+    gb, ab = 7200 / 3600.0 * math.pi / 180.0, 2.0e4 * 1.0e-5
+    r_g, J_g = solver.imu_error_evaluate(mix[5])
+    assert np.allclose(r_g, np.concatenate([mix[5][3:6] / gb, mix[5][6:9] / ab]), rtol=1e-14)
+    J_ref = np.zeros((6, 9))
+    for q in range(3):
+        J_ref[q, 3 + q], J_ref[3 + q, 6 + q] = 1.0 / gb, 1.0 / ab
+    assert np.allclose(J_g, J_ref, rtol=1e-14)
+    # marginalization factor vs the numpy restatement (e = e0 + J0 dx)
+    from tests.test_oracle_lm_trajectory import quat_mul
+    rr = prob["marg_r"]
+    J0 = np.asarray(prob["marg_J0"], float).reshape(rr, rr)
+    x0 = np.asarray(prob["marg_x0"], float)
+    params, dx, xo = [], [], 0
+    for t, ndx in zip(prob["marg_block_type"], prob["marg_block_node"]):
+        if t in (0, 2):
+            x = pose[ndx] if t == 0 else prob["ext"][:7]
+            xl = x0[xo:xo + 7]
+            dq = quat_mul(np.array([-xl[3], -xl[4], -xl[5], xl[6]]) / (xl[3:7] @ xl[3:7]), x[3:7])
+            dx += list(x[:3] - xl[:3]) + list(2.0 * dq[:3] * (1.0 if dq[3] >= 0 else -1.0))
+            xo += 7
+        elif t == 1:
+            x = mix[ndx]
+            dx += list(x - x0[xo:xo + 9])
+            xo += 9
+        else:
+            x = prob["ext"][7:8]
+            dx.append(float(x[0] - x0[xo]))
+            xo += 1
+        params.append(np.array(x, copy=True))
+    e_ref = np.asarray(prob["marg_e0"], float) + J0 @ np.array(dx)
+    res, Js = solver.marg_factor_evaluate(prob["marg_block_type"], params, x0, J0, prob["marg_e0"])
+    assert np.abs(res - e_ref).max() <= 1e-11 * max(1.0, np.abs(e_ref).max())
+    col = 0
+    for t, J in zip(prob["marg_block_type"], Js):
+        l = {0: 6, 1: 9, 2: 6, 3: 1}[int(t)]
+        assert np.array_equal(J[:, :l], J0[:, col:col + l]) and (J.shape[1] == l or np.all(J[:, l:] == 0))
+        col += l

@@ -111,3 +111,50 @@ def test_residual_costs_and_culling_protocol(olib, window):
     rc, gc = oa.ba_residual_costs(olib, p)
     assert 2 * rc[10] > 5.991 and 2 * rc[500] > 5.991
     assert (2 * rc > 5.991).sum() < 0.05 * len(rc)
+
+
+@pytest.fixture(scope="module")
+def window_normal(olib):
+    return synth_ba.make_window(lambda *a: oa.preintegrate(olib, *a), K=6, L=60, seed=77, earth=False)
+
+
+def test_preintegration_normal_jacobians_fd(olib, window_normal):
+    """PreintegrationNormal (iswithearth false; preintegration_normal.cc:38-153): blob tagged, residual / Jacobians vs finite differences."""
+    prob, _ = window_normal
+    pose, mix = prob["pose"].reshape(-1, 7), prob["mix"].reshape(-1, 9)
+    k = 2
+    blob = prob["imu_blob"][480 * k:480 * (k + 1)]
+    assert blob[477] == 1.0 and np.all(blob[20:27] == 0)
+    none = np.zeros((0, 4))
+    args = [pose[k].copy(), mix[k].copy(), pose[k + 1].copy(), mix[k + 1].copy()]
+    r, Js = oa.imu_eval(olib, blob, none, *args)
+    for w in (0, 2):
+        def fun(x, w=w):
+            a = list(args); a[w] = x
+            return oa.imu_eval(olib, blob, none, *a, False)[0]
+        Jfd = fd_pose(fun, args[w], 1e-6, olib)
+        assert np.abs(Jfd - Js[w][:, :6]).max() <= 2e-3 * np.abs(Jfd).max()
+        assert np.all(Js[w][:, 6] == 0)
+    for w in (1, 3):
+        cols = []
+        for c in range(9):
+            eps = 1e-6 if c < 3 else 1e-9
+            a = list(args); a[w] = args[w].copy(); a[w][c] += eps
+            b = list(args); b[w] = args[w].copy(); b[w][c] -= eps
+            cols.append((oa.imu_eval(olib, blob, none, *a, False)[0] - oa.imu_eval(olib, blob, none, *b, False)[0]) / (2 * eps))
+        Jfd = np.stack(cols, axis=1)
+        assert np.abs(Jfd - Js[w]).max() <= 2e-3 * np.abs(Jfd).max()
+
+
+def test_preintegration_normal_consistent_and_solvable(olib):
+    prob, truth = synth_ba.make_window(lambda *a: oa.preintegrate(olib, *a), K=6, L=60, seed=78, earth=False, perturb=False)
+    pose, mix = prob["pose"].reshape(-1, 7), prob["mix"].reshape(-1, 9)
+    for k in range(5):
+        r, _ = oa.imu_eval(olib, prob["imu_blob"][480 * k:480 * (k + 1)], np.zeros((0, 4)), pose[k], mix[k], pose[k + 1], mix[k + 1], False)
+        assert np.abs(r).max() < 6.0
+    prob2, truth2 = synth_ba.make_window(lambda *a: oa.preintegrate(olib, *a), K=6, L=60, seed=78, earth=False)
+    prob2["ext_const"], prob2["td_const"] = 1, 1
+    prob2["ext"] = truth2["ext"].copy()
+    s = oa.ba_solve(olib, prob2, 20)
+    assert s["final_cost"] < 1e-3 * s["initial_cost"]
+    assert np.abs(prob2["pose"].reshape(-1, 7)[:, :3] - truth2["pose"][:, :3]).max() < 0.25
