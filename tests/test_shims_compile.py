@@ -18,6 +18,7 @@ def test_shim_header_compiles_and_links():
         build.build()
     src = r'''
 #include "ic_gvins_b200/host/icg_shims.hpp"
+#include "ic_gvins_b200/host/icg_factors.hpp"
 // instantiate every shim member so that all C-ABI symbols are referenced (never executed: no GPU here)
 int main(int argc, char **) {
     if (argc > 1000) {
@@ -45,6 +46,17 @@ int main(int argc, char **) {
         s.Solve(P, 5);
         s.gvinsOptimization(P, 20, o, culled);
         s.marginalization(P, 1);
+        const double v[16] = {0};
+        const double *params[5] = {v, v, v, v, v};
+        double r[16], *J[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        icg_b200::ReprojectionFactor(v, v, v, v, 0, 0, 1).Evaluate(params, r, J);
+        icg_b200::GnssFactor(v, v, v).Evaluate(params, r, J);
+        icg_b200::ImuErrorFactor().Evaluate(params, r, J);
+        icg_b200::ImuPosePriorFactor(v, v).Evaluate(params, r, J);
+        icg_b200::ImuMixPriorFactor(v, v).Evaluate(params, r, J);
+        std::vector<double> blob(ICG_IMU_BLOB_DOUBLES);
+        icg_b200::PreintegrationFactor(blob.data()).Evaluate(params, r, J);
+        icg_b200::MarginalizationFactor(1, {3}, {0.0}, {1.0}, {0.0}).Evaluate(params, r, J);
     }
     return 0;
 }
