@@ -241,6 +241,7 @@ def run_b200(args):
 
     # ---- KLT inputs: pinned host frames; level-0 planes resident in HBM: slot = f * B + b
     h_frames = [torch.from_numpy(f.copy()).pin_memory() for f in frames]
+    frame_ptrs = [[h_frames[f].data_ptr()] * B for f in range(NFRAMES)]  # the B streams replicate one 6-frame sequence (distinct device slots)
     for f in range(NFRAMES):
         for b in range(B):
             trk.upload_ptr(f * B + b, h_frames[f].data_ptr(), W, build=False)
@@ -313,8 +314,7 @@ def run_b200(args):
 
     def step_e2e(s):
         fb = seq[s + 1]
-        for b in range(B):  # H2D of this step's B new frames from pinned host memory
-            trk.upload_ptr(fb * B + b, h_frames[fb].data_ptr(), W, build=False)
+        trk.upload_batch_ptrs(fb * B, frame_ptrs[fb], W)  # H2D of this step's B new frames from pinned host memory (one call, linear DMA)
         with torch.cuda.stream(stream):
             e_prev.copy_(h_prev[s], non_blocking=True)
             e_init.copy_(h_init[s], non_blocking=True)
@@ -325,13 +325,21 @@ def run_b200(args):
         with torch.cuda.stream(stream):
             h_fwd.copy_(d_fwd, non_blocking=True)
             h_st.copy_(d_st, non_blocking=True)
-        for sv, (pe, init, arr, summ) in zip(solvers, e2e_parts):
+        def begin(k):
+            sv, (pe, init, arr, summ) = solvers[k], e2e_parts[k]
             for w_, ini in zip(pe, init):  # fresh initial guess every step (the solve updates in place)
                 for q, v in ini.items():
                     w_[q][...] = v
             rc = lib().icg_ba_gvins_optimization_begin(sv._h, len(pe), arr, 20)  # pack + upload + enqueue (asynchronous)
             if rc != 0:
                 raise RuntimeError(lib().icg_last_error().decode())
+        # one host thread per solver handle, as the reference has one optimization thread per GVINS object (ctypes releases the GIL)
+        ths = [threading.Thread(target=begin, args=(k,)) for k in range(1, len(solvers))]
+        for t_ in ths:
+            t_.start()
+        begin(0)
+        for t_ in ths:
+            t_.join()
         for sv, (pe, init, arr, summ) in zip(solvers, e2e_parts):
             rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)  # synchronise + write back
             if rc != 0:
@@ -558,7 +566,9 @@ def run_b200(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 (KLT), f64 (BA)", "data": "synthetic",
         "config": {"workload": WORKLOAD if use_ba else WORKLOAD_KLT, "streams_per_gpu": B, "points_per_frame": NPTS, "ba_solver_handles": len(solvers),
-                   "l2": f"inputs larger than L2: {B * 2 * 1.127:.0f} MB of pyramids touched per step"},
+                   "l2": f"inputs larger than L2: {B * 2 * 1.127:.0f} MB of pyramids touched per step",
+                   "replication": "the B streams replay ONE rendered 6-frame sequence (distinct device slots, so HBM traffic and H2D volume are real) and the BA "
+                                  "batch repeats 64 distinct cfg-3 windows"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24) + ba_h2d,
                 "d2h_bytes_per_step": B * NPTS * 9 + ba_d2h},
         "gpu_launches": launches,

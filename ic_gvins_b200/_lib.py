@@ -53,6 +53,7 @@ def _declare(L: C.CDLL) -> None:
     L.icg_klt_track_fb.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int]
     L.icg_klt_upload.argtypes = [vp, C.c_int, vp, C.c_int]
     L.icg_klt_upload_level0.argtypes = [vp, C.c_int, vp, C.c_int]
+    L.icg_klt_upload_batch.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
     L.icg_klt_slot_level0.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_int)]
     L.icg_klt_slot_level.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.icg_klt_build_pyramids.argtypes = [vp, C.c_int, C.c_int]
@@ -115,7 +116,7 @@ def _declare(L: C.CDLL) -> None:
 EXPORTS = [
     "icg_last_error", "icg_version", "icg_launch_count", "icg_launch_count_reset",
     "icg_klt_create", "icg_klt_destroy", "icg_klt_calc_optical_flow_pyr_lk", "icg_klt_track_fb", "icg_klt_upload",
-    "icg_klt_upload_level0", "icg_klt_slot_level0", "icg_klt_slot_level", "icg_klt_build_pyramids",
+    "icg_klt_upload_level0", "icg_klt_upload_batch", "icg_klt_slot_level0", "icg_klt_slot_level", "icg_klt_build_pyramids",
     "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
     "icg_detect_create", "icg_detect_destroy", "icg_detect_blocks", "icg_corner_subpix",
     "icg_camera_undistort_points", "icg_camera_distort_points", "icg_camera_distort_camera_points", "icg_camera_pixel2cam", "icg_camera_world2pixel", "icg_tracking_histogram", "icg_find_fundamental_mat_ransac", "icg_triangulate_points",

@@ -80,9 +80,7 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     double *pose_0, *mix_0, *ext_0, *rho_0;  // initial copy (for re-running the same problem: bench)
     uint8_t *f_active_0;                     // pristine copies of what the two-pass protocol mutates (restart re-solves the UPLOADED problem)
     double *gnss_std_0;
-    int *f_lm, *f_ref, *f_obs;
-    double *f_const;
-    uint8_t *f_active;
+    uint8_t *f_active;                       // by factor id
     int *lm_off;  // CSR offsets of the factor records by landmark
     int *vb_lm0;  // [NW][NVB] first landmark of every lin_vis run (runs hold whole landmarks, <= 128 factors); last entry = run count
     int *f_meta_s;       // per record slot: (landmark, reference node, observing node, factor id)
@@ -1239,13 +1237,14 @@ __global__ void __launch_bounds__(256) ba_cost(BaCaps C, BaDev D, int nblk_vis) 
     const WinDims dm = D.dims[w];
     const double *pose = D.pose_c + (size_t) w * C.K * 7, *ext = D.ext_c + (size_t) w * 8, *rho = D.rho_c + (size_t) w * C.L;
     double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
-    const int f = blockIdx.x * 256 + threadIdx.x;
+    const int q = blockIdx.x * 256 + threadIdx.x;  // record slot (landmark-CSR order): the slot-ordered copies are the only factor data on the device
     double cost = 0;
-    if (f < dm.F && D.f_active[(size_t) w * C.F + f]) {
-        const int lm = D.f_lm[(size_t) w * C.F + f], i = D.f_ref[(size_t) w * C.F + f], j = D.f_obs[(size_t) w * C.F + f];
+    int4 meta = make_int4(0, 0, 0, 0);
+    if (q < dm.F) meta = ((const int4 *) D.f_meta_s)[(size_t) w * C.F + q];  // (landmark, reference node, observing node, factor id)
+    if (q < dm.F && D.f_active[(size_t) w * C.F + meta.w]) {
         double r[2];
-        reproj_eval(pose + i * 7, pose + j * 7, ext, rho[lm], ext[7], D.f_const + ((size_t) w * C.F + f) * 14, dm.reproj_sinv, false, r, nullptr, nullptr, nullptr,
-                    nullptr, nullptr);
+        reproj_eval(pose + meta.y * 7, pose + meta.z * 7, ext, rho[meta.x], ext[7], D.f_const_s + ((size_t) w * C.F + q) * 14, dm.reproj_sinv, false, r, nullptr,
+                    nullptr, nullptr, nullptr, nullptr);
         double sq = r[0] * r[0] + r[1] * r[1], sc;
         if (dm.reproj_huber)
             huber(sq, cost, sc);
@@ -1368,12 +1367,14 @@ __global__ void __launch_bounds__(128) ba_chi2_cull(BaCaps C, BaDev D, int *coun
     WinDims &dm = D.dims[w];
     const int t = blockIdx.x * 128 + threadIdx.x;
     const double *pose = D.pose + (size_t) w * C.K * 7, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
-    if (t < dm.F && D.f_active[(size_t) w * C.F + t]) {
+    int4 meta = make_int4(0, 0, 0, 0);
+    if (t < dm.F) meta = ((const int4 *) D.f_meta_s)[(size_t) w * C.F + t];  // record slot t
+    if (t < dm.F && D.f_active[(size_t) w * C.F + meta.w]) {
         double r[2];
-        reproj_eval(pose + D.f_ref[(size_t) w * C.F + t] * 7, pose + D.f_obs[(size_t) w * C.F + t] * 7, ext, rho[D.f_lm[(size_t) w * C.F + t]], ext[7],
-                    D.f_const + ((size_t) w * C.F + t) * 14, dm.reproj_sinv, false, r, nullptr, nullptr, nullptr, nullptr, nullptr);
+        reproj_eval(pose + meta.y * 7, pose + meta.z * 7, ext, rho[meta.x], ext[7], D.f_const_s + ((size_t) w * C.F + t) * 14, dm.reproj_sinv, false, r, nullptr,
+                    nullptr, nullptr, nullptr, nullptr);
         if ((r[0] * r[0] + r[1] * r[1]) > 5.991) {
-            D.f_active[(size_t) w * C.F + t] = 0;
+            D.f_active[(size_t) w * C.F + meta.w] = 0;
             atomicAdd(&counters[2 * w], 1);
         }
     }
@@ -1402,9 +1403,10 @@ __global__ void ba_residual_costs_kernel(BaCaps C, BaDev D, double *reproj_cost,
     const double *pose = D.pose, *ext = D.ext, *rho = D.rho;
     if (t < dm.F) {
         double r[2];
-        reproj_eval(pose + D.f_ref[t] * 7, pose + D.f_obs[t] * 7, ext, rho[D.f_lm[t]], ext[7], D.f_const + (size_t) t * 14, dm.reproj_sinv, false, r, nullptr, nullptr,
+        const int4 meta = ((const int4 *) D.f_meta_s)[t];  // record slot t -> (landmark, reference node, observing node, factor id)
+        reproj_eval(pose + meta.y * 7, pose + meta.z * 7, ext, rho[meta.x], ext[7], D.f_const_s + (size_t) t * 14, dm.reproj_sinv, false, r, nullptr, nullptr,
                     nullptr, nullptr, nullptr);
-        reproj_cost[t] = 0.5 * (r[0] * r[0] + r[1] * r[1]);  // EvaluateResidualBlock(id, false, &cost, ...) (IG/ic_gvins.cc:1278)
+        reproj_cost[meta.w] = 0.5 * (r[0] * r[0] + r[1] * r[1]);  // EvaluateResidualBlock(id, false, &cost, ...) (IG/ic_gvins.cc:1278)
     }
     if (t < dm.n_gnss) {
         double r[3];
@@ -1576,11 +1578,11 @@ struct icg_ba {
     int use_global_S;
     HostDev<WinDims> dims;
     HostDev<LmState> st;
-    HostDev<double> pose, mix, ext, rho, f_const, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
+    HostDev<double> pose, mix, ext, rho, imu_blob, imu_U, gnss_blh, gnss_std, lever, pose_prior, pose_prior_sinfo, mix_prior, mix_prior_std, marg_x0,
         marg_H0, marg_b0, marg_c0;
     HostDev<int> f_slot, f_meta_s, vb_lm0;  // f_slot / lm_fidx: host-side packing helpers only (factor id <-> record slot)
     HostDev<double> f_const_s;
-    HostDev<int> f_lm, f_ref, f_obs, lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
+    HostDev<int> lm_off, lm_fidx, gnss_node, marg_type, marg_node, pair_off, pair_ro, pair_fidx, npairs;
     HostDev<uint8_t> f_active;
     std::vector<void *> dev_only;
     HostDev<double> scratch;  // single-factor evaluation
@@ -1861,10 +1863,10 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
         set_error("icg_ba_create: allocation of " #field " failed");           \
         return ICG_ENOMEM;                                                     \
     }
-    HD(dims, NW) HD(st, NW) HD(pose, NW * C.K * 7) HD(mix, NW * C.K * 9) HD(ext, NW * 8) HD(rho, NW * C.L) HD(f_const, NW * C.F * 14)
+    HD(dims, NW) HD(st, NW) HD(pose, NW * C.K * 7) HD(mix, NW * C.K * 9) HD(ext, NW * 8) HD(rho, NW * C.L)
     HD(imu_blob, NW * C.K * ICG_IMU_BLOB_DOUBLES) HD(imu_U, NW * C.K * 225) HD(gnss_blh, NW * C.G * 3) HD(gnss_std, NW * C.G * 3) HD(lever, NW * 3)
     HD(pose_prior, NW * 7) HD(pose_prior_sinfo, NW * 6) HD(mix_prior, NW * 9) HD(mix_prior_std, NW * 9) HD(marg_x0, NW * BA_MARG_MAXB * 9)
-    HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW) HD(f_lm, NW * C.F) HD(f_ref, NW * C.F) HD(f_obs, NW * C.F)
+    HD(marg_H0, NW * C.R * C.R) HD(marg_b0, NW * C.R) HD(marg_c0, NW)
     HD(lm_off, NW * (C.L + 1)) HD(lm_fidx, NW * C.F) HD(gnss_node, NW * C.G) HD(marg_type, NW * BA_MARG_MAXB) HD(marg_node, NW * BA_MARG_MAXB) HD(f_active, NW * C.F)
     HD(scratch, 1024) HD(st_save, NW) HD(cull_counters, 2 * NW) HD(f_slot, NW * C.F) HD(f_meta_s, NW * C.F * 4) HD(vb_lm0, NW * C.NVB) HD(f_const_s, NW * C.F * 14)
     HD(pair_off, NW * ((size_t) C.K * (C.K - 1) + 1)) HD(pair_ro, NW * (size_t) C.K * (C.K - 1)) HD(pair_fidx, NW * C.F) HD(npairs, NW)
@@ -1872,7 +1874,7 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     BaDev &D = h->D;
     D.rank = 0, D.world = 1;
     D.dims = h->dims.d, D.st = h->st.d, D.pose = h->pose.d, D.mix = h->mix.d, D.ext = h->ext.d, D.rho = h->rho.d;
-    D.f_lm = h->f_lm.d, D.f_ref = h->f_ref.d, D.f_obs = h->f_obs.d, D.f_const = h->f_const.d, D.f_active = h->f_active.d;
+    D.f_active = h->f_active.d;
     D.pair_off = h->pair_off.d, D.pair_ro = h->pair_ro.d, D.pair_fidx = h->pair_fidx.d, D.npairs = h->npairs.d;
     D.f_meta_s = h->f_meta_s.d, D.vb_lm0 = h->vb_lm0.d, D.f_const_s = h->f_const_s.d;
     D.lm_off = h->lm_off.d, D.imu_blob = h->imu_blob.d, D.imu_U = h->imu_U.d;
@@ -1927,10 +1929,10 @@ void icg_ba_destroy(icg_ba *h) {
     prof_collect(h);
     prof_print(h);
     for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
-    h->dims.release(), h->st.release(), h->pose.release(), h->mix.release(), h->ext.release(), h->rho.release(), h->f_const.release();
+    h->dims.release(), h->st.release(), h->pose.release(), h->mix.release(), h->ext.release(), h->rho.release();
     h->imu_blob.release(), h->imu_U.release(), h->gnss_blh.release(), h->gnss_std.release(), h->lever.release(), h->pose_prior.release();
     h->pose_prior_sinfo.release(), h->mix_prior.release(), h->mix_prior_std.release(), h->marg_x0.release(), h->marg_H0.release(), h->marg_b0.release();
-    h->marg_c0.release(), h->f_lm.release(), h->f_ref.release(), h->f_obs.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
+    h->marg_c0.release(), h->lm_off.release(), h->lm_fidx.release(), h->gnss_node.release();
     h->f_slot.release(), h->f_meta_s.release(), h->vb_lm0.release(), h->f_const_s.release(), h->marg_type.release(), h->marg_node.release(), h->f_active.release(), h->scratch.release(), h->st_save.release(), h->cull_counters.release(), h->pair_off.release(), h->pair_ro.release(), h->pair_fidx.release(), h->npairs.release();
     if (h->comm) nccl_api().CommDestroy((ncclComm_t) h->comm);
     split_release(h);
@@ -1993,10 +1995,6 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
                 seen[l] |= 1u << p.f_obs[f];
             }
         }
-        memcpy(h->f_lm.h + (size_t) w * C.F, p.f_lm, sizeof(int) * p.F);
-        memcpy(h->f_ref.h + (size_t) w * C.F, p.f_ref, sizeof(int) * p.F);
-        memcpy(h->f_obs.h + (size_t) w * C.F, p.f_obs, sizeof(int) * p.F);
-        memcpy(h->f_const.h + (size_t) w * C.F * 14, p.f_const, sizeof(double) * 14 * p.F);
         if (p.f_active)
             memcpy(h->f_active.h + (size_t) w * C.F, p.f_active, p.F);
         else
@@ -2112,7 +2110,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     };
 #undef PK_FAIL
     {
-        const int nthreads = std::max(1, std::min({n / 4, 8, (int) std::thread::hardware_concurrency()}));
+        const int nthreads = std::max(1, std::min({n / 4, 16, (int) std::thread::hardware_concurrency()}));
         std::vector<int> rcs(nthreads, ICG_OK);
         std::vector<std::string> errs(nthreads);
         auto worker = [&](int t) {
@@ -2135,22 +2133,26 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
             }
     }
     cudaStream_t s = h->stream;
-    ICG_CUDA(h->dims.up(s));
-    ICG_CUDA(h->pose.up(s)); ICG_CUDA(h->mix.up(s)); ICG_CUDA(h->ext.up(s)); ICG_CUDA(h->rho.up(s));
-    ICG_CUDA(h->f_lm.up(s)); ICG_CUDA(h->f_ref.up(s)); ICG_CUDA(h->f_obs.up(s)); ICG_CUDA(h->f_const.up(s)); ICG_CUDA(h->f_active.up(s));
-    ICG_CUDA(h->f_meta_s.up(s)); ICG_CUDA(h->vb_lm0.up(s)); ICG_CUDA(h->f_const_s.up(s)); ICG_CUDA(h->lm_off.up(s)); ICG_CUDA(h->pair_off.up(s)); ICG_CUDA(h->pair_ro.up(s)); ICG_CUDA(h->pair_fidx.up(s)); ICG_CUDA(h->npairs.up(s)); ICG_CUDA(h->imu_blob.up(s)); ICG_CUDA(h->imu_U.up(s));
-    ICG_CUDA(h->gnss_node.up(s)); ICG_CUDA(h->gnss_blh.up(s)); ICG_CUDA(h->gnss_std.up(s)); ICG_CUDA(h->lever.up(s));
-    ICG_CUDA(h->pose_prior.up(s)); ICG_CUDA(h->pose_prior_sinfo.up(s)); ICG_CUDA(h->mix_prior.up(s)); ICG_CUDA(h->mix_prior_std.up(s));
-    ICG_CUDA(h->marg_type.up(s)); ICG_CUDA(h->marg_node.up(s)); ICG_CUDA(h->marg_x0.up(s)); ICG_CUDA(h->marg_H0.up(s)); ICG_CUDA(h->marg_b0.up(s));
-    ICG_CUDA(h->marg_c0.up(s));
+    {   // H2D of the n uploaded windows only (the arrays are capacity-strided by window; a partially filled handle moves a prefix)
+        const size_t nn = (size_t) n, PM = (size_t) C.K * (C.K - 1);
+#define UP(field, stride) ICG_CUDA(h->field.up(s, nn * (size_t) (stride)))
+        UP(dims, 1); UP(pose, C.K * 7); UP(mix, C.K * 9); UP(ext, 8); UP(rho, C.L);
+        UP(f_active, C.F);  // factor constants and indices travel once, in record-slot order (f_meta_s / f_const_s)
+        UP(f_meta_s, C.F * 4); UP(vb_lm0, C.NVB); UP(f_const_s, C.F * 14); UP(lm_off, C.L + 1); UP(pair_off, PM + 1); UP(pair_ro, PM); UP(pair_fidx, C.F);
+        UP(npairs, 1); UP(imu_blob, C.K * ICG_IMU_BLOB_DOUBLES); UP(imu_U, C.K * 225);
+        UP(gnss_node, C.G); UP(gnss_blh, C.G * 3); UP(gnss_std, C.G * 3); UP(lever, 3);
+        UP(pose_prior, 7); UP(pose_prior_sinfo, 6); UP(mix_prior, 9); UP(mix_prior_std, 9);
+        UP(marg_type, BA_MARG_MAXB); UP(marg_node, BA_MARG_MAXB); UP(marg_x0, BA_MARG_MAXB * 9); UP(marg_H0, (size_t) C.R * C.R); UP(marg_b0, C.R); UP(marg_c0, 1);
+#undef UP
+    }
     // keep a pristine copy of the parameters (icg_ba_run(restart=1) re-solves the same problems: bench / repeated solves)
     const BaDev &D = h->D;
-    ICG_CUDA(cudaMemcpyAsync(D.pose_0, D.pose, sizeof(double) * (size_t) C.NW * C.K * 7, cudaMemcpyDeviceToDevice, s));
-    ICG_CUDA(cudaMemcpyAsync(D.mix_0, D.mix, sizeof(double) * (size_t) C.NW * C.K * 9, cudaMemcpyDeviceToDevice, s));
-    ICG_CUDA(cudaMemcpyAsync(D.ext_0, D.ext, sizeof(double) * (size_t) C.NW * 8, cudaMemcpyDeviceToDevice, s));
-    ICG_CUDA(cudaMemcpyAsync(D.rho_0, D.rho, sizeof(double) * (size_t) C.NW * C.L, cudaMemcpyDeviceToDevice, s));
-    ICG_CUDA(cudaMemcpyAsync(D.f_active_0, D.f_active, (size_t) C.NW * C.F, cudaMemcpyDeviceToDevice, s));
-    ICG_CUDA(cudaMemcpyAsync(D.gnss_std_0, D.gnss_std, sizeof(double) * (size_t) C.NW * C.G * 3, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.pose_0, D.pose, sizeof(double) * (size_t) n * C.K * 7, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.mix_0, D.mix, sizeof(double) * (size_t) n * C.K * 9, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.ext_0, D.ext, sizeof(double) * (size_t) n * 8, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.rho_0, D.rho, sizeof(double) * (size_t) n * C.L, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.f_active_0, D.f_active, (size_t) n * C.F, cudaMemcpyDeviceToDevice, s));
+    ICG_CUDA(cudaMemcpyAsync(D.gnss_std_0, D.gnss_std, sizeof(double) * (size_t) n * C.G * 3, cudaMemcpyDeviceToDevice, s));
     // the dense SYRK operands keep a fixed sparsity pattern per problem: zero them once here
     h->cur_windows = n;
     return ICG_OK;
@@ -2465,7 +2467,8 @@ int icg_ba_download(icg_ba *h, int n, const icg_ba_problem *P, icg_ba_summary *s
     ICG_CUDA(cudaSetDevice(h->device));
     const BaCaps &C = h->C;
     cudaStream_t s = h->stream;
-    ICG_CUDA(h->pose.down(s)); ICG_CUDA(h->mix.down(s)); ICG_CUDA(h->ext.down(s)); ICG_CUDA(h->rho.down(s)); ICG_CUDA(h->st.down(s, n));
+    ICG_CUDA(h->pose.down(s, (size_t) n * C.K * 7)); ICG_CUDA(h->mix.down(s, (size_t) n * C.K * 9)); ICG_CUDA(h->ext.down(s, (size_t) n * 8));
+    ICG_CUDA(h->rho.down(s, (size_t) n * C.L)); ICG_CUDA(h->st.down(s, n));
     ICG_CUDA(cudaStreamSynchronize(s));
     if (h->D.S.split && icg_ba_shard_error(h) != 0) {
         set_error("icg_ba_download: a peer exchange of the split pipeline timed out (a rank of the shard group did not run the same sequence)");

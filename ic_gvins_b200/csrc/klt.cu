@@ -182,6 +182,25 @@ __global__ void __launch_bounds__(256) pad_fill_kernel(PadArgs P) {
     }
 }
 
+// Scatter `count` linearly staged W x H frames into the level-0 planes of consecutive slots (16-byte chunks; HBM-bound, W * H in + out per
+// frame).  The H2D copies that feed it are LINEAR (full-rate DMA); a strided cudaMemcpy2D into the padded planes runs well below that.
+__global__ void __launch_bounds__(256) klt_unpack_level0_kernel(const uint8_t *__restrict__ stage, uint8_t *__restrict__ plane0, int W, int H, int pitch,
+                                                                size_t slot_stride, int first_slot) {
+    const int slot = first_slot + blockIdx.z;
+    const uint8_t *src = stage + (size_t) blockIdx.z * W * H;
+    uint8_t *dst = plane0 + (size_t) slot * slot_stride + (size_t) KLT_PAD * pitch + KLT_PAD;
+    const int chunks = (W + 15) / 16;
+    const int y = blockIdx.y, c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= chunks || y >= H) return;
+    const uint8_t *sp = src + (size_t) y * W + 16 * c;
+    uint8_t *dp = dst + (size_t) y * pitch + 16 * c;
+    if (16 * c + 16 <= W && ((((size_t) sp) | ((size_t) dp)) & 15) == 0) {
+        *(uint4 *) dp = *(const uint4 *) sp;
+    } else {
+        for (int k = 0; k < 16 && 16 * c + k < W; k++) dp[k] = sp[k];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ LK tracker
 struct WarpSmem {
     uint8_t *iw;    // 48x24 template window, origin ((ipx-1) & ~15, ipy-1)
@@ -652,6 +671,9 @@ struct icg_klt {
     std::vector<uint64_t> slot_hash;
     std::vector<uint64_t> slot_age;
     uint64_t age;
+    // linear device staging of the batched frame upload (icg_klt_upload_batch)
+    uint8_t *d_upstage = nullptr;
+    size_t d_upstage_bytes = 0;
 };
 
 static uint64_t hash_image(const uint8_t *p, int W, int H, int stride) {
@@ -756,6 +778,7 @@ void icg_klt_destroy(icg_klt *h) {
     cudaFree(h->d_err);
     cudaFree(h->d_status);
     cudaFreeHost(h->h_stage);
+    if (h->d_upstage) cudaFree(h->d_upstage);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -814,6 +837,42 @@ int icg_klt_upload_level0(icg_klt *h, int slot, const uint8_t *host_img, int str
     ICG_CUDA(cudaMemcpy2DAsync(h->planes[0] + (size_t) slot * h->lv[0].slot_stride + (size_t) KLT_PAD * h->lv[0].pitch + KLT_PAD, h->lv[0].pitch, host_img, stride,
                                h->W, h->H, cudaMemcpyHostToDevice, h->stream));
     h->slot_hash[slot] = 0;
+    return ICG_OK;
+}
+
+int icg_klt_upload_batch(icg_klt *h, int first_slot, int count, const uint8_t *const *host_imgs, int stride) {
+    if (!h || !host_imgs || first_slot < 0 || count < 1 || first_slot + count > h->n_slots || stride < h->W) {
+        set_error("icg_klt_upload_batch: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    const size_t fb = (size_t) h->W * h->H;
+    if (h->d_upstage_bytes < fb * count) {
+        ICG_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->d_upstage) cudaFree(h->d_upstage);
+        h->d_upstage = nullptr, h->d_upstage_bytes = 0;
+        if (cudaMalloc(&h->d_upstage, fb * count) != cudaSuccess) {
+            set_error("icg_klt_upload_batch: staging allocation of %zu bytes failed", fb * count);
+            return ICG_ENOMEM;
+        }
+        h->d_upstage_bytes = fb * count;
+    }
+    for (int k = 0; k < count; k++) {
+        if (!host_imgs[k]) {
+            set_error("icg_klt_upload_batch: frame %d is NULL", k);
+            return ICG_EINVAL;
+        }
+        if (stride == h->W) {  // one linear copy per frame
+            ICG_CUDA(cudaMemcpyAsync(h->d_upstage + fb * k, host_imgs[k], fb, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            ICG_CUDA(cudaMemcpy2DAsync(h->d_upstage + fb * k, h->W, host_imgs[k], stride, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
+        }
+        h->slot_hash[first_slot + k] = 0;
+    }
+    const dim3 grid(((h->W + 15) / 16 + 255) / 256, h->H, count);
+    klt_unpack_level0_kernel<<<grid, 256, 0, h->stream>>>(h->d_upstage, h->planes[0], h->W, h->H, h->lv[0].pitch, h->lv[0].slot_stride, first_slot);
+    ICG_CHECK_LAUNCH();
+    count_launch();
     return ICG_OK;
 }
 

@@ -84,6 +84,11 @@ class KltTracker:
         f = lib().icg_klt_upload if build else lib().icg_klt_upload_level0
         check(f(self._h, slot, vp(host_ptr), stride), "icg_klt_upload")
 
+    def upload_batch_ptrs(self, first_slot: int, host_ptrs, stride: int):
+        """One call for the new frame of every stream: host_ptrs = iterable of host addresses (pinned), slots first_slot ...; no pyramid build."""
+        arr = (C.c_void_p * len(host_ptrs))(*host_ptrs)
+        check(lib().icg_klt_upload_batch(self._h, first_slot, len(host_ptrs), arr, stride), "icg_klt_upload_batch")
+
     def build_pyramids(self, first_slot: int, count: int):
         check(lib().icg_klt_build_pyramids(self._h, first_slot, count), "icg_klt_build_pyramids")
 

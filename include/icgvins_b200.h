@@ -80,6 +80,10 @@ int icg_klt_track_fb(icg_klt *h, const uint8_t *prev, const uint8_t *next, int s
 int icg_klt_upload(icg_klt *h, int slot, const uint8_t *host_img, int stride);
 /* async H2D of one frame into slot's level 0 only (no pyramid build; pair with icg_klt_build_pyramids) */
 int icg_klt_upload_level0(icg_klt *h, int slot, const uint8_t *host_img, int stride);
+/* async H2D of `count` frames into the level-0 planes of slots [first_slot, first_slot + count) in one call (throughput mode: one new frame
+ * of every stream per step): linear DMA copies into a device staging buffer + one scatter kernel; no pyramid build
+ * (pair with icg_klt_build_pyramids).  host_imgs[k] should be pinned. */
+int icg_klt_upload_batch(icg_klt *h, int first_slot, int count, const uint8_t *const *host_imgs, int stride);
 /* synchronous D2H of one pyramid level of a slot into a host buffer of row stride `stride` (parity tests) */
 int icg_klt_download_level(icg_klt *h, int slot, int level, uint8_t *host_img, int stride);
 /* device pointer + pitch of a slot's level-0 plane, so a producer on the same device can write frames in place */
