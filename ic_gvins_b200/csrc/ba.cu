@@ -2669,9 +2669,31 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
     ba_lin_vis<<<dim3(C.NVB - 2, n), 128, 0, s>>>(C, D);
     ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
     marg_assemble<<<n, 256, smem, s>>>(C, D, M);
-    marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, 0);
+    // eigendecompositions: on-chip cluster-pair kernel when every block of the batch fits (n <= MARG_PAIR_MAXN), global-memory kernel otherwise
+    int max_m = 0, max_r = 0;
+    for (int w = 0; w < n; w++) max_m = std::max(max_m, out[w].m), max_r = std::max(max_r, out[w].r);
+    auto jacobi = [&](int which, int nmax) -> int {
+        if (nmax <= MARG_PAIR_MAXN && !getenv("ICG_MARG_GLOBAL_JACOBI")) {
+            const size_t smem = sizeof(double) * ((size_t) nmax * nmax + 2 * (size_t) (nmax + 2));
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned) (2 * n)), cfg.blockDim = dim3(MARG_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+            cfg.attrs = at, cfg.numAttrs = 1;
+            ICG_CUDA(cudaFuncSetAttribute(marg_jacobi_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            ICG_CUDA(cudaLaunchKernelEx(&cfg, marg_jacobi_pair, M, which));
+        } else {
+            marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, which);
+        }
+        return ICG_OK;
+    };
+    rc = jacobi(0, max_m);
+    if (rc != ICG_OK) return rc;
     marg_schur<<<n, MARG_THREADS, 0, s>>>(M);
-    marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, 1);
+    rc = jacobi(1, max_r);
+    if (rc != ICG_OK) return rc;
     marg_finish<<<n, MARG_THREADS, 0, s>>>(M);
     marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 1);
     ICG_CHECK_LAUNCH();

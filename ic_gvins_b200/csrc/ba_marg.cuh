@@ -303,6 +303,164 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_jacobi(MargDev M, int which
     }
 }
 
+// The same eigensolver for blocks that fit on chip (n <= MARG_PAIR_MAXN): a CLUSTER OF TWO CTAs per window.  CTA 0 keeps G = A V (column-major,
+// n^2 doubles) in its shared memory, generates the plane rotations of a round-robin step (one warp per column pair: three dot products, then
+// the rotation of the pair) and writes the step's (c, s) list into CTA 1's shared memory (DSMEM stores); CTA 1 keeps V in its shared memory and
+// applies the list while CTA 0 already works on the next step (two record slots, one cluster barrier per step).  No L2 round trip sits on
+// the rotation loop any more (the global-memory kernel above pays two per rotation); same rotation formula, ordering and stopping rule, so
+// the decomposition is the same up to rounding.  lambda_i = v_i . g_i is formed by CTA 1 reading G over DSMEM once at the end.
+constexpr int MARG_PAIR_MAXN = 160;  // 160^2 doubles = 204.8 KB per CTA
+__global__ void __launch_bounds__(MARG_THREADS) marg_jacobi_pair(MargDev M, int which) {
+    extern __shared__ double sm_mat[];  // CTA 0: G; CTA 1: V   (n x n, column-major), then the two rotation-record slots (CTA 1)
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cr = (int) cluster.block_rank();
+    const int w = blockIdx.x / 2, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = MARG_THREADS / 32;
+    const int *map = M.map + (size_t) w * M.map_stride;
+    const int m = map[0], r = map[1], n0 = map[2];
+    if (m <= 0) return;  // uniform over the cluster
+    const int n = which == 0 ? m : r;
+    const double *src = which == 0 ? M.H0 + (size_t) w * M.n0cap * M.n0cap : M.Hp + (size_t) w * M.rcap * M.rcap;
+    const int lds = which == 0 ? n0 : r;
+    double *Vout = which == 0 ? M.V1 + (size_t) w * M.mcap * M.mcap : M.V2 + (size_t) w * M.rcap * M.rcap;
+    double *lam = which == 0 ? M.lam1 + (size_t) w * M.mcap : M.lam2 + (size_t) w * M.rcap;
+    const int ne = (n + 1) & ~1, half = ne / 2;
+    double *mat = sm_mat;
+    double *rec = sm_mat + (size_t) n * n;  // [2][half][2] (c, s); c = 2 marks "no rotation"
+    __shared__ int s_any[2];
+    if (cr == 0) {
+        for (int e = tid; e < n * n; e += MARG_THREADS) {
+            const int j = e / n, i = e - j * n;
+            mat[e] = 0.5 * (src[(size_t) i * lds + j] + src[(size_t) j * lds + i]);
+        }
+    } else {
+        for (int e = tid; e < n * n; e += MARG_THREADS) mat[e] = (e / n) == (e % n) ? 1.0 : 0.0;
+    }
+    if (tid < 2) s_any[tid] = 0;
+    // CTA 0 addresses the record slots and the "any rotation" word of CTA 1
+    double *rec_remote = cluster.map_shared_rank(rec, 1);
+    int *any_remote = cluster.map_shared_rank(s_any, 1);
+    cluster.sync();
+    constexpr int RPL = 5;  // rows per lane: n <= 160
+    int pending = -1, pending_slot = 0;  // step (and record slot) CTA 1 still has to apply
+    int gstep = 0;                       // steps executed so far over all sweeps: the record slots alternate on it (ne - 1 is odd)
+    bool stop = false;
+    for (int sweep = 0; sweep < 40 && !stop; sweep++) {
+        for (int step = 0; step < ne - 1; step++, gstep++) {
+            const int slot = gstep & 1;
+            if (cr == 0) {
+                for (int i = warp; i < half; i += nwarps) {
+                    int p = i == 0 ? ne - 1 : (step + i) % (ne - 1);
+                    int q = (step + ne - 1 - i) % (ne - 1);
+                    double c = 2.0, sn = 0.0;
+                    if (p < n && q < n) {
+                        if (p > q) {
+                            const int t = p;
+                            p = q, q = t;
+                        }
+                        double *gp = mat + (size_t) p * n, *gq = mat + (size_t) q * n;
+                        double a[RPL], b[RPL], al = 0, be = 0, ga = 0;
+#pragma unroll
+                        for (int k = 0; k < RPL; k++) {
+                            const int row = lane + 32 * k;
+                            a[k] = row < n ? gp[row] : 0.0;
+                            b[k] = row < n ? gq[row] : 0.0;
+                            al += a[k] * a[k], be += b[k] * b[k], ga += a[k] * b[k];
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            al += __shfl_xor_sync(0xffffffffu, al, o);
+                            be += __shfl_xor_sync(0xffffffffu, be, o);
+                            ga += __shfl_xor_sync(0xffffffffu, ga, o);
+                        }
+                        if (!(ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be))) {
+                            const double zeta = (be - al) / (2.0 * ga);
+                            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                            c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+                            for (int k = 0; k < RPL; k++) {
+                                const int row = lane + 32 * k;
+                                if (row < n) {
+                                    gp[row] = c * a[k] - sn * b[k];
+                                    gq[row] = sn * a[k] + c * b[k];
+                                }
+                            }
+                        }
+                    }
+                    if (lane == 0) {
+                        rec_remote[((size_t) slot * half + i) * 2] = c, rec_remote[((size_t) slot * half + i) * 2 + 1] = sn;
+                        if (c != 2.0) any_remote[sweep & 1] = 1;
+                    }
+                }
+            } else if (pending >= 0) {
+                // apply the previous step's rotations to V (its record was completed before the last cluster barrier)
+                const int pstep = pending, pslot = pending_slot;
+                for (int i = warp; i < half; i += nwarps) {
+                    const double c = rec[((size_t) pslot * half + i) * 2], sn = rec[((size_t) pslot * half + i) * 2 + 1];
+                    if (c == 2.0) continue;
+                    int p = i == 0 ? ne - 1 : (pstep + i) % (ne - 1);
+                    int q = (pstep + ne - 1 - i) % (ne - 1);
+                    if (p > q) {
+                        const int t = p;
+                        p = q, q = t;
+                    }
+                    double *vp = mat + (size_t) p * n, *vq = mat + (size_t) q * n;
+#pragma unroll
+                    for (int k = 0; k < RPL; k++) {
+                        const int row = lane + 32 * k;
+                        if (row < n) {
+                            const double x = vp[row], y = vq[row];
+                            vp[row] = c * x - sn * y;
+                            vq[row] = sn * x + c * y;
+                        }
+                    }
+                }
+            }
+            cluster.sync();  // record of `step` complete and visible in CTA 1; CTA 1 done with the slot CTA 0 writes next
+            pending = step, pending_slot = slot;
+        }
+        // end of sweep: both CTAs read the same flag (it lives in CTA 1; CTA 0 reads it over DSMEM)
+        const int any = cr == 0 ? *((volatile int *) any_remote + (sweep & 1)) : *((volatile int *) s_any + (sweep & 1));
+        cluster.sync();
+        if (cr == 1 && tid == 0) s_any[(sweep + 1) & 1] = 0;
+        cluster.sync();
+        if (!any) stop = true;
+    }
+    // flush: the record of the last executed step has not been applied yet
+    if (cr == 1 && pending >= 0) {
+        const int pstep = pending, pslot = pending_slot;
+        for (int i = warp; i < half; i += nwarps) {
+            const double c = rec[((size_t) pslot * half + i) * 2], sn = rec[((size_t) pslot * half + i) * 2 + 1];
+            if (c == 2.0) continue;
+            int p = i == 0 ? ne - 1 : (pstep + i) % (ne - 1);
+            int q = (pstep + ne - 1 - i) % (ne - 1);
+            if (p > q) {
+                const int t = p;
+                p = q, q = t;
+            }
+            double *vp = mat + (size_t) p * n, *vq = mat + (size_t) q * n;
+            for (int row = lane; row < n; row += 32) {
+                const double x = vp[row], y = vq[row];
+                vp[row] = c * x - sn * y;
+                vq[row] = sn * x + c * y;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- results (CTA 1): V to global (column-major n x n), lambda_j = v_j . g_j with g_j read from CTA 0 over DSMEM
+    const double *G_remote = cluster.map_shared_rank(sm_mat, 0);
+    if (cr == 1) {
+        for (int e = tid; e < n * n; e += MARG_THREADS) Vout[e] = mat[e];
+        for (int j = warp; j < n; j += nwarps) {
+            double s2 = 0;
+            for (int row = lane; row < n; row += 32) s2 += mat[(size_t) j * n + row] * G_remote[(size_t) j * n + row];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            if (lane == 0) lam[j] = s2;
+        }
+    }
+    cluster.sync();  // CTA 0's shared memory must stay alive until CTA 1 has read G
+}
+
 // Hp = Hrr - Hrm Hmm^+ Hmr, bp = br - Hrm Hmm^+ bm with Hmm^+ = V diag(1/lambda > EPS) V^T  (schurElimination)
 __global__ void __launch_bounds__(MARG_THREADS) marg_schur(MargDev M) {
     const int w = blockIdx.x, tid = threadIdx.x;
