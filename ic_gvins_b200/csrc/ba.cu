@@ -1965,7 +1965,8 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
     auto pack_one = [&](int w, std::string &err) -> int {
         const icg_ba_problem &p = P[w];
         if (p.K < 2 || p.K > C.K || p.L < 0 || p.L > C.L || p.F < 0 || p.F > C.F || p.n_imu < 0 || p.n_imu > p.K - 1 || p.n_gnss < 0 || p.n_gnss > C.G ||
-            p.marg_r < 0 || p.marg_r > C.R || p.marg_nblocks < 0 || p.marg_nblocks > 2 * C.K + 2 || !p.pose || !p.mix || !p.ext || !p.invdepth) {
+            p.marg_r < 0 || p.marg_r > C.R || p.marg_nblocks < 0 || p.marg_nblocks > 2 * C.K + 2 || !p.pose || !p.mix || !p.ext || (p.L > 0 && !p.invdepth) ||
+            (p.F > 0 && (!p.f_lm || !p.f_ref || !p.f_obs || !p.f_const))) {
             PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d exceeds the handle's capacity or has null parameter arrays (K=%d L=%d F=%d gnss=%d marg_r=%d)", w, p.K, p.L, p.F,
                       p.n_gnss, p.marg_r);
         }
@@ -1977,7 +1978,7 @@ int icg_ba_upload(icg_ba *h, int n, const icg_ba_problem *P) {
         memcpy(h->pose.h + (size_t) w * C.K * 7, p.pose, sizeof(double) * 7 * p.K);
         memcpy(h->mix.h + (size_t) w * C.K * 9, p.mix, sizeof(double) * 9 * p.K);
         memcpy(h->ext.h + (size_t) w * 8, p.ext, sizeof(double) * 8);
-        memcpy(h->rho.h + (size_t) w * C.L, p.invdepth, sizeof(double) * p.L);
+        if (p.L > 0) memcpy(h->rho.h + (size_t) w * C.L, p.invdepth, sizeof(double) * p.L);
         for (int f = 0; f < p.F; f++) {
             if (p.f_lm[f] < 0 || p.f_lm[f] >= p.L || p.f_ref[f] < 0 || p.f_ref[f] >= p.K || p.f_obs[f] < 0 || p.f_obs[f] >= p.K || p.f_ref[f] == p.f_obs[f]) {
                 PK_FAIL(ICG_EINVAL, "icg_ba_upload: window %d factor %d has invalid indices", w, f);
@@ -2480,7 +2481,7 @@ int icg_ba_download(icg_ba *h, int n, const icg_ba_problem *P, icg_ba_summary *s
             memcpy(p.pose, h->pose.h + (size_t) w * C.K * 7, sizeof(double) * 7 * p.K);
             memcpy(p.mix, h->mix.h + (size_t) w * C.K * 9, sizeof(double) * 9 * p.K);
             memcpy(p.ext, h->ext.h + (size_t) w * 8, sizeof(double) * 8);
-            memcpy(p.invdepth, h->rho.h + (size_t) w * C.L, sizeof(double) * p.L);
+            if (p.L > 0) memcpy(p.invdepth, h->rho.h + (size_t) w * C.L, sizeof(double) * p.L);
         }
         if (summaries) {
             const LmState &st = h->st.h[w];

@@ -45,7 +45,17 @@ struct DetArgs {
     int *out_n;                 // [n_blocks]
     int *overflow;
     double quality, min_distance;
+    // batched frames: block b belongs to frame b / bpf, whose image (and mask) start frame * img_stride bytes further
+    size_t img_stride;
+    int bpf;
 };
+// kernel prologue: point the by-value argument copy at the block's frame
+#define DET_FRAME(A, b)                                           \
+    do {                                                          \
+        const size_t fo_ = (size_t) ((b) / (A).bpf) * (A).img_stride; \
+        (A).img += fo_;                                           \
+        if ((A).mask) (A).mask += fo_;                            \
+    } while (0)
 
 __device__ __forceinline__ int refl(int p, int len) {
     if (len == 1) return 0;
@@ -85,6 +95,7 @@ __global__ void __launch_bounds__(256) detect_eig(DetArgs A) {
     __shared__ float s_xx[ET_H + 2][ET_W + 2], s_xy[ET_H + 2][ET_W + 2], s_yy[ET_H + 2][ET_W + 2];
     __shared__ unsigned int s_max;
     const int b = blockIdx.z;
+    DET_FRAME(A, b);
     const DetRect R = A.rois[b];
     const int tx0 = blockIdx.x * ET_W, ty0 = blockIdx.y * ET_H;
     if (tx0 >= R.w || ty0 >= R.h) return;
@@ -123,6 +134,7 @@ __global__ void __launch_bounds__(256) detect_eig(DetArgs A) {
 // ------------------------------------------------------------------------------------------------ threshold + NMS
 __global__ void __launch_bounds__(256) detect_nms(DetArgs A) {
     const int b = blockIdx.z;
+    DET_FRAME(A, b);
     const DetRect R = A.rois[b];
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x < 1 || y < 1 || x >= R.w - 1 || y >= R.h - 1) return;
@@ -154,6 +166,7 @@ __global__ void __launch_bounds__(1024) detect_select(DetArgs A) {
     __shared__ float s_gx[DET_MAX_CELLS][DET_CELL_CAP], s_gy[DET_MAX_CELLS][DET_CELL_CAP];
     __shared__ unsigned char s_gn[DET_MAX_CELLS];
     const int b = blockIdx.x, tid = threadIdx.x;
+    DET_FRAME(A, b);
     const DetRect R = A.rois[b];
     int n = min(A.ncand[b], DET_MAX_CAND);
     int npow = 1;
@@ -233,6 +246,7 @@ __global__ void __launch_bounds__(128) detect_subpix(DetArgs A, int half_win, in
     __shared__ float s_mask[11 * 11];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
+    DET_FRAME(A, b);
     const int p = blockIdx.x * 4 + warp;
     if (half_win != 5) return;  // the only window the reference uses (tracking.cc:623)
     for (int e = threadIdx.x; e < 121; e += 128) {
@@ -374,7 +388,11 @@ void icg_detect_destroy(icg_detect *h) {
 }
 
 static int run_detect(icg_detect *h, const uint8_t *d_img, const uint8_t *d_mask, int n_blocks, const icg_rect *rois, const int32_t *max_corners, double quality,
-                      double min_distance, int do_select, int do_subpix, int n_given, float *out_xy, int32_t *out_n) {
+                      double min_distance, int do_select, int do_subpix, int n_given, float *out_xy, int32_t *out_n, int pitch = 0, size_t frame_stride = 0,
+                      int n_frames = 1) {
+    // n_frames > 1: `rois` (n_blocks of them) apply to every frame; device block index = frame * n_blocks + roi
+    const int rois_per_frame = n_blocks;
+    n_blocks *= n_frames;
     DetRect *hr = (DetRect *) h->h_stage;
     int *hm = (int *) (hr + h->max_blocks);
     int *hn = hm + h->max_blocks;          // out_n (also input counts when !do_select)
@@ -382,7 +400,7 @@ static int run_detect(icg_detect *h, const uint8_t *d_img, const uint8_t *d_mask
     float *hxy = (float *) (hov + 4);
     int maxw = 0, maxh = 0;
     for (int b = 0; b < n_blocks; b++) {
-        const icg_rect &r = rois[b];
+        const icg_rect &r = rois[b % rois_per_frame];
         if (r.w < 3 || r.h < 3 || r.x < 0 || r.y < 0 || r.x + r.w > h->W || r.y + r.h > h->H || (size_t) r.w * r.h > (size_t) h->roi_cap) {
             set_error("icg_detect: block %d ROI (%d,%d,%d,%d) outside the %dx%d frame or larger than max_roi_pixels", b, r.x, r.y, r.w, r.h, h->W, h->H);
             return ICG_EINVAL;
@@ -397,7 +415,8 @@ static int run_detect(icg_detect *h, const uint8_t *d_img, const uint8_t *d_mask
     ICG_CUDA(cudaMemsetAsync(h->d_ncand, 0, sizeof(int) * (2 * h->max_blocks + 2), s));
     ICG_CUDA(cudaMemsetAsync(h->d_maxkey, 0, sizeof(unsigned int) * h->max_blocks, s));
     DetArgs A;
-    A.img = d_img, A.mask = d_mask, A.W = h->W, A.H = h->H, A.pitch = h->pitch, A.n_blocks = n_blocks, A.cap = h->cap, A.roi_cap = h->roi_cap;
+    A.img = d_img, A.mask = d_mask, A.W = h->W, A.H = h->H, A.pitch = pitch ? pitch : h->pitch, A.n_blocks = n_blocks, A.cap = h->cap, A.roi_cap = h->roi_cap;
+    A.img_stride = frame_stride, A.bpf = rois_per_frame;
     A.rois = h->d_rois, A.max_corners = h->d_maxc, A.eig = h->d_eig, A.maxkey = h->d_maxkey, A.cand = h->d_cand, A.ncand = h->d_ncand;
     A.out_xy = h->d_out_xy, A.out_n = h->d_out_n, A.overflow = h->d_overflow, A.quality = quality, A.min_distance = min_distance;
     if (do_select) {
@@ -444,6 +463,16 @@ int icg_detect_blocks(icg_detect *h, const uint8_t *img, const uint8_t *mask, in
     ICG_CUDA(cudaMemcpy2DAsync(h->d_img, h->pitch, img, stride, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
     if (mask) ICG_CUDA(cudaMemcpy2DAsync(h->d_mask, h->pitch, mask, stride, h->W, h->H, cudaMemcpyHostToDevice, h->stream));
     return run_detect(h, h->d_img, mask ? h->d_mask : nullptr, n_blocks, rois, max_corners, quality, min_distance, 1, do_subpix, 0, out_xy, out_n);
+}
+
+int icg_detect_blocks_dev(icg_detect *h, int n_frames, const uint8_t *dev_img, int pitch, size_t frame_stride, const uint8_t *dev_mask, int n_blocks,
+                          const icg_rect *rois, const int32_t *max_corners, double quality, double min_distance, int do_subpix, float *out_xy, int32_t *out_n) {
+    if (!h || !dev_img || !rois || !out_xy || !out_n || n_frames < 1 || n_blocks < 1 || (long long) n_frames * n_blocks > h->max_blocks || pitch < h->W) {
+        set_error("icg_detect_blocks_dev: bad arguments (n_frames * n_blocks must be <= max_blocks of the handle)");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    return run_detect(h, dev_img, dev_mask, n_blocks, rois, max_corners, quality, min_distance, 1, do_subpix, 0, out_xy, out_n, pitch, frame_stride, n_frames);
 }
 
 int icg_corner_subpix(icg_detect *h, const uint8_t *img, int stride, float *corners_xy, int n) {

@@ -69,6 +69,21 @@ class Detector:
                                       vp(cnt.ctypes.data)), "icg_detect_blocks")
         return [out[b, :cnt[b]].copy() for b in range(n)]
 
+    def detect_blocks_dev(self, n_frames, dev_img, pitch, frame_stride, rois, max_corners, quality=0.01, min_distance=40.0, dev_mask=None, subpix=True):
+        """The same on `n_frames` device-resident frames in ONE call (dev_img: device address of frame 0, row pitch, byte stride between frames).
+        Returns out[f][b] = (n, 2) float32 arrays (block-local coordinates)."""
+        nb = len(rois)
+        r = np.ascontiguousarray(np.array(rois, np.int32).reshape(-1, 4))
+        mc = np.ascontiguousarray(np.array(max_corners, np.int32).reshape(-1))
+        if mc.size == nb:
+            mc = np.tile(mc, n_frames)
+        out = np.zeros((n_frames * nb, self.cap, 2), np.float32)
+        cnt = np.zeros(n_frames * nb, np.int32)
+        check(lib().icg_detect_blocks_dev(self._h, n_frames, vp(dev_img), pitch, frame_stride, vp(dev_mask) if dev_mask else None, nb, vp(r.ctypes.data),
+                                          vp(mc.ctypes.data), float(quality), float(min_distance), 1 if subpix else 0, vp(out.ctypes.data),
+                                          vp(cnt.ctypes.data)), "icg_detect_blocks_dev")
+        return [[out[f * nb + b, :cnt[f * nb + b]].copy() for b in range(nb)] for f in range(n_frames)]
+
     # cv2.goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=...) on the whole frame
     def goodFeaturesToTrack(self, image, maxCorners, qualityLevel, minDistance, mask=None):
         return self.detect_blocks(image, [(0, 0, self.W, self.H)], [maxCorners], qualityLevel, minDistance, mask, subpix=False)[0]

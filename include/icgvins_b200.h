@@ -167,6 +167,13 @@ void icg_detect_destroy(icg_detect *h);
  */
 int icg_detect_blocks(icg_detect *h, const uint8_t *img, const uint8_t *mask, int stride, int n_blocks, const icg_rect *rois,
                       const int32_t *max_corners, double quality, double min_distance, int do_subpix, float *out_xy, int32_t *out_n);
+/* The same for n_frames DEVICE-resident frames in one call (throughput mode / the keyframe path of many streams): frame f starts at
+ * dev_img + f * frame_stride (row pitch `pitch` bytes; e.g. the level-0 planes of consecutive KLT slots, icg_klt_slot_level0), dev_mask (NULL or the
+ * same geometry) likewise; the n_blocks ROIs apply to every frame; max_corners is n_frames x n_blocks (or NULL); outputs are host arrays of
+ * n_frames x n_blocks (x cap x 2).  The handle's max_blocks must cover n_frames * n_blocks. */
+int icg_detect_blocks_dev(icg_detect *h, int n_frames, const uint8_t *dev_img, int pitch, size_t frame_stride, const uint8_t *dev_mask, int n_blocks,
+                          const icg_rect *rois, const int32_t *max_corners, double quality, double min_distance, int do_subpix, float *out_xy,
+                          int32_t *out_n);
 /* Drop-in for cv::cornerSubPix(img, corners, Size(5,5), Size(-1,-1), (COUNT+EPS, 20, 0.01)) on the whole frame; corners in/out */
 int icg_corner_subpix(icg_detect *h, const uint8_t *img, int stride, float *corners_xy, int n);
 

@@ -101,3 +101,34 @@ def test_empty_mask_and_errors(detectors):
     assert len(d.goodFeaturesToTrack(img, 17, 0.01, 40.0, mask=np.zeros((186, 213), np.uint8))) == 0
     with pytest.raises(IcgError):
         d.detect_blocks(img, [(100, 100, 200, 200)], [5])
+
+
+def test_batched_device_resident_detection_equals_per_frame_calls():
+    """icg_detect_blocks_dev on the level-0 planes of consecutive KLT slots (one call for all frames) == icg_detect_blocks frame by frame."""
+    import ctypes as C
+    from ic_gvins_b200._lib import lib, vp
+    from ic_gvins_b200.detect import Detector, block_rois
+    from ic_gvins_b200.klt import KltTracker
+    from datagen import synth_klt as synth
+    W, H, NF = 1280, 560, 3
+    st = synth.KltStream(W, H, 300, 77)
+    frames = [st.frame(t) for t in range(NF)]
+    rois, quota, min_dist, _ = block_rois(W, H, 300)
+    want = [quota - (b % 4) for b in range(len(rois))]
+    d1 = Detector(W, H, max_blocks=32, max_corners_per_block=32)
+    ref = [d1.detect_blocks(f, rois, want, 0.01, float(min_dist), None, subpix=True) for f in frames]
+    d1.close()
+    trk = KltTracker(W, H, n_slots=NF, max_points=64)
+    for k, f in enumerate(frames):
+        trk.upload(k, f, build=False)
+    trk.sync()
+    p0, p1, pitch = vp(), vp(), C.c_int()
+    lib().icg_klt_slot_level0(trk._h, 0, C.byref(p0), C.byref(pitch))
+    lib().icg_klt_slot_level0(trk._h, 1, C.byref(p1), C.byref(pitch))
+    dN = Detector(W, H, max_blocks=NF * len(rois), max_corners_per_block=32, max_roi_pixels=213 * 186)
+    got = dN.detect_blocks_dev(NF, p0.value, pitch.value, p1.value - p0.value, rois, want, 0.01, float(min_dist))
+    dN.close()
+    trk.close()
+    for f in range(NF):
+        for b in range(len(rois)):
+            assert got[f][b].shape == ref[f][b].shape and np.array_equal(got[f][b], ref[f][b]), (f, b)
