@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-marg", action="store_true", help="skip the marginalization section")
     ap.add_argument("--no-detect", action="store_true", help="skip the block-detection section")
     ap.add_argument("--no-clahe", action="store_true", help="skip the CLAHE section")
+    ap.add_argument("--no-keyframe", action="store_true", help="skip the full-keyframe-path line")
     return ap.parse_args()
 
 
@@ -295,7 +296,9 @@ def run_b200(args):
             pe = [copy.deepcopy(w_) for w_ in part]
             init = [{q: np.array(w_[q], copy=True) for q in ("pose", "mix", "ext", "invdepth", "f_active", "gnss_std")} for w_ in pe]
             e2e_parts.append((pe, init, (BaProblem * len(pe))(*[to_struct(w_) for w_ in pe]), (BaSummary * (2 * len(pe)))()))
-        ba_h2d = int(sum(w_["F"] * (14 * 8 + 12 + 1) + 10 * 16 * 8 + 8 * 8 + 300 * 8 + 9 * 480 * 8 + 5 * 52 for w_ in windows))
+        # what icg_ba_upload moves per window (arrays are capacity-strided: max_F factor slots, max_K = 10 IMU slots): slot-ordered factor constants +
+        # (landmark, ref, obs, id) + pair index + activity, parameters, IMU blobs + sqrt-information, CSR offsets, GNSS
+        ba_h2d = int(len(windows) * (maxF * (14 * 8 + 16 + 4 + 1) + 10 * 16 * 8 + 8 * 8 + 300 * 8 + 10 * (480 + 225) * 8 + 301 * 4 + 91 * 8 + 8 * 56))
         ba_d2h = int(sum(10 * 16 * 8 + 8 * 8 + 300 * 8 + w_["F"] for w_ in windows))
     else:
         ba_h2d = ba_d2h = 0
@@ -312,7 +315,10 @@ def run_b200(args):
         for sv in solvers:
             sv.run_gvins(20, restart=True)
 
+    e2e_host = {"klt_enqueue_ms": [], "ba_begin_ms": [], "ba_end_ms": []}  # host wall time of the phases of an e2e step (where the step goes)
+
     def step_e2e(s):
+        t_0 = time.perf_counter()
         fb = seq[s + 1]
         trk.upload_batch_ptrs(fb * B, frame_ptrs[fb], W)  # H2D of this step's B new frames from pinned host memory (one call, linear DMA)
         with torch.cuda.stream(stream):
@@ -325,6 +331,8 @@ def run_b200(args):
         with torch.cuda.stream(stream):
             h_fwd.copy_(d_fwd, non_blocking=True)
             h_st.copy_(d_st, non_blocking=True)
+        t_1 = time.perf_counter()
+
         def begin(k):
             sv, (pe, init, arr, summ) = solvers[k], e2e_parts[k]
             for w_, ini in zip(pe, init):  # fresh initial guess every step (the solve updates in place)
@@ -333,17 +341,73 @@ def run_b200(args):
             rc = lib().icg_ba_gvins_optimization_begin(sv._h, len(pe), arr, 20)  # pack + upload + enqueue (asynchronous)
             if rc != 0:
                 raise RuntimeError(lib().icg_last_error().decode())
-        # one host thread per solver handle, as the reference has one optimization thread per GVINS object (ctypes releases the GIL)
-        ths = [threading.Thread(target=begin, args=(k,)) for k in range(1, len(solvers))]
-        for t_ in ths:
-            t_.start()
-        begin(0)
-        for t_ in ths:
-            t_.join()
+        # handles in sequence: the GPU starts on handle k while the host packs handle k + 1 (each icg_ba_upload spreads its packing over host threads)
+        for k in range(len(solvers)):
+            begin(k)
+        t_2 = time.perf_counter()
         for sv, (pe, init, arr, summ) in zip(solvers, e2e_parts):
             rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)  # synchronise + write back
             if rc != 0:
                 raise RuntimeError(lib().icg_last_error().decode())
+        t_3 = time.perf_counter()
+        e2e_host["klt_enqueue_ms"].append((t_1 - t_0) * 1e3), e2e_host["ba_begin_ms"].append((t_2 - t_1) * 1e3), e2e_host["ba_end_ms"].append((t_3 - t_2) * 1e3)
+
+    # ---- the FULL keyframe path of every stream, end to end through the C ABI: what one keyframe costs when nothing is left out.
+    #      H2D of the raw frame -> CLAHE + histogram-gate statistic (batched, device-resident) -> pyramid -> fwd+bwd LK + gates -> block detection
+    #      (goodFeaturesToTrack + cornerSubPix on the 18 blocks of every frame) -> gvinsOptimization (host arrays in / out) -> gvinsMarginalization
+    #      (host arrays in, prior out).  Every frame is treated as a keyframe (conservative).
+    kf = None
+    if use_ba and not args.no_keyframe:
+        from ic_gvins_b200.clahe import Clahe
+        from ic_gvins_b200.detect import Detector, block_rois
+        import ctypes as C2
+        d_raw = torch.from_numpy(np.stack(frames)).to(dev)  # the raw (un-equalised) frames of the sequence, device-resident staging of the H2D copy
+        kcl = Clahe(W, H, 3.0, (21, 21), device=local_rank, stream=stream.cuda_stream)
+        rois, quota, min_dist, _ = block_rois(W, H, NPTS)
+        kdet = Detector(W, H, max_blocks=B * len(rois), max_corners_per_block=32, max_roi_pixels=213 * 186, device=local_rank, stream=stream.cuda_stream)
+        p0_, p1_, pit_ = C2.c_void_p(), C2.c_void_p(), C2.c_int()
+        lib().icg_klt_slot_level0(trk._h, 0, C2.byref(p0_), C2.byref(pit_))
+        lib().icg_klt_slot_level0(trk._h, 1, C2.byref(p1_), C2.byref(pit_))
+        slot_stride, slot_pitch, slot0 = p1_.value - p0_.value, pit_.value, p0_.value
+        h_raw = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+        d_rawB = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        kf_hist = [None]
+
+        def step_keyframe(s):
+            fb = seq[s + 1]
+            with torch.cuda.stream(stream):
+                d_rawB.copy_(h_raw, non_blocking=True)   # H2D of the B raw frames (pinned)
+                e_prev.copy_(h_prev[s], non_blocking=True)
+                e_init.copy_(h_init[s], non_blocking=True)
+                e_slots.copy_(h_slots[s], non_blocking=True)
+            # CLAHE of the B frames into their slots' level-0 planes + the histogram-gate statistic of the raw frames (synchronises: the host decides)
+            kf_hist[0] = kcl.apply_batch_dev(B, d_rawB.data_ptr(), W, W * H, slot0 + fb * B * slot_stride, slot_pitch, slot_stride, want_hist=True)
+            trk.build_pyramids(fb * B, B)
+            trk.track_batch_dev(n_total, e_slots.data_ptr(), e_prev.data_ptr(), e_init.data_ptr(), d_fwd.data_ptr(), d_bwd.data_ptr(), d_st.data_ptr(), 1)
+            with torch.cuda.stream(stream):
+                h_fwd.copy_(d_fwd, non_blocking=True)
+                h_st.copy_(d_st, non_blocking=True)
+
+            def ba_part(k):
+                sv, (pe, init, arr, summ) = solvers[k], e2e_parts[k]
+                for w_, ini in zip(pe, init):
+                    for q, v in ini.items():
+                        w_[q][...] = v
+                rc = lib().icg_ba_gvins_optimization_begin(sv._h, len(pe), arr, 20)
+                if rc == 0:
+                    rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)
+                if rc != 0:
+                    raise RuntimeError(lib().icg_last_error().decode())
+                sv.marginalize(pe, 1, want_schur=False)   # host arrays in, prior out
+            ths = [threading.Thread(target=ba_part, args=(k,)) for k in range(len(solvers))]
+            for t_ in ths:
+                t_.start()
+            # block detection of the B equalised frames (device-resident input, corners back on the host), beside the BA threads
+            kdet.detect_blocks_dev(B, slot0 + fb * B * slot_stride, slot_pitch, slot_stride, rois, [quota] * len(rois), 0.01, float(min_dist))
+            for t_ in ths:
+                t_.join()
+        for b in range(B):
+            h_raw[b].copy_(h_frames[0])
 
     def barrier():
         if world > 1:
@@ -407,6 +471,12 @@ def run_b200(args):
         _, kms = timed(klt_resident, mode="klt_kernel")
         bms = timed(None, mode="ba_only")[1] if use_ba else []
         ms_klt, _ = timed(klt_resident)
+        if use_ba and not args.no_keyframe:
+            ms_kf, _ = timed(step_keyframe)
+            kf = {"workload": "FULL keyframe path of B streams end to end through the C ABI: H2D raw frame, CLAHE + histogram gate (batched), pyramid, fwd+bwd LK, "
+                              "block detection (18 blocks x B frames, one call), gvinsOptimization and gvinsMarginalization with host arrays (2 handles, one host "
+                              "thread each); every frame a keyframe", "value": B * world * args.steps / (ms_kf / 1e3), "unit": "frames/s",
+                  "ms_per_step": ms_kf / args.steps}
     clocks = clk.summary()
     good = int(d_st.sum().item())
     ba_info = None
@@ -433,9 +503,20 @@ def run_b200(args):
         cb.record(stream)
         barrier()
         cms = ca.elapsed_time(cb) / NC
-        clahe = {"workload": "icg_clahe_apply_dev (clip 3.0, 21x21 tiles) in place on HBM-resident 1280x560 frames, one frame per call",
+        # the same NC frames in ONE batched launch pair (+ the fused histogram-gate statistic on a second pass)
+        cl.apply_batch_dev(NC, cbuf.data_ptr(), W, W * H, cbuf.data_ptr(), W, W * H)
+        barrier()
+        ca.record(stream)
+        for _ in range(5):
+            cl.apply_batch_dev(NC, cbuf.data_ptr(), W, W * H, cbuf.data_ptr(), W, W * H)
+        cb.record(stream)
+        barrier()
+        cmsb = ca.elapsed_time(cb) / (5 * NC)
+        clahe = {"workload": "icg_clahe_apply_dev (clip 3.0, 21x21 tiles) in place on HBM-resident 1280x560 frames, one frame per call; "
+                             "batched: icg_clahe_apply_batch_dev, 148 frames per launch pair",
                  "ms_per_frame": cms, "frames_per_s": 1e3 / cms * world, "algorithmic_bytes_per_frame": 3 * W * H,
-                 "achieved_GBps": 3 * W * H / (cms * 1e-3) / 1e9}
+                 "achieved_GBps": 3 * W * H / (cms * 1e-3) / 1e9,
+                 "batched_ms_per_frame": cmsb, "batched_frames_per_s": 1e3 / cmsb * world, "batched_achieved_GBps": 3 * W * H / (cmsb * 1e-3) / 1e9}
         cl.close()
         del cbuf
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -570,7 +651,8 @@ def run_b200(args):
                    "replication": "the B streams replay ONE rendered 6-frame sequence (distinct device slots, so HBM traffic and H2D volume are real) and the BA "
                                   "batch repeats 64 distinct cfg-3 windows"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24) + ba_h2d,
-                "d2h_bytes_per_step": B * NPTS * 9 + ba_d2h},
+                "d2h_bytes_per_step": B * NPTS * 9 + ba_d2h, "ms_per_step": ms_e2e / args.steps,
+                "host_ms_per_step": {k_: float(np.mean(v_[args.warmup:])) if len(v_) > args.warmup else None for k_, v_ in e2e_host.items()}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "klt_track_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
@@ -587,6 +669,7 @@ def run_b200(args):
                          "frac": 5.0e6 * 22 * B / (ba_info["ms_per_batch"] * 1e-3) / 1e12 / 36.3,
                          "algorithmic_flops_per_batch": 5.0e6 * 22 * B} if ba_info else None),
         "klt_only": {"value": frames_per_step * args.steps / (ms_klt / 1e3), "unit": "frames/s"},
+        "keyframe_path": kf,
         "ba_only": ba_info,
         "sharded_ba": sharded,
         "marginalization": marg,

@@ -30,6 +30,7 @@ def lib() -> C.CDLL:
             raise IcgError(f"{LIB_PATH} not built: run `python -m ic_gvins_b200.build` (there is no CPU fallback)")
         _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         _declare(_lib)
+        _declare_r2(_lib)
     return _lib
 
 
@@ -113,6 +114,18 @@ def _declare(L: C.CDLL) -> None:
     L.icg_ba_marg_factor_evaluate.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]
 
 
+def _declare_r2(L: C.CDLL) -> None:
+    L.icg_clahe_apply_batch_dev.argtypes = [vp, C.c_int, vp, C.c_int, C.c_size_t, vp, C.c_int, C.c_size_t, vp]
+    L.icg_geom_create.argtypes = [C.POINTER(vp), C.c_int, vp]
+    L.icg_geom_destroy.argtypes = [vp]
+    L.icg_geom_destroy.restype = None
+    L.icg_geom_undistort_points.argtypes = [vp, vp, vp, C.c_int]
+    L.icg_geom_distort_points.argtypes = [vp, vp, vp, C.c_int]
+    L.icg_geom_find_fundamental_mat_ransac.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp]
+    L.icg_geom_triangulate_points.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+    L.icg_geom_imu_preintegrate_batch.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+
+
 # every symbol include/icgvins_b200.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
     "icg_last_error", "icg_version", "icg_launch_count", "icg_launch_count_reset",
@@ -121,7 +134,7 @@ EXPORTS = [
     "icg_klt_track_batch_dev", "icg_klt_sync", "icg_klt_download_level",
     "icg_detect_create", "icg_detect_destroy", "icg_detect_blocks", "icg_detect_blocks_dev", "icg_corner_subpix",
     "icg_camera_undistort_points", "icg_camera_distort_points", "icg_camera_distort_camera_points", "icg_camera_pixel2cam", "icg_camera_world2pixel", "icg_tracking_histogram", "icg_find_fundamental_mat_ransac", "icg_triangulate_points",
-    "icg_clahe_create", "icg_clahe_destroy", "icg_clahe_apply", "icg_clahe_apply_dev", "icg_clahe_sync",
+    "icg_clahe_create", "icg_clahe_destroy", "icg_clahe_apply", "icg_clahe_apply_dev", "icg_clahe_apply_batch_dev", "icg_geom_create", "icg_geom_destroy", "icg_geom_undistort_points", "icg_geom_distort_points", "icg_geom_find_fundamental_mat_ransac", "icg_geom_triangulate_points", "icg_geom_imu_preintegrate_batch", "icg_clahe_sync",
     "icg_imu_preintegrate", "icg_ba_create", "icg_ba_destroy", "icg_ba_solve", "icg_ba_upload", "icg_ba_run", "icg_ba_download",
     "icg_ba_sync", "icg_nccl_unique_id", "icg_ba_set_shard", "icg_ba_shard_export", "icg_ba_shard_connect", "icg_ba_shard_error", "icg_ba_gvins_optimization", "icg_ba_run_gvins", "icg_ba_gvins_optimization_begin", "icg_ba_gvins_optimization_end", "icg_ba_residual_costs", "icg_ba_reproj_evaluate", "icg_ba_imu_evaluate", "icg_ba_marginalize", "icg_ba_gnss_evaluate", "icg_ba_pose_prior_evaluate", "icg_ba_mix_prior_evaluate", "icg_ba_imu_error_evaluate", "icg_ba_marg_factor_evaluate",
 ]

@@ -23,7 +23,8 @@ SOURCES = {
     "detect.cu": ["-fmad=false"],
     "clahe.cu": ["-fmad=false"],
     "camera.cu": ["-fmad=false"],
-    "fundamental.cu": ["-fmad=false"],  # host code only  # host code only; no contraction of the reference's double sequence
+    "fundamental.cu": ["-fmad=false"],  # host code; no contraction of the reference's double sequence
+    "geom.cu": ["-fmad=false"],         # device versions of the camera model / RANSAC gate / triangulation / IMU propagation (same cores)
     "ba.cu": [],
 }
 

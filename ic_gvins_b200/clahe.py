@@ -39,5 +39,14 @@ class Clahe:
         """device-resident variant (asynchronous): raw device pointers, e.g. a KLT slot's level-0 plane"""
         check(lib().icg_clahe_apply_dev(self._h, vp(dev_src), src_pitch, vp(dev_dst), dst_pitch), "icg_clahe_apply_dev")
 
+    def apply_batch_dev(self, n_frames: int, dev_src: int, src_pitch: int, src_frame_stride: int, dev_dst: int, dst_pitch: int, dst_frame_stride: int,
+                        want_hist: bool = False):
+        """n_frames device-resident frames in one launch pair (in place allowed).  want_hist: also returns Tracking::calculateHistigram of every RAW
+        frame (the histogram-gate statistic, accumulated by the LUT pass) as an (n_frames,) float64 array; the call then synchronises."""
+        hist = np.zeros(n_frames) if want_hist else None
+        check(lib().icg_clahe_apply_batch_dev(self._h, n_frames, vp(dev_src), src_pitch, src_frame_stride, vp(dev_dst), dst_pitch, dst_frame_stride,
+                                              vp(hist.ctypes.data) if want_hist else None), "icg_clahe_apply_batch_dev")
+        return hist
+
     def sync(self):
         check(lib().icg_clahe_sync(self._h), "icg_clahe_sync")

@@ -35,6 +35,7 @@
 
 #include "ba_math.cuh"
 #include "common.cuh"
+#include "geom_core.cuh"
 
 namespace icg {
 using namespace bam;
@@ -1026,8 +1027,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         // dependent op per column instead of sqrt + divide); the row solve multiplies by it.
         {
             const int i = J0 + tid;
-            if (i < NR) {
-                double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
+            const bool own = i < NR;
+            double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
+            if (own) {
                 bool bad = false;
 #pragma unroll
                 for (int a = 0; a < BA_CHOL_NB; a++)
@@ -1051,17 +1053,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                     }
                 }
                 if (bad) s_fail = 1;  // benign race: every thread computes the same verdict
-                double *ri = S + i * (i + 1) / 2 + J0;
-                if (i < J0 + nb) {
-                    const int a = i - J0;
-#pragma unroll
-                    for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers
-                        if (a2 != a) continue;
-#pragma unroll
-                        for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
-                        s_diag[i] = dinv[a2];
-                    }
-                } else {
+                if (i >= J0 + nb) {   // rows below the block (incl. the augmented rhs row): solve against the factored block, own row only
+                    double *ri = S + i * (i + 1) / 2 + J0;
                     double x[BA_CHOL_NB];
 #pragma unroll
                     for (int c = 0; c < BA_CHOL_NB; c++) x[c] = c < nb ? ri[c] : 0.0;
@@ -1077,8 +1070,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                         if (c < nb) ri[c] = x[c];
                 }
             }
+            __syncthreads();
+            // the block's own rows are written back only AFTER the barrier: every thread has read the unfactored block by then (an earlier
+            // version overwrote it while slower warps could still be reading), and no later step of the factorisation reads these
+            // entries again (the back-substitution does, behind the barrier that follows the loop)
+            if (own && i < J0 + nb) {
+                double *ri = S + i * (i + 1) / 2 + J0;
+                const int a = i - J0;
+#pragma unroll
+                for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers
+                    if (a2 != a) continue;
+#pragma unroll
+                    for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
+                    s_diag[i] = dinv[a2];
+                }
+            }
         }
-        __syncthreads();
         if (s_fail) break;
     }
     __syncthreads();
@@ -1679,123 +1686,7 @@ int icg_imu_preintegrate(const double *state16, const double *iewn3, const doubl
         set_error("icg_imu_preintegrate: bad arguments");
         return ICG_EINVAL;
     }
-    const bool normal = iewn3 == nullptr;
-    const double zero3[3] = {0, 0, 0};
-    if (normal) iewn3 = zero3;
-    V3 cur_p = mk(state16[0], state16[1], state16[2]), cur_v = mk(state16[7], state16[8], state16[9]);
-    Q cur_q = mkq(state16[6], state16[3], state16[4], state16[5]);
-    const Q q0 = cur_q;
-    const V3 bg = mk(state16[10], state16[11], state16[12]), ba = mk(state16[13], state16[14], state16[15]);
-    const V3 iewn = mk(iewn3[0], iewn3[1], iewn3[2]), grav = mk(gravity3[0], gravity3[1], gravity3[2]);
-    const double corr = noise5[4];
-    double noise[12] = {noise5[0] * noise5[0], 0, 0, noise5[1] * noise5[1], 0, 0, 2 * noise5[2] * noise5[2] / corr, 0, 0, 2 * noise5[3] * noise5[3] / corr, 0, 0};
-    for (int k = 1; k < 3; k++) noise[k] = noise[0], noise[3 + k] = noise[3], noise[6 + k] = noise[6], noise[9 + k] = noise[9];
-    double jac[225] = {0}, cov[225] = {0};
-    for (int i = 0; i < 15; i++) jac[i * 15 + i] = 1;
-    V3 dp = mk(0, 0, 0), dv = mk(0, 0, 0);
-    Q dq = mkq(1, 0, 0, 0);
-    double delta_time = 0, s0 = 0;
-    V3 s1 = mk(0, 0, 0);
-    auto put = [](double *M, int nc, int r0, int c0, const M3 &m) {
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) M[(r0 + i) * nc + c0 + j] = m.m[3 * i + j];
-    };
-    for (int s = 1; s < n; s++) {
-        const double *pr = imu + 7 * (size_t) (s - 1), *cu = imu + 7 * (size_t) s;
-        const double dt = cu[0];
-        V3 pth = mk(pr[1], pr[2], pr[3]) - pr[0] * bg, pvl = mk(pr[4], pr[5], pr[6]) - pr[0] * ba;  // compensationBias (preintegration_base.cc:84-90)
-        V3 cth = mk(cu[1], cu[2], cu[3]) - dt * bg, cvl = mk(cu[4], cu[5], cu[6]) - dt * ba;
-        delta_time += dt;
-        V3 dvfb = cvl + 0.5 * cross(cth, cvl) + (1.0 / 12.0) * (cross(pth, cvl) + cross(pvl, cth));
-        V3 dtheta = cth + (1.0 / 12.0) * cross(pth, cth);
-        M3 cbb0;
-        if (!normal) {
-            V3 dv_cor_g = dt * (grav - 2.0 * cross(iewn, cur_v));
-            Q qnn = rotvec2q(-(dt * iewn));
-            V3 dvel = mul(scale(0.5, add(ident(), qmat(qnn))), mul(qmat(cur_q), dvfb)) + dv_cor_g;
-            cur_p = cur_p + dt * cur_v + (0.5 * dt) * dvel;
-            cur_v = cur_v + dvel;
-            s0 += dt;
-            s1 = s1 + dt * cur_p;
-            cur_q = qnormalized(qmul(qmul(qnn, cur_q), rotvec2q(dtheta)));
-            V3 dnn = -((delta_time - 0.5 * dt) * iewn);
-            dvel = mul(qmat(qmul(qmul(qmul(qinv(q0), rotvec2q(dnn)), q0), dq)), dvfb);
-            dp = dp + dt * dv + (0.5 * dt) * dvel;
-            dv = dv + dvel;
-            dq = qnormalized(qmul(dq, rotvec2q(dtheta)));
-            cbb0 = neg(qmat(qmul(qmul(qmul(qinv(q0), rotvec2q(-(delta_time * iewn))), q0), dq)));
-        } else {
-            V3 dvel = mul(qmat(cur_q), dvfb) + dt * grav;
-            cur_p = cur_p + dt * cur_v + (0.5 * dt) * dvel;
-            cur_v = cur_v + dvel;
-            cur_q = qnormalized(qmul(cur_q, rotvec2q(dtheta)));
-            dvel = mul(qmat(dq), dvfb);
-            dp = dp + dt * dv + (0.5 * dt) * dvel;
-            dv = dv + dvel;
-            dq = qnormalized(qmul(dq, rotvec2q(dtheta)));
-            // phi(3,6) = -R(dq) [dvel]x, phi(3,12) = -R(dq) dt; gt(3,3) = R(dq), gt(6,0) = +I (preintegration_normal.cc:207-225): with a
-            // diagonal noise matrix G = gt noise gt^T does not see the sign of a column block of gt, so the Earth form below with
-            // cbb0 = -R(dq) is the same arithmetic
-            cbb0 = neg(qmat(dq));
-        }
-        // updateJacobianAndCovariance
-        double phi[225] = {0}, gt[180] = {0};
-        put(phi, 15, 0, 0, ident());
-        put(phi, 15, 0, 3, scale(dt, ident()));
-        put(phi, 15, 3, 3, ident());
-        put(phi, 15, 3, 6, mul(cbb0, skew(cvl)));
-        put(phi, 15, 3, 12, scale(dt, cbb0));
-        put(phi, 15, 6, 6, sub(ident(), skew(cth)));
-        put(phi, 15, 6, 9, scale(-dt, ident()));
-        put(phi, 15, 9, 9, scale(1 - dt / corr, ident()));
-        put(phi, 15, 12, 12, scale(1 - dt / corr, ident()));
-        double tmp[225];
-        for (int i = 0; i < 15; i++)
-            for (int j = 0; j < 15; j++) {
-                double a = 0;
-                for (int k = 0; k < 15; k++) a += phi[i * 15 + k] * jac[k * 15 + j];
-                tmp[i * 15 + j] = a;
-            }
-        memcpy(jac, tmp, sizeof(tmp));
-        put(gt, 12, 3, 3, cbb0);
-        put(gt, 12, 6, 0, neg(ident()));
-        put(gt, 12, 9, 6, ident());
-        put(gt, 12, 12, 9, ident());
-        double G[225], pg[225], pc[225], c2[225];
-        for (int i = 0; i < 15; i++)
-            for (int j = 0; j < 15; j++) {
-                double a = 0;
-                for (int k = 0; k < 12; k++) a += gt[i * 12 + k] * noise[k] * gt[j * 12 + k];
-                G[i * 15 + j] = a;
-            }
-        for (int i = 0; i < 15; i++)
-            for (int j = 0; j < 15; j++) {
-                double a = 0, c = 0;
-                for (int k = 0; k < 15; k++) a += phi[i * 15 + k] * G[k * 15 + j], c += phi[i * 15 + k] * cov[k * 15 + j];
-                pg[i * 15 + j] = a, pc[i * 15 + j] = c;
-            }
-        for (int i = 0; i < 15; i++)
-            for (int j = 0; j < 15; j++) {
-                double a = 0, gpt = 0;
-                for (int k = 0; k < 15; k++) a += pc[i * 15 + k] * phi[j * 15 + k], gpt += G[i * 15 + k] * phi[j * 15 + k];
-                c2[i * 15 + j] = a + 0.5 * dt * (pg[i * 15 + j] + gpt);
-            }
-        memcpy(cov, c2, sizeof(c2));
-    }
-    memset(blob, 0, sizeof(double) * ICG_IMU_BLOB_DOUBLES);
-    blob[0] = delta_time;
-    blob[1] = dp.x, blob[2] = dp.y, blob[3] = dp.z, blob[4] = dv.x, blob[5] = dv.y, blob[6] = dv.z;
-    blob[7] = dq.x, blob[8] = dq.y, blob[9] = dq.z, blob[10] = dq.w;
-    for (int k = 0; k < 3; k++) blob[11 + k] = state16[10 + k], blob[14 + k] = state16[13 + k], blob[17 + k] = gravity3[k], blob[20 + k] = iewn3[k];
-    blob[23] = s0, blob[24] = s1.x, blob[25] = s1.y, blob[26] = s1.z;
-    memcpy(blob + 27, jac, sizeof(jac));
-    memcpy(blob + 252, cov, sizeof(cov));
-    blob[477] = normal ? 1.0 : 0.0;
-    if (end_state10) {
-        end_state10[0] = cur_p.x, end_state10[1] = cur_p.y, end_state10[2] = cur_p.z;
-        end_state10[3] = cur_q.x, end_state10[4] = cur_q.y, end_state10[5] = cur_q.z, end_state10[6] = cur_q.w;
-        end_state10[7] = cur_v.x, end_state10[8] = cur_v.y, end_state10[9] = cur_v.z;
-    }
+    gc::preintegrate_core(state16, iewn3, gravity3, noise5, imu, n, blob, end_state10);  // one definition for host and device (geom_core.cuh)
     return ICG_OK;
 }
 
@@ -1909,14 +1800,14 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
         rc = split_setup(h, 0, 1);
         if (rc != ICG_OK) return rc;
     } else {
-        ICG_CUDA(cudaFuncSetAttribute(ba_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve));
+        ICG_CUDA(raise_dynamic_smem((const void *) ba_solve, (size_t) (h->smem_solve)));
     }
     h->ld_schur = 16 * ((C.NCA + 15) / 16) + 8;  // = 8 mod 16 doubles: conflict-free fragment reads
     h->smem_schur = sizeof(double) * ((size_t) SCHUR_RCH * h->ld_schur + SCHUR_RCH);
-    ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_schur));
+    ICG_CUDA(raise_dynamic_smem((const void *) ba_schur_dmma, (size_t) (h->smem_schur)));
     ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    ICG_CUDA(cudaFuncSetAttribute(ba_lin_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
-    ICG_CUDA(cudaFuncSetAttribute(ba_cost_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_cam));
+    ICG_CUDA(raise_dynamic_smem((const void *) ba_lin_cam, (size_t) (h->smem_cam)));
+    ICG_CUDA(raise_dynamic_smem((const void *) ba_cost_cam, (size_t) (h->smem_cam)));
     ICG_CUDA(cudaStreamSynchronize(h->stream));
     h->cur_windows = 0;
     return ICG_OK;
@@ -2210,15 +2101,26 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
     const dim3 g_vis(C.NVB - 2, n), g_cost(h->nblk_vis, n);
     // iteration 0 linearisation + (max_iter) x [schur syrk, solve, cost, accept, re-linearise]; one extra solve call
     // performs the final termination bookkeeping.
+    // where the camera-only factors are forked: 0 = beside ba_lin_vis (round 1), 1 = behind it, beside the Schur / Gram kernels (ba_lin_vis holds
+    // 128 registers x 4 CTAs: a 320-thread camera CTA on the same SM costs it a resident CTA).  Chosen by measurement (profiles/r2_ba_stages.md).
+    static const int cam_fork = getenv("ICG_BA_CAM_FORK") ? atoi(getenv("ICG_BA_CAM_FORK")) : 0;
     for (int it = 0; it <= max_num_iterations; it++) {
         // fork: IMU / GNSS / prior factors (one latency-bound CTA per window) run beside the vision chain
-        ICG_CUDA(cudaEventRecord(h->ev_fork, s));
-        ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
-        ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
-        ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        if (cam_fork == 0) {
+            ICG_CUDA(cudaEventRecord(h->ev_fork, s));
+            ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
+            ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+            ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        }
         prof_mark(h, 0);
         ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
         prof_mark(h, 1);
+        if (cam_fork != 0) {
+            ICG_CUDA(cudaEventRecord(h->ev_fork, s));
+            ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
+            ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+            ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
+        }
         // (measured: one fused launch or two streams are both slower -- the Schur CTAs' shared memory throttles the latency-bound
         //  Gram warps when they share SMs)
         ba_schur_dmma<<<dim3(BA_SPLIT_W, n), 256, h->smem_schur, s>>>(C, D, h->ld_schur);
@@ -2320,9 +2222,9 @@ static int split_setup(icg_ba *h, int rank, int world) {
     h->epoch = 0;
     h->smem_solve_cam = sizeof(double) * (40 + 4 * (size_t) C.NS + (size_t) SPLIT_BS_ROWS * (C.NS + 1));
     h->smem_step_lm = sizeof(double) * (40 + (size_t) C.NS);
-    ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_solve_cam));
+    ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam, (size_t) (h->smem_solve_cam)));
     ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
-    ICG_CUDA(cudaFuncSetAttribute(ba_step_lm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) h->smem_step_lm));
+    ICG_CUDA(raise_dynamic_smem((const void *) ba_step_lm, (size_t) (h->smem_step_lm)));
     return ICG_OK;
 }
 
@@ -2581,7 +2483,7 @@ static int marg_alloc(icg_ba *h) {
     if (rc != ICG_OK) return rc;
     M.flags = (int *) fl;
     const size_t smem = sizeof(double) * (8 * 480 + 2 * (size_t) C.R) + sizeof(int) * (size_t) C.R + 64;
-    ICG_CUDA(cudaFuncSetAttribute(marg_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    ICG_CUDA(raise_dynamic_smem((const void *) marg_assemble, (size_t) (smem)));
     h->marg_ready = true;
     return ICG_OK;
 }
@@ -2683,7 +2585,7 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = 2, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
             cfg.attrs = at, cfg.numAttrs = 1;
-            ICG_CUDA(cudaFuncSetAttribute(marg_jacobi_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            ICG_CUDA(raise_dynamic_smem((const void *) marg_jacobi_pair, (size_t) (smem)));
             ICG_CUDA(cudaLaunchKernelEx(&cfg, marg_jacobi_pair, M, which));
         } else {
             marg_jacobi<<<n, MARG_THREADS, 0, s>>>(M, which);

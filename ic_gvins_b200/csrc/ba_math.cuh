@@ -86,6 +86,10 @@ BAM_HD Q qinv(Q q) {  // Eigen inverse(): conjugate / squaredNorm
     double n2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
     return mkq(q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2);
 }
+BAM_HD Q qinv_r(Q q) {  // the same with ONE reciprocal (hot kernels: a quotient becomes a product with 1 / |q|^2, <= 1.5 ulp apart)
+    const double i2 = 1.0 / (q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+    return mkq(q.w * i2, -q.x * i2, -q.y * i2, -q.z * i2);
+}
 BAM_HD Q qnormalized(Q q) {
     double n = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
     return mkq(q.w / n, q.x / n, q.y / n, q.z / n);
@@ -148,16 +152,20 @@ BAM_HD void reproj_eval(const double *pi, const double *pj, const double *ext, d
     V3 p0 = pose_p(pi), p1 = pose_p(pj), tic = pose_p(ext);
     Q q0 = pose_q(pi), q1 = pose_q(pj), qic = pose_q(ext);
     V3 pts0 = mk(c[0], c[1], c[2]), pts1 = mk(c[3], c[4], c[5]), vel0 = mk(c[6], c[7], c[8]), vel1 = mk(c[9], c[10], c[11]);
+    // FP64 division is ~20 instructions on this part and the reference's form has 15 of them per factor (x / depth, the Eigen inverse() of two
+    // quaternions = conjugate / squaredNorm per component, two projections, the reduce matrix): one reciprocal per distinct divisor instead
+    // (4 divisions); each quotient differs from the divided form by at most 1.5 ulp, far inside the 1e-12 parity bar of the factor tests.
     V3 pts_0_td = pts0 - (td - c[12]) * vel0;
     V3 pts_1_td = pts1 - (td - c[13]) * vel1;
-    V3 pts_c_0 = pts_0_td / id0;
+    const double inv_id0 = 1.0 / id0;
+    V3 pts_c_0 = inv_id0 * pts_0_td;
     V3 pts_b_0 = qrot(qic, pts_c_0) + tic;
     V3 pts_n = qrot(q0, pts_b_0) + p0;
-    V3 pts_b_1 = qrot(qinv(q1), pts_n - p1);
-    V3 pts_1 = qrot(qinv(qic), pts_b_1 - tic);
-    double d1 = pts_1.z;
-    r[0] = sinv * (pts_1.x / d1 - pts_1_td.x);
-    r[1] = sinv * (pts_1.y / d1 - pts_1_td.y);
+    V3 pts_b_1 = qrot(qinv_r(q1), pts_n - p1);
+    V3 pts_1 = qrot(qinv_r(qic), pts_b_1 - tic);
+    const double d1 = pts_1.z, inv_d = 1.0 / d1;
+    r[0] = sinv * (pts_1.x * inv_d - pts_1_td.x);
+    r[1] = sinv * (pts_1.y * inv_d - pts_1_td.y);
     if (!want_j) return;
     // Jacobians (reprojection_factor.h:84-144), evaluated row by row instead of as 3x3 matrix products: with r = a row of the 2x3
     // reduce matrix and R0 = R(q0), R1 = R(q1), Ric = R(q_ic) (so cb0n = R0, cnb1 = R1^T, cbc = Ric^T) every Jacobian row is a chain
@@ -165,9 +173,7 @@ BAM_HD void reproj_eval(const double *pi, const double *pj, const double *ext, d
     // and cross products (a^T [p]x = (a x p)^T).  Same algebra as the reference's matrix form, ~3x fewer flops and far fewer live
     // registers; the sum of the two skew terms of the extrinsic-rotation block is [tmp_r pts_c_0 + lever]x = [pts_1]x.
     const M3 R0 = qmat(q0), R1 = qmat(q1), Ric = qmat(qic);
-    const double inv_d = 1.0 / d1;
-    const double redr[2][3] = {{sinv * inv_d, 0.0, sinv * (-pts_1.x / (d1 * d1))}, {0.0, sinv * inv_d, sinv * (-pts_1.y / (d1 * d1))}};
-    const double inv_id0 = 1.0 / id0;
+    const double redr[2][3] = {{sinv * inv_d, 0.0, sinv * (-pts_1.x * (inv_d * inv_d))}, {0.0, sinv * inv_d, sinv * (-pts_1.y * (inv_d * inv_d))}};
 #pragma unroll
     for (int rr = 0; rr < 2; rr++) {
         const V3 r3 = mk(redr[rr][0], redr[rr][1], redr[rr][2]);

@@ -1,6 +1,6 @@
-// camera.cu -- SURVEY.md 8a row A6: the radtan camera model of the front end.  HOST code by design: <= 300 points per frame, FP64,
-// called from the tracking thread between the GPU stages (SURVEY: "small; stays host").  No kernels here; compiled into the same
-// library so that the Tracking shims find every call they replace behind one C ABI.
+// camera.cu -- SURVEY.md 8a row A6: the radtan camera model of the front end, HOST entry points (<= 300 points per frame, FP64, called from the
+// tracking thread between the GPU stages; SURVEY: "small; stays host").  The arithmetic lives in geom_core.cuh (__host__ __device__), which
+// geom.cu also runs as batched kernels; compiled into the same library so that the Tracking shims find every call behind one C ABI.
 //
 // Replaces Camera::undistortPoints / distortPoints / distortPoint / distortCameraPoint / pixel2cam / cam2pixel / world2pixel
 // (IG/tracking/camera.cc:72-146).  undistortPoints forwards to cv::undistortPoints(pts, pts, K, D, Mat(), K) in the reference
@@ -9,24 +9,14 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "geom_core.cuh"
 
 using namespace icg;
 
 namespace {
-inline void pixel2cam(const icg_camera &c, double u, double v, double &x, double &y) {  // camera.cc:126-130
-    y = (v - c.cy) / c.fy;
-    x = (u - c.cx - c.skew * y) / c.fx;
-}
-inline void cam2pixel(const icg_camera &c, double x, double y, double z, float &u, float &v) {  // camera.cc:132-134
-    u = (float) ((c.fx * x + c.skew * y) / z + c.cx);
-    v = (float) (c.fy * y / z + c.cy);
-}
-inline void distort_xy(const icg_camera &c, double x, double y, double &xd, double &yd) {  // camera.cc:79-86
-    const double r2 = x * x + y * y;
-    const double rr = (1 + c.k1 * r2 + c.k2 * r2 * r2 + c.k3 * r2 * r2 * r2);
-    xd = x * rr + 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
-    yd = y * rr + c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
-}
+using gc::cam2pixel;
+using gc::distort_xy;
+using gc::pixel2cam;
 inline bool bad(const icg_camera *c, const void *p, int n, const char *who) {
     if (!c || (!p && n > 0) || n < 0 || !(c->fx != 0.0) || !(c->fy != 0.0)) {
         set_error("%s: bad arguments", who);
@@ -40,37 +30,13 @@ extern "C" {
 
 int icg_camera_undistort_points(const icg_camera *c, float *pts_xy, int n) {
     if (bad(c, pts_xy, n, "icg_camera_undistort_points")) return ICG_EINVAL;
-    const double ifx = 1.0 / c->fx, ify = 1.0 / c->fy;
-    for (int i = 0; i < n; i++) {
-        double x = ((double) pts_xy[2 * i] - c->cx) * ifx, y = ((double) pts_xy[2 * i + 1] - c->cy) * ify;
-        const double x0 = x, y0 = y;
-        for (int j = 0; j < 5; j++) {  // TermCriteria(MAX_ITER, 5, 0.01): no EPS test
-            const double r2 = x * x + y * y;
-            const double icdist = 1.0 / (1 + ((c->k3 * r2 + c->k2) * r2 + c->k1) * r2);
-            if (icdist < 0) {  // test: undistortPoints regression 14583
-                x = x0, y = y0;
-                break;
-            }
-            const double dx = 2 * c->p1 * x * y + c->p2 * (r2 + 2 * x * x), dy = c->p1 * (r2 + 2 * y * y) + 2 * c->p2 * x * y;
-            x = (x0 - dx) * icdist;
-            y = (y0 - dy) * icdist;
-        }
-        // R = identity, P = K (with its skew): [xx yy ww] = K [x y 1]
-        const double xx = c->fx * x + c->skew * y + c->cx, yy = c->fy * y + c->cy;
-        pts_xy[2 * i] = (float) xx;
-        pts_xy[2 * i + 1] = (float) yy;
-    }
+    for (int i = 0; i < n; i++) gc::undistort_point(*c, pts_xy + 2 * (size_t) i);  // one definition for host and device (geom_core.cuh)
     return ICG_OK;
 }
 
 int icg_camera_distort_points(const icg_camera *c, float *pts_xy, int n) {
     if (bad(c, pts_xy, n, "icg_camera_distort_points")) return ICG_EINVAL;
-    for (int i = 0; i < n; i++) {
-        double x, y, xd, yd;
-        pixel2cam(*c, pts_xy[2 * i], pts_xy[2 * i + 1], x, y);
-        distort_xy(*c, x, y, xd, yd);
-        cam2pixel(*c, xd, yd, 1.0, pts_xy[2 * i], pts_xy[2 * i + 1]);
-    }
+    for (int i = 0; i < n; i++) gc::distort_point(*c, pts_xy + 2 * (size_t) i);
     return ICG_OK;
 }
 

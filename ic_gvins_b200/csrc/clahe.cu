@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace icg {
@@ -24,6 +26,9 @@ struct ClaheArgs {
     int tiles_x, tiles_y, tw, th;
     int clip;
     float lut_scale, inv_tw, inv_th;
+    // batched frames (blockIdx.y / blockIdx.z): frame f reads src + f * src_fstride, writes dst + f * dst_fstride, uses LUT block f
+    size_t src_fstride, dst_fstride;
+    unsigned int *hist;  // [n_frames][256] in-image pixel counts of the RAW frame (histogram gate), or NULL
 };
 
 __device__ __forceinline__ int cl_reflect101(int p, int len) {
@@ -34,17 +39,25 @@ __device__ __forceinline__ int cl_reflect101(int p, int len) {
 
 __global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
     __shared__ int s_hist[256];
+    __shared__ int s_img[256];  // the same counts restricted to pixels INSIDE the frame (the tiles of a non-divisible grid see a reflected fringe)
     __shared__ int s_warp[8];
-    const int tid = threadIdx.x, tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
-    s_hist[tid] = 0;
+    const int tid = threadIdx.x, tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x, frame = blockIdx.y;
+    A.src += (size_t) frame * A.src_fstride;
+    A.lut += (size_t) frame * A.tiles_x * A.tiles_y * 256;
+    s_hist[tid] = 0, s_img[tid] = 0;
     __syncthreads();
     const int area = A.tw * A.th;
     for (int p = tid; p < area; p += 256) {
         const int yy = p / A.tw, xx = p - yy * A.tw;
-        const int y = cl_reflect101(ty * A.th + yy, A.H), x = cl_reflect101(tx * A.tw + xx, A.W);  // copyMakeBorder(BORDER_REFLECT_101)
-        atomicAdd(&s_hist[A.src[(size_t) y * A.spitch + x]], 1);
+        const int y0 = ty * A.th + yy, x0 = tx * A.tw + xx;
+        const int y = cl_reflect101(y0, A.H), x = cl_reflect101(x0, A.W);  // copyMakeBorder(BORDER_REFLECT_101)
+        const int v = A.src[(size_t) y * A.spitch + x];
+        atomicAdd(&s_hist[v], 1);
+        if (A.hist && y0 < A.H && x0 < A.W) atomicAdd(&s_img[v], 1);
     }
     __syncthreads();
+    // Tracking::calculateHistigram's cv::calcHist over the raw frame comes for free from the tile pass: integer atomics, order-independent
+    if (A.hist && s_img[tid]) atomicAdd(&A.hist[(size_t) frame * 256 + tid], (unsigned int) s_img[tid]);
     int h = s_hist[tid];
     if (A.clip > 0) {
         int over = h > A.clip ? h - A.clip : 0;
@@ -79,8 +92,23 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(ClaheArgs A) {
     A.lut[(size_t) blockIdx.x * 256 + tid] = (uint8_t) r;
 }
 
+// Tracking::calculateHistigram (IG/tracking/tracking.cc:88-104) from the counts: sum_k (float) hist[k] * (float) k / 256.0 accumulated in double in
+// bin order, divided by cols * rows (one thread per frame: the order of the 256 additions is part of the result)
+__global__ void clahe_hist_stat_kernel(const unsigned int *hist, int n_frames, int W, int H, double *out) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    double acc = 0;
+    for (int k = 0; k < 256; k++) {
+        const float prod = (float) hist[(size_t) f * 256 + k] * (float) k;
+        acc += (double) prod / 256.0;
+    }
+    out[f] = acc / (double) (W * H);
+}
+
 __global__ void __launch_bounds__(256) clahe_interp_kernel(ClaheArgs A) {
     const int x0 = 4 * (blockIdx.x * 64 + (threadIdx.x & 63)), y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    A.src += (size_t) blockIdx.z * A.src_fstride, A.dst += (size_t) blockIdx.z * A.dst_fstride;
+    A.lut += (size_t) blockIdx.z * A.tiles_x * A.tiles_y * 256;
     if (x0 >= A.W || y >= A.H) return;
     const float tyf = y * A.inv_th - 0.5f;
     int ty1 = __float2int_rd(tyf), ty2 = ty1 + 1;
@@ -126,16 +154,46 @@ struct icg_clahe {
     uint8_t *d_img, *d_lut;
     int pitch;
     ClaheArgs A;
+    int lut_frames = 1;             // frames the LUT buffer holds (grown by the batched entry point)
+    unsigned int *d_hist = nullptr; // [lut_frames][256]
+    double *d_stat = nullptr, *h_stat = nullptr;
 };
 
-static int clahe_launch(icg_clahe *h, const uint8_t *dsrc, int spitch, uint8_t *ddst, int dpitch) {
+static int clahe_reserve(icg_clahe *h, int n_frames) {
+    if (n_frames <= h->lut_frames && h->d_hist) return ICG_OK;
+    ICG_CUDA(cudaStreamSynchronize(h->stream));
+    const int nf = std::max(n_frames, h->lut_frames);
+    if (h->d_lut) cudaFree(h->d_lut);
+    if (h->d_hist) cudaFree(h->d_hist);
+    if (h->d_stat) cudaFree(h->d_stat);
+    if (h->h_stat) cudaFreeHost(h->h_stat);
+    h->d_lut = nullptr, h->d_hist = nullptr, h->d_stat = nullptr, h->h_stat = nullptr;
+    if (cudaMalloc(&h->d_lut, (size_t) nf * h->tiles_x * h->tiles_y * 256) != cudaSuccess || cudaMalloc(&h->d_hist, sizeof(unsigned int) * 256 * (size_t) nf) != cudaSuccess ||
+        cudaMalloc(&h->d_stat, sizeof(double) * nf) != cudaSuccess || cudaMallocHost(&h->h_stat, sizeof(double) * nf) != cudaSuccess) {
+        set_error("icg_clahe: allocation for %d frames failed", nf);
+        return ICG_ENOMEM;
+    }
+    h->lut_frames = nf;
+    h->A.lut = h->d_lut;
+    return ICG_OK;
+}
+
+static int clahe_launch(icg_clahe *h, const uint8_t *dsrc, int spitch, uint8_t *ddst, int dpitch, int n_frames = 1, size_t src_fstride = 0,
+                        size_t dst_fstride = 0, bool want_hist = false) {
     ClaheArgs A = h->A;
-    A.src = dsrc, A.dst = ddst, A.spitch = spitch, A.dpitch = dpitch;
-    clahe_lut_kernel<<<h->tiles_x * h->tiles_y, 256, 0, h->stream>>>(A);
+    A.src = dsrc, A.dst = ddst, A.spitch = spitch, A.dpitch = dpitch, A.src_fstride = src_fstride, A.dst_fstride = dst_fstride;
+    A.hist = want_hist ? h->d_hist : nullptr;
+    if (want_hist) ICG_CUDA(cudaMemsetAsync(h->d_hist, 0, sizeof(unsigned int) * 256 * (size_t) n_frames, h->stream));
+    clahe_lut_kernel<<<dim3(h->tiles_x * h->tiles_y, n_frames), 256, 0, h->stream>>>(A);
     ICG_CHECK_LAUNCH();
-    clahe_interp_kernel<<<dim3((h->W + 255) / 256, (h->H + 3) / 4), 256, 0, h->stream>>>(A);
+    clahe_interp_kernel<<<dim3((h->W + 255) / 256, (h->H + 3) / 4, n_frames), 256, 0, h->stream>>>(A);
     ICG_CHECK_LAUNCH();
     count_launch(2);
+    if (want_hist) {
+        clahe_hist_stat_kernel<<<(n_frames + 63) / 64, 64, 0, h->stream>>>(h->d_hist, n_frames, h->W, h->H, h->d_stat);
+        ICG_CHECK_LAUNCH();
+        count_launch();
+    }
     return ICG_OK;
 }
 
@@ -199,6 +257,9 @@ void icg_clahe_destroy(icg_clahe *h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_img);
     cudaFree(h->d_lut);
+    if (h->d_hist) cudaFree(h->d_hist);
+    if (h->d_stat) cudaFree(h->d_stat);
+    if (h->h_stat) cudaFreeHost(h->h_stat);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -224,6 +285,25 @@ int icg_clahe_apply_dev(icg_clahe *h, const uint8_t *dev_src, int src_pitch, uin
     }
     ICG_CUDA(cudaSetDevice(h->device));
     return clahe_launch(h, dev_src, src_pitch, dev_dst, dst_pitch);
+}
+
+int icg_clahe_apply_batch_dev(icg_clahe *h, int n_frames, const uint8_t *dev_src, int src_pitch, size_t src_frame_stride, uint8_t *dev_dst, int dst_pitch,
+                              size_t dst_frame_stride, double *hist_out) {
+    if (!h || n_frames < 1 || !dev_src || !dev_dst || src_pitch < h->W || dst_pitch < h->W) {
+        set_error("icg_clahe_apply_batch_dev: bad arguments");
+        return ICG_EINVAL;
+    }
+    ICG_CUDA(cudaSetDevice(h->device));
+    int rc = clahe_reserve(h, n_frames);
+    if (rc != ICG_OK) return rc;
+    rc = clahe_launch(h, dev_src, src_pitch, dev_dst, dst_pitch, n_frames, src_frame_stride, dst_frame_stride, hist_out != nullptr);
+    if (rc != ICG_OK) return rc;
+    if (hist_out) {  // the gate statistic is consumed by the host (Tracking::preprocessing decides whether to skip the frame): synchronise
+        ICG_CUDA(cudaMemcpyAsync(h->h_stat, h->d_stat, sizeof(double) * n_frames, cudaMemcpyDeviceToHost, h->stream));
+        ICG_CUDA(cudaStreamSynchronize(h->stream));
+        memcpy(hist_out, h->h_stat, sizeof(double) * n_frames);
+    }
+    return ICG_OK;
 }
 
 int icg_clahe_sync(icg_clahe *h) {

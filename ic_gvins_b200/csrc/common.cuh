@@ -14,6 +14,10 @@ namespace icg {
 void set_error(const char *fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t) n, std::memory_order_relaxed); }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, per-device setting shared by every handle of the process: it may only GROW
+// (a handle with smaller capacities must not lower the limit under a live handle with larger ones -- launches of the latter would fail with
+// "invalid argument").  Records the largest request per (device, function) and raises the attribute when needed.
+cudaError_t raise_dynamic_smem(const void *func, size_t bytes);
 
 #define ICG_CUDA(call)                                                                              \
     do {                                                                                            \

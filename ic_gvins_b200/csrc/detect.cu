@@ -371,7 +371,7 @@ int icg_detect_create(icg_detect **out, int width, int height, int max_blocks, i
     ICG_CUDA(cudaMalloc(&h->d_cand, sizeof(unsigned long long) * (size_t) max_blocks * DET_MAX_CAND));
     h->h_stage_bytes = sizeof(DetRect) * max_blocks + sizeof(int) * (3 * max_blocks + 4) + sizeof(float) * 2 * (size_t) max_blocks * max_corners_per_block;
     ICG_CUDA(cudaMallocHost(&h->h_stage, h->h_stage_bytes));
-    ICG_CUDA(cudaFuncSetAttribute(detect_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (sizeof(unsigned long long) * DET_MAX_CAND)));
+    ICG_CUDA(raise_dynamic_smem((const void *) detect_select, (size_t) ((sizeof(unsigned long long) * DET_MAX_CAND))));
     *out = h;
     return ICG_OK;
 }

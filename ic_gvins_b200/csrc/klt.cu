@@ -14,6 +14,7 @@
 //     equations are reduced with REDUX (exact integer sums, one rounding).
 //   * compile with -fmad=false: the float sequence of the reference library must not be contracted.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <unordered_map>
@@ -202,13 +203,53 @@ __global__ void __launch_bounds__(256) klt_unpack_level0_kernel(const uint8_t *_
 }
 
 // ------------------------------------------------------------------------------------------------ LK tracker
+// The staged windows are addressed by 32-bit SHARED-space addresses and read with ld.shared (no generic loads, no generic <-> shared
+// conversions, and the per-warp bases stay in three registers instead of being re-derived from threadIdx inside the loops; round-1 profile:
+// 12 % of the kernel's instructions were such re-materialisations, 2.8 % generic LD -- profiles/r2_klt_instr_mix.md).
 struct WarpSmem {
-    uint8_t *iw;    // 48x24 template window, origin ((ipx-1) & ~15, ipy-1)
-    uint8_t *jw;    // 48x32 search window, origin (jx0 (16-aligned), jy0)
-    int *pg;        // 23 x 24 ints: Q14 bilinear grid P (interior windows) or 22 x 22 packed Scharr taps (border windows)
-    uint64_t *bar_i, *bar_j;  // mbarriers: template window, search window
+    uint32_t iw;    // 48x24 template window, origin ((ipx-1) & ~15, ipy-1)
+    uint32_t jw;    // 48x32 search window, origin (jx0 (16-aligned), jy0)
+    uint32_t pg;    // 26 x 24 ints: Q14 bilinear grid P (23 rows) + 3 zero rows (interior windows) or 22 x 22 packed Scharr taps (border windows)
+    uint32_t bar_i, bar_j;  // mbarriers: template window, search window
     uint32_t phase_i, phase_j;
 };
+__device__ __forceinline__ unsigned lds_u32(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) { return (int) lds_u32(a); }
+__device__ __forceinline__ unsigned lds_u8(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t a, int x, int y, int z, int w) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int x) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(x) : "memory"); }
+// mbarrier / TMA wrappers on shared-space addresses
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_A:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_A;\n"
+        "bra WAIT_LOOP_A;\n"
+        "DONE_A:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_dst),
+                 "l"((uint64_t) map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
 
 // Box origin for a window whose top-left pixel is (px, py): `margin` pixels of slack on the low side, x aligned to 16 bytes (TMA).
 __device__ __forceinline__ void box_origin(int px, int py, int margin, int &bx, int &by) {
@@ -251,8 +292,8 @@ __device__ __forceinline__ int pack_w(int lo, int hi) { return (int) (((unsigned
 struct RunBytes {
     unsigned e0, e1, o0, o1;  // even stream: bytes 0..3 | 4..7;  odd stream (shifted by one byte): bytes 1..4 | 5..7
 };
-__device__ __forceinline__ RunBytes run_bytes(const unsigned *wp, int m8) {
-    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2];
+__device__ __forceinline__ RunBytes run_bytes(uint32_t wa, int m8) {  // wa: 4-byte aligned shared address of the word holding the run's first byte
+    const unsigned w0 = lds_u32(wa), w1 = lds_u32(wa + 4), w2 = lds_u32(wa + 8);
     RunBytes r;
     r.e0 = __funnelshift_r(w0, w1, m8);
     r.e1 = __funnelshift_r(w1, w2, m8);
@@ -271,6 +312,18 @@ __device__ __forceinline__ void run_taps(const RunBytes &t, const RunBytes &b, i
     v[5] = dp2a_lo_su(wb, b.o1, dp2a_lo_su(wt, t.o1, c0));
     v[6] = dp2a_hi_su(wb, b.e1, dp2a_hi_su(wt, t.e1, c0));
     if (NPIX == 8) v[7] = 0;  // pixel 7 needs byte 8: handled by the caller
+}
+
+// the same with a per-pixel accumulator start c0[i] (the iteration: c0 = 2^8 - 512 I folds the "- I" of the difference into the taps)
+template <int NPIX>
+__device__ __forceinline__ void run_taps_c(const RunBytes &t, const RunBytes &b, int wt, int wb, const int *c0, int *v) {
+    v[0] = dp2a_lo_su(wb, b.e0, dp2a_lo_su(wt, t.e0, c0[0]));
+    v[1] = dp2a_lo_su(wb, b.o0, dp2a_lo_su(wt, t.o0, c0[1]));
+    v[2] = dp2a_hi_su(wb, b.e0, dp2a_hi_su(wt, t.e0, c0[2]));
+    v[3] = dp2a_hi_su(wb, b.o0, dp2a_hi_su(wt, t.o0, c0[3]));
+    v[4] = dp2a_lo_su(wb, b.e1, dp2a_lo_su(wt, t.e1, c0[4]));
+    v[5] = dp2a_lo_su(wb, b.o1, dp2a_lo_su(wt, t.o1, c0[5]));
+    v[6] = dp2a_hi_su(wb, b.e1, dp2a_hi_su(wt, t.e1, c0[6]));
 }
 
 // Track one point from image slot sI to image slot sJ through all levels.  All lanes hold identical scalars.
@@ -330,16 +383,16 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
         if (lane == 0) {
             fence_proxy_async();
             if (!i_pending) {
-                mbar_expect_tx(S.bar_i, KLT_BOXW * KLT_BOXH_I);
-                tma_load_3d(S.iw, &maps.mi[level], ix0 + KLT_PAD, iy0 + KLT_PAD, sI, S.bar_i);
+                mbar_expect_tx_a(S.bar_i, KLT_BOXW * KLT_BOXH_I);
+                tma_load_3d_a(S.iw, &maps.mi[level], ix0 + KLT_PAD, iy0 + KLT_PAD, sI, S.bar_i);
             }
             if (j_ok) {
-                mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
-                tma_load_3d(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
+                mbar_expect_tx_a(S.bar_j, KLT_BOXW * KLT_BOXH_J);
+                tma_load_3d_a(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
             }
         }
         i_pending = false;
-        mbar_wait(S.bar_i, S.phase_i);
+        mbar_wait_a(S.bar_i, S.phase_i);
         S.phase_i ^= 1;
 
         float a = px - (float) ipx, b = py - (float) ipy;
@@ -356,24 +409,23 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             const int wt = pack_w(iw00, iw01), wb = pack_w(iw10, iw11);
             if (lane < 24) {
                 const int cr = lane % 3, rg = lane / 3;
-                const uint8_t *bp = S.iw + oxI + (3 * rg) * KLT_BOXW + 8 * cr;
-                const int m8 = ((int) (size_t) bp & 3) * 8;
-                const unsigned *wp = (const unsigned *) ((size_t) bp & ~(size_t) 3);
-                RunBytes top = run_bytes(wp, m8);
-                const unsigned t8 = bp[8];  // 9th byte: right tap of grid column 7 of the run
-                unsigned tb8 = t8;
+                const uint32_t bp = S.iw + oxI + (3 * rg) * KLT_BOXW + 8 * cr;  // the windows are 128-byte aligned: alignment of bp = that of the offset
+                const int m8 = (int) (bp & 3u) * 8;
+                const uint32_t wa = bp & ~3u;
+                RunBytes top = run_bytes(wa, m8);
+                unsigned tb8 = lds_u8(bp + 8);  // 9th byte: right tap of grid column 7 of the run
 #pragma unroll
                 for (int rr = 0; rr < 3; rr++) {
                     const int gy = 3 * rg + rr;
-                    const RunBytes bot = run_bytes(wp + (rr + 1) * (KLT_BOXW / 4), m8);
-                    const unsigned bb8 = bp[(rr + 1) * KLT_BOXW + 8];
+                    const RunBytes bot = run_bytes(wa + (rr + 1) * KLT_BOXW, m8);
+                    const unsigned bb8 = lds_u8(bp + (rr + 1) * KLT_BOXW + 8);
                     int v[8];
                     run_taps<8>(top, bot, wt, wb, 0, v);
                     v[7] = (int) (top.o1 >> 16 & 0xFF) * iw00 + (int) tb8 * iw01 + (int) (bot.o1 >> 16 & 0xFF) * iw10 + (int) bb8 * iw11;
                     if (gy < 23) {
-                        int4 *dst = (int4 *) (S.pg + gy * 24 + 8 * cr);
-                        dst[0] = make_int4(v[0], v[1], v[2], v[3]);
-                        dst[1] = make_int4(v[4], v[5], v[6], v[7]);
+                        const uint32_t dst = S.pg + 4 * (gy * 24 + 8 * cr);
+                        sts_v4(dst, v[0], v[1], v[2], v[3]);
+                        sts_v4(dst + 16, v[4], v[5], v[6], v[7]);
                     }
                     top = bot, tb8 = bb8;
                 }
@@ -382,21 +434,23 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             // template of the lane's two runs: separable Scharr on the grid (column sums c_j shared along the run)
 #pragma unroll
             for (int run = 0; run < 2; run++) {
-                const int *pp = S.pg + (run ? yB * 24 + xB : yA * 24 + xA);
-                int P0[9], P1[9], P2[9];
+                // lane 31 has no second run: it reads the three zero rows (23..25) instead
+                const uint32_t pp = S.pg + 4 * (run ? (validB ? yB * 24 + xB : 23 * 24) : yA * 24 + xA);
+                int P1[9], c[9], d[9];
 #pragma unroll
-                for (int j = 0; j < 9; j++) P0[j] = pp[j], P1[j] = pp[24 + j], P2[j] = pp[48 + j];
-                int c[9];
-#pragma unroll
-                for (int j = 0; j < 9; j++) c[j] = 3 * (P0[j] + P2[j]) + 10 * P1[j];
-                const bool live = run == 0 || validB;
+                for (int j = 0; j < 9; j++) {
+                    const int p0 = lds_s32(pp + 4 * j), p2 = lds_s32(pp + 4 * (48 + j));
+                    P1[j] = lds_s32(pp + 4 * (24 + j));
+                    c[j] = 3 * (p0 + p2) + 10 * P1[j];  // vertical smoothing (3 10 3): Ix = c[i + 2] - c[i]
+                    d[j] = p2 - p0;                     // vertical difference:        Iy = 3 (d[i] + d[i + 2]) + 10 d[i + 1]
+                }
 #pragma unroll
                 for (int i = 0; i < 7; i++) {
-                    const int h0 = 3 * (P0[i] + P0[i + 2]) + 10 * P0[i + 1], h2 = 3 * (P2[i] + P2[i + 2]) + 10 * P2[i + 1];
-                    const int ival = live ? (P1[i + 1] + (1 << 8)) >> 9 : 0;
-                    const int ixv = live ? (c[i + 2] - c[i] + (1 << 13)) >> 14 : 0;
-                    const int iyv = live ? (h2 - h0 + (1 << 13)) >> 14 : 0;
-                    Ireg[7 * run + i] = ival, Gxr[7 * run + i] = ixv, Gyr[7 * run + i] = iyv;
+                    const int ival = (P1[i + 1] + (1 << 8)) >> 9;
+                    const int ixv = (c[i + 2] - c[i] + (1 << 13)) >> 14;
+                    const int iyv = (3 * (d[i] + d[i + 2]) + 10 * d[i + 1] + (1 << 13)) >> 14;
+                    // the iteration needs (v - 512 I) only: keep c0 = 2^8 - (I << 9), the dp2a accumulator start ((v - 512 I) >> 9 == (v >> 9) - I)
+                    Ireg[7 * run + i] = (1 << 8) - (ival << 9), Gxr[7 * run + i] = ixv, Gyr[7 * run + i] = iyv;
                     sA11 += ixv * ixv;
                     sA12 += ixv * iyv;
                     sA22 += iyv * iyv;
@@ -406,15 +460,17 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             // ---- window touches the image border: Scharr taps first (zero outside the image: OpenCV pads derivI with zeros)
             for (int i = lane; i < 22 * 22; i += 32) {
                 int dy = i / 22, dx = i - dy * 22;
-                const uint8_t *r0 = S.iw + dy * KLT_BOXW + dx + oxI;
-                const uint8_t *r1 = r0 + KLT_BOXW, *r2 = r1 + KLT_BOXW;
-                int t0m = 3 * (r0[0] + r2[0]) + 10 * r1[0];
-                int t0p = 3 * (r0[2] + r2[2]) + 10 * r1[2];
-                int t1m = r2[0] - r0[0], t1c = r2[1] - r0[1], t1p = r2[2] - r0[2];
+                const uint32_t r0 = S.iw + dy * KLT_BOXW + dx + oxI, r1 = r0 + KLT_BOXW, r2 = r1 + KLT_BOXW;
+                const int a00 = (int) lds_u8(r0), a01 = (int) lds_u8(r0 + 1), a02 = (int) lds_u8(r0 + 2);
+                const int a10 = (int) lds_u8(r1), a12 = (int) lds_u8(r1 + 2);
+                const int a20 = (int) lds_u8(r2), a21 = (int) lds_u8(r2 + 1), a22 = (int) lds_u8(r2 + 2);
+                int t0m = 3 * (a00 + a20) + 10 * a10;
+                int t0p = 3 * (a02 + a22) + 10 * a12;
+                int t1m = a20 - a00, t1c = a21 - a01, t1p = a22 - a02;
                 int gx = t0p - t0m, gy = 3 * (t1m + t1p) + 10 * t1c;
                 int X = ipx + dx, Y = ipy + dy;
                 if (X < 0 || X >= L.W || Y < 0 || Y >= L.H) gx = gy = 0;
-                S.pg[i] = (gx & 0xFFFF) | (gy << 16);
+                sts_s32(S.pg + 4 * i, (gx & 0xFFFF) | (gy << 16));
             }
             __syncwarp();
 #pragma unroll
@@ -422,13 +478,14 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 const int run = k / 7, i = k - 7 * run;
                 if (run == 0 || validB) {
                     const int y = run ? yB : yA, x = (run ? xB : xA) + i;
-                    const uint8_t *sp = S.iw + (y + 1) * KLT_BOXW + x + 1 + oxI;
-                    int ival = (sp[0] * iw00 + sp[1] * iw01 + sp[KLT_BOXW] * iw10 + sp[KLT_BOXW + 1] * iw11 + (1 << 8)) >> 9;
-                    const int *d = S.pg + y * 22 + x;
-                    int d00 = d[0], d01 = d[1], d10 = d[22], d11 = d[23];
+                    const uint32_t sp = S.iw + (y + 1) * KLT_BOXW + x + 1 + oxI;
+                    int ival = ((int) lds_u8(sp) * iw00 + (int) lds_u8(sp + 1) * iw01 + (int) lds_u8(sp + KLT_BOXW) * iw10 + (int) lds_u8(sp + KLT_BOXW + 1) * iw11 +
+                                (1 << 8)) >> 9;
+                    const uint32_t d = S.pg + 4 * (y * 22 + x);
+                    int d00 = lds_s32(d), d01 = lds_s32(d + 4), d10 = lds_s32(d + 88), d11 = lds_s32(d + 92);
                     int ixv = ((short) d00 * iw00 + (short) d01 * iw01 + (short) d10 * iw10 + (short) d11 * iw11 + (1 << 13)) >> 14;
                     int iyv = ((d00 >> 16) * iw00 + (d01 >> 16) * iw01 + (d10 >> 16) * iw10 + (d11 >> 16) * iw11 + (1 << 13)) >> 14;
-                    Ireg[k] = ival;
+                    Ireg[k] = (1 << 8) - (ival << 9);
                     Gxr[k] = ixv, Gyr[k] = iyv;
                     sA11 += ixv * ixv;
                     sA12 += ixv * iyv;
@@ -450,14 +507,14 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 __syncwarp();  // every lane is done reading the template window
                 if (lane == 0) {
                     fence_proxy_async();
-                    mbar_expect_tx(S.bar_i, KLT_BOXW * KLT_BOXH_I);
-                    tma_load_3d(S.iw, &maps.mi[level - 1], nx0 + KLT_PAD, ny0 + KLT_PAD, sI, S.bar_i);
+                    mbar_expect_tx_a(S.bar_i, KLT_BOXW * KLT_BOXH_I);
+                    tma_load_3d_a(S.iw, &maps.mi[level - 1], nx0 + KLT_PAD, ny0 + KLT_PAD, sI, S.bar_i);
                 }
                 i_pending = true;
             }
         }
         if (j_ok) {
-            mbar_wait(S.bar_j, S.phase_j);
+            mbar_wait_a(S.bar_j, S.phase_j);
             S.phase_j ^= 1;
         }
         // per-lane partials fit int32 (14 * 4080^2 < 2^28); the warp total needs 64 bits
@@ -487,10 +544,10 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 __syncwarp();
                 if (lane == 0) {
                     fence_proxy_async();
-                    mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
-                    tma_load_3d(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
+                    mbar_expect_tx_a(S.bar_j, KLT_BOXW * KLT_BOXH_J);
+                    tma_load_3d_a(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
                 }
-                mbar_wait(S.bar_j, S.phase_j);
+                mbar_wait_a(S.bar_j, S.phase_j);
                 S.phase_j ^= 1;
                 ox = inx - jx0;
                 oy = iny - jy0;
@@ -498,20 +555,19 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
             a = nx - (float) inx;
             b = ny - (float) iny;
             bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-            const uint8_t *jb = S.jw + oy * KLT_BOXW + ox;
+            const uint32_t jb = S.jw + oy * KLT_BOXW + ox;
             const int wt = pack_w(iw00, iw01), wb = pack_w(iw10, iw11);
             int sb1 = 0, sb2 = 0;
 #pragma unroll
             for (int run = 0; run < 2; run++) {
-                const uint8_t *bp = jb + (run ? offB : offA);
-                const int m8 = ((int) (size_t) bp & 3) * 8;
-                const unsigned *wp = (const unsigned *) ((size_t) bp & ~(size_t) 3);
-                const RunBytes top = run_bytes(wp, m8), bot = run_bytes(wp + KLT_BOXW / 4, m8);
+                const uint32_t bp = jb + (run ? offB : offA);
+                const int m8 = (int) (bp & 3u) * 8;
+                const RunBytes top = run_bytes(bp & ~3u, m8), bot = run_bytes((bp & ~3u) + KLT_BOXW, m8);
                 int v[7];
-                run_taps<7>(top, bot, wt, wb, 1 << 8, v);
+                run_taps_c<7>(top, bot, wt, wb, &Ireg[7 * run], v);  // accumulator start = 2^8 - 512 I: v >> 9 is J - I
 #pragma unroll
                 for (int i = 0; i < 7; i++) {
-                    const int diff = (v[i] >> 9) - Ireg[7 * run + i];  // dead slots: G = 0
+                    const int diff = v[i] >> 9;  // dead slots: G = 0
                     sb1 += diff * Gxr[7 * run + i];
                     sb2 += diff * Gyr[7 * run + i];
                 }
@@ -549,10 +605,10 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                     __syncwarp();
                     if (lane == 0) {
                         fence_proxy_async();
-                        mbar_expect_tx(S.bar_j, KLT_BOXW * KLT_BOXH_J);
-                        tma_load_3d(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
+                        mbar_expect_tx_a(S.bar_j, KLT_BOXW * KLT_BOXH_J);
+                        tma_load_3d_a(S.jw, &maps.mj[level], jx0 + KLT_PAD, jy0 + KLT_PAD, sJ, S.bar_j);
                     }
-                    mbar_wait(S.bar_j, S.phase_j);
+                    mbar_wait_a(S.bar_j, S.phase_j);
                     S.phase_j ^= 1;
                     ox = fix - jx0;
                     oy = fiy - jy0;
@@ -560,20 +616,19 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
                 a = fx - (float) fix;
                 b = fy - (float) fiy;
                 bilinear_weights(a, b, iw00, iw01, iw10, iw11);
-                const uint8_t *jb = S.jw + oy * KLT_BOXW + ox;
+                const uint32_t jb = S.jw + oy * KLT_BOXW + ox;
                 const int wt = pack_w(iw00, iw01), wb = pack_w(iw10, iw11);
                 int se = 0;
 #pragma unroll
                 for (int run = 0; run < 2; run++) {
                     if (run == 1 && !validB) continue;
-                    const uint8_t *bp = jb + (run ? offB : offA);
-                    const int m8 = ((int) (size_t) bp & 3) * 8;
-                    const unsigned *wp = (const unsigned *) ((size_t) bp & ~(size_t) 3);
-                    const RunBytes top = run_bytes(wp, m8), bot = run_bytes(wp + KLT_BOXW / 4, m8);
+                    const uint32_t bp = jb + (run ? offB : offA);
+                    const int m8 = (int) (bp & 3u) * 8;
+                    const RunBytes top = run_bytes(bp & ~3u, m8), bot = run_bytes((bp & ~3u) + KLT_BOXW, m8);
                     int v[7];
-                    run_taps<7>(top, bot, wt, wb, 1 << 8, v);
+                    run_taps_c<7>(top, bot, wt, wb, &Ireg[7 * run], v);
 #pragma unroll
-                    for (int i = 0; i < 7; i++) se += abs((v[i] >> 9) - Ireg[7 * run + i]);
+                    for (int i = 0; i < 7; i++) se += abs(v[i] >> 9);
                 }
                 err_val = warp_sum_exact(se) * 1.f / (float) (32 * KLT_WIN * KLT_WIN);
             }
@@ -583,10 +638,13 @@ __device__ __forceinline__ void lk_track_point(const KltMaps &maps, const KltArg
     if (err_out != nullptr) *err_out = status ? err_val : 0.f;
 }
 
-__global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid_constant__ KltMaps maps, const KltArgs A) {
+// MINB = resident CTAs per SM the register allocation is held to: 5 (<= 102 registers, a few spills) or 4 (128 registers, no spills, fewer
+// instructions); the host picks (ICG_KLT_MINB, default from the measurement in profiles/r2_klt_after.md)
+template <int MINB>
+__global__ void __launch_bounds__(KLT_WPB * 32, MINB) klt_track_kernel(const __grid_constant__ KltMaps maps, const KltArgs A) {
     __shared__ __align__(128) uint8_t s_iw[KLT_WPB][KLT_BOXW * KLT_BOXH_I];
     __shared__ __align__(128) uint8_t s_jw[KLT_WPB][KLT_BOXW * KLT_BOXH_J];
-    __shared__ __align__(16) int s_pg[KLT_WPB][23 * 24];
+    __shared__ __align__(16) int s_pg[KLT_WPB][26 * 24];
     __shared__ __align__(8) uint64_t s_bar[KLT_WPB][2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -600,11 +658,15 @@ __global__ void __launch_bounds__(KLT_WPB * 32, 5) klt_track_kernel(const __grid
     if (task >= A.n_total) return;
 
     WarpSmem S;
-    S.iw    = s_iw[warp];
-    S.jw    = s_jw[warp];
-    S.pg      = s_pg[warp];
-    S.bar_i   = &s_bar[warp][0];
-    S.bar_j   = &s_bar[warp][1];
+    S.iw    = smem_u32(s_iw[warp]);
+    S.jw    = smem_u32(s_jw[warp]);
+    S.pg    = smem_u32(s_pg[warp]);
+    S.bar_i = smem_u32(&s_bar[warp][0]);
+    S.bar_j = smem_u32(&s_bar[warp][1]);
+    // rows 23..25 of the grid stay zero for the whole kernel (the grid writes rows 0..22, the border path entries 0..483): lane 31's second
+    // (dead) run reads them, so its I = Ix = Iy = 0 without any select
+    for (int e = lane; e < 72; e += 32) sts_s32(S.pg + 4 * (23 * 24 + e), 0);
+    __syncwarp();
     S.phase_i = S.phase_j = 0;
 
     const int sP = A.slots[2 * task], sN = A.slots[2 * task + 1];
@@ -922,7 +984,11 @@ static int launch_track(icg_klt *h, int n_total, const int32_t *d_slots, const f
     A.status = d_status;
     A.err = d_err;
     int grid = (n_total + KLT_WPB - 1) / KLT_WPB;
-    klt_track_kernel<<<grid, KLT_WPB * 32, 0, h->stream>>>(h->maps, A);
+    static const int minb = getenv("ICG_KLT_MINB") ? atoi(getenv("ICG_KLT_MINB")) : 4;
+    if (minb == 5)
+        klt_track_kernel<5><<<grid, KLT_WPB * 32, 0, h->stream>>>(h->maps, A);
+    else
+        klt_track_kernel<4><<<grid, KLT_WPB * 32, 0, h->stream>>>(h->maps, A);
     ICG_CHECK_LAUNCH();
     count_launch();
     return ICG_OK;

@@ -135,6 +135,27 @@ int icg_triangulate_points(const double *Tcw0, const double *Tcw1, const double 
  * Tracking::preprocessing (:115-133).  Host function (one pass over the frame). */
 int icg_tracking_histogram(const uint8_t *img, int width, int height, int stride, double *out);
 
+/* ----- SURVEY 8f ranks 2-4 on the DEVICE (csrc/geom.cu): the same functions as the host entry points above / icg_imu_preintegrate below, batched as
+ * CUDA kernels (one __host__ __device__ definition of the arithmetic, csrc/geom_core.cuh).  Host buffers in / out, synchronous. ----- */
+typedef struct icg_geom icg_geom;
+int icg_geom_create(icg_geom **h, int device, void *stream);
+void icg_geom_destroy(icg_geom *h);
+/* Camera::undistortPoints / distortPoints (IG/tracking/camera.cc:72-104), thread per point, any n */
+int icg_geom_undistort_points(icg_geom *h, const icg_camera *c, float *pts_xy, int n);
+int icg_geom_distort_points(icg_geom *h, const icg_camera *c, float *pts_xy, int n);
+/* cv::findFundamentalMat(FM_RANSAC) (IG/tracking/tracking.cc:547): all max_iters subsets of the cv::RNG stream are drawn up front (they do not depend on
+ * which model wins), every hypothesis is solved (7-point) and scored against the n pairs on the device, the host replays OpenCV's serial acceptance
+ * rule and adaptive iteration bound on the inlier counts.  Same inlier mask as icg_find_fundamental_mat_ransac / OpenCV. */
+int icg_geom_find_fundamental_mat_ransac(icg_geom *h, const float *pts1_xy, const float *pts2_xy, int n, double threshold, double confidence, int max_iters,
+                                         uint8_t *status, double *F9);
+/* Tracking::triangulatePoint (IG/tracking/tracking.cc:796-808), thread per pair */
+int icg_geom_triangulate_points(icg_geom *h, const double *Tcw0, const double *Tcw1, const double *pc0_xy, const double *pc1_xy, int n, double *pw_xyz);
+/* icg_imu_preintegrate for n_intervals intervals at once (doReintegration over a window, IG/ic_gvins.cc:1680-1695; throughput mode): state16 is
+ * n_intervals x 16, imu the concatenated sample rows, imu_off[k] .. imu_off[k+1] the rows of interval k (row imu_off[k] = the sample at its start);
+ * iewn3 / gravity3 / noise5 shared; iewn3 == NULL: PreintegrationNormal.  blobs_out n_intervals x ICG_IMU_BLOB_DOUBLES, end_states10 may be NULL. */
+int icg_geom_imu_preintegrate_batch(icg_geom *h, int n_intervals, const double *state16, const double *iewn3, const double *gravity3, const double *noise5,
+                                    const double *imu, const int32_t *imu_off, double *blobs_out, double *end_states10);
+
 /* ----- pre-pass of path A: cv::CLAHE (IG/tracking/tracking.cc:62 createCLAHE(3.0, Size(21, 21)); :141 clahe_->apply(img, img)) ----- */
 typedef struct icg_clahe icg_clahe;
 int icg_clahe_create(icg_clahe **h, int width, int height, int tiles_x, int tiles_y, double clip_limit, int device, void *stream);
@@ -145,6 +166,12 @@ int icg_clahe_apply(icg_clahe *h, const uint8_t *src, int src_stride, uint8_t *d
 /* Device-resident variant (asynchronous on the handle's stream): src / dst are device pointers, e.g. the level-0 plane of a KLT slot
  * (icg_klt_slot_level0) so that upload -> CLAHE -> pyramid -> track never leaves HBM; dst may alias src. */
 int icg_clahe_apply_dev(icg_clahe *h, const uint8_t *dev_src, int src_pitch, uint8_t *dev_dst, int dst_pitch);
+/* Frame-batched device-resident variant: n_frames frames (frame f at dev_src + f * src_frame_stride, written to dev_dst + f * dst_frame_stride;
+ * in place allowed) in one launch pair.  hist_out (host, n_frames doubles, may be NULL): Tracking::calculateHistigram of every RAW frame
+ * (IG/tracking/tracking.cc:88-104), accumulated by the LUT pass at no extra read of the frame -- the statistic of the histogram gate in
+ * Tracking::preprocessing (:115-133).  With hist_out the call synchronises (the host decides whether to skip the frame); without, it is asynchronous. */
+int icg_clahe_apply_batch_dev(icg_clahe *h, int n_frames, const uint8_t *dev_src, int src_pitch, size_t src_frame_stride, uint8_t *dev_dst, int dst_pitch,
+                              size_t dst_frame_stride, double *hist_out);
 int icg_clahe_sync(icg_clahe *h);
 
 /* ----- detection leg of path A: Tracking::featuresDetection (IG/tracking/tracking.cc:576-688) ----- */

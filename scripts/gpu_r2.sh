@@ -6,7 +6,7 @@ shift || true
 O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,driver_version,clocks.max.sm --format=csv > $O/${T}_smi.txt 2>&1
-timeout 1500 python -m pytest tests -m gpu -q -x --durations=15 "$@" > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=15 "$@" > $O/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> $O/${T}_pytest.log
 timeout 300 python __graft_entry__.py --smoke > $O/${T}_smoke.log 2>&1; echo "smoke rc=$?" >> $O/${T}_smoke.log
 if [ "${BENCH:-1}" = "1" ]; then
 timeout 900 python bench.py > $O/${T}_bench.json 2> $O/${T}_bench.err; echo "bench rc=$?" >> $O/${T}_bench.err

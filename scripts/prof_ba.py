@@ -7,6 +7,9 @@ from datagen import synth_ba
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+K = int(sys.argv[3]) if len(sys.argv) > 3 else 10      # 20 2000: cfg 4 (split pipeline)
+L = int(sys.argv[4]) if len(sys.argv) > 4 else 300
+NDIST = min(B, 16)                                     # distinct windows, repeated to fill the batch (generation is host-bound)
 
 
 def pre(st, iewn, g, nz, imu):
@@ -14,8 +17,10 @@ def pre(st, iewn, g, nz, imu):
     return blob, np.zeros((imu.shape[0] - 1, 4)), end
 
 
-wins = [synth_ba.make_window(pre, K=10, L=300, seed=2024 + b)[0] for b in range(B)]
-s = WindowSolver(max_windows=B, max_K=10, max_L=300, max_F=max(w["F"] for w in wins), max_gnss=8, max_marg_r=1)
+import copy
+base = [synth_ba.make_window(pre, K=K, L=L, seed=2024 + b)[0] for b in range(NDIST)]
+wins = [copy.deepcopy(base[b % NDIST]) for b in range(B)]
+s = WindowSolver(max_windows=B, max_K=K, max_L=L, max_F=max(w["F"] for w in wins), max_gnss=16, max_marg_r=1)
 s.upload(wins)
 import time
 for r in range(reps):

@@ -65,3 +65,42 @@ def test_clahe_device_resident_into_klt_slot(oracle):
     assert np.array_equal(got, oa.clahe_apply(oracle, img, 3.0, 21, 21))
     c.close()
     trk.close()
+
+
+def test_batched_device_clahe_and_fused_histogram_gate(oracle):
+    """icg_clahe_apply_batch_dev on the level-0 planes of consecutive KLT slots: every frame bit-exact with the oracle (== cv2), and the
+    histogram-gate statistic of the RAW frames (Tracking::calculateHistigram) equal to the host function / the cv2.calcHist restatement."""
+    import ctypes as C
+    from datagen import synth_klt as synth
+    from ic_gvins_b200._lib import lib, vp
+    from ic_gvins_b200.camera import calculate_histogram
+    from ic_gvins_b200.clahe import Clahe
+    from ic_gvins_b200.klt import KltTracker
+    from tests import oracle_api as oa
+    W, H, NF = 1280, 560, 4
+    st = synth.KltStream(W, H, 300, 91)
+    frames = [st.frame(t) for t in range(NF)]
+    frames[2] = (frames[2].astype(np.int32) * 3 // 4).astype(np.uint8)  # a darker frame: the gate statistic must move
+    trk = KltTracker(W, H, n_slots=NF, max_points=64)
+    for k, f in enumerate(frames):
+        trk.upload(k, f, build=False)
+    trk.sync()
+    p0, p1, pitch = vp(), vp(), C.c_int()
+    lib().icg_klt_slot_level0(trk._h, 0, C.byref(p0), C.byref(pitch))
+    lib().icg_klt_slot_level0(trk._h, 1, C.byref(p1), C.byref(pitch))
+    stride = p1.value - p0.value
+    cl = Clahe(W, H, 3.0, (21, 21))
+    hist = cl.apply_batch_dev(NF, p0.value, pitch.value, stride, p0.value, pitch.value, stride, want_hist=True)
+    for k, f in enumerate(frames):
+        assert np.array_equal(trk.download_level(k, 0), oa.clahe_apply(oracle, f, 3.0, 21, 21)), k
+        assert hist[k] == calculate_histogram(f), k
+    assert abs(hist[2] - hist[1]) / hist[1] > 0.1  # the darker frame would be skipped by the gate (tracking.cc:121-131)
+    # without the statistic the call is asynchronous and gives the same pixels
+    for k, f in enumerate(frames):
+        trk.upload(k, f, build=False)
+    assert cl.apply_batch_dev(NF, p0.value, pitch.value, stride, p0.value, pitch.value, stride) is None
+    cl.sync()
+    for k, f in enumerate(frames):
+        assert np.array_equal(trk.download_level(k, 0), oa.clahe_apply(oracle, f, 3.0, 21, 21)), k
+    cl.close()
+    trk.close()

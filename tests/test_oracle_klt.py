@@ -15,12 +15,15 @@ SMALL = ["small_plain", "small_noisy", "small_flat", "small_edge", "odd_size"]
 TOL_PX = 1e-3
 
 
-def assert_px(a, b, ok, name):
-    """<= 1e-3 px.  Exception, stated: `small_flat` puts points on the rim of a texture-less patch where the 2x2
-    system is near-singular (minEig just above the 1e-4 gate); OpenCV's own SIMD float accumulation order moves
-    such points by a few 1e-3 px, so there >= 98 % of the points must be within 1e-3 px and all within 5e-3 px."""
+def assert_px(a, b, ok, name, chained_backward=False):
+    """<= 1e-3 px, without exception for anything computed from the SAME inputs as cv2 (forward results; backward results started from cv2's
+    forward result: test_backward_from_cv2_forward_matches_cv2).  One stated, explained exception: the backward positions of the CHAINED
+    forward+backward call in `small_flat` -- there the backward pass starts from this implementation's own forward result (<= 3e-4 px from
+    cv2's), and for point 52, the worst-conditioned tracked point of the case (on the rim of the texture-less patch, 2x2 condition number 9,
+    forward-backward distance 0.07 px), that 3e-4 px start difference moves the backward result by 2.9e-3 px; from cv2's own forward result the
+    same point reproduces cv2 to 1.8e-4 px.  The backward position only feeds the 0.5 px gate."""
     d = np.abs(a - b)[ok].max(axis=1)
-    if name == "small_flat":
+    if name == "small_flat" and chained_backward:
         assert (d <= TOL_PX).mean() >= 0.98 and d.max() <= 5e-3, d.max()
     else:
         assert d.max() <= TOL_PX, d.max()
@@ -40,7 +43,18 @@ def test_track_fb_matches_cv2(oracle, klt_golden, name):
     q, back, good = oa.track_fb(oracle, g[name + "_f0"], g[name + "_f1"], g[name + "_p0"], g[name + "_init"])
     assert np.array_equal(good, g[name + "_good"])
     assert_px(q, g[name + "_fwd"], good == 1, name)
-    assert_px(back, g[name + "_bwd"], good == 1, name)
+    assert_px(back, g[name + "_bwd"], good == 1, name, chained_backward=True)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_backward_from_cv2_forward_matches_cv2(oracle, klt_golden, name):
+    """The backward LK call exactly as cv2 received it (prevPts = cv2's forward result, initial flow = the original points): <= 1e-3 px in
+    every case, including the rim points of `small_flat`."""
+    g = klt_golden
+    b, st, _ = oa.lk(oracle, g[name + "_f1"], g[name + "_f0"], g[name + "_fwd"], g[name + "_p0"])
+    ok = (g[name + "_st"] == 1) & (st == 1)
+    assert np.array_equal(st[g[name + "_st"] == 1], g[name + "_st2"][g[name + "_st"] == 1])
+    assert np.abs(b - g[name + "_bwd"])[ok].max() <= TOL_PX
 
 
 @pytest.mark.parametrize("name", ["small_plain", "odd_size"])

@@ -1,11 +1,17 @@
 """Stream-level parity of the front end (north_star: "feature IDs bit-exact"): the 200-frame cfg-2 stream through
    CLAHE -> forward/backward LK + gates -> compaction (reduceVector) -> block detection with the occupancy mask -> append
 run twice in lockstep -- once on cv2 (the reference's OpenCV calls, IG/tracking/tracking.cc:62,141, 351-455, 576-688, 831-849) and once on the
-CUDA path through the C ABI -- asserting IDENTICAL feature-ID lists after every frame and positions within 1e-3 px.
+CUDA path through the C ABI.  Two statements are asserted every frame:
 
-Both arms are free-running (each feeds on its own results).  A status decision that sits on a knife edge (forward-backward distance
-within 5e-3 px of the 0.5 px gate, or a point within 5e-3 px of the 5 px border gate: OpenCV's own SIMD summation order moves positions
-by ~1e-4 px) is reported, must be explained by the cv2 arm's own margin, and the CUDA arm is re-synchronised; at most 2 such events are
+  (1) SAME INPUTS -> status identical, positions within 1e-3 px: the CUDA tracker is run on the cv2 arm's own state (previous image, points,
+      predictions) and compared with the cv2 arm's result point by point;
+  (2) FREE-RUNNING (each arm feeds on its own results for 200 frames) -> IDENTICAL feature-ID lists after every frame, identical detection
+      decisions, new corners within 1e-3 px.  Free-running positions are only sanity-bounded (2e-2 px): LK stops on a 0.01 px step criterion, so two
+      runs whose start points differ by 1e-4 px can stop one iteration apart on ill-conditioned points (cv2 does the same against itself) --
+      that is why (1) is the position statement and (2) the identity statement.
+
+A status decision that sits on a knife edge (forward-backward distance within 5e-3 px of the 0.5 px gate, or a point within 5e-3 px of the 5 px
+border gate) is reported, must be explained by the cv2 arm's own margin, and the CUDA arm is re-synchronised; at most 2 such events are
 tolerated over the 60 000 point-tracks of the stream, none is expected."""
 import math
 
@@ -108,18 +114,28 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
     arms = [Cv2Arm(oracle), GpuArm()]
     try:
         state = [dict(ids=[], pts=np.zeros((0, 2), np.float32), next_id=0, prev=None) for _ in arms]
-        resyncs, n_tracks, max_dpx, n_detect = 0, 0, 0.0, 0
+        resyncs, n_tracks, max_dpx, n_detect, max_same = 0, 0, 0.0, 0, 0.0
         for t in range(NFRAMES):
             raw = stream.frame(t)
             imgs = [arm.preprocess(raw) for arm in arms]
             assert np.array_equal(imgs[0], imgs[1]), f"frame {t}: CLAHE differs"
             results = []
-            for arm, st, img in zip(arms, state, imgs):
+            for k_arm, (arm, st, img) in enumerate(zip(arms, state, imgs)):
                 margin = None
                 if t > 0 and len(st["ids"]):
                     rng = np.random.Generator(np.random.PCG64(977 + t))  # same noise for both arms
                     pred = flow_prediction(st["pts"], t, rng)
                     fwd, good, margin = arm.track(st["prev"], img, st["pts"], pred)
+                    if k_arm == 0:
+                        # statement (1): the CUDA tracker on exactly the cv2 arm's inputs
+                        gfwd, ggood, _ = arms[1].track(st["prev"], img, st["pts"], pred)
+                        flips = np.nonzero(ggood != good)[0]
+                        assert all(margin[i] <= 5e-3 for i in flips), f"frame {t}: same inputs, status differs off the knife edge at {flips.tolist()}"
+                        both = (good != 0) & (ggood != 0)
+                        if both.any():
+                            d_same = float(np.abs(gfwd - fwd)[both].max())
+                            max_same = max(max_same, d_same)
+                            assert d_same <= 1e-3, f"frame {t}: same inputs, positions differ by {d_same:.2e} px"
                     keep = good != 0
                     st["ids"] = [i for i, k in zip(st["ids"], keep) if k]         # reduceVector (tracking.cc:831-839)
                     st["pts"] = fwd[keep]
@@ -139,7 +155,7 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
                 if len(state[0]["ids"]):
                     d = float(np.abs(state[0]["pts"] - state[1]["pts"]).max())
                     max_dpx = max(max_dpx, d)
-                    assert d <= 1e-3, f"frame {t}: tracked positions differ by {d:.2e} px"
+                    assert d <= 2e-2, f"frame {t}: free-running positions drifted apart by {d:.2e} px"
             # featuresDetection (ismask = frame > 0): skipped when enough features are alive (tracking.cc:579-582)
             for k, (arm, st, img) in enumerate(zip(arms, state, imgs)):
                 st["det"] = None
@@ -166,6 +182,6 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
             assert state[0]["ids"] == state[1]["ids"] and state[0]["next_id"] == state[1]["next_id"], f"frame {t}: ID lists differ after detection"
         assert n_detect >= 20 and state[0]["next_id"] > MAXF, "the stream must lose and re-detect features"
         print(f"stream parity: {NFRAMES} frames, {n_tracks} point-tracks, {state[0]['next_id']} feature IDs issued, {n_detect} detection passes, "
-              f"max |d| = {max_dpx:.2e} px, knife-edge re-syncs = {resyncs}")
+              f"same-input max |d| = {max_same:.2e} px, free-running max |d| = {max_dpx:.2e} px, knife-edge re-syncs = {resyncs}")
     finally:
         arms[1].close()
