@@ -48,11 +48,12 @@ def parse():
     ap.add_argument("--no-ba", action="store_true")
     ap.add_argument("--ba-handles", type=int, default=2, help="solver handles (CUDA streams) the B windows are split over")
     ap.add_argument("--no-sharded", action="store_true", help="skip the cfg-4 landmark-sharded BA section")
-    ap.add_argument("--sharded-windows", type=int, default=32, help="cfg-4 windows in the landmark-sharded batch")
+    ap.add_argument("--sharded-windows", type=int, default=128, help="cfg-4 windows in the landmark-sharded batch")
     ap.add_argument("--no-marg", action="store_true", help="skip the marginalization section")
     ap.add_argument("--no-detect", action="store_true", help="skip the block-detection section")
     ap.add_argument("--no-clahe", action="store_true", help="skip the CLAHE section")
     ap.add_argument("--no-keyframe", action="store_true", help="skip the full-keyframe-path line")
+    ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e: one set of solver handles (the host packs and the GPU solves in turn)")
     return ap.parse_args()
 
 
@@ -272,7 +273,7 @@ def run_b200(args):
     e_slots = torch.empty((n_total, 2), dtype=torch.int32, device=dev)
 
     # ---- BA inputs: one cfg-3 window per stream (the product's own host-side preintegration builds the IMU factors)
-    solvers = []
+    solvers, e2e_parts, e2e_sets = [], [], [([], [])]
     if use_ba:
         def pre(st, iewn, g, nz, imu):
             blob, end = imu_preintegrate(st, iewn, g, nz, imu)
@@ -296,6 +297,20 @@ def run_b200(args):
             pe = [copy.deepcopy(w_) for w_ in part]
             init = [{q: np.array(w_[q], copy=True) for q in ("pose", "mix", "ext", "invdepth", "f_active", "gnss_std")} for w_ in pe]
             e2e_parts.append((pe, init, (BaProblem * len(pe))(*[to_struct(w_) for w_ in pe]), (BaSummary * (2 * len(pe)))()))
+        # e2e: a second set of handles, so that the host packs keyframe s + 1 while the GPU solves keyframe s (the reference's optimization thread
+        # runs beside its tracking thread the same way); every step still moves its own inputs H2D and its own results D2H inside the timed region
+        solvers_b, e2e_parts_b = [], []
+        if not args.no_e2e_pipeline:
+            for k in range(NH):
+                part = windows[bounds[k]:bounds[k + 1]]
+                st_b = torch.cuda.Stream(device=dev)
+                ba_streams.append(st_b)
+                sv = WindowSolver(max_windows=len(part), max_K=10, max_L=300, max_F=maxF, max_gnss=8, max_marg_r=1, device=local_rank, stream=st_b.cuda_stream)
+                solvers_b.append(sv)
+                pe = [copy.deepcopy(w_) for w_ in part]
+                init = [{q: np.array(w_[q], copy=True) for q in ("pose", "mix", "ext", "invdepth", "f_active", "gnss_std")} for w_ in pe]
+                e2e_parts_b.append((pe, init, (BaProblem * len(pe))(*[to_struct(w_) for w_ in pe]), (BaSummary * (2 * len(pe)))()))
+        e2e_sets = [(solvers, e2e_parts)] + ([(solvers_b, e2e_parts_b)] if solvers_b else [])
         # what icg_ba_upload moves per window (arrays are capacity-strided: max_F factor slots, max_K = 10 IMU slots): slot-ordered factor constants +
         # (landmark, ref, obs, id) + pair index + activity, parameters, IMU blobs + sqrt-information, CSR offsets, GNSS
         ba_h2d = int(len(windows) * (maxF * (14 * 8 + 16 + 4 + 1) + 10 * 16 * 8 + 8 * 8 + 300 * 8 + 10 * (480 + 225) * 8 + 301 * 4 + 91 * 8 + 8 * 56))
@@ -333,24 +348,34 @@ def run_b200(args):
             h_st.copy_(d_st, non_blocking=True)
         t_1 = time.perf_counter()
 
-        def begin(k):
-            sv, (pe, init, arr, summ) = solvers[k], e2e_parts[k]
+        if not use_ba:
+            return
+        svs, parts = e2e_sets[s % len(e2e_sets)]
+        for k in range(len(svs)):
+            sv, (pe, init, arr, summ) = svs[k], parts[k]
             for w_, ini in zip(pe, init):  # fresh initial guess every step (the solve updates in place)
                 for q, v in ini.items():
                     w_[q][...] = v
             rc = lib().icg_ba_gvins_optimization_begin(sv._h, len(pe), arr, 20)  # pack + upload + enqueue (asynchronous)
             if rc != 0:
                 raise RuntimeError(lib().icg_last_error().decode())
-        # handles in sequence: the GPU starts on handle k while the host packs handle k + 1 (each icg_ba_upload spreads its packing over host threads)
-        for k in range(len(solvers)):
-            begin(k)
         t_2 = time.perf_counter()
-        for sv, (pe, init, arr, summ) in zip(solvers, e2e_parts):
-            rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)  # synchronise + write back
-            if rc != 0:
-                raise RuntimeError(lib().icg_last_error().decode())
+        e2e_pending.append(s)
+        e2e_finish(keep=len(e2e_sets) - 1)  # two handle sets: collect the PREVIOUS keyframe while this one is on the GPU
         t_3 = time.perf_counter()
         e2e_host["klt_enqueue_ms"].append((t_1 - t_0) * 1e3), e2e_host["ba_begin_ms"].append((t_2 - t_1) * 1e3), e2e_host["ba_end_ms"].append((t_3 - t_2) * 1e3)
+
+    e2e_pending = []
+
+    def e2e_finish(keep=0):
+        """synchronise + write back the keyframes in flight (all but the newest `keep`)"""
+        while len(e2e_pending) > keep:
+            s_ = e2e_pending.pop(0)
+            svs, parts = e2e_sets[s_ % len(e2e_sets)]
+            for sv, (pe, init, arr, summ) in zip(svs, parts):
+                rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)
+                if rc != 0:
+                    raise RuntimeError(lib().icg_last_error().decode())
 
     # ---- the FULL keyframe path of every stream, end to end through the C ABI: what one keyframe costs when nothing is left out.
     #      H2D of the raw frame -> CLAHE + histogram-gate statistic (batched, device-resident) -> pyramid -> fwd+bwd LK + gates -> block detection
@@ -369,6 +394,9 @@ def run_b200(args):
         lib().icg_klt_slot_level0(trk._h, 0, C2.byref(p0_), C2.byref(pit_))
         lib().icg_klt_slot_level0(trk._h, 1, C2.byref(p1_), C2.byref(pit_))
         slot_stride, slot_pitch, slot0 = p1_.value - p0_.value, pit_.value, p0_.value
+        kf_mcalls = [solvers[k].marg_prepare(e2e_parts[k][0], 1, want_schur=False) for k in range(len(solvers))]
+        for k in range(len(solvers)):
+            solvers[k].marginalize(e2e_parts[k][0][:2], 1, want_schur=False)  # marginalization workspace allocation, outside the timed region
         h_raw = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
         d_rawB = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
         kf_hist = [None]
@@ -398,7 +426,7 @@ def run_b200(args):
                     rc = lib().icg_ba_gvins_optimization_end(sv._h, len(pe), arr, summ, None)
                 if rc != 0:
                     raise RuntimeError(lib().icg_last_error().decode())
-                sv.marginalize(pe, 1, want_schur=False)   # host arrays in, prior out
+                sv.marg_run(kf_mcalls[k], resident=True)  # gvinsMarginalization of the window just optimised: prior out to host arrays
             ths = [threading.Thread(target=ba_part, args=(k,)) for k in range(len(solvers))]
             for t_ in ths:
                 t_.start()
@@ -414,13 +442,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, mode="step"):
+    def timed(step_fn, mode="step", finish_fn=None):
         for s in range(args.warmup):
             if step_fn is not None:
                 step_fn(s)
             elif mode == "ba_only":
                 for sv in solvers:
                     sv.run_gvins(20, restart=True)
+        if finish_fn is not None:
+            finish_fn()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kev = []
@@ -451,6 +481,8 @@ def run_b200(args):
                 kev.append((a, b_))
             else:
                 step_fn(s)
+        if finish_fn is not None:
+            finish_fn()                 # the last keyframe in flight is collected inside the timed region
         for bs in ba_streams:
             stream.wait_stream(bs)      # the step ends when the tracking and all optimization streams are done
         ev1.record(stream)
@@ -467,15 +499,15 @@ def run_b200(args):
     with ClockSampler(local_rank) as clk:
         ms_res, _ = timed(step_resident)
         launches = int(lib().icg_launch_count())
-        ms_e2e, _ = timed(step_e2e)
+        ms_e2e, _ = timed(step_e2e, finish_fn=e2e_finish)
         _, kms = timed(klt_resident, mode="klt_kernel")
         bms = timed(None, mode="ba_only")[1] if use_ba else []
         ms_klt, _ = timed(klt_resident)
         if use_ba and not args.no_keyframe:
             ms_kf, _ = timed(step_keyframe)
             kf = {"workload": "FULL keyframe path of B streams end to end through the C ABI: H2D raw frame, CLAHE + histogram gate (batched), pyramid, fwd+bwd LK, "
-                              "block detection (18 blocks x B frames, one call), gvinsOptimization and gvinsMarginalization with host arrays (2 handles, one host "
-                              "thread each); every frame a keyframe", "value": B * world * args.steps / (ms_kf / 1e3), "unit": "frames/s",
+                              "block detection (18 blocks x B frames, one call), gvinsOptimization (host arrays in / out) and gvinsMarginalization of the window "
+                              "just optimised (icg_ba_marginalize_resident, prior out to host arrays); 2 handles, one host thread each; every frame a keyframe", "value": B * world * args.steps / (ms_kf / 1e3), "unit": "frames/s",
                   "ms_per_step": ms_kf / args.steps}
     clocks = clk.summary()
     good = int(d_st.sum().item())
@@ -571,14 +603,27 @@ def run_b200(args):
         part = windows[bounds[0]:bounds[1]]
         solvers[0].marginalize(part[:2], 1, want_schur=False)  # workspace allocation + warm-up
         barrier()
-        reps = 3
+        reps = 5
+        mcall = solvers[0].marg_prepare(part, 1, want_schur=False)  # argument block (structs over host arrays, output arrays): kept across keyframes
+        solvers[0].marg_run(mcall)
         t0 = time.perf_counter()
         for _ in range(reps):
-            pri = solvers[0].marginalize(part, 1, want_schur=False)
+            solvers[0].marg_run(mcall)                 # icg_ba_marginalize: pack + upload + linearise + 2 eigendecompositions + D2H + write-out
         dtm = (time.perf_counter() - t0) / reps
+        msum = (BaSummary * (2 * len(part)))()
+        if lib().icg_ba_gvins_optimization(solvers[0]._h, len(part), mcall["arr"], 20, msum, None) != 0:  # two-pass solve, written back to `part`
+            raise RuntimeError(lib().icg_last_error().decode())
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            solvers[0].marg_run(mcall, resident=True)  # icg_ba_marginalize_resident: the windows the handle has just solved (no pack / upload)
+        dtr = (time.perf_counter() - t0) / reps
+        pri = solvers[0].marg_collect(mcall)
         marg = {"workload": "icg_ba_marginalize: oldest node + the landmarks anchored in it out of a cfg-3 window (host buffers in, prior out; "
-                            "upload + linearisation + two Jacobi eigendecompositions + D2H inside the timed region)",
+                            "pack + upload + linearisation + two Jacobi eigendecompositions + D2H inside the timed region); resident_*: "
+                            "icg_ba_marginalize_resident on the windows the handle has just solved (the reference's order: gvinsOptimization, then "
+                            "gvinsMarginalization on the same window), prior out to host arrays",
                 "windows_per_call": len(part), "ms_per_call": dtm * 1e3, "windows_per_s": len(part) / dtm * world,
+                "resident_ms_per_call": dtr * 1e3, "resident_windows_per_s": len(part) / dtr * world,
                 "m": int(pri[0]["m"]), "r": int(pri[0]["r"])}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             import ctypes as C
@@ -598,7 +643,10 @@ def run_b200(args):
     if use_ba and not args.no_sharded:
         from ic_gvins_b200.ba import connect_shards, shard_window
         NW4 = args.sharded_windows
-        big = [__import__("datagen.synth_ba", fromlist=["x"]).make_window(pre, K=20, L=2000, seed=4000 + i)[0] for i in range(NW4)]
+        import copy as _copy
+        nd4 = min(NW4, 8)  # distinct cfg-4 windows (host-side generation is ~1 s each), repeated to fill the batch
+        big0 = [__import__("datagen.synth_ba", fromlist=["x"]).make_window(pre, K=20, L=2000, seed=4000 + i)[0] for i in range(nd4)]
+        big = [_copy.deepcopy(big0[i % nd4]) for i in range(NW4)]
         shards = [shard_window(p_, rank, world) for p_ in big]
         s4 = WindowSolver(max_windows=NW4, max_K=20, max_L=max(x["L"] for x in shards), max_F=max(x["F"] for x in shards), max_gnss=16,
                           max_marg_r=1, device=local_rank, stream=stream_ba.cuda_stream)
@@ -652,6 +700,7 @@ def run_b200(args):
                                   "batch repeats 64 distinct cfg-3 windows"},
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": B * (W * H + NPTS * 24) + ba_h2d,
                 "d2h_bytes_per_step": B * NPTS * 9 + ba_d2h, "ms_per_step": ms_e2e / args.steps,
+                "keyframes_in_flight": len(e2e_sets) if use_ba else 1,
                 "host_ms_per_step": {k_: float(np.mean(v_[args.warmup:])) if len(v_) > args.warmup else None for k_, v_ in e2e_host.items()}},
         "gpu_launches": launches,
         "clocks": clocks,
@@ -688,7 +737,7 @@ def run_b200(args):
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     trk.close()
-    for sv in solvers:
+    for sv in solvers + (solvers_b if use_ba else []):
         sv.close()
     if world > 1:
         dist.destroy_process_group()

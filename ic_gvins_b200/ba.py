@@ -249,12 +249,20 @@ class WindowSolver:
         s2 = self.solve(prob, second)[0]
         return dict(pass1=s1, pass2=s2, reproj_removed=int(out.sum()), gnss_reweighted=n_gnss_out)
 
-    def marginalize(self, problems, num_marg=1, want_schur=True):
+    def marginalize(self, problems, num_marg=1, want_schur=True, resident=False):
         """MarginalizationInfo::marginalization as GVINS::gvinsMarginalization drives it (IG/ic_gvins.cc:1412-1640) on a list of
         windows: removes the `num_marg` oldest nodes + the landmarks anchored in them.  Returns one dict per window with the new
-        prior in the layout the problem dict's marg_* entries use (node indices already shifted)."""
+        prior in the layout the problem dict's marg_* entries use (node indices already shifted).  resident=True: the windows are the
+        ones this handle has just solved (icg_ba_marginalize_resident: nothing is uploaded again)."""
         if isinstance(problems, dict):
             problems = [problems]
+        call = self.marg_prepare(problems, num_marg, want_schur)
+        self.marg_run(call, resident)
+        return self.marg_collect(call)
+
+    def marg_prepare(self, problems, num_marg=1, want_schur=True):
+        """The argument block of one icg_ba_marginalize call (struct array over the problems' host arrays + caller-allocated output arrays):
+        what a C++ caller keeps alive across keyframes.  marg_run issues the call, marg_collect turns the outputs into dicts."""
         n = len(problems)
         nm = np.full(n, num_marg, np.int32) if np.isscalar(num_marg) else np.ascontiguousarray(num_marg, np.int32)
         arr = (BaProblem * n)(*[to_struct(p) for p in problems])
@@ -263,17 +271,26 @@ class WindowSolver:
         for w, p in enumerate(problems):
             rcap = 15 * p["K"] + 7
             b = dict(bt=np.zeros(2 * p["K"] + 2, np.int32), bn=np.zeros(2 * p["K"] + 2, np.int32), x0=np.zeros(16 * p["K"] + 8),
-                     J0=np.zeros(rcap * rcap), e0=np.zeros(rcap), Hp=np.zeros(rcap * rcap), bp=np.zeros(rcap))
+                     J0=np.zeros(rcap * rcap), e0=np.zeros(rcap))
+            if want_schur:
+                b.update(Hp=np.zeros(rcap * rcap), bp=np.zeros(rcap))
             bufs.append(b)
             pri[w].rcap = rcap
             pri[w].block_type, pri[w].block_node = b["bt"].ctypes.data_as(ip), b["bn"].ctypes.data_as(ip)
             pri[w].x0, pri[w].J0, pri[w].e0 = b["x0"].ctypes.data_as(dp), b["J0"].ctypes.data_as(dp), b["e0"].ctypes.data_as(dp)
             if want_schur:
                 pri[w].Hp, pri[w].bp = b["Hp"].ctypes.data_as(dp), b["bp"].ctypes.data_as(dp)
-        check(lib().icg_ba_marginalize(self._h, n, arr, vp(nm.ctypes.data), pri), "icg_ba_marginalize")
+        return dict(n=n, nm=nm, arr=arr, pri=pri, bufs=bufs, want_schur=want_schur, problems=problems)
+
+    def marg_run(self, call, resident=False):
+        fn = lib().icg_ba_marginalize_resident if resident else lib().icg_ba_marginalize
+        check(fn(self._h, call["n"], call["arr"], vp(call["nm"].ctypes.data), call["pri"]), "icg_ba_marginalize")
+
+    def marg_collect(self, call):
         out = []
         gs = {0: 7, 1: 9, 2: 7, 3: 1}
-        for w, b in enumerate(bufs):
+        pri, want_schur = call["pri"], call["want_schur"]
+        for w, b in enumerate(call["bufs"]):
             r, nb = pri[w].r, pri[w].nblocks
             nx = sum(gs[int(t)] for t in b["bt"][:nb])
             out.append(dict(m=pri[w].m, r=r, block_type=b["bt"][:nb].copy(), block_node=b["bn"][:nb].copy(), x0=b["x0"][:nx].copy(),

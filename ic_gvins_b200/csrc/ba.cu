@@ -2488,7 +2488,7 @@ static int marg_alloc(icg_ba *h) {
     return ICG_OK;
 }
 
-int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out) {
+static int marginalize_body(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out, bool resident) {
     if (!h || !problems || !num_marg || !out || n_windows < 1 || n_windows > h->C.NW) {
         set_error("icg_ba_marginalize: bad arguments");
         return ICG_EINVAL;
@@ -2497,8 +2497,19 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
         set_error("icg_ba_marginalize: not available on a landmark-sharded handle (icg_ba_set_shard(world = 1) first)");
         return ICG_EUNSUPPORTED;
     }
-    int rc = icg_ba_upload(h, n_windows, problems);
-    if (rc != ICG_OK) return rc;
+    int rc = ICG_OK;
+    if (resident) {
+        // the windows of the last upload / solve are still on the device (parameters at their optimised values, factor activity and GNSS
+        // weights as the two-pass solve left them): `problems` is read for the structure and for x0 only
+        if (h->cur_windows != n_windows) {
+            set_error("icg_ba_marginalize_resident: the handle holds %d uploaded windows, the call names %d", h->cur_windows, n_windows);
+            return ICG_EINVAL;
+        }
+        ICG_CUDA(cudaSetDevice(h->device));
+    } else {
+        rc = icg_ba_upload(h, n_windows, problems);
+        if (rc != ICG_OK) return rc;
+    }
     rc = marg_alloc(h);
     if (rc != ICG_OK) return rc;
     const BaCaps &C = h->C;
@@ -2576,7 +2587,11 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
     int max_m = 0, max_r = 0;
     for (int w = 0; w < n; w++) max_m = std::max(max_m, out[w].m), max_r = std::max(max_r, out[w].r);
     auto jacobi = [&](int which, int nmax) -> int {
-        if (nmax <= MARG_PAIR_MAXN && !getenv("ICG_MARG_GLOBAL_JACOBI")) {
+        if (nmax <= MARG_CTA_MAXN && !getenv("ICG_MARG_GLOBAL_JACOBI") && !getenv("ICG_MARG_PAIR_JACOBI")) {
+            const size_t smem = sizeof(double) * 2 * (size_t) nmax * nmax;
+            ICG_CUDA(raise_dynamic_smem((const void *) marg_jacobi_cta, smem));
+            marg_jacobi_cta<<<n, MARG_CTA_THREADS, smem, s>>>(M, which);
+        } else if (nmax <= MARG_PAIR_MAXN && !getenv("ICG_MARG_GLOBAL_JACOBI")) {
             const size_t smem = sizeof(double) * ((size_t) nmax * nmax + 2 * (size_t) (nmax + 2));
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
@@ -2601,12 +2616,18 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
     marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 1);
     ICG_CHECK_LAUNCH();
     count_launch(10);
-    ICG_CUDA(h->marg_oJ0.down(s, (size_t) n * M.rcap * M.rcap));
-    ICG_CUDA(h->marg_oe0.down(s, (size_t) n * M.rcap));
-    ICG_CUDA(h->marg_oHp.down(s, (size_t) n * M.rcap * M.rcap));
-    ICG_CUDA(h->marg_obp.down(s, (size_t) n * M.rcap));
+    // D2H: every window's r x r result sits at the start of its rcap^2 slot -- move the used prefix of each slot only (one strided copy)
+    {
+        const size_t pitch = sizeof(double) * (size_t) M.rcap * M.rcap, used = sizeof(double) * (size_t) max_r * max_r;
+        bool want_Hp = false;
+        for (int w = 0; w < n; w++) want_Hp = want_Hp || out[w].Hp != nullptr;
+        if (used) ICG_CUDA(cudaMemcpy2DAsync(h->marg_oJ0.h, pitch, h->marg_oJ0.d, pitch, used, (size_t) n, cudaMemcpyDeviceToHost, s));
+        ICG_CUDA(h->marg_oe0.down(s, (size_t) n * M.rcap));
+        if (want_Hp && used) ICG_CUDA(cudaMemcpy2DAsync(h->marg_oHp.h, pitch, h->marg_oHp.d, pitch, used, (size_t) n, cudaMemcpyDeviceToHost, s));
+        ICG_CUDA(h->marg_obp.down(s, (size_t) n * M.rcap));
+    }
     ICG_CUDA(cudaStreamSynchronize(s));
-    for (int w = 0; w < n; w++) {
+    auto write_back = [&](int w) {
         const icg_ba_problem &p = problems[w];
         icg_ba_prior &o = out[w];
         const int nm = num_marg[w], r = o.r;
@@ -2619,13 +2640,31 @@ int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems,
             memcpy(o.x0 + xo, src, sizeof(double) * gs);
             xo += gs;
         }
-        if (o.m <= 0) continue;
+        if (o.m <= 0) return;
         memcpy(o.J0, h->marg_oJ0.h + (size_t) w * M.rcap * M.rcap, sizeof(double) * (size_t) r * r);
         memcpy(o.e0, h->marg_oe0.h + (size_t) w * M.rcap, sizeof(double) * r);
         if (o.Hp) memcpy(o.Hp, h->marg_oHp.h + (size_t) w * M.rcap * M.rcap, sizeof(double) * (size_t) r * r);
         if (o.bp) memcpy(o.bp, h->marg_obp.h + (size_t) w * M.rcap, sizeof(double) * r);
+    };
+    {   // the copies into the caller's arrays are memcpy-bound (r^2 doubles per window): a few host threads, like the packing of icg_ba_upload
+        const int nthreads = std::max(1, std::min({n / 8, 8, (int) std::thread::hardware_concurrency()}));
+        auto worker = [&](int t) {
+            for (int w = t; w < n; w += nthreads) write_back(w);
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; t++) th.emplace_back(worker, t);
+        worker(0);
+        for (auto &x : th) x.join();
     }
     return ICG_OK;
+}
+
+int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out) {
+    return marginalize_body(h, n_windows, problems, num_marg, out, false);
+}
+
+int icg_ba_marginalize_resident(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out) {
+    return marginalize_body(h, n_windows, problems, num_marg, out, true);
 }
 
 int icg_nccl_unique_id(uint8_t *id128) {

@@ -218,6 +218,20 @@ __global__ void __launch_bounds__(256) marg_assemble(BaCaps C, BaDev D, MargDev 
     }
 }
 
+// Plane rotation that orthogonalises two columns with squared norms al, be and inner product ga (one-sided Jacobi / Hestenes):
+// tan(2 theta) = 2 ga / (be - al), smaller root.  Returns false (c, s untouched) when the pair is orthogonal to rounding level,
+// |ga| <= 1e-15 sqrt(al be) (tested squared: no square root).  The scalar chain sits on the critical path of every round-robin step and
+// every lane of the warp executes it, so it is written with reciprocals and one rsqrt (a general FP64 divide or sqrt is a 20-30
+// instruction sequence on this part): 2 reciprocals, 1 sqrt, 1 rsqrt instead of 3 divisions and 3 square roots.
+__device__ __forceinline__ bool jacobi_rotation(double al, double be, double ga, double &c, double &s) {
+    if (ga == 0.0 || ga * ga <= 1e-30 * (al * be)) return false;
+    const double zeta = (be - al) * (0.5 / ga);
+    if (!(fabs(zeta) < 1e300)) return false;  // denormal inner product: nothing to rotate
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    c = rsqrt(1.0 + t * t), s = c * t;
+    return true;
+}
+
 // One-sided Jacobi eigensolver of a symmetric n x n block (rows/cols [off, off+n) of src, leading dimension lds; the block is
 // symmetrised as 0.5 (A + A^T) like schurElimination does).  G (= A V) and V are column-major n x n in global memory (L2).
 // One warp per column pair, round-robin (circle) ordering: the n/2 pairs of a step are disjoint, a barrier separates steps.
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_jacobi(MargDev M, int which
                 }
                 double *gp = G + (size_t) p * n, *gq = G + (size_t) q * n, *vp = V + (size_t) p * n, *vq = V + (size_t) q * n;
                 double a[RPL], b[RPL];
-                double al = 0, be = 0, ga = 0;
+                double al = 0, be = 0, ga = 0, c, s;
 #pragma unroll
                 for (int k = 0; k < RPL; k++) {
                     const int row = lane + 32 * k;
@@ -268,10 +282,7 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_jacobi(MargDev M, int which
                     be += __shfl_xor_sync(0xffffffffu, be, o);
                     ga += __shfl_xor_sync(0xffffffffu, ga, o);
                 }
-                if (ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be)) continue;
-                const double zeta = (be - al) / (2.0 * ga);
-                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+                if (!jacobi_rotation(al, be, ga, c, s)) continue;
 #pragma unroll
                 for (int k = 0; k < RPL; k++) {
                     const int row = lane + 32 * k;
@@ -372,10 +383,7 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_jacobi_pair(MargDev M, int 
                             be += __shfl_xor_sync(0xffffffffu, be, o);
                             ga += __shfl_xor_sync(0xffffffffu, ga, o);
                         }
-                        if (!(ga == 0.0 || fabs(ga) <= 1e-15 * sqrt(al * be))) {
-                            const double zeta = (be - al) / (2.0 * ga);
-                            const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                            c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+                        if (jacobi_rotation(al, be, ga, c, sn)) {
 #pragma unroll
                             for (int k = 0; k < RPL; k++) {
                                 const int row = lane + 32 * k;
@@ -459,6 +467,96 @@ __global__ void __launch_bounds__(MARG_THREADS) marg_jacobi_pair(MargDev M, int 
         }
     }
     cluster.sync();  // CTA 0's shared memory must stay alive until CTA 1 has read G
+}
+
+// The same eigensolver for the sizes the sliding window actually produces (n <= MARG_CTA_MAXN: marginalising one keyframe of a 10-frame window
+// gives m = 15 + its landmarks and r <= 70): ONE CTA per window with G = A V and V both in shared memory, eight lanes per column pair (four pairs
+// per warp share the warp-wide scalar chain; all n/2 pairs of a round-robin step run in one round), one block barrier per step.  Against the
+// cluster-pair kernel: no cluster barrier (~380 cycles) on the step, and the grid is one wave of the 148 SMs instead of two.
+constexpr int MARG_CTA_MAXN = 118;     // 2 * 118^2 doubles = 222.8 KB
+constexpr int MARG_CTA_THREADS = 512;  // 64 pair slots >= MARG_CTA_MAXN / 2
+__global__ void __launch_bounds__(MARG_CTA_THREADS) marg_jacobi_cta(MargDev M, int which) {
+    extern __shared__ double sm_mat[];  // G | V (n x n each, column-major)
+    __shared__ int s_any[2];
+    const int w = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = lane >> 3, sl = lane & 7;
+    const int *map = M.map + (size_t) w * M.map_stride;
+    const int m = map[0], r = map[1], n0 = map[2];
+    if (m <= 0) return;
+    const int n = which == 0 ? m : r;
+    const double *src = which == 0 ? M.H0 + (size_t) w * M.n0cap * M.n0cap : M.Hp + (size_t) w * M.rcap * M.rcap;
+    const int lds = which == 0 ? n0 : r;
+    double *Vout = which == 0 ? M.V1 + (size_t) w * M.mcap * M.mcap : M.V2 + (size_t) w * M.rcap * M.rcap;
+    double *lam = which == 0 ? M.lam1 + (size_t) w * M.mcap : M.lam2 + (size_t) w * M.rcap;
+    double *G = sm_mat, *V = sm_mat + (size_t) n * n;
+    for (int e = tid; e < n * n; e += MARG_CTA_THREADS) {
+        const int j = e / n, i = e - j * n;
+        G[e] = 0.5 * (src[(size_t) i * lds + j] + src[(size_t) j * lds + i]);
+        V[e] = i == j ? 1.0 : 0.0;
+    }
+    if (tid < 2) s_any[tid] = 0;
+    __syncthreads();
+    const int ne = (n + 1) & ~1, half = ne / 2;
+    const int i = warp * 4 + sub;                 // pair slot of this eight-lane group
+    const unsigned gmask = 0xFFu << (8 * sub);
+    constexpr int RPL = 15;                       // rows per lane: n <= 120
+    for (int sweep = 0; sweep < 40; sweep++) {
+        for (int step = 0; step < ne - 1; step++) {
+            if (i < half) {
+                int p = i == 0 ? ne - 1 : (step + i) % (ne - 1);
+                int q = (step + ne - 1 - i) % (ne - 1);
+                if (p < n && q < n) {
+                    if (p > q) {
+                        const int t = p;
+                        p = q, q = t;
+                    }
+                    double *gp = G + (size_t) p * n, *gq = G + (size_t) q * n;
+                    double a[RPL], b[RPL], al = 0, be = 0, ga = 0, c, s;
+#pragma unroll
+                    for (int k = 0; k < RPL; k++) {
+                        const int row = sl + 8 * k;
+                        a[k] = row < n ? gp[row] : 0.0;
+                        b[k] = row < n ? gq[row] : 0.0;
+                        al += a[k] * a[k], be += b[k] * b[k], ga += a[k] * b[k];
+                    }
+#pragma unroll
+                    for (int o = 4; o > 0; o >>= 1) {
+                        al += __shfl_xor_sync(gmask, al, o);
+                        be += __shfl_xor_sync(gmask, be, o);
+                        ga += __shfl_xor_sync(gmask, ga, o);
+                    }
+                    if (jacobi_rotation(al, be, ga, c, s)) {
+                        double *vp = V + (size_t) p * n, *vq = V + (size_t) q * n;
+#pragma unroll
+                        for (int k = 0; k < RPL; k++) {
+                            const int row = sl + 8 * k;
+                            if (row < n) {
+                                gp[row] = c * a[k] - s * b[k];
+                                gq[row] = s * a[k] + c * b[k];
+                                const double x = vp[row], y = vq[row];
+                                vp[row] = c * x - s * y;
+                                vq[row] = s * x + c * y;
+                            }
+                        }
+                        if (sl == 0) s_any[sweep & 1] = 1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int any = s_any[sweep & 1];
+        __syncthreads();
+        if (tid == 0) s_any[(sweep + 1) & 1] = 0;
+        __syncthreads();
+        if (!any) break;
+    }
+    for (int e = tid; e < n * n; e += MARG_CTA_THREADS) Vout[e] = V[e];
+    for (int j = warp; j < n; j += MARG_CTA_THREADS / 32) {
+        double s2 = 0;
+        for (int row = lane; row < n; row += 32) s2 += V[(size_t) j * n + row] * G[(size_t) j * n + row];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (lane == 0) lam[j] = s2;
+    }
 }
 
 // Hp = Hrr - Hrm Hmm^+ Hmr, bp = br - Hrm Hmm^+ bm with Hmm^+ = V diag(1/lambda > EPS) V^T  (schurElimination)

@@ -123,7 +123,7 @@ public:
         std::vector<int32_t> block_type, block_node;  // remainedBlock*: type 0 pose 1 mix 2 extrinsic 3 td; node index after the removal
         std::vector<double> x0, J0, e0;               // remainedBlockData(), linearizedJacobians() (r x r row-major), linearizedResiduals()
     };
-    Prior marginalization(const icg_ba_problem &problem, int num_marg) {
+    Prior marginalization(const icg_ba_problem &problem, int num_marg, bool after_solve = false) {  // after_solve: the window this solver just optimised (no re-upload)
         Prior P;
         const int rcap = 15 * problem.K + 7;
         P.block_type.resize(2 * problem.K + 2), P.block_node.resize(2 * problem.K + 2);
@@ -131,7 +131,7 @@ public:
         icg_ba_prior o{};
         o.rcap = rcap, o.block_type = P.block_type.data(), o.block_node = P.block_node.data(), o.x0 = P.x0.data(), o.J0 = P.J0.data(), o.e0 = P.e0.data();
         const int32_t nm = num_marg;
-        check(icg_ba_marginalize(h_, 1, &problem, &nm, &o), "icg_ba_marginalize");
+        check(after_solve ? icg_ba_marginalize_resident(h_, 1, &problem, &nm, &o) : icg_ba_marginalize(h_, 1, &problem, &nm, &o), "icg_ba_marginalize");
         P.m = o.m, P.r = o.r;
         P.block_type.resize(o.nblocks), P.block_node.resize(o.nblocks);
         P.J0.resize((size_t) o.r * o.r), P.e0.resize(o.r);

@@ -337,6 +337,11 @@ typedef struct icg_ba_prior {
     double *Hp, *bp;                  /* out, may be NULL */
 } icg_ba_prior;
 int icg_ba_marginalize(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out);
+/* The same on the windows the handle already holds: gvinsMarginalization runs right after gvinsOptimization on the same window
+ * (IG/ic_gvins.cc:560-567 -> 1412), so after icg_ba_gvins_optimization[_end] / icg_ba_solve the device copy already has the optimised
+ * parameters, the culled factor set and the re-weighted GNSS sigmas; nothing is packed or uploaded again.  `problems` must be the array
+ * of that solve (n_windows equal to the uploaded count; read for the factor structure and x0 only). */
+int icg_ba_marginalize_resident(icg_ba *h, int n_windows, const icg_ba_problem *problems, const int32_t *num_marg, icg_ba_prior *out);
 /*
  * Landmark sharding of the window solve across the GPUs of one box: every process (one per GPU) uploads the same
  * camera-side problem but only ITS landmarks and their reprojection factors; per LM attempt one NCCL sum all-reduce of the packed

@@ -24,7 +24,12 @@ base = [synth_ba.make_window(pre, K=10, L=300, seed=2024 + b)[0] for b in range(
 wins = [copy.deepcopy(base[b % len(base)]) for b in range(B)]
 s = WindowSolver(max_windows=B, max_K=10, max_L=300, max_F=max(w["F"] for w in wins), max_gnss=8, max_marg_r=1)
 s.marginalize(wins[:2], 1, want_schur=False)
+call = s.marg_prepare(wins, 1, want_schur=False)
 for r in range(reps):
     t0 = time.perf_counter()
-    pri = s.marginalize(wins, 1, want_schur=False)
-    print("rep", r, "ms", (time.perf_counter() - t0) * 1e3, "m", pri[0]["m"], "r", pri[0]["r"])
+    s.marg_run(call)
+    t1 = time.perf_counter()
+    s.marg_run(call, resident=True)
+    t2 = time.perf_counter()
+    pri = s.marg_collect(call)
+    print("rep", r, "icg_ba_marginalize ms", (t1 - t0) * 1e3, "resident ms", (t2 - t1) * 1e3, "m", [p["m"] for p in pri[:8]], "r", [p["r"] for p in pri[:8]])

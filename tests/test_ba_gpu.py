@@ -373,7 +373,9 @@ def test_landmark_sharded_p2p_in_process_matches_oracle(olib, world, K, L, nwin)
 
 def test_landmark_sharded_two_pass_in_process(olib):
     """gvinsOptimization (5 + chi2 culling + 15) on landmark shards: culling is local to the shard that owns the factor, GNSS re-weighting
-    is replicated; merged result == the single-handle two-pass result (bitwise identical LM decisions, solution within 1e-9)."""
+    is replicated; merged result == the single-handle two-pass result (identical LM decisions; solution within 1e-8: the shard partials
+    are summed in a different order than the single-handle Gram products, and 20 LM iterations on the weakly observed camera-IMU
+    extrinsic carry that rounding to ~1e-9 relative)."""
     from ic_gvins_b200.ba import WindowSolver
     probs = []
     for w in range(2):
@@ -393,7 +395,7 @@ def test_landmark_sharded_two_pass_in_process(olib):
         assert out[0][w]["gnss_reweighted"] == info[w]["gnss_reweighted"] >= 1
         assert out[0][w]["pass2"]["iterations"] == info[w]["pass2"]["iterations"]
         assert np.array_equal(merged[w]["f_active"], single[w]["f_active"])
-        _compare_solution(merged[w], single[w], rel=1e-9)
+        _compare_solution(merged[w], single[w], rel=1e-8)
 
 
 def test_preintegration_normal_matches_oracle(olib, solver):

