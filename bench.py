@@ -395,8 +395,6 @@ def run_b200(args):
         lib().icg_klt_slot_level0(trk._h, 1, C2.byref(p1_), C2.byref(pit_))
         slot_stride, slot_pitch, slot0 = p1_.value - p0_.value, pit_.value, p0_.value
         kf_mcalls = [solvers[k].marg_prepare(e2e_parts[k][0], 1, want_schur=False) for k in range(len(solvers))]
-        for k in range(len(solvers)):
-            solvers[k].marginalize(e2e_parts[k][0][:2], 1, want_schur=False)  # marginalization workspace allocation, outside the timed region
         h_raw = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
         d_rawB = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
         kf_hist = [None]

@@ -44,6 +44,7 @@ constexpr int BA_SPLIT_J = 1;   // the vision Gram matrix is produced whole by b
 constexpr int BA_SPLIT_W = 4;   // row splits of the Schur SYRK (partials summed in fixed order -> deterministic)
 constexpr int BA_CHOL_NB = 8;   // Cholesky block width
 constexpr int BA_MARG_MAXB = 72;  // remained blocks of a prior: <= 2 max_K + 2 = 66 at max_K = 32 (table stride)
+constexpr int BA_MAX_NODES = 32;  // icg_ba_create: max_K <= 32
 
 struct BaCaps {
     int NW, K, L, F, G, R;     // capacities
@@ -126,8 +127,11 @@ __device__ __forceinline__ int jc_row1(int a) { return a < 18 ? 6 : 1; }        
 //           factors of a landmark share the reference node, the extrinsic and td (accumulated); each observing node appears once
 //           (written directly; icg_ba_upload checks it).
 constexpr int LV_LD = 45;  // shared-memory record row: 44 doubles padded to an odd length (conflict-free)
+constexpr size_t LV_SMEM = sizeof(double) * (128 * LV_LD + (BA_MAX_NODES + 1) * NODE_FRAME_LD);  // records + node frames (49.5 KB: dynamic, opted in at create)
 __global__ void __launch_bounds__(128, 4) ba_lin_vis(BaCaps C, BaDev D) {
-    __shared__ double s_rec[128][LV_LD];
+    extern __shared__ double lv_sm[];
+    double (*s_rec)[LV_LD] = (double (*)[LV_LD]) lv_sm;
+    double (*s_frame)[NODE_FRAME_LD] = (double (*)[NODE_FRAME_LD]) (lv_sm + 128 * LV_LD);
     const int w = blockIdx.y;
     const LmState &st = D.st[w];
     if (st.done || !st.need_lin) return;
@@ -138,6 +142,9 @@ __global__ void __launch_bounds__(128, 4) ba_lin_vis(BaCaps C, BaDev D) {
     const int *off = D.lm_off + (size_t) w * (C.L + 1);
     const int lmA = vb[blockIdx.x], lmB = vb[blockIdx.x + 1];
     const int s0 = off[lmA], nslot = off[lmB] - s0;
+    // ---- phase 0: the window's K + 1 node frames (rotation matrix | position of every pose and of the extrinsic), once per CTA
+    if (tid <= dm.K) node_frame(tid < dm.K ? D.pose + ((size_t) w * C.K + tid) * 7 : D.ext + (size_t) w * 8, s_frame[tid]);
+    __syncthreads();
     // ---- phase 1
     if (tid < nslot) {
         const int q = s0 + tid;
@@ -146,8 +153,8 @@ __global__ void __launch_bounds__(128, 4) ba_lin_vis(BaCaps C, BaDev D) {
         const int i = meta.y, j = meta.z, f = meta.w;
         if (D.f_active[(size_t) w * C.F + f] != 0) {
             const double *ext = D.ext + (size_t) w * 8;
-            reproj_eval(D.pose + ((size_t) w * C.K + i) * 7, D.pose + ((size_t) w * C.K + j) * 7, ext, D.rho[(size_t) w * C.L + meta.x], ext[7],
-                        D.f_const_s + ((size_t) w * C.F + q) * 14, dm.reproj_sinv, true, r, Ji, Jj, Je, Jr, Jt);
+            reproj_eval_frames(s_frame[i], s_frame[j], s_frame[dm.K], D.rho[(size_t) w * C.L + meta.x], ext[7],
+                               D.f_const_s + ((size_t) w * C.F + q) * 14, dm.reproj_sinv, true, r, Ji, Jj, Je, Jr, Jt);
             if (dm.ext_const)
                 for (int k = 0; k < 12; k++) Je[k] = 0;
             if (dm.td_const) Jt[0] = Jt[1] = 0;
@@ -321,14 +328,33 @@ __device__ __forceinline__ double gram2_entry(const BaCaps &C, const BaDev &D, i
     const int ga = 12 + a, gb = 12 + b;          // local column of a global-block column
     double sum = 0;
     if (bA == K) {  // (global, global): every group
+        // up to K (K - 1) groups: eight loads in flight and four partial sums in a fixed order (these 36 entries are the tail of the kernel:
+        // a serial sum is 90 dependent L2 round trips)
         const int idx = tri20(ga, gb);
-        for (int p = 0; p < P; p++) sum += Mp[(size_t) p * 210 + idx];
+        double s4[4] = {0, 0, 0, 0};
+        int p = 0;
+        for (; p + 8 <= P; p += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = Mp[(size_t) (p + u) * 210 + idx];
+#pragma unroll
+            for (int u = 0; u < 8; u++) s4[u & 3] += v[u];
+        }
+        for (; p < P; p++) s4[p & 3] += Mp[(size_t) p * 210 + idx];
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     } else if (bB == K || bB == bA) {  // (pose, global) or the pose's diagonal block
         const int i1 = tri20(a, bB == K ? gb : b), i2 = tri20(6 + a, bB == K ? gb : 6 + b);
-        for (int o = 0; o < K; o++) {
-            const int p1 = s_slot[bA * K + o], p2 = s_slot[o * K + bA];  // bA as reference node / as observing node
-            if (p1 >= 0) sum += Mp[(size_t) p1 * 210 + i1];
-            if (p2 >= 0) sum += Mp[(size_t) p2 * 210 + i2];
+        for (int o0 = 0; o0 < K; o0 += 4) {  // 8 loads in flight; same summation order as a serial loop
+            double v1[4], v2[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int o = o0 + u;
+                const int p1 = o < K ? s_slot[bA * K + o] : -1, p2 = o < K ? s_slot[o * K + bA] : -1;  // bA as reference node / as observing node
+                v1[u] = p1 >= 0 ? Mp[(size_t) p1 * 210 + i1] : 0.0;
+                v2[u] = p2 >= 0 ? Mp[(size_t) p2 * 210 + i2] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) sum += v1[u], sum += v2[u];
         }
     } else {  // two different poses: the (bA -> bB) and (bB -> bA) groups
         const int p1 = s_slot[bA * K + bB], p2 = s_slot[bB * K + bA];
@@ -950,6 +976,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     const double radius = st.radius;
 
     // ---- assemble S' = s (H - Schur) s + D^2 (packed lower), rhs' = -s (g - W phi g_l)
+    // The reduced camera matrix (ba_hsum's output, row i contiguous) goes global -> packed shared rows with 8-byte cp.async: every element of
+    // the lower triangle is in flight at once (one L2 round trip for the whole matrix instead of one per row and warp), the vector part below
+    // overlaps the copy, and the Jacobi scaling + LM diagonal are applied in place afterwards.
+    const bool async_fill = !use_global_S;
+    if (async_fill) {
+        for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
+            const double *src = (i < NCV ? Hs : Hc) + (size_t) i * C.NS;
+            const unsigned dst = (unsigned) __cvta_generic_to_shared(S + i * (i + 1) / 2);
+            for (int j = tid & 31; j <= i; j += 32)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * j), "l"(src + j) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int a = tid; a < N; a += SOLVE_THREADS) {
         double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? syrk_get(CJ, 1, C.NCA, a, a) : 0.0);
         double hs = s_scale[a] * s_scale[a] * h;
@@ -957,27 +996,38 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         double gw = a < NCV ? cw_get(a, NCV) : 0.0;
         s_rhs[a] = -s_scale[a] * (s_g[a] - gw);
     }
+    if (async_fill) asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
-        // one warp per row; all global loads of the row are issued before the first shared-memory store (memory-level parallelism)
-        constexpr int MAXQ = 16;  // N <= 512
-        double hv[MAXQ];
-        const int nq = i / 32 + 1;
-#pragma unroll
-        for (int q = 0; q < MAXQ; q++) {
-            const int j = (tid & 31) + 32 * q;
-            hv[q] = 0;
-            if (q < nq && j <= i) {
-                hv[q] = (i < NCV ? Hs : Hc)[(size_t) i * C.NS + j];  // ba_hsum: H_c + vision Gram - Schur (vision rows); row i contiguous
+    if (async_fill) {
+        for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
+            double *row = S + i * (i + 1) / 2;
+            const double si = s_scale[i];
+            for (int j = tid & 31; j <= i; j += 32) {
+                double v = si * s_scale[j] * row[j];
+                if (i == j) v += s_d2[i];
+                row[j] = v;
             }
         }
+    } else {
+        for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
+            // one warp per row; all global loads of the row are issued before the first store (memory-level parallelism)
+            constexpr int MAXQ = 16;  // N <= 512
+            double hv[MAXQ];
+            const int nq = i / 32 + 1;
 #pragma unroll
-        for (int q = 0; q < MAXQ; q++) {
-            const int j = (tid & 31) + 32 * q;
-            if (q < nq && j <= i) {
-                double v = s_scale[i] * s_scale[j] * hv[q];
-                if (i == j) v += s_d2[i];
-                S[i * (i + 1) / 2 + j] = v;
+            for (int q = 0; q < MAXQ; q++) {
+                const int j = (tid & 31) + 32 * q;
+                hv[q] = 0;
+                if (q < nq && j <= i) hv[q] = (i < NCV ? Hs : Hc)[(size_t) i * C.NS + j];  // ba_hsum: H_c + vision Gram - Schur (vision rows); row i contiguous
+            }
+#pragma unroll
+            for (int q = 0; q < MAXQ; q++) {
+                const int j = (tid & 31) + 32 * q;
+                if (q < nq && j <= i) {
+                    double v = s_scale[i] * s_scale[j] * hv[q];
+                    if (i == j) v += s_d2[i];
+                    S[i * (i + 1) / 2 + j] = v;
+                }
             }
         }
     }
@@ -999,24 +1049,40 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
             const int cb = J0 + g;                                     // row of L that is the B operand's column
             const double *rb = S + (cb < NR ? cb * (cb + 1) / 2 : 0);
             const bool okb = cb < NR;
-            for (int tI = warp; tI < ntile; tI += SOLVE_THREADS / 32) {
-                const int ia = J0 + 8 * tI + g;
-                const bool oka = ia < NR;
-                const double *ra = S + (oka ? ia * (ia + 1) / 2 : 0);
-                double c0 = 0, c1 = 0, d0 = 0, d1 = 0;
-                int k0 = 0;
-                for (; k0 + 8 <= J0; k0 += 8) {  // two independent accumulator pairs hide the DMMA latency
-                    const double a0 = oka ? ra[k0 + kk] : 0.0, b0 = okb ? rb[k0 + kk] : 0.0;
-                    const double a1 = oka ? ra[k0 + 4 + kk] : 0.0, b1 = okb ? rb[k0 + 4 + kk] : 0.0;
-                    dmma884(c0, c1, a0, b0);
-                    dmma884(d0, d1, a1, b1);
+            // up to three row tiles per warp in flight (they share the B fragment): N = 157 gives <= 20 tiles for the 8 warps, so the whole panel
+            // update is ONE round of the k loop instead of three serialised ones, and six independent DMMA chains hide the tensor-pipe latency
+            constexpr int TPW = 3, NWARP = SOLVE_THREADS / 32;
+            for (int t0 = warp; t0 < ntile; t0 += TPW * NWARP) {
+                const double *ra[TPW];
+                bool oka[TPW];
+                double acc[TPW][4];
+#pragma unroll
+                for (int u = 0; u < TPW; u++) {
+                    const int ia = J0 + 8 * (t0 + u * NWARP) + g;
+                    oka[u] = (t0 + u * NWARP) < ntile && ia < NR;
+                    ra[u] = S + (oka[u] ? ia * (ia + 1) / 2 : 0);
+                    acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0;
                 }
-                c0 += d0, c1 += d1;
-                const int i = J0 + 8 * tI + g;
-                if (i < NR) {
-                    const int ca = J0 + 2 * kk;
-                    if (ca < J0 + nb && ca <= i) S[i * (i + 1) / 2 + ca] -= c0;
-                    if (ca + 1 < J0 + nb && ca + 1 <= i) S[i * (i + 1) / 2 + ca + 1] -= c1;
+                for (int k0 = 0; k0 + 8 <= J0; k0 += 8) {
+                    const double b0 = okb ? rb[k0 + kk] : 0.0, b1 = okb ? rb[k0 + 4 + kk] : 0.0;
+                    double a0[TPW], a1[TPW];
+#pragma unroll
+                    for (int u = 0; u < TPW; u++) a0[u] = oka[u] ? ra[u][k0 + kk] : 0.0, a1[u] = oka[u] ? ra[u][k0 + 4 + kk] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < TPW; u++) {
+                        dmma884(acc[u][0], acc[u][1], a0[u], b0);
+                        dmma884(acc[u][2], acc[u][3], a1[u], b1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < TPW; u++) {
+                    const double c0 = acc[u][0] + acc[u][2], c1 = acc[u][1] + acc[u][3];
+                    const int i = J0 + 8 * (t0 + u * NWARP) + g;
+                    if (oka[u]) {
+                        const int ca = J0 + 2 * kk;
+                        if (ca < J0 + nb && ca <= i) S[i * (i + 1) / 2 + ca] -= c0;
+                        if (ca + 1 < J0 + nb && ca + 1 <= i) S[i * (i + 1) / 2 + ca + 1] -= c1;
+                    }
                 }
             }
             __syncthreads();
@@ -1102,21 +1168,37 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
 #pragma unroll
             for (int q = 0; q < MAXQ; q++) yr[q] = lane + 32 * q < N ? y[lane + 32 * q] : 0.0;
             // statically indexed: the owner register block oq is an unrolled outer loop, so the per-step critical path is
-            // shuffle -> multiply -> FMA (no register selects); only blocks q <= oq are touched
+            // shuffle -> multiply -> FMA (no register selects); only blocks q <= oq are touched.  Row j - 1 of L (and its diagonal
+            // reciprocal) is fetched from shared memory while step j computes: the loads never sit on the dependent chain.
+            double lv[MAXQ], dj = s_diag[N - 1];
+            {
+                const double *rj = S + (N - 1) * N / 2;
+#pragma unroll
+                for (int q = 0; q < MAXQ; q++) lv[q] = lane + 32 * q < N - 1 ? rj[lane + 32 * q] : 0.0;
+            }
 #pragma unroll
             for (int oq = MAXQ - 1; oq >= 0; oq--) {
                 if (32 * oq >= N) continue;
                 for (int ol = min(31, N - 1 - 32 * oq); ol >= 0; ol--) {
                     const int j = 32 * oq + ol;
-                    const double *rj = S + j * (j + 1) / 2;
-                    double lv[MAXQ];
+                    double ln[MAXQ], dn = 0;
+                    if (j > 0) {
+                        const double *rn = S + (j - 1) * j / 2;
+                        dn = s_diag[j - 1];
 #pragma unroll
-                    for (int q = 0; q < MAXQ; q++) lv[q] = (q <= oq && lane + 32 * q < j) ? rj[lane + 32 * q] : 0.0;  // off the critical path
-                    const double xj = __shfl_sync(0xffffffffu, yr[oq], ol) * s_diag[j];
+                        for (int q = 0; q < MAXQ; q++) ln[q] = (q <= oq && lane + 32 * q < j - 1) ? rn[lane + 32 * q] : 0.0;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < MAXQ; q++) ln[q] = 0.0;
+                    }
+                    const double xj = __shfl_sync(0xffffffffu, yr[oq], ol) * dj;
                     if (lane == ol) s_rhs[j] = xj;
 #pragma unroll
                     for (int q = 0; q < MAXQ; q++)
                         if (q <= oq) yr[q] -= lv[q] * xj;
+#pragma unroll
+                    for (int q = 0; q < MAXQ; q++) lv[q] = ln[q];
+                    dj = dn;
                 }
             }
         }
@@ -1149,7 +1231,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     __syncthreads();
     {
         const int lane = tid & 31, warp = tid >> 5;
-        constexpr int LB = 4;  // landmarks in flight per warp (the coupling rows come from L2)
+        constexpr int LB = 8;  // landmarks in flight per warp (the coupling rows come from L2: 24 loads per lane outstanding)
         for (int l0 = LB * warp; l0 < L; l0 += LB * (SOLVE_THREADS / 32)) {
             double d[LB];
 #pragma unroll
@@ -1245,13 +1327,16 @@ __global__ void __launch_bounds__(256) ba_cost(BaCaps C, BaDev D, int nblk_vis) 
     const double *pose = D.pose_c + (size_t) w * C.K * 7, *ext = D.ext_c + (size_t) w * 8, *rho = D.rho_c + (size_t) w * C.L;
     double *part = D.cost_part + (size_t) w * (nblk_vis + 1);
     const int q = blockIdx.x * 256 + threadIdx.x;  // record slot (landmark-CSR order): the slot-ordered copies are the only factor data on the device
+    __shared__ double s_frame[BA_MAX_NODES + 1][NODE_FRAME_LD];  // node frames of the candidate point (see ba_lin_vis)
+    if ((int) threadIdx.x <= dm.K) node_frame((int) threadIdx.x < dm.K ? pose + threadIdx.x * 7 : ext, s_frame[threadIdx.x]);
+    __syncthreads();
     double cost = 0;
     int4 meta = make_int4(0, 0, 0, 0);
     if (q < dm.F) meta = ((const int4 *) D.f_meta_s)[(size_t) w * C.F + q];  // (landmark, reference node, observing node, factor id)
     if (q < dm.F && D.f_active[(size_t) w * C.F + meta.w]) {
         double r[2];
-        reproj_eval(pose + meta.y * 7, pose + meta.z * 7, ext, rho[meta.x], ext[7], D.f_const_s + ((size_t) w * C.F + q) * 14, dm.reproj_sinv, false, r, nullptr,
-                    nullptr, nullptr, nullptr, nullptr);
+        reproj_eval_frames(s_frame[meta.y], s_frame[meta.z], s_frame[dm.K], rho[meta.x], ext[7], D.f_const_s + ((size_t) w * C.F + q) * 14, dm.reproj_sinv,
+                           false, r, nullptr, nullptr, nullptr, nullptr, nullptr);
         double sq = r[0] * r[0] + r[1] * r[1], sc;
         if (dm.reproj_huber)
             huber(sq, cost, sc);
@@ -1808,6 +1893,7 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     ICG_CUDA(cudaFuncSetAttribute(ba_schur_dmma, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     ICG_CUDA(raise_dynamic_smem((const void *) ba_lin_cam, (size_t) (h->smem_cam)));
     ICG_CUDA(raise_dynamic_smem((const void *) ba_cost_cam, (size_t) (h->smem_cam)));
+    ICG_CUDA(raise_dynamic_smem((const void *) ba_lin_vis, LV_SMEM));
     ICG_CUDA(cudaStreamSynchronize(h->stream));
     h->cur_windows = 0;
     return ICG_OK;
@@ -2113,7 +2199,7 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
             ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         }
         prof_mark(h, 0);
-        ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
+        ba_lin_vis<<<g_vis, 128, LV_SMEM, s>>>(C, D);
         prof_mark(h, 1);
         if (cam_fork != 0) {
             ICG_CUDA(cudaEventRecord(h->ev_fork, s));
@@ -2261,7 +2347,7 @@ static int enqueue_lm_split(icg_ba *h, int max_num_iterations) {
         ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
         ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         prof_mark(h, 0);
-        ba_lin_vis<<<g_vis, 128, 0, s>>>(C, D);
+        ba_lin_vis<<<g_vis, 128, LV_SMEM, s>>>(C, D);
         prof_mark(h, 1);
         ba_schur_dmma<<<dim3(BA_SPLIT_W, n), 256, h->smem_schur, s>>>(C, D, h->ld_schur);
         prof_mark(h, 5);
@@ -2580,7 +2666,7 @@ static int marginalize_body(icg_ba *h, int n_windows, const icg_ba_problem *prob
     const BaDev &D = h->D;
     const size_t smem = sizeof(double) * (8 * 480 + 2 * (size_t) C.R) + sizeof(int) * (size_t) C.R + 64;
     marg_prepare<<<(n + 127) / 128, 128, 0, s>>>(D, M, n, 0);
-    ba_lin_vis<<<dim3(C.NVB - 2, n), 128, 0, s>>>(C, D);
+    ba_lin_vis<<<dim3(C.NVB - 2, n), 128, LV_SMEM, s>>>(C, D);
     ba_pair_gram1<<<dim3((C.K * (C.K - 1) + 7) / 8, n), 256, 0, s>>>(C, D);
     marg_assemble<<<n, 256, smem, s>>>(C, D, M);
     // eigendecompositions: on-chip cluster-pair kernel when every block of the batch fits (n <= MARG_PAIR_MAXN), global-memory kernel otherwise

@@ -194,6 +194,62 @@ BAM_HD void reproj_eval(const double *pi, const double *pj, const double *ext, d
     }
 }
 
+// The same factor over pre-computed NODE FRAMES (hot kernels: ba_lin_vis, ba_cost).  Every factor of a window rotates with the matrices of
+// its reference node, its observing node and the extrinsic -- K + 1 distinct rotations per window against ~2700 factors -- so the CTA
+// builds them once (node_frame: R = toRotationMatrix(q) row-major | p) and the factor does matrix-vector products: four of them replace the
+// reference's quaternion sandwich products and the two quaternion inverses, and the Jacobian rows use the same matrices.  For the unit
+// quaternions PoseParameterization::Plus maintains, q v q^-1 = R(q) v and q^-1 v q = R(q)^T v up to rounding (the factor tests hold this
+// form to the oracle's quaternion form at 1e-12).  About 40 % fewer FP64 instructions per factor than reproj_eval.
+constexpr int NODE_FRAME_LD = 13;  // 9 + 3, padded to an odd length (shared-memory banks)
+BAM_HD void node_frame(const double *pose7, double *F) {
+    const M3 R = qmat(pose_q(pose7));
+#pragma unroll
+    for (int i = 0; i < 9; i++) F[i] = R.m[i];
+    F[9] = pose7[0], F[10] = pose7[1], F[11] = pose7[2];
+}
+BAM_HD V3 mulT(const M3 &a, V3 v) {  // a^T v
+    return mk(a.m[0] * v.x + a.m[3] * v.y + a.m[6] * v.z, a.m[1] * v.x + a.m[4] * v.y + a.m[7] * v.z, a.m[2] * v.x + a.m[5] * v.y + a.m[8] * v.z);
+}
+BAM_HD void reproj_eval_frames(const double *Fi, const double *Fj, const double *Fe, double id0, double td, const double *c, double sinv, bool want_j,
+                               double *r, double *Ji, double *Jj, double *Je, double *Jr, double *Jt) {
+    M3 R0, R1, Ric;
+#pragma unroll
+    for (int i = 0; i < 9; i++) R0.m[i] = Fi[i], R1.m[i] = Fj[i], Ric.m[i] = Fe[i];
+    const V3 p0 = mk(Fi[9], Fi[10], Fi[11]), p1 = mk(Fj[9], Fj[10], Fj[11]), tic = mk(Fe[9], Fe[10], Fe[11]);
+    V3 pts0 = mk(c[0], c[1], c[2]), pts1 = mk(c[3], c[4], c[5]), vel0 = mk(c[6], c[7], c[8]), vel1 = mk(c[9], c[10], c[11]);
+    V3 pts_0_td = pts0 - (td - c[12]) * vel0;
+    V3 pts_1_td = pts1 - (td - c[13]) * vel1;
+    const double inv_id0 = 1.0 / id0;
+    V3 pts_c_0 = inv_id0 * pts_0_td;
+    V3 pts_b_0 = mul(Ric, pts_c_0) + tic;
+    V3 pts_n = mul(R0, pts_b_0) + p0;
+    V3 pts_b_1 = mulT(R1, pts_n - p1);
+    V3 pts_1 = mulT(Ric, pts_b_1 - tic);
+    const double d1 = pts_1.z, inv_d = 1.0 / d1;
+    r[0] = sinv * (pts_1.x * inv_d - pts_1_td.x);
+    r[1] = sinv * (pts_1.y * inv_d - pts_1_td.y);
+    if (!want_j) return;
+    const double redr[2][3] = {{sinv * inv_d, 0.0, sinv * (-pts_1.x * (inv_d * inv_d))}, {0.0, sinv * inv_d, sinv * (-pts_1.y * (inv_d * inv_d))}};
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {  // same row-by-row chain as reproj_eval
+        const V3 r3 = mk(redr[rr][0], redr[rr][1], redr[rr][2]);
+        const V3 a1 = mul(Ric, r3);
+        const V3 a2 = mul(R1, a1);
+        const V3 a3 = mulT(R0, a2);
+        const V3 a4 = mulT(Ric, a3);
+        const V3 ji_rot = cross(pts_b_0, a3);
+        const V3 jj_rot = cross(a1, pts_b_1);
+        const V3 je_pos = a3 - a1;
+        const V3 je_rot = cross(pts_c_0, a4) + cross(r3, pts_1);
+        double *ji = Ji + 6 * rr, *jj = Jj + 6 * rr, *je = Je + 6 * rr;
+        ji[0] = a2.x, ji[1] = a2.y, ji[2] = a2.z, ji[3] = ji_rot.x, ji[4] = ji_rot.y, ji[5] = ji_rot.z;
+        jj[0] = -a2.x, jj[1] = -a2.y, jj[2] = -a2.z, jj[3] = jj_rot.x, jj[4] = jj_rot.y, jj[5] = jj_rot.z;
+        je[0] = je_pos.x, je[1] = je_pos.y, je[2] = je_pos.z, je[3] = je_rot.x, je[4] = je_rot.y, je[5] = je_rot.z;
+        Jr[rr] = -dot(a4, pts_0_td) * (inv_id0 * inv_id0);
+        Jt[rr] = -dot(a4, vel0) * inv_id0 + sinv * (rr == 0 ? vel1.x : vel1.y);
+    }
+}
+
 // GnssFactor::Evaluate (IG/factors/gnss_factor.h:43-71); J local 3x6 row-major
 BAM_HD void gnss_eval(const double *pose, const double *blh, const double *std3, const double *lever, bool want_j, double *r, double *J) {
     V3 p = pose_p(pose);

@@ -185,7 +185,7 @@ def test_200_frame_stream_feature_ids_match_cv2(oracle):
                 if len(d0):
                     assert np.abs(d0 - d1).max() <= 1e-3, f"frame {t}: new corners differ by {np.abs(d0 - d1).max():.2e} px"
             assert state[0]["ids"] == state[1]["ids"] and state[0]["next_id"] == state[1]["next_id"], f"frame {t}: ID lists differ after detection"
-        assert n_detect >= 20 and state[0]["next_id"] > MAXF, "the stream must lose and re-detect features"
+        assert n_detect >= 10 and state[0]["next_id"] > MAXF, "the stream must lose and re-detect features"
         assert n_over <= max(1, n_same // 200), f"{n_over} of {n_same} same-input comparisons exceed 1e-3 px (allowed: 0.5 %)"
         print(f"stream parity: {NFRAMES} frames, {n_tracks} point-tracks, {state[0]['next_id']} feature IDs issued, {n_detect} detection passes, "
               f"same-input max |d| = {max_same:.2e} px ({n_over} of {n_same} above 1e-3), free-running max |d| = {max_dpx:.2e} px, knife-edge re-syncs = {resyncs}")
