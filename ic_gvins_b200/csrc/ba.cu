@@ -107,6 +107,7 @@ struct BaDev {  // device pointers (flat, capacity-strided by window)
     int rank, world;    // landmark shard of this process (camera-only terms are counted on rank 0 only)
     double *step_c, *step_l;
     double *Sglobal;    // fallback Cholesky workspace when the packed system does not fit shared memory
+    unsigned long long *clk;  // ICG_BA_PROFILE: SM-clock totals of ba_solve's phases for window 0 (nullptr otherwise)
 };
 
 __device__ __forceinline__ int col_pose(int k) { return 6 * k; }
@@ -885,6 +886,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     const int w = blockIdx.x, tid = threadIdx.x;
     LmState &st = D.st[w];
     if (st.done) return;
+    // phase clocks (profiling handles only): thread 0 of window 0 adds the SM cycles since the previous mark
+    unsigned long long clk_prev = D.clk ? clock64() : 0ull;
+#define SOLVE_CLK(k)                                              \
+    if (D.clk && w == 0 && tid == 0) {                            \
+        const unsigned long long t_ = clock64();                  \
+        atomicAdd(&D.clk[k], t_ - clk_prev), atomicAdd(&D.clk[8 + (k)], 1ull); \
+        clk_prev = t_;                                            \
+    }
     const WinDims dm = D.dims[w];
     const int K = dm.K, L = dm.L, NCV = 6 * K + 7, N = 15 * K + 7;
     const int f_first = st.first, f_fresh = st.fresh_lin, f_last = st.last_success, f_iter = st.iter;
@@ -974,6 +983,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     __syncthreads();
     if (tid == 0) st.iter++;
     const double radius = st.radius;
+    SOLVE_CLK(0)  // gradient, cost, termination tests
 
     // ---- assemble S' = s (H - Schur) s + D^2 (packed lower), rhs' = -s (g - W phi g_l)
     // The reduced camera matrix (ba_hsum's output, row i contiguous) goes global -> packed shared rows with 8-byte cp.async: every element of
@@ -1034,6 +1044,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     // augmented row N = rhs': the factorisation then leaves y = L^-1 rhs' in it (forward substitution for free)
     for (int a = tid; a < N; a += SOLVE_THREADS) S[N * (N + 1) / 2 + a] = s_rhs[a];
     __syncthreads();
+    SOLVE_CLK(1)  // assembly
     // ---- blocked left-looking Cholesky on the packed lower triangle (3 barriers per 8 columns); failure -> invalid step
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
@@ -1156,6 +1167,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     }
     __syncthreads();
     bool valid = !s_fail;
+    SOLVE_CLK(2)  // Cholesky
     // ---- backward substitution L^T x = y, column oriented, by ONE warp with y in registers: for j = N-1 .. 0:
     //      x_j = y_j / L_jj (owner lane, broadcast by shuffle), then y_i -= L_ji x_j for i < j -- row j of the packed lower triangle
     //      is contiguous, so every step is one coalesced shared-memory row read and no reduction or block barrier.
@@ -1204,6 +1216,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         }
     }
     __syncthreads();
+    SOLVE_CLK(3)  // camera back-substitution
     // ---- landmark back-substitution + model cost change  (-1/2 step'.g' + 1/2 step'.D^2 step', exact identity of
     //      Ceres' -(J' step)^T (r + J' step / 2) for the damped normal-equation solution)
     double *step_l = D.step_l + (size_t) w * C.L;
@@ -1259,6 +1272,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         }
     }
     __syncthreads();
+    SOLVE_CLK(4)  // landmark back-substitution
     const double mcc = block_sum(part, s_red);
     const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
     // ---- candidate point x (+) delta, delta = step' * scale; |x - x_cand|^2 over active blocks (camera part counted on shard 0)
@@ -1304,6 +1318,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         st.chol_ok = 1, st.step_valid = 1;  // provisional: ba_accept validates with the reduced model cost change
         R2[0] = mcc, R2[1] = sn, R2[2] = nfin, R2[3] = 0;
     }
+    SOLVE_CLK(5)  // candidate point, reductions
+#undef SOLVE_CLK
 }
 
 // ------------------------------------------------------------------------------------------------ candidate cost
@@ -1825,6 +1841,11 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->prof = getenv("ICG_BA_PROFILE") != nullptr;
+    if (h->prof) {
+        double *ck = nullptr;
+        if (dmalloc(h, &ck, 16) != ICG_OK) return ICG_ENOMEM;
+        h->D.clk = (unsigned long long *) ck;
+    }
     if (getenv("ICG_BA_PROFILE_SKIP")) h->prof_skip = atoi(getenv("ICG_BA_PROFILE_SKIP"));
     BaCaps &C = h->C;
     max_L = std::max(1, max_L), max_F = std::max(1, max_F);  // capacities stay >= 1; windows without landmarks (first keyframes, IG/ic_gvins.cc:1698) are accepted
@@ -2174,6 +2195,15 @@ static void prof_print(icg_ba *h) {
     for (int t = 0; t < 16; t++)
         if (h->prof_cnt[t])
             fprintf(stderr, "  %-28s %9.3f ms  %8.1f us  %5.1f %%\n", PROF_NAMES[t], h->prof_ms[t], 1e3 * h->prof_ms[t] / h->prof_cnt[t], 100.0 * h->prof_ms[t] / tot);
+    if (h->D.clk) {
+        unsigned long long ck[16];
+        if (cudaMemcpy(ck, h->D.clk, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char *nm[6] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions"};
+            fprintf(stderr, "[icg_ba profile] ba_solve phases of window 0 (SM cycles per call, mean):\n");
+            for (int k = 0; k < 6; k++)
+                if (ck[8 + k]) fprintf(stderr, "  %-28s %9.0f cycles\n", nm[k], (double) ck[k] / (double) ck[8 + k]);
+        }
+    }
 }
 
 static int enqueue_lm_split(icg_ba *h, int max_num_iterations);
