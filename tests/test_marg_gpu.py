@@ -36,7 +36,7 @@ def make(olib, **kw):
     return synth_ba.make_window(lambda *a: oa.preintegrate(olib, *a), **kw)[0]
 
 
-def compare(g, o, tol_h=5e-6):
+def compare(g, o, tol_h=5e-6, tol_sqrt=1e-9):
     assert g["m"] == o["m"] and g["r"] == o["r"]
     assert np.array_equal(g["block_type"], o["block_type"]) and np.array_equal(g["block_node"], o["block_node"])
     assert np.array_equal(g["x0"], o["x0"])
@@ -53,7 +53,7 @@ def compare(g, o, tol_h=5e-6):
     S, U = np.linalg.eigh(g["Hp"])
     keep = S > 1e-8
     Hk = (U[:, keep] * S[keep]) @ U[:, keep].T
-    assert np.abs((g["J0"].T @ g["J0"] - Hk) / np.outer(sc, sc)).max() < 1e-9
+    assert np.abs((g["J0"].T @ g["J0"] - Hk) / np.outer(sc, sc)).max() < tol_sqrt
     # rows sorted by ascending eigenvalue (Eigen::SelfAdjointEigenSolver order)
     rn = (g["J0"] ** 2).sum(axis=1)
     assert np.all(np.diff(rn) >= -1e-9 * rn.max())
@@ -142,7 +142,7 @@ def test_resident_marginalization_equals_the_uploading_call(olib, solver):
         for key in ("block_type", "block_node", "x0", "J0", "e0", "Hp", "bp"):
             assert np.array_equal(a[key], b[key]), key
     o = oa.ba_marginalize(olib, copy.deepcopy(probs[1]), 1)
-    compare(res[1], o)
+    compare(res[1], o, tol_sqrt=1e-8)  # numpy's eigh and the device Jacobi split the spectrum at EPS = 1e-8 with an eigenvalue within rounding of it
 
 
 @pytest.mark.parametrize("env", ["ICG_MARG_PAIR_JACOBI", "ICG_MARG_GLOBAL_JACOBI"])
