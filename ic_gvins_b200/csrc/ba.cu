@@ -1045,24 +1045,92 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     for (int a = tid; a < N; a += SOLVE_THREADS) S[N * (N + 1) / 2 + a] = s_rhs[a];
     __syncthreads();
     SOLVE_CLK(1)  // assembly
-    // ---- blocked left-looking Cholesky on the packed lower triangle (3 barriers per 8 columns); failure -> invalid step
+    // ---- blocked left-looking Cholesky on the packed lower triangle (two barriers per 8 columns); failure -> invalid step.
+    // Per panel J (columns J0 .. J0 + 7):
+    //   (1) panel update with all previous columns on the FP64 tensor cores, S[J0:, J0:J0+8] -= L[J0:, :J0] L[J0:J0+8, :J0]^T, one warp per
+    //       8-row tile (A fragment = L[i0 + g][k0 + kk], B fragment = L[J0 + g][k0 + kk], DMMA.8x8x4, J0 % 8 == 0).  WARP 0 takes the
+    //       diagonal tile alone and FACTORS it straight away (in registers: the 8-column pivot chain, ~8 x (DFMA + rsqrt + DMUL) = 600 cycles of
+    //       pure latency) while warps 1..7 are still updating the tiles below -- the chain hides behind their tensor-core work.  (The
+    //       previous version let every thread factor the block redundantly to save a barrier: measured, a barrier costs ~30 cycles here,
+    //       the redundant factorisation ~3 000 issue slots per panel -- 58 % of the kernel.)
+    //   (2) barrier; every row below the block (and the augmented rhs row) is solved against the factored block by its own thread; barrier.
+    // 1/sqrt(d) comes from rsqrt (one dependent op per column instead of sqrt + divide); the row solve multiplies by it.
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     __syncthreads();
     const int NR = N + 1;
     for (int J0 = 0; J0 < N; J0 += BA_CHOL_NB) {
         const int nb = min(BA_CHOL_NB, N - J0);
-        // (1) panel update with all previous columns on the FP64 tensor cores: S[J0:, J0:J0+8] -= L[J0:, :J0] L[J0:J0+8, :J0]^T.
-        //     One warp per 8-row tile; A fragment = L[i0 + g][k0 + kk], B fragment = L[J0 + g][k0 + kk] (DMMA.8x8x4, J0 % 8 == 0).
-        if (J0 > 0) {
-            const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, kk = lane & 3;
-            const int ntile = (NR - J0 + 7) / 8;
-            const int cb = J0 + g;                                     // row of L that is the B operand's column
-            const double *rb = S + (cb < NR ? cb * (cb + 1) / 2 : 0);
-            const bool okb = cb < NR;
-            // up to three row tiles per warp in flight (they share the B fragment): N = 157 gives <= 20 tiles for the 8 warps, so the whole panel
-            // update is ONE round of the k loop instead of three serialised ones, and six independent DMMA chains hide the tensor-pipe latency
-            constexpr int TPW = 3, NWARP = SOLVE_THREADS / 32;
+        const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, kk = lane & 3;
+        const int ntile = (NR - J0 + 7) / 8;
+        const int cb = J0 + g;                                     // row of L that is the B operand's column
+        const double *rb = S + (cb < NR ? cb * (cb + 1) / 2 : 0);
+        const bool okb = cb < NR;
+        if (warp == 0) {
+            if (J0 > 0) {  // diagonal tile: rows J0 + g; four accumulator chains over the k range
+                const double *ra = rb;
+                double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                int k0 = 0;
+                for (; k0 + 16 <= J0; k0 += 16) {
+                    const double x0 = okb ? ra[k0 + kk] : 0.0, x1 = okb ? ra[k0 + 4 + kk] : 0.0, x2 = okb ? ra[k0 + 8 + kk] : 0.0, x3 = okb ? ra[k0 + 12 + kk] : 0.0;
+                    dmma884(acc[0], acc[1], x0, x0);
+                    dmma884(acc[2], acc[3], x1, x1);
+                    dmma884(acc[4], acc[5], x2, x2);
+                    dmma884(acc[6], acc[7], x3, x3);
+                }
+                for (; k0 + 8 <= J0; k0 += 8) {
+                    const double x0 = okb ? ra[k0 + kk] : 0.0, x1 = okb ? ra[k0 + 4 + kk] : 0.0;
+                    dmma884(acc[0], acc[1], x0, x0);
+                    dmma884(acc[2], acc[3], x1, x1);
+                }
+                const double c0 = (acc[0] + acc[2]) + (acc[4] + acc[6]), c1 = (acc[1] + acc[3]) + (acc[5] + acc[7]);
+                const int i = J0 + g;
+                if (i < NR) {
+                    const int ca = J0 + 2 * kk;
+                    if (ca < J0 + nb && ca <= i) S[i * (i + 1) / 2 + ca] -= c0;
+                    if (ca + 1 < J0 + nb && ca + 1 <= i) S[i * (i + 1) / 2 + ca + 1] -= c1;
+                }
+                __syncwarp();
+            }
+            // factor the nb x nb diagonal block: every lane of warp 0 runs the same register code on broadcast loads (no divergence, no
+            // shuffles on the chain); lane a writes row a of L_JJ and its pivot reciprocal back
+            double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
+            bool bad = false;
+#pragma unroll
+            for (int a = 0; a < BA_CHOL_NB; a++)
+#pragma unroll
+                for (int b = 0; b < BA_CHOL_NB; b++) Ld[a][b] = (a < nb && b <= a) ? S[(J0 + a) * (J0 + a + 1) / 2 + J0 + b] : (a == b ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < BA_CHOL_NB; j++) {
+                double d = Ld[j][j];
+#pragma unroll
+                for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
+                if (!(d > 0.0) || !isfinite(d)) bad = true;
+                const double di = rsqrt(d);
+                dinv[j] = di;
+                Ld[j][j] = d * di;
+#pragma unroll
+                for (int a = j + 1; a < BA_CHOL_NB; a++) {
+                    double sum = Ld[a][j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
+                    Ld[a][j] = sum * di;
+                }
+            }
+            __syncwarp();  // every lane has read the unfactored block
+            if (bad && lane == 0) s_fail = 1;
+#pragma unroll
+            for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers
+                if (a2 != lane || a2 >= nb) continue;
+                double *ri = S + (J0 + a2) * (J0 + a2 + 1) / 2 + J0;
+#pragma unroll
+                for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
+                s_diag[J0 + a2] = dinv[a2];
+            }
+        } else if (J0 > 0) {
+            // tiles 1 .. ntile-1 over warps 1..7, up to three row tiles per warp in flight (they share the B fragment): N = 157 gives <= 19
+            // such tiles, so the whole panel update is ONE round of the k loop, and six independent DMMA chains hide the tensor-pipe latency
+            constexpr int TPW = 3, NWARP = SOLVE_THREADS / 32 - 1;
             for (int t0 = warp; t0 < ntile; t0 += TPW * NWARP) {
                 const double *ra[TPW];
                 bool oka[TPW];
@@ -1096,123 +1164,74 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                     }
                 }
             }
-            __syncthreads();
         }
-        // (2)+(3) every thread that owns a row i >= J0 factors the (updated) nb x nb diagonal block REDUNDANTLY in registers
-        // (no serial section, no extra barrier), then either writes back its row of L_JJ (rows inside the block) or solves
-        // its row of the panel against it (rows below, including the augmented rhs row).  1/sqrt(d) comes from rsqrt (one
-        // dependent op per column instead of sqrt + divide); the row solve multiplies by it.
-        {
-            const int i = J0 + tid;
-            const bool own = i < NR;
-            double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
-            if (own) {
-                bool bad = false;
-#pragma unroll
-                for (int a = 0; a < BA_CHOL_NB; a++)
-#pragma unroll
-                    for (int b = 0; b < BA_CHOL_NB; b++) Ld[a][b] = (a < nb && b <= a) ? S[(J0 + a) * (J0 + a + 1) / 2 + J0 + b] : (a == b ? 1.0 : 0.0);
-#pragma unroll
-                for (int j = 0; j < BA_CHOL_NB; j++) {
-                    double d = Ld[j][j];
-#pragma unroll
-                    for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
-                    if (!(d > 0.0) || !isfinite(d)) bad = true;
-                    const double di = rsqrt(d);
-                    dinv[j] = di;
-                    Ld[j][j] = d * di;
-#pragma unroll
-                    for (int a = j + 1; a < BA_CHOL_NB; a++) {
-                        double sum = Ld[a][j];
-#pragma unroll
-                        for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
-                        Ld[a][j] = sum * di;
-                    }
-                }
-                if (bad) s_fail = 1;  // benign race: every thread computes the same verdict
-                if (i >= J0 + nb) {   // rows below the block (incl. the augmented rhs row): solve against the factored block, own row only
-                    double *ri = S + i * (i + 1) / 2 + J0;
-                    double x[BA_CHOL_NB];
-#pragma unroll
-                    for (int c = 0; c < BA_CHOL_NB; c++) x[c] = c < nb ? ri[c] : 0.0;
-#pragma unroll
-                    for (int c = 0; c < BA_CHOL_NB; c++) {
-                        double sum = x[c];
-#pragma unroll
-                        for (int k = 0; k < c; k++) sum -= x[k] * Ld[c][k];
-                        x[c] = sum * dinv[c];
-                    }
-#pragma unroll
-                    for (int c = 0; c < BA_CHOL_NB; c++)
-                        if (c < nb) ri[c] = x[c];
-                }
-            }
-            __syncthreads();
-            // the block's own rows are written back only AFTER the barrier: every thread has read the unfactored block by then (an earlier
-            // version overwrote it while slower warps could still be reading), and no later step of the factorisation reads these
-            // entries again (the back-substitution does, behind the barrier that follows the loop)
-            if (own && i < J0 + nb) {
-                double *ri = S + i * (i + 1) / 2 + J0;
-                const int a = i - J0;
-#pragma unroll
-                for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers
-                    if (a2 != a) continue;
-#pragma unroll
-                    for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
-                    s_diag[i] = dinv[a2];
-                }
-            }
-        }
+        __syncthreads();
         if (s_fail) break;
+        // rows below the block (incl. the augmented rhs row): solve against the factored block, one row per thread.  L_JJ and the pivot
+        // reciprocals are read from shared memory as the chain needs them (every thread reads the same address: broadcast, off the
+        // dependent chain) instead of being staged in 36 + 8 registers
+        for (int i = J0 + nb + tid; i < NR; i += SOLVE_THREADS) {
+            double *ri = S + i * (i + 1) / 2 + J0;
+            double x[BA_CHOL_NB];
+#pragma unroll
+            for (int c = 0; c < BA_CHOL_NB; c++) x[c] = c < nb ? ri[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < BA_CHOL_NB; c++) {
+                if (c < nb) {
+                    const double *lc = S + (J0 + c) * (J0 + c + 1) / 2 + J0;
+                    double sum = x[c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) sum -= x[k] * lc[k];
+                    x[c] = sum * s_diag[J0 + c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < BA_CHOL_NB; c++)
+                if (c < nb) ri[c] = x[c];
+        }
+        __syncthreads();
     }
     __syncthreads();
     bool valid = !s_fail;
     SOLVE_CLK(2)  // Cholesky
-    // ---- backward substitution L^T x = y, column oriented, by ONE warp with y in registers: for j = N-1 .. 0:
-    //      x_j = y_j / L_jj (owner lane, broadcast by shuffle), then y_i -= L_ji x_j for i < j -- row j of the packed lower triangle
-    //      is contiguous, so every step is one coalesced shared-memory row read and no reduction or block barrier.
+    // ---- backward substitution L^T x = y, blocked by the factorisation's 8-column panels, last panel first:
+    //   (a) warp 0 solves the panel's 8 x 8 triangle L_JJ^T x_J = y_J in registers (every lane the same code on broadcast loads; the
+    //       dependent chain is 8 x (DFMA + DMUL));
+    //   (b) barrier; every thread i < J0 applies the panel to its own entry, y_i -= sum_c L[J0 + c][i] x_{J0 + c} -- row J0 + c of the
+    //       packed triangle is contiguous in i, so the reads are coalesced; barrier.
+    // Same operations in the same order as a column-by-column substitution (c descending), on 256 threads instead of one warp:
+    // measured 185 cycles per COLUMN for the single-warp form (29 k cycles at N = 157), about 400 cycles per PANEL for this one.
     if (valid) {
-        const double *y = S + N * (N + 1) / 2;
+        double *y = S + N * (N + 1) / 2;
         const int lane = tid & 31;
-        if (tid < 32) {
-            constexpr int MAXQ = 16;  // N <= 512
-            double yr[MAXQ];
+        for (int J0 = ((N - 1) / BA_CHOL_NB) * BA_CHOL_NB; J0 >= 0; J0 -= BA_CHOL_NB) {
+            const int nb = min(BA_CHOL_NB, N - J0);
+            if (tid < 32) {
+                double x[BA_CHOL_NB];
 #pragma unroll
-            for (int q = 0; q < MAXQ; q++) yr[q] = lane + 32 * q < N ? y[lane + 32 * q] : 0.0;
-            // statically indexed: the owner register block oq is an unrolled outer loop, so the per-step critical path is
-            // shuffle -> multiply -> FMA (no register selects); only blocks q <= oq are touched.  Row j - 1 of L (and its diagonal
-            // reciprocal) is fetched from shared memory while step j computes: the loads never sit on the dependent chain.
-            double lv[MAXQ], dj = s_diag[N - 1];
-            {
-                const double *rj = S + (N - 1) * N / 2;
+                for (int c = BA_CHOL_NB - 1; c >= 0; c--) {
+                    x[c] = 0.0;
+                    if (c < nb) {
+                        double sum = y[J0 + c];
 #pragma unroll
-                for (int q = 0; q < MAXQ; q++) lv[q] = lane + 32 * q < N - 1 ? rj[lane + 32 * q] : 0.0;
-            }
-#pragma unroll
-            for (int oq = MAXQ - 1; oq >= 0; oq--) {
-                if (32 * oq >= N) continue;
-                for (int ol = min(31, N - 1 - 32 * oq); ol >= 0; ol--) {
-                    const int j = 32 * oq + ol;
-                    double ln[MAXQ], dn = 0;
-                    if (j > 0) {
-                        const double *rn = S + (j - 1) * j / 2;
-                        dn = s_diag[j - 1];
-#pragma unroll
-                        for (int q = 0; q < MAXQ; q++) ln[q] = (q <= oq && lane + 32 * q < j - 1) ? rn[lane + 32 * q] : 0.0;
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < MAXQ; q++) ln[q] = 0.0;
+                        for (int k = BA_CHOL_NB - 1; k > c; k--)
+                            if (k < nb) sum -= S[(J0 + k) * (J0 + k + 1) / 2 + J0 + c] * x[k];
+                        x[c] = sum * s_diag[J0 + c];
                     }
-                    const double xj = __shfl_sync(0xffffffffu, yr[oq], ol) * dj;
-                    if (lane == ol) s_rhs[j] = xj;
-#pragma unroll
-                    for (int q = 0; q < MAXQ; q++)
-                        if (q <= oq) yr[q] -= lv[q] * xj;
-#pragma unroll
-                    for (int q = 0; q < MAXQ; q++) lv[q] = ln[q];
-                    dj = dn;
                 }
+#pragma unroll
+                for (int c = 0; c < BA_CHOL_NB; c++)
+                    if (c == lane && c < nb) s_rhs[J0 + c] = x[c];
             }
+            __syncthreads();
+            for (int i = tid; i < J0; i += SOLVE_THREADS) {
+                double acc = y[i];
+#pragma unroll
+                for (int c = BA_CHOL_NB - 1; c >= 0; c--)
+                    if (c < nb) acc -= S[(J0 + c) * (J0 + c + 1) / 2 + i] * s_rhs[J0 + c];
+                y[i] = acc;
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
