@@ -881,7 +881,7 @@ __device__ __forceinline__ double block_max(double v, double *s_red) {
     return s_red[32];
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, int use_global_S) {
+__global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D) {
     extern __shared__ double sm[];
     const int w = blockIdx.x, tid = threadIdx.x;
     LmState &st = D.st[w];
@@ -906,7 +906,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     double *s_rhs = s_g + C.NS;         // N   -> step' (scaled space)
     double *s_d2 = s_rhs + C.NS;        // N
     double *s_diag = s_d2 + C.NS;       // N   Cholesky diagonal
-    double *S = use_global_S ? D.Sglobal + (size_t) w * ((size_t) (C.N + 1) * (C.N + 2) / 2) : s_diag + C.NS;  // packed lower, N + 1 rows
+    // packed lower triangle, N + 1 rows, ALWAYS in shared memory (systems that do not fit are driven by the split pipeline, ba_solve_cam): a
+    // pointer that could also be global made every access a generic LD / ST (longer latency, long-scoreboard tracked)
+    double *S = s_diag + C.NS;
     const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS, *Hs = D.Hs + (size_t) w * C.NS * C.NS;
     // Reduction operands.  Landmark-sharded solve: the packed, all-reduced buffer (identical on every shard, written by ba_pack1).
     // Single GPU: read the producers' outputs directly (vision Gram matrix; the BA_SPLIT_W Schur partials summed in fixed order).
@@ -989,7 +991,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
     // The reduced camera matrix (ba_hsum's output, row i contiguous) goes global -> packed shared rows with 8-byte cp.async: every element of
     // the lower triangle is in flight at once (one L2 round trip for the whole matrix instead of one per row and warp), the vector part below
     // overlaps the copy, and the Jacobi scaling + LM diagonal are applied in place afterwards.
-    const bool async_fill = !use_global_S;
+    constexpr bool async_fill = true;
     if (async_fill) {
         for (int i = tid >> 5; i < N; i += SOLVE_THREADS / 32) {
             const double *src = (i < NCV ? Hs : Hc) + (size_t) i * C.NS;
@@ -1063,6 +1065,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
         const int nb = min(BA_CHOL_NB, N - J0);
         const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, kk = lane & 3;
         const int ntile = (NR - J0 + 7) / 8;
+        const unsigned long long pc0 = D.clk ? clock64() : 0ull;  // profiling: warp 0's own work / the row-solve phase of this panel
         const int cb = J0 + g;                                     // row of L that is the B operand's column
         const double *rb = S + (cb < NR ? cb * (cb + 1) / 2 : 0);
         const bool okb = cb < NR;
@@ -1127,6 +1130,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                 for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
                 s_diag[J0 + a2] = dinv[a2];
             }
+            if (D.clk && w == 0 && tid == 0) atomicAdd(&D.clk[6], clock64() - pc0), atomicAdd(&D.clk[14], 1ull);
         } else if (J0 > 0) {
             // tiles 1 .. ntile-1 over warps 1..7, up to three row tiles per warp in flight (they share the B fragment): N = 157 gives <= 19
             // such tiles, so the whole panel update is ONE round of the k loop, and six independent DMMA chains hide the tensor-pipe latency
@@ -1166,6 +1170,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
             }
         }
         __syncthreads();
+        const unsigned long long pc1 = D.clk ? clock64() : 0ull;
         if (s_fail) break;
         // rows below the block (incl. the augmented rhs row): solve against the factored block, one row per thread.  L_JJ and the pivot
         // reciprocals are read from shared memory as the chain needs them (every thread reads the same address: broadcast, off the
@@ -1190,6 +1195,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D, 
                 if (c < nb) ri[c] = x[c];
         }
         __syncthreads();
+        if (D.clk && w == 0 && tid == 0) atomicAdd(&D.clk[7], clock64() - pc1), atomicAdd(&D.clk[15], 1ull);
     }
     __syncthreads();
     bool valid = !s_fail;
@@ -1700,6 +1706,7 @@ struct icg_ba {
     bool own_stream = false;
     int nblk_vis = 0;
     int cur_windows = 0;
+    int cam_threads = 320;  // CTA size of the camera-only factor kernels (<= CAM_THREADS; ICG_BA_CAM_THREADS)
     size_t smem_cam, smem_solve, smem_schur;
     int ld_schur;
     int use_global_S;
@@ -1860,6 +1867,7 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ICG_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->prof = getenv("ICG_BA_PROFILE") != nullptr;
+    if (getenv("ICG_BA_CAM_THREADS")) h->cam_threads = std::min(CAM_THREADS, std::max(128, atoi(getenv("ICG_BA_CAM_THREADS")) & ~31));
     if (h->prof) {
         double *ck = nullptr;
         if (dmalloc(h, &ck, 16) != ICG_OK) return ICG_ENOMEM;
@@ -2217,9 +2225,10 @@ static void prof_print(icg_ba *h) {
     if (h->D.clk) {
         unsigned long long ck[16];
         if (cudaMemcpy(ck, h->D.clk, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
-            static const char *nm[6] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions"};
+            static const char *nm[8] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions",
+                                        "  per panel: warp 0 tile+factor", "  per panel: row solve phase"};
             fprintf(stderr, "[icg_ba profile] ba_solve phases of window 0 (SM cycles per call, mean):\n");
-            for (int k = 0; k < 6; k++)
+            for (int k = 0; k < 8; k++)
                 if (ck[8 + k]) fprintf(stderr, "  %-28s %9.0f cycles\n", nm[k], (double) ck[k] / (double) ck[8 + k]);
         }
     }
@@ -2244,7 +2253,7 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         if (cam_fork == 0) {
             ICG_CUDA(cudaEventRecord(h->ev_fork, s));
             ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
-            ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+            ba_lin_cam<<<n, h->cam_threads, h->smem_cam, h->stream_cam>>>(C, D);
             ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         }
         prof_mark(h, 0);
@@ -2253,7 +2262,7 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         if (cam_fork != 0) {
             ICG_CUDA(cudaEventRecord(h->ev_fork, s));
             ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
-            ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+            ba_lin_cam<<<n, h->cam_threads, h->smem_cam, h->stream_cam>>>(C, D);
             ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         }
         // (measured: one fused launch or two streams are both slower -- the Schur CTAs' shared memory throttles the latency-bound
@@ -2278,13 +2287,13 @@ static int enqueue_lm(icg_ba *h, int max_num_iterations) {
         }
         ba_hsum<<<dim3(((C.NCV + 1) * (C.NCV + 1) + 255) / 256, n), 256, 0, s>>>(C, D);
         prof_mark(h, 12);
-        ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D, h->use_global_S);
+        ba_solve<<<n, SOLVE_THREADS, h->smem_solve, s>>>(C, D);
         prof_mark(h, 8);
         count_launch(h->comm ? 8 : 6);
         if (it == max_num_iterations) break;
         ICG_CUDA(cudaEventRecord(h->ev_fork, s));
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
-        ba_cost_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D, h->nblk_vis);
+        ba_cost_cam<<<n, h->cam_threads, h->smem_cam, h->stream_cam>>>(C, D, h->nblk_vis);
         ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         ba_cost<<<g_cost, 256, 0, s>>>(C, D, h->nblk_vis);
         ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
@@ -2393,7 +2402,7 @@ static int enqueue_lm_split(icg_ba *h, int max_num_iterations) {
         const unsigned long long epoch = ++h->epoch;
         ICG_CUDA(cudaEventRecord(h->ev_fork, s));
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
-        ba_lin_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D);
+        ba_lin_cam<<<n, h->cam_threads, h->smem_cam, h->stream_cam>>>(C, D);
         ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         prof_mark(h, 0);
         ba_lin_vis<<<g_vis, 128, LV_SMEM, s>>>(C, D);
@@ -2418,7 +2427,7 @@ static int enqueue_lm_split(icg_ba *h, int max_num_iterations) {
         if (it == max_num_iterations) break;
         ICG_CUDA(cudaEventRecord(h->ev_fork, s));
         ICG_CUDA(cudaStreamWaitEvent(h->stream_cam, h->ev_fork, 0));
-        ba_cost_cam<<<n, CAM_THREADS, h->smem_cam, h->stream_cam>>>(C, D, h->nblk_vis);
+        ba_cost_cam<<<n, h->cam_threads, h->smem_cam, h->stream_cam>>>(C, D, h->nblk_vis);
         ICG_CUDA(cudaEventRecord(h->ev_join, h->stream_cam));
         ba_cost<<<g_cost, 256, 0, s>>>(C, D, h->nblk_vis);
         ICG_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
