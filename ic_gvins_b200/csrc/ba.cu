@@ -1131,11 +1131,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D) 
                 s_diag[J0 + a2] = dinv[a2];
             }
             if (D.clk && w == 0 && tid == 0) atomicAdd(&D.clk[6], clock64() - pc0), atomicAdd(&D.clk[14], 1ull);
-        } else if (J0 > 0) {
-            // tiles 1 .. ntile-1 over warps 1..7, up to three row tiles per warp in flight (they share the B fragment): N = 157 gives <= 19
-            // such tiles, so the whole panel update is ONE round of the k loop, and six independent DMMA chains hide the tensor-pipe latency
-            constexpr int TPW = 3, NWARP = SOLVE_THREADS / 32 - 1;
-            for (int t0 = warp; t0 < ntile; t0 += TPW * NWARP) {
+        } else if (J0 > 0 && warp != 4) {
+            // tiles 1 .. ntile-1 over warps 1, 2, 3, 5, 6, 7, up to four row tiles per warp in flight (they share the B fragment): N = 157 gives
+            // <= 19 such tiles, so the whole panel update is ONE round of the k loop, and eight independent DMMA chains hide the tensor-pipe
+            // latency.  Warp 4 sits out: it shares warp 0's scheduler and FP64 pipe (warp id mod 4), and every DMMA holds that pipe for 16
+            // cycles -- measured, warp 0's 130-operation pivot chain took 3 600 cycles per panel queuing behind warp 4's tiles.
+            constexpr int TPW = 4, NWARP = 6;
+            const int wslot = warp < 4 ? warp - 1 : warp - 2;  // 0..5
+            for (int t0 = 1 + wslot; t0 < ntile; t0 += TPW * NWARP) {
                 const double *ra[TPW];
                 bool oka[TPW];
                 double acc[TPW][4];
@@ -1270,7 +1273,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D) 
     {
         const int lane = tid & 31, warp = tid >> 5;
         constexpr int LB = 8;  // landmarks in flight per warp (the coupling rows come from L2: 24 loads per lane outstanding)
+        // after the transposing reduction below, lane holds the dot product of landmark l0 + lu; its per-landmark scalars are loaded at the top
+        // of the round, together with the coupling rows (one L2 round trip per round instead of two)
+        const int lu = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
         for (int l0 = LB * warp; l0 < L; l0 += LB * (SOLVE_THREADS / 32)) {
+            const int l = l0 + lu;
+            const bool lok = l < L;
+            const double sl = lok ? scale_l[l] : 0.0, hh = lok ? hl[l] : 0.0, gg = lok ? gl[l] : 0.0;
             double d[LB];
 #pragma unroll
             for (int u = 0; u < LB; u++) d[u] = 0;
@@ -1279,20 +1288,38 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D) 
 #pragma unroll
                 for (int u = 0; u < LB; u++) d[u] += (l0 + u < L ? AW[(size_t) (l0 + u) * C.NCA + c] : 0.0) * sx;
             }
-            double mine = 0;  // lane u keeps landmark l0 + u
+            const double hs = sl * sl * hh, d2 = fmin(fmax(hs, 1e-6), 1e32) / radius, den = hs + d2, sg = sl * gg;
+            // transposing butterfly: 8 values x 32 lanes -> 1 value per lane in 4 + 2 + 1 + 1 + 1 exchanges (a plain butterfly needs 8 x 5)
+            double e4[4], e2[2];
+            {
+                const bool hi = lane & 16;
 #pragma unroll
-            for (int u = 0; u < LB; u++) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
-                if (lane == u) mine = d[u];
+                for (int u = 0; u < 4; u++) {
+                    const double keep = hi ? d[u + 4] : d[u], send = hi ? d[u] : d[u + 4];
+                    e4[u] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
             }
-            if (lane < LB && l0 + lane < L) {
-                const int l = l0 + lane;
-                double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
-                double sp = (-sl * gl[l] - sl * mine) / (hs + d2);
+            {
+                const bool hi = lane & 8;
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const double keep = hi ? e4[u + 2] : e4[u], send = hi ? e4[u] : e4[u + 2];
+                    e2[u] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+            }
+            double mine;
+            {
+                const bool hi = lane & 4;
+                const double keep = hi ? e2[1] : e2[0], send = hi ? e2[0] : e2[1];
+                mine = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+            mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+            if ((lane & 3) == 0 && lok) {
+                double sp = (-sg - sl * mine) / den;
                 finite = finite && isfinite(sp);
                 step_l[l] = sp;
-                part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
+                part += -0.5 * sp * sg + 0.5 * d2 * sp * sp;
             }
         }
     }
@@ -1706,7 +1733,8 @@ struct icg_ba {
     bool own_stream = false;
     int nblk_vis = 0;
     int cur_windows = 0;
-    int cam_threads = 320;  // CTA size of the camera-only factor kernels (<= CAM_THREADS; ICG_BA_CAM_THREADS)
+    int cam_threads = 160;  // CTA size of the camera-only factor kernels (<= CAM_THREADS; ICG_BA_CAM_THREADS): 160 x 168 registers leave room for two
+                            // ba_lin_vis CTAs on the SM (320 threads take 82 % of the register file: nothing else fits beside them)
     size_t smem_cam, smem_solve, smem_schur;
     int ld_schur;
     int use_global_S;
