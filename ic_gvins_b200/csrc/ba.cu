@@ -591,6 +591,13 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
     double *s_pp = s_misc, *s_mp = s_misc + 48, *s_dx = s_mp + 16, *s_y = s_dx + C.R, *s_cost = s_y + C.R;
     int *s_colmap = (int *) (s_cost + 8);
     __shared__ double s_total;
+    unsigned long long cclk = D.clk ? clock64() : 0ull;  // profiling handles: phase clocks of the linearising call, window 0
+#define CAM_CLK(k)                                                 \
+    if (D.clk && lin && w == 0 && tid == 0) {                      \
+        const unsigned long long t_ = clock64();                   \
+        atomicAdd(&D.clk[16 + (k)], t_ - cclk), atomicAdd(&D.clk[24 + (k)], 1ull); \
+        cclk = t_;                                                 \
+    }
     // ---- phase 1: evaluate
     for (int k = warp; k < dm.n_imu; k += nwarps)
         imu_factor_warp(D.imu_blob + ((size_t) w * C.K + k) * ICG_IMU_BLOB_DOUBLES, D.imu_U + ((size_t) w * C.K + k) * 225, pose + k * 7, mix + k * 9,
@@ -616,6 +623,7 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
         for (int k = 0; k < 9; k++) s_mp[k] = (mix[k] - D.mix_prior[(size_t) w * 9 + k]) / D.mix_prior_std[(size_t) w * 9 + k];
     if (dm.marg_r > 0) marg_dx(C, D, w, dm, pose, mix, ext, s_dx, s_colmap, tid, blockDim.x);
     __syncthreads();
+    CAM_CLK(0)  // factor evaluation
     const double *H0 = D.marg_H0 + (size_t) w * C.R * C.R, *b0 = D.marg_b0 + (size_t) w * C.R;
     if (dm.marg_r > 0) {
         for (int i = tid; i < dm.marg_r; i += blockDim.x) {
@@ -663,10 +671,12 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
         __syncthreads();
         return s_total;
     }
+    CAM_CLK(1)  // prior product + cost
     // ---- phase 2: H_c = sum J^T J, g_c = sum J^T r   (every entry has exactly one writer per round -> deterministic)
     for (int e = tid; e < N * C.NS; e += blockDim.x) Hc[e] = 0;
     for (int e = tid; e < N; e += blockDim.x) gc[e] = 0;
     __syncthreads();
+    CAM_CLK(2)  // zero H_c
     if (dm.marg_r > 0) {
         const int r = dm.marg_r;
         for (int e = tid; e < r * r; e += blockDim.x) {
@@ -678,6 +688,7 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
             if (s_colmap[i] >= 0) gc[s_colmap[i]] = b0[i] + s_y[i];
     }
     __syncthreads();
+    CAM_CLK(3)  // prior blocks
     for (int parity = 0; parity < 2; parity++) {  // IMU factors k and k+2 touch disjoint nodes
         const int nf = (dm.n_imu - parity + 1) / 2;
         for (int e = tid; e < nf * 930; e += blockDim.x) {
@@ -698,6 +709,7 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
         }
         __syncthreads();
     }
+    CAM_CLK(4)  // IMU J^T J
     // pose-diagonal blocks: GNSS + pose prior; mix-diagonal: bias-magnitude factor + mix prior
     for (int e = tid; e < K * 42; e += blockDim.x) {
         const int k = e / 42, q = e % 42;
@@ -739,6 +751,8 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
         gc[col_mix(K, 0) + tid] += s_mp[tid] / sd;
     }
     __syncthreads();
+    CAM_CLK(5)  // GNSS / prior diagonal blocks
+#undef CAM_CLK
     return s_total;
 }
 
@@ -1898,7 +1912,7 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     if (getenv("ICG_BA_CAM_THREADS")) h->cam_threads = std::min(CAM_THREADS, std::max(128, atoi(getenv("ICG_BA_CAM_THREADS")) & ~31));
     if (h->prof) {
         double *ck = nullptr;
-        if (dmalloc(h, &ck, 16) != ICG_OK) return ICG_ENOMEM;
+        if (dmalloc(h, &ck, 32) != ICG_OK) return ICG_ENOMEM;
         h->D.clk = (unsigned long long *) ck;
     }
     if (getenv("ICG_BA_PROFILE_SKIP")) h->prof_skip = atoi(getenv("ICG_BA_PROFILE_SKIP"));
@@ -2251,8 +2265,12 @@ static void prof_print(icg_ba *h) {
         if (h->prof_cnt[t])
             fprintf(stderr, "  %-28s %9.3f ms  %8.1f us  %5.1f %%\n", PROF_NAMES[t], h->prof_ms[t], 1e3 * h->prof_ms[t] / h->prof_cnt[t], 100.0 * h->prof_ms[t] / tot);
     if (h->D.clk) {
-        unsigned long long ck[16];
+        unsigned long long ck[32];
         if (cudaMemcpy(ck, h->D.clk, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            static const char *cn[6] = {"factor evaluation", "prior product + cost", "zero H_c", "prior blocks", "IMU J^T J", "GNSS / prior diagonals"};
+            fprintf(stderr, "[icg_ba profile] ba_lin_cam phases of window 0 (SM cycles per call, mean):\n");
+            for (int k = 0; k < 6; k++)
+                if (ck[24 + k]) fprintf(stderr, "  %-28s %9.0f cycles\n", cn[k], (double) ck[16 + k] / (double) ck[24 + k]);
             static const char *nm[8] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions",
                                         "  per panel: warp 0 tile+factor", "  per panel: row solve phase"};
             fprintf(stderr, "[icg_ba profile] ba_solve phases of window 0 (SM cycles per call, mean):\n");
