@@ -43,29 +43,32 @@ def _stale(out: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, prof: bool = False) -> str:
+    """prof=True builds libicgvins_b200_prof.so beside the product library: same sources with -DICG_BA_PHASE_CLOCKS (in-kernel phase clocks of
+    ba_solve / ba_lin_cam; the instrumentation perturbs register allocation, so it never goes into the product build)."""
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".hpp"))]
     headers.append(os.path.join(HERE, "..", "include", "icgvins_b200.h"))
     objs = []
+    lib = LIB.replace(".so", "_prof.so") if prof else LIB
     for src, extra in SOURCES.items():
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", "_prof.o" if prof else ".o"))
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+            cmd = [nvcc] + ARCH + COMMON + extra + (["-DICG_BA_PHASE_CLOCKS"] if prof else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
             if verbose:
                 print(" ".join(cmd))
             subprocess.run(cmd, check=True)
         objs.append(obj)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + LINK_LIBS
+    if force or _stale(lib, objs):
+        cmd = [nvcc] + ARCH + ["-shared", "-o", lib] + objs + LINK_LIBS
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, prof="--prof" in sys.argv))

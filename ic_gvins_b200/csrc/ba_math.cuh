@@ -293,7 +293,9 @@ struct ImuMid {
     Q qb0b1, corrected_q;
     M3 cnb0;
 };
-BAM_HD void imu_residual_raw(const double *b, const double *pose0, const double *mix0, const double *pose1, const double *mix1, double *r, ImuMid &M) {
+// mode_slot: where the mode word sits in `b` (IB_MODE in a full blob; callers that stage only the head of the blob pass their own slot)
+BAM_HD void imu_residual_raw(const double *b, const double *pose0, const double *mix0, const double *pose1, const double *mix1, double *r, ImuMid &M,
+                             int mode_slot = IB_MODE) {
     V3 p0 = pose_p(pose0), p1 = pose_p(pose1);
     Q q0 = pose_q(pose0), q1 = pose_q(pose1);
     V3 v0 = mk(mix0[0], mix0[1], mix0[2]), bg0 = mk(mix0[3], mix0[4], mix0[5]), ba0 = mk(mix0[6], mix0[7], mix0[8]);
@@ -324,7 +326,7 @@ BAM_HD void imu_residual_raw(const double *b, const double *pose0, const double 
     M.cnb0 = qmat(qinv(q0));
     M.qb0b1 = qmul(qmul(qinv(q1), qnn), q0);
     V3 rp = mul(M.cnb0, M.dpn) - corrected_p, rv = mul(M.cnb0, M.dvn) - corrected_v, rq = 2.0 * qv(qmul(M.qb0b1, M.corrected_q));
-    if (b[IB_MODE] != 0.0) {
+    if (b[mode_slot] != 0.0) {
         // PreintegrationNormal::evaluate (IG/preintegration/preintegration_normal.cc:38-75): iewn = 0 in the blob, so dpn / dvn / cnb0 above
         // are already its terms; the attitude residual is 2 (corrected_q^-1 q0^-1 q1).vec().  M.qb0b1 carries q1^-1 q0 for the Jacobians.
         rq = 2.0 * qv(qmul(qmul(qinv(M.corrected_q), qinv(q0)), q1));
@@ -336,7 +338,7 @@ BAM_HD void imu_residual_raw(const double *b, const double *pose0, const double 
 
 // Unwhitened IMU Jacobian in LOCAL coordinates, 15 x 30 row-major, columns [pose0 6 | mix0 9 | pose1 6 | mix1 9]
 // (residualJacobianPose0/Mix0/Pose1/Mix1, IG/preintegration/preintegration_earth.cc:92-164).
-BAM_HD void imu_jacobian_raw(const double *b, const ImuMid &M, double *J /* 450, zero-initialised by the caller */) {
+BAM_HD void imu_jacobian_raw(const double *b, const ImuMid &M, double *J /* 450, zero-initialised by the caller */, int mode_slot = IB_MODE) {
     const double *Jc = b + IB_JAC;
     auto blk = [&](int r0, int c0) {
         M3 m;
@@ -385,7 +387,7 @@ BAM_HD void imu_jacobian_raw(const double *b, const ImuMid &M, double *J /* 450,
     put(3, 21, M.cnb0);
     put(9, 24, ident());
     put(12, 27, ident());
-    if (b[IB_MODE] != 0.0) {
+    if (b[mode_slot] != 0.0) {
         // PreintegrationNormal::residualJacobianPose0/Pose1/Mix0 (preintegration_normal.cc:77-140): only the attitude rows differ from the
         // Earth form evaluated with iewn = 0 (M.qb0b1 = q1^-1 q0):
         //   pose0 (6,3) = -(quaternionleft(q1^-1 q0) quaternionright(corrected_q)).bottomRight
