@@ -585,18 +585,14 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int K = dm.K, N = 15 * K + 7;
     double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gc = D.gc + (size_t) w * C.NS;
-    double *s_imu = smem;                              // n_imu * 480: whitened residual 15 | raw residual 15 | Jacobian 15 x 30
-    double *s_blob = s_imu + (size_t) C.K * 480;       // n_imu * 256: head of every factor's blob (state, bias Jacobian blocks, mode)
-    double *s_U = s_blob + (size_t) C.K * 256;         // n_imu * 228: sqrt information (upper triangular 15 x 15)
-    double *s_gnss = s_U + (size_t) C.K * 228;         // G * 24 : r[3] J[18] cost scale
+    double *s_imu = smem;                              // n_imu * 480
+    double *s_gnss = s_imu + (size_t) C.K * 480;       // G * 24 : r[3] J[18] cost scale
     double *s_misc = s_gnss + (size_t) C.G * 24;       // pose prior r[6] J[36] | mix prior r[9] | marg dx[R] y[R] | costs
     double *s_pp = s_misc, *s_mp = s_misc + 48, *s_dx = s_mp + 16, *s_y = s_dx + C.R, *s_cost = s_y + C.R;
     int *s_colmap = (int *) (s_cost + 8);
     __shared__ double s_total;
 #ifdef ICG_BA_PHASE_CLOCKS
     unsigned long long cclk = D.clk ? clock64() : 0ull;  // profiling build: phase clocks of the linearising call, window 0
-#endif
-#ifdef ICG_BA_PHASE_CLOCKS
 #define CAM_CLK(k)                                                 \
     if (D.clk && lin && w == 0 && tid == 0) {                      \
         const unsigned long long t_ = clock64();                   \
@@ -606,36 +602,11 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
 #else
 #define CAM_CLK(k)
 #endif
-    // ---- phase 1: evaluate.  The unwhitened IMU residual + Jacobian is a long single-thread computation (quaternion algebra, two sincos):
-    //      ONE LANE PER FACTOR of warp 0 runs it for all n_imu factors at once, on blob heads staged in shared memory (a warp per factor with
-    //      only lane 0 working, straight from global memory, cost 23 k cycles per factor and round: measured 46 k of the kernel's 123 k at
-    //      five warps).  Meanwhile the other warps stage the sqrt-information matrices; the whitening then runs on all threads.
-    (void) nwarps;
-    for (int e = tid; e < dm.n_imu * 256; e += blockDim.x) {
-        const int k = e >> 8, q = e & 255;  // doubles 0..251 + the mode word (blob[477]) in slot 252
-        s_blob[e] = q < 252 ? D.imu_blob[((size_t) w * C.K + k) * ICG_IMU_BLOB_DOUBLES + q] : q == 252 ? D.imu_blob[((size_t) w * C.K + k) * ICG_IMU_BLOB_DOUBLES + IB_MODE] : 0.0;
-    }
-    if (lin)
-        for (int e = tid; e < dm.n_imu * 480; e += blockDim.x)
-            if (e % 480 >= 30) s_imu[e] = 0;  // raw Jacobians: the evaluation writes the non-zero blocks only
-    __syncthreads();
-    if (warp == 0) {
-        if (lane < dm.n_imu) {
-            const int k = lane;
-            ImuMid M;
-            double *rw = s_imu + (size_t) k * 480;
-            imu_residual_raw(s_blob + k * 256, pose + k * 7, mix + k * 9, pose + (k + 1) * 7, mix + (k + 1) * 9, rw + 15, M, 252);
-            if (lin) imu_jacobian_raw(s_blob + k * 256, M, rw + 30, 252);
-        }
-    } else {
-        for (int e = tid - 32; e < dm.n_imu * 225; e += blockDim.x - 32) {
-            const int k = e / 225, q = e - 225 * k;
-            s_U[k * 228 + q] = D.imu_U[((size_t) w * C.K + k) * 225 + q];
-        }
-    }
-    const int gt = tid - 32;  // GNSS factors on warp 1 (warp 0 is busy with the IMU chain)
-    if (gt >= 0 && gt < dm.n_gnss) {
-        const int tid = gt;
+    // ---- phase 1: evaluate
+    for (int k = warp; k < dm.n_imu; k += nwarps)
+        imu_factor_warp(D.imu_blob + ((size_t) w * C.K + k) * ICG_IMU_BLOB_DOUBLES, D.imu_U + ((size_t) w * C.K + k) * 225, pose + k * 7, mix + k * 9,
+                        pose + (k + 1) * 7, mix + (k + 1) * 9, lin, s_imu + (size_t) k * 480, s_imu + (size_t) k * 480 + 30, lane);
+    if (tid < dm.n_gnss) {
         const int nd = D.gnss_node[(size_t) w * C.G + tid];
         double *o = s_gnss + tid * 24;
         gnss_eval(pose + nd * 7, D.gnss_blh + ((size_t) w * C.G + tid) * 3, D.gnss_std + ((size_t) w * C.G + tid) * 3, D.lever + (size_t) w * 3, lin, o, o + 3);
@@ -655,28 +626,6 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
     if (tid == 96 && dm.has_mix_prior)
         for (int k = 0; k < 9; k++) s_mp[k] = (mix[k] - D.mix_prior[(size_t) w * 9 + k]) / D.mix_prior_std[(size_t) w * 9 + k];
     if (dm.marg_r > 0) marg_dx(C, D, w, dm, pose, mix, ext, s_dx, s_colmap, tid, blockDim.x);
-    __syncthreads();
-    // whitening by the upper-triangular sqrt information, one thread per (factor, Jacobian column) / (factor, residual):
-    // out[i] = sum_{k >= i} U[i][k] in[k], in place, rows ascending (row i is final before any later row reads it: they read k > i only)
-    for (int t = tid; t < dm.n_imu * 31; t += blockDim.x) {
-        const int k = t / 31, c = t - 31 * k;
-        const double *U = s_U + k * 228;
-        double *rw = s_imu + (size_t) k * 480, *Jw = rw + 30;
-        if (c < 30) {
-            if (lin)
-                for (int i = 0; i < 15; i++) {
-                    double acc = 0;
-                    for (int k2 = i; k2 < 15; k2++) acc += U[i * 15 + k2] * Jw[k2 * 30 + c];
-                    Jw[i * 30 + c] = acc;
-                }
-        } else {
-            for (int i = 0; i < 15; i++) {
-                double acc = 0;
-                for (int k2 = i; k2 < 15; k2++) acc += U[i * 15 + k2] * rw[15 + k2];
-                rw[i] = acc;
-            }
-        }
-    }
     __syncthreads();
     CAM_CLK(0)  // factor evaluation
     const double *H0 = D.marg_H0 + (size_t) w * C.R * C.R, *b0 = D.marg_b0 + (size_t) w * C.R;
@@ -745,43 +694,22 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
     __syncthreads();
     CAM_CLK(3)  // prior blocks
     for (int parity = 0; parity < 2; parity++) {  // IMU factors k and k+2 touch disjoint nodes
-        const int nf = (dm.n_imu - parity + 1) / 2, tot = nf * 930;
-        // four entries per thread and pass: the read-modify-write of H_c is a dependent L2 round trip, so the four loads are issued together
-        // (measured with one entry at a time: 50 k cycles of the kernel's 123 k were this loop waiting on its own loads)
-        constexpr int EB = 4;
-        for (int e0 = tid; e0 < tot; e0 += EB * blockDim.x) {
-            double *dst[EB], old[EB], sum[EB];
-#pragma unroll
-            for (int u = 0; u < EB; u++) {
-                const int e = e0 + u * blockDim.x;
-                dst[u] = nullptr, old[u] = 0, sum[u] = 0;
-                if (e < tot) {
-                    const int k = parity + 2 * (e / 930), q = e % 930;
-                    auto gcol = [&](int c) { return c < 6 ? col_pose(k) + c : c < 15 ? col_mix(K, k) + c - 6 : c < 21 ? col_pose(k + 1) + c - 15 : col_mix(K, k + 1) + c - 21; };
-                    dst[u] = q < 900 ? Hc + (size_t) gcol(q / 30) * C.NS + gcol(q % 30) : gc + gcol(q - 900);
-                    old[u] = *dst[u];
-                }
+        const int nf = (dm.n_imu - parity + 1) / 2;
+        for (int e = tid; e < nf * 930; e += blockDim.x) {
+            const int k = parity + 2 * (e / 930), q = e % 930;
+            const double *rw = s_imu + (size_t) k * 480, *Jw = rw + 30;
+            auto gcol = [&](int c) { return c < 6 ? col_pose(k) + c : c < 15 ? col_mix(K, k) + c - 6 : c < 21 ? col_pose(k + 1) + c - 15 : col_mix(K, k + 1) + c - 21; };
+            if (q < 900) {
+                int a = q / 30, b = q - a * 30;
+                double s = 0;
+                for (int m = 0; m < 15; m++) s += Jw[m * 30 + a] * Jw[m * 30 + b];
+                Hc[(size_t) gcol(a) * C.NS + gcol(b)] += s;
+            } else {
+                int a = q - 900;
+                double s = 0;
+                for (int m = 0; m < 15; m++) s += Jw[m * 30 + a] * rw[m];
+                gc[gcol(a)] += s;
             }
-#pragma unroll
-            for (int u = 0; u < EB; u++) {
-                const int e = e0 + u * blockDim.x;
-                if (e < tot) {
-                    const int k = parity + 2 * (e / 930), q = e % 930;
-                    const double *rw = s_imu + (size_t) k * 480, *Jw = rw + 30;
-                    double sacc = 0;
-                    if (q < 900) {
-                        const int a = q / 30, b = q - a * 30;
-                        for (int m = 0; m < 15; m++) sacc += Jw[m * 30 + a] * Jw[m * 30 + b];
-                    } else {
-                        const int a = q - 900;
-                        for (int m = 0; m < 15; m++) sacc += Jw[m * 30 + a] * rw[m];
-                    }
-                    sum[u] = sacc;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < EB; u++)
-                if (dst[u]) *dst[u] = old[u] + sum[u];
         }
         __syncthreads();
     }
@@ -833,7 +761,7 @@ __device__ double cam_factors(const BaCaps &C, const BaDev &D, int w, const WinD
 }
 
 constexpr int CAM_THREADS = 320;  // 10 warps: the K - 1 = 9 IMU factors of a 10-node window are evaluated in one round (warp per factor)
-__global__ void __launch_bounds__(CAM_THREADS, 1) ba_lin_cam(BaCaps C, BaDev D) {
+__global__ void __launch_bounds__(CAM_THREADS) ba_lin_cam(BaCaps C, BaDev D) {
     extern __shared__ double smem[];
     const int w = blockIdx.x;
     LmState &st = D.st[w];
@@ -1480,7 +1408,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D) 
 
 // ------------------------------------------------------------------------------------------------ candidate cost
 // camera-only factors at the candidate point (one CTA per window; runs beside the vision blocks on the handle's second stream)
-__global__ void __launch_bounds__(CAM_THREADS, 1) ba_cost_cam(BaCaps C, BaDev D, int nblk_vis) {
+__global__ void __launch_bounds__(CAM_THREADS) ba_cost_cam(BaCaps C, BaDev D, int nblk_vis) {
     extern __shared__ double smem[];
     const int w = blockIdx.x;
     const LmState &st = D.st[w];
@@ -2054,7 +1982,7 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     }
     if (rc != ICG_OK) return rc;
     // shared-memory budgets
-    h->smem_cam = sizeof(double) * ((size_t) C.K * (480 + 256 + 228) + (size_t) C.G * 24 + 48 + 16 + 2 * (size_t) C.R + 8) + sizeof(int) * (size_t) C.R + 64;
+    h->smem_cam = sizeof(double) * ((size_t) C.K * 480 + (size_t) C.G * 24 + 48 + 16 + 2 * (size_t) C.R + 8) + sizeof(int) * (size_t) C.R + 64;
     size_t vec = sizeof(double) * (40 + 5 * (size_t) C.NS);
     size_t packed = sizeof(double) * ((size_t) (C.N + 1) * (C.N + 2) / 2);
     h->use_global_S = (vec + packed > 220 * 1024) ? 1 : 0;

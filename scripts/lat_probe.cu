@@ -83,18 +83,54 @@ __global__ void probe(double *out, long long *cyc, double seed) {
         x = r + 1.5;
     }
     t1 = clock64(); if (t == 0) cyc[12] = t1 - t0; acc += x;
+    // 13: the 8 x 8 in-register Cholesky of ba_solve's diagonal tile (every lane the same code on broadcast shared-memory loads), repeated
+    {
+        __syncthreads();
+        if (t < 64) {
+            for (int a = 0; a < 8; a++) sm[a * 8 + (t & 7)] = (a == (t & 7)) ? 40.0 + a : 1.0 / (1.0 + a + (t & 7));
+        }
+        __syncthreads();
+        constexpr int NB = 8, REP = 32;
+        double sink = 0;
+        t0 = clock64();
+        for (int rep = 0; rep < REP; rep++) {
+            double Ld[NB][NB], dinv[NB];
+#pragma unroll
+            for (int a = 0; a < NB; a++)
+#pragma unroll
+                for (int b = 0; b < NB; b++) Ld[a][b] = b <= a ? sm[a * 8 + b] + sink * 1e-300 : 0.0;
+#pragma unroll
+            for (int j = 0; j < NB; j++) {
+                double d = Ld[j][j];
+#pragma unroll
+                for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
+                const double di = rsqrt(d);
+                dinv[j] = di;
+                Ld[j][j] = d * di;
+#pragma unroll
+                for (int a = j + 1; a < NB; a++) {
+                    double sum = Ld[a][j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
+                    Ld[a][j] = sum * di;
+                }
+            }
+            sink += Ld[7][7] + dinv[3] + Ld[7][0];
+        }
+        t1 = clock64(); if (t == 0) cyc[13] = (t1 - t0) * (long long) N / REP; acc += sink;   // scaled so that the print divides by N
+    }
     out[blockIdx.x * blockDim.x + t] = acc;
 }
 int main() {
     double *out; long long *cyc;
     cudaMalloc(&out, sizeof(double) * 4096); cudaMallocManaged(&cyc, sizeof(long long) * 16);
-    const char *nm[13] = {"DFMA", "DMUL", "rsqrt(double)+DADD", "sqrt(double)+DADD", "1.0/x+DADD", "y/x+DADD", "DMMA.884 (acc chain)", "LDS.64 chase (+F2I,IADD,LOP)",
-                          "shfl double + DADD", "__syncthreads", "DADD", "FFMA", "rsqrtf + 2 Newton (double) + DADD"};
+    const char *nm[14] = {"DFMA", "DMUL", "rsqrt(double)+DADD", "sqrt(double)+DADD", "1.0/x+DADD", "y/x+DADD", "DMMA.884 (acc chain)", "LDS.64 chase (+F2I,IADD,LOP)",
+                          "shfl double + DADD", "__syncthreads", "DADD", "FFMA", "rsqrtf + 2 Newton (double) + DADD", "8x8 register Cholesky (whole block)"};
     for (int threads : {32, 256}) {
         probe<<<1, threads>>>(out, cyc, 1.25);
         cudaDeviceSynchronize();
         printf("-- %d threads in the CTA (one CTA on the SM): cycles per dependent operation\n", threads);
-        for (int k = 0; k < 13; k++) printf("  %-34s %8.1f\n", nm[k], (double) cyc[k] / N);
+        for (int k = 0; k < 14; k++) printf("  %-34s %8.1f\n", nm[k], (double) cyc[k] / N);
     }
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
