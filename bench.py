@@ -399,7 +399,10 @@ def run_b200(args):
         d_rawB = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
         kf_hist = [None]
 
+        kf_host = {"clahe_ms": [], "klt_enqueue_ms": [], "detect_ms": [], "ba_marg_join_ms": []}  # host wall time of the phases (BA threads run beside detection)
+
         def step_keyframe(s):
+            t_0 = time.perf_counter()
             fb = seq[s + 1]
             with torch.cuda.stream(stream):
                 d_rawB.copy_(h_raw, non_blocking=True)   # H2D of the B raw frames (pinned)
@@ -408,11 +411,13 @@ def run_b200(args):
                 e_slots.copy_(h_slots[s], non_blocking=True)
             # CLAHE of the B frames into their slots' level-0 planes + the histogram-gate statistic of the raw frames (synchronises: the host decides)
             kf_hist[0] = kcl.apply_batch_dev(B, d_rawB.data_ptr(), W, W * H, slot0 + fb * B * slot_stride, slot_pitch, slot_stride, want_hist=True)
+            t_1 = time.perf_counter()
             trk.build_pyramids(fb * B, B)
             trk.track_batch_dev(n_total, e_slots.data_ptr(), e_prev.data_ptr(), e_init.data_ptr(), d_fwd.data_ptr(), d_bwd.data_ptr(), d_st.data_ptr(), 1)
             with torch.cuda.stream(stream):
                 h_fwd.copy_(d_fwd, non_blocking=True)
                 h_st.copy_(d_st, non_blocking=True)
+            t_2 = time.perf_counter()
 
             def ba_part(k):
                 sv, (pe, init, arr, summ) = solvers[k], e2e_parts[k]
@@ -430,8 +435,12 @@ def run_b200(args):
                 t_.start()
             # block detection of the B equalised frames (device-resident input, corners back on the host), beside the BA threads
             kdet.detect_blocks_dev(B, slot0 + fb * B * slot_stride, slot_pitch, slot_stride, rois, [quota] * len(rois), 0.01, float(min_dist))
+            t_3 = time.perf_counter()
             for t_ in ths:
                 t_.join()
+            t_4 = time.perf_counter()
+            kf_host["clahe_ms"].append((t_1 - t_0) * 1e3), kf_host["klt_enqueue_ms"].append((t_2 - t_1) * 1e3)
+            kf_host["detect_ms"].append((t_3 - t_2) * 1e3), kf_host["ba_marg_join_ms"].append((t_4 - t_3) * 1e3)
         for b in range(B):
             h_raw[b].copy_(h_frames[0])
 
@@ -506,7 +515,8 @@ def run_b200(args):
             kf = {"workload": "FULL keyframe path of B streams end to end through the C ABI: H2D raw frame, CLAHE + histogram gate (batched), pyramid, fwd+bwd LK, "
                               "block detection (18 blocks x B frames, one call), gvinsOptimization (host arrays in / out) and gvinsMarginalization of the window "
                               "just optimised (icg_ba_marginalize_resident, prior out to host arrays); 2 handles, one host thread each; every frame a keyframe", "value": B * world * args.steps / (ms_kf / 1e3), "unit": "frames/s",
-                  "ms_per_step": ms_kf / args.steps}
+                  "ms_per_step": ms_kf / args.steps,
+                  "host_ms_per_step": {k_: float(np.mean(v_[args.warmup:])) for k_, v_ in kf_host.items() if len(v_) > args.warmup}}
     clocks = clk.summary()
     good = int(d_st.sum().item())
     ba_info = None
