@@ -2420,7 +2420,7 @@ static int split_setup(icg_ba *h, int rank, int world) {
     h->xbuf_doubles = off;
     if (cudaMalloc(&h->xbuf, sizeof(double) * off) != cudaSuccess || cudaMalloc(&S.redv, sizeof(double) * NW * S.RV) != cudaSuccess ||
         cudaMalloc(&S.err, sizeof(int) * 4) != cudaSuccess ||
-        cudaMalloc(&h->D.Sglobal, sizeof(double) * NWo * ((size_t) (C.N + 1) * (C.N + 2) / 2)) != cudaSuccess) {
+        cudaMalloc(&h->D.Sglobal, sizeof(double) * NWo * split_S_stride(C)) != cudaSuccess) {
         set_error("split pipeline: allocation of the exchange buffers failed (%zu doubles)", off);
         return ICG_ENOMEM;
     }

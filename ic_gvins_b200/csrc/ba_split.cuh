@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(256) ba_reduce(BaCaps C, BaDev D, unsigned lon
     }
 }
 
+__host__ __device__ inline size_t split_S_stride(const BaCaps &C) { return (size_t) (C.N + 1) * (C.N + 2) / 2 + (size_t) C.NS; }
+
 // ------------------------------------------------------------------------------------------------ solve_cam (owner, cluster per window)
 // The camera-side half of ba_solve for systems that do not fit one CTA: S lives packed in global memory (L2-resident, written and read by all
 // CTAs of the cluster between cluster barriers -- cluster.sync orders the global accesses at cluster scope and invalidates L1).
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
     double *s_rhs = s_g + C.NS;          // N   rhs' then step'
     double *s_d2 = s_rhs + C.NS;         // N
     double *s_blk = s_d2 + C.NS;         // SPLIT_BS_ROWS x (NS + 1): row block of L for the back-substitution (CTA 0)
-    double *S = D.Sglobal + (size_t) (w / D.world) * ((size_t) (C.N + 1) * (C.N + 2) / 2);  // one workspace per OWNED window
+    double *S = D.Sglobal + (size_t) (w / D.world) * split_S_stride(C);  // one workspace per OWNED window: packed triangle | pivot reciprocals
     const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS, *Hs = D.Hs + (size_t) w * C.NS * C.NS;
     const double *rv = D.S.redv + (size_t) w * D.S.RV;   // [diag H_vis | g_vis | W phi g_l | cost, sum rho^2, max |g_l|]
     double *scale_c = D.scale_c + (size_t) w * C.NS;
@@ -254,49 +256,66 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
     }
     for (int a = ctid; a < N; a += CT) S[(size_t) N * (N + 1) / 2 + a] = s_rhs[a];
     cluster.sync();
-    // ---- blocked left-looking Cholesky, 8 columns per step; panel update (DMMA) and row solves spread over the cluster
+    // ---- blocked left-looking Cholesky, 8 columns per step; panel update (DMMA) and row solves spread over the cluster.  Per panel:
+    //   (0) every CTA stages the panel's B operand (rows J0 .. J0 + 7 of L, columns < J0) in its shared memory: one coalesced L2 sweep
+    //       instead of a dependent L2 round trip per k-step and warp;
+    //   (1) DMMA update of the 8-row tiles: A operands from L2, 64 columns (16 loads per lane) in flight per pass.  Cluster warp 0 takes the
+    //       diagonal tile and FACTORS it straight away (registers), writes L_JJ back in place and the pivot reciprocals to dinv[] (a negative
+    //       entry = breakdown), while the other 31 cluster warps update the tiles below;
+    //   (2) cluster barrier; every row below is solved by its own thread against L_JJ / dinv read from L2; cluster barrier.
+    // The round-2-start form read both DMMA operands from L2 four columns at a time and let all 1 024 threads factor the block redundantly
+    // (each loading it from L2): 20 k cycles per panel, 392 us per launch at N = 307.
+    double *dinvg = S + (size_t) (C.N + 1) * (C.N + 2) / 2;  // [NS] behind the capacity-sized triangle of this window's workspace
+    double *s_b = s_blk;                                      // [8][ldbp]: aliases the back-substitution staging (used after the factorisation)
+    const int ldbp = ((C.N + 15) / 16) * 16 + 8;              // = 8 mod 16 doubles: conflict-free fragment reads
     int fail = 0;
     for (int J0 = 0; J0 < N; J0 += BA_CHOL_NB) {
         const int nb = min(BA_CHOL_NB, N - J0);
+        const int g = lane >> 2, kk = lane & 3;
+        const int ntile = (NR - J0 + 7) / 8;
         if (J0 > 0) {
-            const int g = lane >> 2, kk = lane & 3;
-            const int ntile = (NR - J0 + 7) / 8;
-            const int cb = J0 + g;
-            const bool okb = cb < NR;
-            const double *rb = S + (okb ? (size_t) cb * (cb + 1) / 2 : 0);
-            for (int tI = cwarp; tI < ntile; tI += ncwarps) {
-                const int ia = J0 + 8 * tI + g;
-                const bool oka = ia < NR;
-                const double *ra = S + (oka ? (size_t) ia * (ia + 1) / 2 : 0);
-                double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
-                int k0 = 0;
-                for (; k0 + 16 <= J0; k0 += 16) {  // four independent accumulator pairs: the operands come from L2
-                    const double a0 = oka ? ra[k0 + kk] : 0.0, b0 = okb ? rb[k0 + kk] : 0.0;
-                    const double a1 = oka ? ra[k0 + 4 + kk] : 0.0, b1 = okb ? rb[k0 + 4 + kk] : 0.0;
-                    const double a2 = oka ? ra[k0 + 8 + kk] : 0.0, b2 = okb ? rb[k0 + 8 + kk] : 0.0;
-                    const double a3 = oka ? ra[k0 + 12 + kk] : 0.0, b3 = okb ? rb[k0 + 12 + kk] : 0.0;
-                    dmma884(c0, c1, a0, b0);
-                    dmma884(d0, d1, a1, b1);
-                    dmma884(e0, e1, a2, b2);
-                    dmma884(f0, f1, a3, b3);
-                }
-                for (; k0 + 4 <= J0; k0 += 4) {
-                    const double a0 = oka ? ra[k0 + kk] : 0.0, b0 = okb ? rb[k0 + kk] : 0.0;
-                    dmma884(c0, c1, a0, b0);
-                }
-                c0 += d0 + (e0 + f0), c1 += d1 + (e1 + f1);
-                const int i = J0 + 8 * tI + g;
-                if (i < NR) {
-                    const int ca = J0 + 2 * kk;
-                    double *ri = S + (size_t) i * (i + 1) / 2;
-                    if (ca < J0 + nb && ca <= i) ri[ca] -= c0;
-                    if (ca + 1 < J0 + nb && ca + 1 <= i) ri[ca + 1] -= c1;
+            for (int e = tid; e < 8 * J0; e += SOLVE_THREADS) {
+                const int r = e / J0, c = e - r * J0, row = J0 + r;
+                s_b[r * ldbp + c] = row < NR ? S[(size_t) row * (row + 1) / 2 + c] : 0.0;
+            }
+            __syncthreads();
+        }
+        // one 8-row tile: S[rows, J0 : J0 + 8] -= L[rows, : J0] L[J0 : J0 + 8, : J0]^T
+        auto tile_update = [&](int tI) {
+            const int ia = J0 + 8 * tI + g;
+            const bool oka = ia < NR;
+            const double *ra = S + (oka ? (size_t) ia * (ia + 1) / 2 : 0);
+            const double *sb = s_b + g * ldbp;
+            double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+            for (int k0 = 0; k0 < J0; k0 += 64) {
+                double a[16];
+#pragma unroll
+                for (int u = 0; u < 16; u++) a[u] = (oka && k0 + 4 * u < J0) ? ra[k0 + 4 * u + kk] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    if (k0 + 4 * u < J0) {  // J0 is a multiple of 8: k-steps come in pairs; zero-padded beyond J0
+                        const double b0 = sb[k0 + 4 * u + kk], b1 = k0 + 4 * u + 4 < J0 ? sb[k0 + 4 * u + 4 + kk] : 0.0;
+                        const double b2 = k0 + 4 * u + 8 < J0 ? sb[k0 + 4 * u + 8 + kk] : 0.0, b3 = k0 + 4 * u + 12 < J0 ? sb[k0 + 4 * u + 12 + kk] : 0.0;
+                        dmma884(c0, c1, a[u], b0);
+                        dmma884(d0, d1, a[u + 1], b1);
+                        dmma884(e0, e1, a[u + 2], b2);
+                        dmma884(f0, f1, a[u + 3], b3);
+                    }
                 }
             }
-            cluster.sync();
-        }
-        {
-            // every thread factors the nb x nb diagonal block redundantly (identical verdict everywhere), row owners solve / write back
+            c0 += d0 + (e0 + f0), c1 += d1 + (e1 + f1);
+            if (oka) {
+                const int ca = J0 + 2 * kk;
+                double *ri = S + (size_t) ia * (ia + 1) / 2;
+                if (ca < J0 + nb && ca <= ia) ri[ca] -= c0;
+                if (ca + 1 < J0 + nb && ca + 1 <= ia) ri[ca + 1] -= c1;
+            }
+        };
+        if (cwarp == 0) {
+            if (J0 > 0) {
+                tile_update(0);
+                __syncwarp();
+            }
             double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
             bool bad = false;
 #pragma unroll
@@ -320,40 +339,44 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
                     Ld[a][j] = sum * di;
                 }
             }
-            if (bad) fail = 1;
-            // rows below the block: solve against the factored diagonal block (each thread touches its own row only)
-            const int i = J0 + ctid;
-            if (i >= J0 + nb && i < NR && !fail) {
-                double *ri = S + (size_t) i * (i + 1) / 2 + J0;
-                double x[BA_CHOL_NB];
+            __syncwarp();  // every lane has read the unfactored block
 #pragma unroll
-                for (int c = 0; c < BA_CHOL_NB; c++) x[c] = c < nb ? ri[c] : 0.0;
+            for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers: lane a writes row a
+                if (a2 != lane || a2 >= nb) continue;
+                double *ri = S + (size_t) (J0 + a2) * (J0 + a2 + 1) / 2 + J0;
 #pragma unroll
-                for (int c = 0; c < BA_CHOL_NB; c++) {
-                    double sum = x[c];
-#pragma unroll
-                    for (int k = 0; k < c; k++) sum -= x[k] * Ld[c][k];
-                    x[c] = sum * dinv[c];
-                }
-#pragma unroll
-                for (int c = 0; c < BA_CHOL_NB; c++)
-                    if (c < nb) ri[c] = x[c];
+                for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
+                dinvg[J0 + a2] = bad ? -1.0 : dinv[a2];
             }
-            cluster.sync();
-            // the block's own rows are written back only now: every thread of the cluster has read the unfactored block above, and no
-            // later step of the factorisation reads these entries again (the back-substitution does)
-            if (i < J0 + nb && !fail) {
-                double *ri = S + (size_t) i * (i + 1) / 2 + J0;
-                const int a = i - J0;
-#pragma unroll
-                for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {
-                    if (a2 != a) continue;
-#pragma unroll
-                    for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
-                }
-            }
+        } else if (J0 > 0) {
+            for (int tI = cwarp; tI < ntile; tI += ncwarps - 1) tile_update(tI);
         }
-        if (fail) break;  // identical on every thread of the cluster
+        cluster.sync();
+        fail = dinvg[J0] < 0.0;  // identical on every thread of the cluster
+        if (fail) break;
+        // rows below the block (incl. the augmented rhs row): solve against the factored block, one row per thread of the cluster
+        for (int i = J0 + nb + ctid; i < NR; i += CT) {
+            double *ri = S + (size_t) i * (i + 1) / 2 + J0;
+            double x[BA_CHOL_NB], Lb[BA_CHOL_NB * (BA_CHOL_NB - 1) / 2], dv[BA_CHOL_NB];
+#pragma unroll
+            for (int c = 0; c < BA_CHOL_NB; c++) {
+                x[c] = c < nb ? ri[c] : 0.0;
+                dv[c] = c < nb ? dinvg[J0 + c] : 1.0;
+#pragma unroll
+                for (int k = 0; k < c; k++) Lb[c * (c - 1) / 2 + k] = c < nb ? S[(size_t) (J0 + c) * (J0 + c + 1) / 2 + J0 + k] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < BA_CHOL_NB; c++) {
+                double sum = x[c];
+#pragma unroll
+                for (int k = 0; k < c; k++) sum -= x[k] * Lb[c * (c - 1) / 2 + k];
+                x[c] = sum * dv[c];
+            }
+#pragma unroll
+            for (int c = 0; c < BA_CHOL_NB; c++)
+                if (c < nb) ri[c] = x[c];
+        }
+        cluster.sync();
     }
     if (cr != 0) return;
     // ---- CTA 0: blocked backward substitution L^T x = y.  Blocks of SPLIT_BS_ROWS rows, last block first: the block's rows (all columns

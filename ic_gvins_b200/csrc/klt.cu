@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(const uint8_t *__restrict
     if (x >= dW || y >= dH) return;
     const int y0 = 2 * y - 2;
     uint8_t *drow = dst + (size_t) y * dpitch;
-    if (t >= 1 && 8 * t + 8 < sW && x + 3 < dW && y0 >= 0 && y0 + 4 < sH) {
+    // the source plane's reflect-101 padding is already filled (icg_klt_build_pyramids pads a level before it reduces it), and reflect-101 is
+    // cv::pyrDown's border rule: border outputs take the packed path too, reading into the padding.  (With the scalar border path, every warp
+    // that held an edge thread -- 2 of 5 at level 1, all of them at level 3 -- ran both paths: 690 .. 1 380 instructions per thread, the kernel
+    // was issue-bound at 83 % and 0.84 TB/s; profiles/r2_pyr_down.md.)
+    if (x + 3 < dW) {
         const uint8_t *r = src + (size_t) y0 * spitch;
         int h0[4], h1[4], h2[4], h3[4], h4[4];
         pd_row4(r, t, h0);
@@ -867,8 +871,24 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
     ICG_CUDA(cudaSetDevice(h->device));
     // a producer may have written these level-0 planes in place (icg_klt_slot_level0): the host API's content cache must not hit on them
     for (int sl = first_slot; sl < first_slot + count; sl++) h->slot_hash[sl] = 0;
+    // level by level: pad level l - 1 (reflect-101), then reduce it -- the reduction reads its border taps from the padding
+    auto pad_level = [&](int lv) -> int {
+        PadArgs P;
+        for (int l = 0; l < KLT_LEVELS; l++) {
+            P.base[l] = h->planes[l], P.W[l] = h->lv[l].W, P.H[l] = h->lv[l].H, P.pitch[l] = h->lv[l].pitch, P.slot_stride[l] = h->lv[l].slot_stride;
+        }
+        P.first_slot = first_slot;
+        P.off[0] = 0;
+        for (int l = 0; l < KLT_LEVELS; l++) P.off[l + 1] = P.off[l] + (l == lv ? pad_chunks(h->lv[l].W, h->lv[l].H) : 0);
+        pad_fill_kernel<<<dim3((P.off[KLT_LEVELS] + 255) / 256, count), 256, 0, h->stream>>>(P);
+        ICG_CHECK_LAUNCH();
+        count_launch();
+        return ICG_OK;
+    };
     for (int l = 1; l < KLT_LEVELS; l++) {
         const KltLevel &s = h->lv[l - 1], &d = h->lv[l];
+        int rc = pad_level(l - 1);
+        if (rc != ICG_OK) return rc;
         dim3 grid((d.W + 255) / 256, (d.H + 3) / 4, count);
         pyr_down_kernel<<<grid, 256, 0, h->stream>>>(s.base, s.W, s.H, s.pitch, s.slot_stride, h->planes[l], d.W, d.H, d.pitch,
                                                      d.slot_stride, first_slot);
@@ -876,16 +896,8 @@ int icg_klt_build_pyramids(icg_klt *h, int first_slot, int count) {
         count_launch();
     }
     {
-        PadArgs P;
-        for (int l = 0; l < KLT_LEVELS; l++) {
-            P.base[l] = h->planes[l], P.W[l] = h->lv[l].W, P.H[l] = h->lv[l].H, P.pitch[l] = h->lv[l].pitch, P.slot_stride[l] = h->lv[l].slot_stride;
-        }
-        P.first_slot = first_slot;
-        P.off[0] = 0;
-        for (int l = 0; l < KLT_LEVELS; l++) P.off[l + 1] = P.off[l] + pad_chunks(h->lv[l].W, h->lv[l].H);
-        pad_fill_kernel<<<dim3((P.off[KLT_LEVELS] + 255) / 256, count), 256, 0, h->stream>>>(P);
-        ICG_CHECK_LAUNCH();
-        count_launch();
+        int rc = pad_level(KLT_LEVELS - 1);
+        if (rc != ICG_OK) return rc;
     }
     return ICG_OK;
 }
