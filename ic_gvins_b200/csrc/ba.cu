@@ -2294,10 +2294,16 @@ static void prof_print(icg_ba *h) {
             fprintf(stderr, "[icg_ba profile] ba_lin_cam phases of window 0 (SM cycles per call, mean):\n");
             for (int k = 0; k < 6; k++)
                 if (ck[24 + k]) fprintf(stderr, "  %-28s %9.0f cycles\n", cn[k], (double) ck[16 + k] / (double) ck[24 + k]);
+            if (h->D.S.split) {
+                static const char *sn[5] = {"per panel: stage B operand", "per panel: warp 0 tile + factor", "per panel: tiles + barrier 1", "per panel: row solve + barrier 2", "whole factorisation"};
+                fprintf(stderr, "[icg_ba profile] ba_solve_cam phases of window 0 (SM cycles, mean):\n");
+                for (int k = 0; k < 5; k++)
+                    if (ck[8 + k]) fprintf(stderr, "  %-34s %9.0f cycles\n", sn[k], (double) ck[k] / (double) ck[8 + k]);
+            }
             static const char *nm[8] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions",
                                         "  per panel: warp 0 tile+factor", "  per panel: row solve phase"};
-            fprintf(stderr, "[icg_ba profile] ba_solve phases of window 0 (SM cycles per call, mean):\n");
-            for (int k = 0; k < 8; k++)
+            if (!h->D.S.split) fprintf(stderr, "[icg_ba profile] ba_solve phases of window 0 (SM cycles per call, mean):\n");
+            for (int k = 0; k < 8 && !h->D.S.split; k++)
                 if (ck[8 + k]) fprintf(stderr, "  %-28s %9.0f cycles\n", nm[k], (double) ck[k] / (double) ck[8 + k]);
         }
     }

@@ -269,10 +269,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
     double *s_b = s_blk;                                      // [8][ldbp]: aliases the back-substitution staging (used after the factorisation)
     const int ldbp = ((C.N + 15) / 16) * 16 + 8;              // = 8 mod 16 doubles: conflict-free fragment reads
     int fail = 0;
+#ifdef ICG_BA_PHASE_CLOCKS
+#define CAMS_CLK(k, t0)                                                                                             \
+    if (D.clk && w == 0 && ctid == 0) atomicAdd(&D.clk[k], clock64() - (t0)), atomicAdd(&D.clk[8 + (k)], 1ull);
+#define CAMS_NOW() clock64()
+#else
+#define CAMS_CLK(k, t0)
+#define CAMS_NOW() 0ull
+#endif
+    const unsigned long long tc_all = CAMS_NOW();
+    (void) tc_all;
     for (int J0 = 0; J0 < N; J0 += BA_CHOL_NB) {
         const int nb = min(BA_CHOL_NB, N - J0);
         const int g = lane >> 2, kk = lane & 3;
         const int ntile = (NR - J0 + 7) / 8;
+        const unsigned long long tc0 = CAMS_NOW();
+        (void) tc0;
         if (J0 > 0) {
             for (int e = tid; e < 8 * J0; e += SOLVE_THREADS) {
                 const int r = e / J0, c = e - r * J0, row = J0 + r;
@@ -280,6 +292,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
             }
             __syncthreads();
         }
+        CAMS_CLK(0, tc0)  // staging of the B operand
+        const unsigned long long tc1 = CAMS_NOW();
+        (void) tc1;
         // one 8-row tile: S[rows, J0 : J0 + 8] -= L[rows, : J0] L[J0 : J0 + 8, : J0]^T
         auto tile_update = [&](int tI) {
             const int ia = J0 + 8 * tI + g;
@@ -348,10 +363,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
                 for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
                 dinvg[J0 + a2] = bad ? -1.0 : dinv[a2];
             }
+            CAMS_CLK(1, tc1)  // cluster warp 0: diagonal tile + factorisation
         } else if (J0 > 0) {
             for (int tI = cwarp; tI < ntile; tI += ncwarps - 1) tile_update(tI);
         }
         cluster.sync();
+        CAMS_CLK(2, tc1)  // tile updates + first cluster barrier
+        const unsigned long long tc2 = CAMS_NOW();
+        (void) tc2;
         fail = dinvg[J0] < 0.0;  // identical on every thread of the cluster
         if (fail) break;
         // rows below the block (incl. the augmented rhs row): solve against the factored block, one row per thread of the cluster
@@ -377,7 +396,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
                 if (c < nb) ri[c] = x[c];
         }
         cluster.sync();
+        CAMS_CLK(3, tc2)  // row solves + second cluster barrier
     }
+    CAMS_CLK(4, tc_all)   // whole factorisation
     if (cr != 0) return;
     // ---- CTA 0: blocked backward substitution L^T x = y.  Blocks of SPLIT_BS_ROWS rows, last block first: the block's rows (all columns
     //      up to the diagonal) are staged in shared memory with one coalesced sweep; one warp solves the triangle, every thread then
