@@ -327,8 +327,39 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
             }
         };
         if (cwarp == 0) {
-            if (J0 > 0) {
-                tile_update(0);
+            // diagonal tile: its A operand IS the staged B operand (shared memory, no L2 round trip on the k loop); the block's current values are
+            // fetched from L2 before the loop (they arrive while it runs), updated in registers and handed to the factorisation through a
+            // 64-double shared buffer instead of a global write + read
+            double *s_jj = s_b + 8 * ldbp;  // [8][8] behind the B rows
+            {
+                const int ia = J0 + g;
+                const bool oka = ia < NR;
+                const int ca = J0 + 2 * kk;
+                double v0 = 0, v1 = 0;
+                if (oka && ca <= ia && ca < J0 + nb) v0 = S[(size_t) ia * (ia + 1) / 2 + ca];
+                if (oka && ca + 1 <= ia && ca + 1 < J0 + nb) v1 = S[(size_t) ia * (ia + 1) / 2 + ca + 1];
+                if (J0 > 0) {
+                    const double *sa = s_b + g * ldbp;
+                    double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+                    int k0 = 0;
+                    for (; k0 + 16 <= J0; k0 += 16) {
+                        const double x0 = sa[k0 + kk], x1 = sa[k0 + 4 + kk], x2 = sa[k0 + 8 + kk], x3 = sa[k0 + 12 + kk];
+                        dmma884(c0, c1, x0, x0);
+                        dmma884(d0, d1, x1, x1);
+                        dmma884(e0, e1, x2, x2);
+                        dmma884(f0, f1, x3, x3);
+                    }
+                    for (; k0 + 4 <= J0; k0 += 4) {
+                        const double x0 = sa[k0 + kk];
+                        dmma884(c0, c1, x0, x0);
+                    }
+                    v0 -= c0 + d0 + (e0 + f0), v1 -= c1 + d1 + (e1 + f1);
+                }
+                s_jj[g * 8 + 2 * kk] = v0, s_jj[g * 8 + 2 * kk + 1] = v1;
+                if (oka && ia >= J0 + nb) {  // last panel (nb < 8): the tile also holds rows BELOW the block (the augmented rhs row): back to S
+                    if (ca < J0 + nb) S[(size_t) ia * (ia + 1) / 2 + ca] = v0;
+                    if (ca + 1 < J0 + nb) S[(size_t) ia * (ia + 1) / 2 + ca + 1] = v1;
+                }
                 __syncwarp();
             }
             double Ld[BA_CHOL_NB][BA_CHOL_NB], dinv[BA_CHOL_NB];
@@ -336,7 +367,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
 #pragma unroll
             for (int a = 0; a < BA_CHOL_NB; a++)
 #pragma unroll
-                for (int b = 0; b < BA_CHOL_NB; b++) Ld[a][b] = (a < nb && b <= a) ? S[(size_t) (J0 + a) * (J0 + a + 1) / 2 + J0 + b] : (a == b ? 1.0 : 0.0);
+                for (int b = 0; b < BA_CHOL_NB; b++) Ld[a][b] = (a < nb && b <= a) ? s_jj[a * 8 + b] : (a == b ? 1.0 : 0.0);
 #pragma unroll
             for (int j = 0; j < BA_CHOL_NB; j++) {
                 double d = Ld[j][j];
