@@ -1795,6 +1795,7 @@ struct icg_ba {
     void *ipc_opened[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     unsigned long long epoch = 0;
     size_t smem_solve_cam = 0, smem_step_lm = 0;
+    bool solve_cam_stage_a = false;  // per-warp shared-memory strips for the DMMA A operand (ba_solve_cam)
     // in-situ stage timing (ICG_BA_PROFILE=1): events between the kernels of the LM sequence on the main stream, read back in
     // icg_ba_sync / icg_ba_download and printed by icg_ba_destroy (warm caches, real launch gaps -- unlike an ncu replay)
     bool prof = false;
@@ -2439,7 +2440,13 @@ static int split_setup(icg_ba *h, int rank, int world) {
     h->D.rank = rank, h->D.world = world;
     h->x_world = world;
     h->epoch = 0;
-    h->smem_solve_cam = sizeof(double) * (40 + 4 * (size_t) C.NS + (size_t) SPLIT_BS_ROWS * (C.NS + 1));
+    {   // ba_solve_cam: vectors + the larger of the back-substitution staging and [B rows | 8 x 8 hand-over | one A strip per warp]; the A strips are
+        // dropped when they do not fit (max_K > 20)
+        const size_t ldbp = ((size_t) (C.N + 15) / 16) * 16 + 8;
+        const size_t bs = (size_t) SPLIT_BS_ROWS * (C.NS + 1), base = 8 * ldbp + 64, strips = (size_t) (SOLVE_THREADS / 32) * 8 * ldbp;
+        h->solve_cam_stage_a = sizeof(double) * (40 + 4 * (size_t) C.NS + std::max(bs, base + strips)) <= 220 * 1024;
+        h->smem_solve_cam = sizeof(double) * (40 + 4 * (size_t) C.NS + std::max(bs, base + (h->solve_cam_stage_a ? strips : 0)));
+    }
     h->smem_step_lm = sizeof(double) * (40 + (size_t) C.NS);
     ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam, (size_t) (h->smem_solve_cam)));
     ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
@@ -2456,7 +2463,7 @@ static int launch_solve_cam(icg_ba *h, int n, unsigned long long epoch) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = SPLIT_CLUSTER, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
-    ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam, h->C, h->D, epoch));
+    ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam, h->C, h->D, epoch, (int) h->solve_cam_stage_a));
     return ICG_OK;
 }
 

@@ -171,7 +171,7 @@ __host__ __device__ inline size_t split_S_stride(const BaCaps &C) { return (size
 // The camera-side half of ba_solve for systems that do not fit one CTA: S lives packed in global memory (L2-resident, written and read by all
 // CTAs of the cluster between cluster barriers -- cluster.sync orders the global accesses at cluster scope and invalidates L1).
 // Row i of the packed lower triangle starts at i (i + 1) / 2; the augmented row N carries the right-hand side.
-__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D, unsigned long long epoch) {
+__global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D, unsigned long long epoch, int stage_a) {
     extern __shared__ double sm[];
     cg::cluster_group cluster = cg::this_cluster();
     const int CL = (int) cluster.num_blocks(), cr = (int) cluster.block_rank();
@@ -295,26 +295,60 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
         CAMS_CLK(0, tc0)  // staging of the B operand
         const unsigned long long tc1 = CAMS_NOW();
         (void) tc1;
-        // one 8-row tile: S[rows, J0 : J0 + 8] -= L[rows, : J0] L[J0 : J0 + 8, : J0]^T
+        // one 8-row tile: S[rows, J0 : J0 + 8] -= L[rows, : J0] L[J0 : J0 + 8, : J0]^T.
+        // stage_a (the launch gave every warp an 8 x ldbp shared-memory strip): the tile's A rows come in with 8-byte cp.async, ALL columns in
+        // flight at once (one L2 round trip per tile; measured 2 k cycles per 64-column pass when the operand is read from L2 in the k loop),
+        // then both DMMA operands are conflict-free shared-memory reads.  Without the strips (max_K beyond the shared-memory budget): 64 columns
+        // (16 loads per lane) in flight per pass.
         auto tile_update = [&](int tI) {
             const int ia = J0 + 8 * tI + g;
             const bool oka = ia < NR;
             const double *ra = S + (oka ? (size_t) ia * (ia + 1) / 2 : 0);
             const double *sb = s_b + g * ldbp;
             double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
-            for (int k0 = 0; k0 < J0; k0 += 64) {
-                double a[16];
+            if (stage_a) {
+                double *sw = s_b + 8 * ldbp + 64 + (size_t) warp * 8 * ldbp;  // this warp's strip (behind the B rows and the 8 x 8 hand-over buffer)
+                __syncwarp();  // the strip's previous tile has been consumed
+#pragma unroll 1
+                for (int r = 0; r < 8; r++) {
+                    const int row = J0 + 8 * tI + r;
+                    if (row < NR) {
+                        const double *src = S + (size_t) row * (row + 1) / 2;
+                        const unsigned dst = (unsigned) __cvta_generic_to_shared(sw + r * ldbp);
+                        for (int c = lane; c < J0; c += 32) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c) : "memory");
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+                const double *sa = sw + g * ldbp;
+                int k0 = 0;
+                for (; k0 + 16 <= J0; k0 += 16) {
+                    const double a0 = oka ? sa[k0 + kk] : 0.0, a1 = oka ? sa[k0 + 4 + kk] : 0.0, a2 = oka ? sa[k0 + 8 + kk] : 0.0, a3 = oka ? sa[k0 + 12 + kk] : 0.0;
+                    dmma884(c0, c1, a0, sb[k0 + kk]);
+                    dmma884(d0, d1, a1, sb[k0 + 4 + kk]);
+                    dmma884(e0, e1, a2, sb[k0 + 8 + kk]);
+                    dmma884(f0, f1, a3, sb[k0 + 12 + kk]);
+                }
+                for (; k0 + 4 <= J0; k0 += 4) {
+                    const double a0 = oka ? sa[k0 + kk] : 0.0;
+                    dmma884(c0, c1, a0, sb[k0 + kk]);
+                }
+            } else {
+                for (int k0 = 0; k0 < J0; k0 += 64) {
+                    double a[16];
 #pragma unroll
-                for (int u = 0; u < 16; u++) a[u] = (oka && k0 + 4 * u < J0) ? ra[k0 + 4 * u + kk] : 0.0;
+                    for (int u = 0; u < 16; u++) a[u] = (oka && k0 + 4 * u < J0) ? ra[k0 + 4 * u + kk] : 0.0;
 #pragma unroll
-                for (int u = 0; u < 16; u += 4) {
-                    if (k0 + 4 * u < J0) {  // J0 is a multiple of 8: k-steps come in pairs; zero-padded beyond J0
-                        const double b0 = sb[k0 + 4 * u + kk], b1 = k0 + 4 * u + 4 < J0 ? sb[k0 + 4 * u + 4 + kk] : 0.0;
-                        const double b2 = k0 + 4 * u + 8 < J0 ? sb[k0 + 4 * u + 8 + kk] : 0.0, b3 = k0 + 4 * u + 12 < J0 ? sb[k0 + 4 * u + 12 + kk] : 0.0;
-                        dmma884(c0, c1, a[u], b0);
-                        dmma884(d0, d1, a[u + 1], b1);
-                        dmma884(e0, e1, a[u + 2], b2);
-                        dmma884(f0, f1, a[u + 3], b3);
+                    for (int u = 0; u < 16; u += 4) {
+                        if (k0 + 4 * u < J0) {  // J0 is a multiple of 8: k-steps come in pairs; zero-padded beyond J0
+                            const double b0 = sb[k0 + 4 * u + kk], b1 = k0 + 4 * u + 4 < J0 ? sb[k0 + 4 * u + 4 + kk] : 0.0;
+                            const double b2 = k0 + 4 * u + 8 < J0 ? sb[k0 + 4 * u + 8 + kk] : 0.0, b3 = k0 + 4 * u + 12 < J0 ? sb[k0 + 4 * u + 12 + kk] : 0.0;
+                            dmma884(c0, c1, a[u], b0);
+                            dmma884(d0, d1, a[u + 1], b1);
+                            dmma884(e0, e1, a[u + 2], b2);
+                            dmma884(f0, f1, a[u + 3], b3);
+                        }
                     }
                 }
             }
