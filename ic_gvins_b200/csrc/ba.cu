@@ -1796,6 +1796,8 @@ struct icg_ba {
     unsigned long long epoch = 0;
     size_t smem_solve_cam = 0, smem_step_lm = 0;
     bool solve_cam_stage_a = false;  // per-warp shared-memory strips for the DMMA A operand (ba_solve_cam)
+    bool solve_cam_dsm = false;      // the packed system fits the cluster's shared memory: ba_solve_cam_dsm (max_K <= 22)
+    size_t smem_solve_cam_dsm = 0;
     // in-situ stage timing (ICG_BA_PROFILE=1): events between the kernels of the LM sequence on the main stream, read back in
     // icg_ba_sync / icg_ba_download and printed by icg_ba_destroy (warm caches, real launch gaps -- unlike an ncu replay)
     bool prof = false;
@@ -2296,9 +2298,11 @@ static void prof_print(icg_ba *h) {
             for (int k = 0; k < 6; k++)
                 if (ck[24 + k]) fprintf(stderr, "  %-28s %9.0f cycles\n", cn[k], (double) ck[16 + k] / (double) ck[24 + k]);
             if (h->D.S.split) {
-                static const char *sn[5] = {"per panel: stage B operand", "per panel: warp 0 tile + factor", "per panel: tiles + barrier 1", "per panel: row solve + barrier 2", "whole factorisation"};
-                fprintf(stderr, "[icg_ba profile] ba_solve_cam phases of window 0 (SM cycles, mean):\n");
-                for (int k = 0; k < 5; k++)
+                static const char *sn_l2[6] = {"per panel: stage B operand", "per panel: warp 0 tile + factor", "per panel: tiles + barrier 1", "per panel: row solve + barrier 2", "whole factorisation", ""};
+                static const char *sn_dsm[6] = {"assembly", "per panel: warp 0 tile + factor", "per panel: until block barrier", "per panel: row solve + cl. barrier", "whole factorisation", "backward substitution"};
+                const char **sn = h->solve_cam_dsm ? sn_dsm : sn_l2;
+                fprintf(stderr, "[icg_ba profile] %s phases of window 0 (SM cycles, mean):\n", h->solve_cam_dsm ? "ba_solve_cam_dsm" : "ba_solve_cam");
+                for (int k = 0; k < 6; k++)
                     if (ck[8 + k]) fprintf(stderr, "  %-34s %9.0f cycles\n", sn[k], (double) ck[k] / (double) ck[8 + k]);
             }
             static const char *nm[8] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions",
@@ -2439,6 +2443,9 @@ static int split_setup(icg_ba *h, int rank, int world) {
     S.split = 1;
     h->D.rank = rank, h->D.world = world;
     h->x_world = world;
+    // landmark shards: the owner's camera-only kernels are on the attempt's critical path (the vision kernels shrink with the shard, the
+    // per-window IMU chain does not): all 10 warps, two rounds of IMU factors at K = 20 instead of four
+    if (!getenv("ICG_BA_CAM_THREADS")) h->cam_threads = world > 1 ? CAM_THREADS : 160;
     h->epoch = 0;
     {   // ba_solve_cam: vectors + the larger of the back-substitution staging and [B rows | 8 x 8 hand-over | one A strip per warp]; the A strips are
         // dropped when they do not fit (max_K > 20)
@@ -2448,6 +2455,9 @@ static int split_setup(icg_ba *h, int rank, int world) {
         h->smem_solve_cam = sizeof(double) * (40 + 4 * (size_t) C.NS + std::max(bs, base + (h->solve_cam_stage_a ? strips : 0)));
     }
     h->smem_step_lm = sizeof(double) * (40 + (size_t) C.NS);
+    h->smem_solve_cam_dsm = sizeof(double) * dsm_smem_doubles(C);
+    h->solve_cam_dsm = h->smem_solve_cam_dsm <= 227 * 1024 && !getenv("ICG_BA_SOLVE_CAM_L2");
+    if (h->solve_cam_dsm) ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam_dsm, h->smem_solve_cam_dsm));
     ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam, (size_t) (h->smem_solve_cam)));
     ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     ICG_CUDA(raise_dynamic_smem((const void *) ba_step_lm, (size_t) (h->smem_step_lm)));
@@ -2458,12 +2468,13 @@ static int launch_solve_cam(icg_ba *h, int n, unsigned long long epoch) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned) (n * SPLIT_CLUSTER)), cfg.blockDim = dim3(SOLVE_THREADS);
-    cfg.dynamicSmemBytes = h->smem_solve_cam, cfg.stream = h->stream;
+    cfg.dynamicSmemBytes = h->solve_cam_dsm ? h->smem_solve_cam_dsm : h->smem_solve_cam, cfg.stream = h->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = SPLIT_CLUSTER, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
-    ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam, h->C, h->D, epoch, (int) h->solve_cam_stage_a));
+    if (h->solve_cam_dsm) ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam_dsm, h->C, h->D, epoch));
+    else ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam, h->C, h->D, epoch, (int) h->solve_cam_stage_a));
     return ICG_OK;
 }
 

@@ -525,6 +525,392 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
     for (int q = tid; q < D.world; q += SOLVE_THREADS) st_release_sys(x_flagB(D, q, w), epoch);
 }
 
+// ------------------------------------------------------------------------------------------------ solve_cam, distributed-shared-memory form
+// The same job as ba_solve_cam with the packed system RESIDENT IN THE CLUSTER'S SHARED MEMORY: nothing of the factorisation touches L2.
+// (The L2 form above spends 15 k cycles per 8-column panel -- 2 cluster barriers, the B operand, the A strips and the factored block all
+// fetched from L2 behind them; profiles/r2_ba_solve_cam_dsm.md.)
+//
+// Layout.  The (N + 1) x (N + 1) augmented lower triangle (row N = right-hand side) is cut into 8 x 8 tiles, each stored row-major (64 doubles:
+// the DMMA C fragment of lane l is the 16 bytes at 2 l -- one conflict-free 128-bit access per lane).  Tile row T lives on CTA T mod 4; a CTA
+// keeps the strictly-lower tiles (T, tc < T) of its tile rows.  The DIAGONAL tiles are replicated: every CTA keeps all of them and applies every
+// update to them redundantly (bit-identical), so the 8 x 8 factorisation of a panel needs no hand-over between CTAs.
+//
+// Right-looking blocked Cholesky, ONE cluster barrier per panel:
+//   (1) warp 0: Dg[J] -= P_J P_J^T (the previous panel's update of the tile it is about to factor), 8 x 8 factorisation in registers ->
+//       L_JJ, reciprocal pivots; meanwhile warps 1,2,3,5,6,7 apply the previous panel's rank-8 update to the CTA's tiles and to the other
+//       diagonal replicas: 2 DMMAs per tile, operands = the panel column P (all-gathered, below), k permuted so that a lane's two operand
+//       values are adjacent (128-bit loads).  Warp 4 sits out: it shares warp 0's scheduler and FP64 pipe.
+//   (2) block barrier; a thread per local row below the panel solves its 8 entries against L_JJ and STORES THE SOLVED ROW INTO THE PANEL-COLUMN
+//       BUFFER OF ALL FOUR CTAs (distributed shared memory, fire-and-forget); P is double-buffered by panel parity.
+//   (3) cluster barrier (the stores have landed); the right-hand-side row's entries of the panel are y = L^-1 rhs.
+// Backward substitution L^T x = y, distributed: tile rows last to first; the owner of tile row T solves the 8 x 8 triangle (one warp), adds the
+// row's contributions to its own partial sums for the columns on the left and pushes the partial sums of the next three tile rows (final by
+// construction: its next own tile row is T - 4) to their owners' inboxes; one cluster barrier per tile row.
+constexpr int DSM_CL = 4;
+static_assert(SOLVE_THREADS == 256 && DSM_CL == SPLIT_CLUSTER, "ba_solve_cam_dsm: warp r assembles row r of a tile row; one launch geometry for both forms");
+__host__ __device__ inline int dsm_tile_off(int cr, int m) { return m * cr + 2 * m * (m - 1); }  // tiles ahead of local tile row m (T = cr + 4 m)
+__host__ __device__ inline int dsm_ntiles(int NR) { return (NR + 7) / 8; }
+__host__ inline size_t dsm_smem_doubles(const BaCaps &C) {
+    const int nt = dsm_ntiles(C.N + 1);
+    int mx = 0;
+    for (int cr = 0; cr < DSM_CL; cr++) {
+        int s = 0;
+        for (int T = cr; T < nt; T += DSM_CL) s += T;
+        mx = s > mx ? s : mx;
+    }
+    return 40 + 8 * (size_t) nt * 8 + 64 + 8 + 8 * DSM_CL + 8 + 8 + (size_t) nt * 64 * 3 + (size_t) mx * 64;
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, BaDev D, unsigned long long epoch) {
+    extern __shared__ double sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int CL = DSM_CL;
+    const int cr = (int) cluster.block_rank();
+    const int w = blockIdx.x / CL, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (w % D.world != D.rank) return;   // uniform over the cluster
+    LmState &st = D.st[w];
+    if (st.done) return;
+    const WinDims dm = D.dims[w];
+    const int K = dm.K, NCV = 6 * K + 7, N = 15 * K + 7, NR = N + 1;
+    const int ntc = dsm_ntiles(C.N + 1), VL = ntc * 8;   // capacity: tiles per side, vector length
+    const int nt = dsm_ntiles(NR), npan = (N + 7) / 8;   // this window: tile rows (incl. the rhs row), column panels
+    const int Tn = N >> 3, rn = N & 7;                   // tile row / row in the tile of the augmented right-hand-side row
+    const int f_first = st.first, f_fresh = st.fresh_lin, f_last = st.last_success, f_iter = st.iter, f_maxit = st.max_iter;
+    const double radius = st.radius, cost_cam = st.cost_cam, gmax_old = st.gmax, xcost_old = st.x_cost, init_old = st.initial_cost;
+    double *s_red = sm;                       // 40
+    double *s_scale = s_red + 40;             // VL each
+    double *s_g = s_scale + VL;
+    double *s_rhs = s_g + VL;
+    double *s_d2 = s_rhs + VL;
+    double *s_y = s_d2 + VL;                  // y = L^-1 rhs'
+    double *s_contrib = s_y + VL;             // back-substitution: this CTA's partial sums  sum_rows L[row][c] x[row]
+    double *s_x = s_contrib + VL;             // the solution (complete on CTA 0)
+    double *s_dinv = s_x + VL;                // reciprocal pivots (0 beyond N)
+    double *s_Lf = s_dinv + VL;               // 64: the panel's factored diagonal block, identity-padded
+    double *s_dv = s_Lf + 64;                 // 8: its reciprocal pivots
+    double *s_inbox = s_dv + 8;               // [CL][8]
+    double *s_xT = s_inbox + 8 * CL;          // 8
+    int *s_fail = (int *) (s_xT + 8);         // (8 doubles reserved)
+    double *s_dg = s_xT + 16;                 // [ntc][64] replicated diagonal tiles
+    double *s_P = s_dg + (size_t) ntc * 64;   // [2][ntc][64] panel column, by panel parity
+    double *s_tiles = s_P + (size_t) 2 * ntc * 64;
+    const double *Hc = D.Hc + (size_t) w * C.NS * C.NS, *gcam = D.gc + (size_t) w * C.NS, *Hs = D.Hs + (size_t) w * C.NS * C.NS;
+    const double *rv = D.S.redv + (size_t) w * D.S.RV;   // [diag H_vis | g_vis | W phi g_l | cost, sum rho^2, max |g_l|]
+    double *scale_c = D.scale_c + (size_t) w * C.NS;
+    // ---- gradient, Jacobi scaling (first linearisation), LM diagonal, rhs: every CTA keeps its own copy
+    for (int a = tid; a < VL; a += SOLVE_THREADS) {
+        double g = 0, sc = 0, d2 = 0, rh = 0;
+        if (a < N) {
+            g = gcam[a] + (a < NCV ? rv[NCV + a] : 0.0);
+            const double h = Hc[(size_t) a * C.NS + a] + (a < NCV ? rv[a] : 0.0);
+            sc = f_first ? 1.0 / (1.0 + sqrt(h)) : scale_c[a];
+            const double hs = sc * sc * h;
+            d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
+            rh = -sc * (g - (a < NCV ? rv[2 * NCV + a] : 0.0));
+        }
+        s_g[a] = g, s_scale[a] = sc, s_d2[a] = d2, s_rhs[a] = rh;
+        s_y[a] = 0, s_contrib[a] = 0, s_x[a] = 0, s_dinv[a] = 0;
+    }
+    if (tid < 8 * CL) s_inbox[tid] = 0;
+    if (tid == 0) *s_fail = 0;
+    __syncthreads();
+    double gmax_now = gmax_old, x_cost = xcost_old;
+    if (f_fresh) {
+        double gm = 0;
+        for (int a = tid; a < N; a += SOLVE_THREADS) gm = fmax(gm, fabs(s_g[a]));
+        gm = fmax(block_max(gm, s_red), rv[3 * NCV + 2]);
+        gmax_now = gm;
+        x_cost = rv[3 * NCV] + cost_cam;
+    }
+    int term = 0;
+    if (f_iter >= f_maxit) term = 1;                               // NO_CONVERGENCE
+    else if (f_last && gmax_now <= 1e-10) term = 2;                // gradient tolerance
+    else if (f_last && radius <= 1e-32) term = 2;                  // min trust region radius
+    cluster.sync();  // every CTA has read the state it needs (and is running: its shared memory may be written from now on)
+    if (cr == 0 && tid == 0) {
+        st.x_cost = x_cost, st.gmax = gmax_now;
+        if (f_first) st.initial_cost = x_cost;
+        st.fresh_lin = 0, st.first = 0, st.need_lin = 0;
+        if (term) st.done = term, st.step_valid = 0;
+        else st.iter = f_iter + 1;
+    }
+    if (cr == 0 && f_first)
+        for (int a = tid; a < N; a += SOLVE_THREADS) scale_c[a] = s_scale[a];
+    double *BC = nullptr;
+    if (term) {
+        if (cr == 0) {
+            __syncthreads();
+            for (int q = tid; q < D.world; q += SOLVE_THREADS) {
+                BC = x_bcast(D, q, w);
+                BC[0] = (double) term, BC[1] = 0.0, BC[2] = x_cost, BC[3] = gmax_now, BC[4] = f_first ? x_cost : init_old, BC[5] = 0.0;
+                __threadfence_system();
+                st_release_sys(x_flagB(D, q, w), epoch);
+            }
+        }
+        return;
+    }
+#ifdef ICG_BA_PHASE_CLOCKS
+#define DSM_CLK(k, t0)                                                                                             \
+    if (D.clk && w == 0 && cr == 0 && tid == 0) atomicAdd(&D.clk[k], clock64() - (t0)), atomicAdd(&D.clk[8 + (k)], 1ull);
+#define DSM_NOW() clock64()
+#else
+#define DSM_CLK(k, t0)
+#define DSM_NOW() 0ull
+#endif
+    const unsigned long long tq0 = DSM_NOW();
+    (void) tq0;
+    // ---- assembly of S' = s H s + D^2 into the tiles: warp r takes row r of every local tile row (coalesced row reads, 4 loads in flight)
+    for (int m = 0, T = cr; T < nt; m++, T += CL) {
+        double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + warp * 8;
+        const int i = 8 * T + warp, ncol = 8 * T;
+        const double *src = (i < NCV ? Hs : Hc) + (size_t) (i < N ? i : 0) * C.NS;
+        const double si = i < N ? s_scale[i] : 0.0;
+        for (int j0 = 0; j0 < ncol; j0 += 128) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + 32 * u + lane;
+                v[u] = (j < ncol && i < N) ? src[j] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + 32 * u + lane;
+                if (j < ncol) trow[(j >> 3) * 64 + (j & 7)] = i < N ? si * s_scale[j] * v[u] : (i == N ? s_rhs[j] : 0.0);
+            }
+        }
+    }
+    for (int e = tid; e < nt * 64; e += SOLVE_THREADS) {   // every diagonal tile, on every CTA
+        const int T = e >> 6, r = (e >> 3) & 7, c = e & 7, i = 8 * T + r, j = 8 * T + c;
+        double v = 0;
+        if (c <= r) {
+            if (i < N) {
+                v = s_scale[i] * s_scale[j] * ((i < NCV ? Hs : Hc)[(size_t) i * C.NS + j]);
+                if (i == j) v += s_d2[i];
+            } else if (i == N && j < N)
+                v = s_rhs[j];
+        }
+        s_dg[e] = v;
+    }
+    double *rP[CL];
+#pragma unroll
+    for (int q = 0; q < CL; q++) rP[q] = cluster.map_shared_rank(s_P, q);
+    __syncthreads();
+    DSM_CLK(0, tq0)  // assembly
+    const int wi = warp < 4 ? warp - 1 : warp - 2;   // worker index 0 .. 5 of warps 1,2,3,5,6,7
+    int fail = 0;
+    const unsigned long long tc_all = DSM_NOW();
+    (void) tc_all;
+    for (int J = 0; J < npan; J++) {
+        const int nb = min(8, N - 8 * J);
+        const double *PJ = s_P + (size_t) ((J - 1) & 1) * ntc * 64;   // panel J - 1's solved rows (J > 0)
+        const unsigned long long tc1 = DSM_NOW();
+        (void) tc1;
+        if (warp == 0) {
+            double *dg = s_dg + (size_t) J * 64;
+            if (J > 0) {   // the previous panel's update of the tile about to be factored
+                const double2 p = *(const double2 *) (PJ + (size_t) J * 64 + 2 * lane);
+                double2 c = *(double2 *) (dg + 2 * lane);
+                dmma884(c.x, c.y, -p.x, p.x);
+                dmma884(c.x, c.y, -p.y, p.y);
+                *(double2 *) (dg + 2 * lane) = c;
+                __syncwarp();
+            }
+            double Ld[8][8], dinv[8];
+            bool bad = false;
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 8; b++) Ld[a][b] = (a < nb && b <= a) ? dg[a * 8 + b] : (a == b ? 1.0 : 0.0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double d = Ld[j][j];
+#pragma unroll
+                for (int k = 0; k < j; k++) d -= Ld[j][k] * Ld[j][k];
+                if (!(d > 0.0) || !isfinite(d)) bad = true;
+                const double di = rsqrt(d);
+                dinv[j] = di;
+                Ld[j][j] = d * di;
+#pragma unroll
+                for (int a = j + 1; a < 8; a++) {
+                    double sum = Ld[a][j];
+#pragma unroll
+                    for (int k = 0; k < j; k++) sum -= Ld[a][k] * Ld[j][k];
+                    Ld[a][j] = sum * di;
+                }
+            }
+            __syncwarp();  // every lane has read the unfactored block
+#pragma unroll
+            for (int a2 = 0; a2 < 8; a2++) {  // static indexing keeps Ld in registers: lane a writes row a
+                if (a2 != lane) continue;
+#pragma unroll
+                for (int b = 0; b < 8; b++) s_Lf[a2 * 8 + b] = b <= a2 ? Ld[a2][b] : 0.0;
+                s_dv[a2] = dinv[a2];
+                if (a2 < nb) {
+#pragma unroll
+                    for (int b = 0; b <= a2; b++) dg[a2 * 8 + b] = Ld[a2][b];   // kept for the backward substitution
+                    s_dinv[8 * J + a2] = dinv[a2];
+                }
+            }
+            if (lane == 0 && bad) *s_fail = 1;
+            DSM_CLK(1, tc1)  // warp 0: diagonal-tile update + factorisation
+        } else if (J > 0 && warp != 4) {
+            const int Jp = J - 1;
+            // local tiles (T, tc), Jp < tc < T
+            int m = (Jp + 2 - cr + CL - 1) / CL;
+            for (int T = cr + CL * m; T < nt; m++, T += CL) {
+                const double2 pa = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
+                const double a0 = -pa.x, a1 = -pa.y;
+                double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + 2 * lane;
+                const double *pb = PJ + 2 * lane;
+                int tc = Jp + 1 + (wi + m) % 6;
+                for (; tc + 18 < T; tc += 24) {
+                    double2 b[4], c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) b[u] = *(const double2 *) (pb + (size_t) (tc + 6 * u) * 64), c[u] = *(double2 *) (trow + (size_t) (tc + 6 * u) * 64);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a0, b[u].x);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a1, b[u].y);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) *(double2 *) (trow + (size_t) (tc + 6 * u) * 64) = c[u];
+                }
+                for (; tc < T; tc += 6) {
+                    const double2 b = *(const double2 *) (pb + (size_t) tc * 64);
+                    double2 c = *(double2 *) (trow + (size_t) tc * 64);
+                    dmma884(c.x, c.y, a0, b.x);
+                    dmma884(c.x, c.y, a1, b.y);
+                    *(double2 *) (trow + (size_t) tc * 64) = c;
+                }
+            }
+            // the other diagonal replicas (every tile row, on every CTA)
+            for (int T = Jp + 2 + wi; T < nt; T += 6) {
+                const double2 p = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
+                double2 c = *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane);
+                dmma884(c.x, c.y, -p.x, p.x);
+                dmma884(c.x, c.y, -p.y, p.y);
+                *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane) = c;
+            }
+        }
+        __syncthreads();
+        DSM_CLK(2, tc1)  // ... until the slower of factorisation and trailing update is through
+        const unsigned long long tc2 = DSM_NOW();
+        (void) tc2;
+        fail = *s_fail;  // identical on every CTA of the cluster (redundant bit-identical factorisations)
+        if (fail) break;
+        {   // rows below the panel: one thread per row of the local tile rows T > J
+            const int m = (J + 1 - cr + CL - 1) / CL + (tid >> 3), r = tid & 7, T = cr + CL * m;
+            if (T < nt) {
+                double *tp = s_tiles + ((size_t) dsm_tile_off(cr, m) + J) * 64 + r * 8;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 t2 = *(const double2 *) (tp + c);
+                    x[c] = t2.x, x[c + 1] = t2.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double sum = x[c];
+#pragma unroll
+                    for (int k = 0; k < c; k++) sum -= x[k] * s_Lf[c * 8 + k];
+                    x[c] = sum * s_dv[c];
+                }
+                const size_t po = (size_t) (J & 1) * ntc * 64 + (size_t) T * 64 + r * 8;
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 t2 = make_double2(x[c], x[c + 1]);
+                    *(double2 *) (tp + c) = t2;
+#pragma unroll
+                    for (int q = 0; q < CL; q++) *(double2 *) (rP[q] + po + c) = t2;
+                }
+            }
+        }
+        cluster.sync();
+        if (tid < 8 && Tn > J) s_y[8 * J + tid] = s_P[(size_t) (J & 1) * ntc * 64 + (size_t) Tn * 64 + rn * 8 + tid];
+        DSM_CLK(3, tc2)  // row solves + cluster barrier
+    }
+    DSM_CLK(4, tc_all)   // whole factorisation
+    const bool valid = !fail;
+    const unsigned long long tb0 = DSM_NOW();
+    (void) tb0;
+    if (valid) {
+        if (rn > 0 && tid == 0) {   // the right-hand-side row shares the last diagonal tile with the last rn columns
+            double x[8];
+            for (int c = 0; c < rn; c++) {
+                double sum = s_dg[(size_t) Tn * 64 + rn * 8 + c];
+                for (int k = 0; k < c; k++) sum -= x[k] * s_Lf[c * 8 + k];
+                x[c] = sum * s_dv[c];
+                s_y[8 * Tn + c] = x[c];
+            }
+        }
+        __syncthreads();
+        // ---- distributed backward substitution
+        double *rX0 = cluster.map_shared_rank(s_x, 0);
+        for (int T = npan - 1; T >= 0; T--) {
+            if (cr == T % CL) {
+                const int nbT = min(8, N - 8 * T), m = T / CL;
+                const double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64;
+                if (warp == 0) {
+                    const int c = lane & 7;
+                    double v = 0, lcol[8];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) lcol[r] = s_dg[(size_t) T * 64 + r * 8 + c];
+                    if (lane < nbT) {
+                        v = s_y[8 * T + c] - s_contrib[8 * T + c];
+#pragma unroll
+                        for (int q = 0; q < CL; q++)
+                            if (q != cr) v -= s_inbox[q * 8 + c];
+                    }
+#pragma unroll
+                    for (int r = 7; r >= 0; r--) {   // x_r = (v_r - sum_{i > r} L_ir x_i) / L_rr; rows beyond N have a zero reciprocal pivot
+                        const double xr = __shfl_sync(0xffffffffu, v, r) * s_dinv[8 * T + r];
+                        if (lane == r) v = xr;
+                        else if (lane < r) v -= lcol[r] * xr;
+                    }
+                    if (lane < 8) s_xT[lane] = v, rX0[8 * T + lane] = v;
+                }
+                __syncthreads();
+                for (int col = tid; col < 8 * T; col += SOLVE_THREADS) {
+                    const double *tp = trow + (col >> 3) * 64 + (col & 7);
+                    double acc = s_contrib[col];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) acc += tp[r * 8] * s_xT[r];
+                    s_contrib[col] = acc;
+                }
+                __syncthreads();
+                if (tid < 24) {   // partial sums of the next three tile rows: final on this CTA (its next own tile row is T - 4)
+                    const int k = 1 + (tid >> 3), c = tid & 7, Tt = T - k;
+                    if (Tt >= 0) cluster.map_shared_rank(s_inbox, Tt % CL)[cr * 8 + c] = s_contrib[8 * Tt + c];
+                }
+            }
+            cluster.sync();
+        }
+    }
+    DSM_CLK(5, tb0)  // backward substitution
+    if (cr != 0) return;
+    // ---- camera part of the model cost change, broadcast of [header | delta = step' * scale]
+    double part = 0;
+    bool finite = true;
+    if (valid)
+        for (int a = tid; a < N; a += SOLVE_THREADS) {
+            const double sp = s_x[a];
+            finite = finite && isfinite(sp);
+            part += -0.5 * sp * (s_scale[a] * s_g[a]) + 0.5 * s_d2[a] * sp * sp;
+        }
+    const double mcc = block_sum(part, s_red);
+    const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
+    for (int q = 0; q < D.world; q++) {
+        BC = x_bcast(D, q, w);
+        if (valid)
+            for (int a = tid; a < N; a += SOLVE_THREADS) BC[SPLIT_HDR + a] = s_x[a] * s_scale[a];
+        if (tid == 0) {
+            BC[0] = 0.0, BC[1] = (valid && nfin == 0.0) ? 1.0 : 0.0, BC[2] = x_cost, BC[3] = gmax_now, BC[4] = f_first ? x_cost : init_old, BC[5] = mcc;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int q = tid; q < D.world; q += SOLVE_THREADS) st_release_sys(x_flagB(D, q, w), epoch);
+}
+
 // ------------------------------------------------------------------------------------------------ step_lm (every rank, CTA per window)
 __global__ void __launch_bounds__(SOLVE_THREADS) ba_step_lm(BaCaps C, BaDev D, unsigned long long epoch) {
     extern __shared__ double sm[];
