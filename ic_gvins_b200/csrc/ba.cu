@@ -1798,6 +1798,7 @@ struct icg_ba {
     bool solve_cam_stage_a = false;  // per-warp shared-memory strips for the DMMA A operand (ba_solve_cam)
     bool solve_cam_dsm = false;      // the packed system fits the cluster's shared memory: ba_solve_cam_dsm (max_K <= 22)
     size_t smem_solve_cam_dsm = 0;
+    int dsm_variant = 0;             // ba_solve_cam_dsm: DSM_V_* bits (ICG_BA_DSM_VARIANT)
     // in-situ stage timing (ICG_BA_PROFILE=1): events between the kernels of the LM sequence on the main stream, read back in
     // icg_ba_sync / icg_ba_download and printed by icg_ba_destroy (warm caches, real launch gaps -- unlike an ncu replay)
     bool prof = false;
@@ -1938,7 +1939,7 @@ static int ba_create_body(icg_ba *h, int max_windows, int max_K, int max_L, int 
     if (getenv("ICG_BA_CAM_THREADS")) h->cam_threads = std::min(CAM_THREADS, std::max(128, atoi(getenv("ICG_BA_CAM_THREADS")) & ~31));
     if (h->prof) {
         double *ck = nullptr;
-        if (dmalloc(h, &ck, 32) != ICG_OK) return ICG_ENOMEM;
+        if (dmalloc(h, &ck, 48) != ICG_OK) return ICG_ENOMEM;
         h->D.clk = (unsigned long long *) ck;
     }
     if (getenv("ICG_BA_PROFILE_SKIP")) h->prof_skip = atoi(getenv("ICG_BA_PROFILE_SKIP"));
@@ -2291,7 +2292,7 @@ static void prof_print(icg_ba *h) {
         if (h->prof_cnt[t])
             fprintf(stderr, "  %-28s %9.3f ms  %8.1f us  %5.1f %%\n", PROF_NAMES[t], h->prof_ms[t], 1e3 * h->prof_ms[t] / h->prof_cnt[t], 100.0 * h->prof_ms[t] / tot);
     if (h->D.clk) {
-        unsigned long long ck[32];
+        unsigned long long ck[48];
         if (cudaMemcpy(ck, h->D.clk, sizeof(ck), cudaMemcpyDeviceToHost) == cudaSuccess) {
             static const char *cn[6] = {"factor evaluation", "prior product + cost", "zero H_c", "prior blocks", "IMU J^T J", "GNSS / prior diagonals"};
             fprintf(stderr, "[icg_ba profile] ba_lin_cam phases of window 0 (SM cycles per call, mean):\n");
@@ -2304,6 +2305,9 @@ static void prof_print(icg_ba *h) {
                 fprintf(stderr, "[icg_ba profile] %s phases of window 0 (SM cycles, mean):\n", h->solve_cam_dsm ? "ba_solve_cam_dsm" : "ba_solve_cam");
                 for (int k = 0; k < 6; k++)
                     if (ck[8 + k]) fprintf(stderr, "  %-34s %9.0f cycles\n", sn[k], (double) ck[k] / (double) ck[8 + k]);
+                static const char *sn2[5] = {"per panel: wait for the panel column", "per panel: trailing update, all warps (serial form)", "per panel: warp 0 diagonal-tile update", "per panel: warp 0 loads + 8x8 factorisation", "per panel: warp 0 write-back"};
+                for (int k = 0; k < 5 && h->solve_cam_dsm; k++)
+                    if (ck[40 + k]) fprintf(stderr, "  %-50s %9.0f cycles\n", sn2[k], (double) ck[32 + k] / (double) ck[40 + k]);
             }
             static const char *nm[8] = {"gradient / cost / tests", "assembly", "Cholesky", "camera back-substitution", "landmark back-substitution", "candidate + reductions",
                                         "  per panel: warp 0 tile+factor", "  per panel: row solve phase"};
@@ -2458,6 +2462,7 @@ static int split_setup(icg_ba *h, int rank, int world) {
     h->smem_solve_cam_dsm = sizeof(double) * dsm_smem_doubles(C);
     h->solve_cam_dsm = h->smem_solve_cam_dsm <= 227 * 1024 && !getenv("ICG_BA_SOLVE_CAM_L2");
     if (h->solve_cam_dsm) ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam_dsm, h->smem_solve_cam_dsm));
+    h->dsm_variant = getenv("ICG_BA_DSM_VARIANT") ? atoi(getenv("ICG_BA_DSM_VARIANT")) : 0;
     ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam, (size_t) (h->smem_solve_cam)));
     ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     ICG_CUDA(raise_dynamic_smem((const void *) ba_step_lm, (size_t) (h->smem_step_lm)));
@@ -2473,7 +2478,7 @@ static int launch_solve_cam(icg_ba *h, int n, unsigned long long epoch) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = SPLIT_CLUSTER, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
     cfg.attrs = at, cfg.numAttrs = 1;
-    if (h->solve_cam_dsm) ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam_dsm, h->C, h->D, epoch));
+    if (h->solve_cam_dsm) ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam_dsm, h->C, h->D, epoch, h->dsm_variant));
     else ICG_CUDA(cudaLaunchKernelEx(&cfg, ba_solve_cam, h->C, h->D, epoch, (int) h->solve_cam_stage_a));
     return ICG_OK;
 }

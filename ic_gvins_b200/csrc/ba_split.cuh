@@ -561,7 +561,47 @@ __host__ inline size_t dsm_smem_doubles(const BaCaps &C) {
     return 40 + 8 * (size_t) nt * 8 + 64 + 8 + 8 * DSM_CL + 8 + 8 + (size_t) nt * 64 * 3 + (size_t) mx * 64;
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, BaDev D, unsigned long long epoch) {
+// ---- distributed-shared-memory plumbing: cluster addresses, mbarriers with transaction counts, asynchronous remote stores
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsm_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void dsm_mbar_arrive_local(unsigned bar) { asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// arrive on a barrier of another CTA of the cluster and announce the bytes this CTA has sent towards it (st.async below completes them)
+__device__ __forceinline__ void dsm_mbar_arrive_expect_tx_remote(unsigned bar_cluster, unsigned tx) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void st_async_v2(unsigned dst_cluster, double a, double b, unsigned bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(dst_cluster), "d"(a), "d"(b), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void st_async_f64(unsigned dst_cluster, double a, unsigned bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(dst_cluster), "d"(a), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ bool dsm_mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait (~0.2 s): a protocol error raises the handle's error word and poisons the later waits of this CTA instead of hanging the GPU
+__device__ __forceinline__ void dsm_mbar_wait(unsigned bar, unsigned parity, volatile int *s_dead, int *err) {
+    if (dsm_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!dsm_mbar_try_wait(bar, parity)) {
+        if (*s_dead) return;
+        if (clock64() - t0 > 400000000ll) {
+            *s_dead = 1;
+            atomicExch(err, 1);
+            return;
+        }
+    }
+}
+
+// variant: bit 0 = hand-over of the panel column / the back-substitution sums with asynchronous stores + mbarriers (no cluster barrier in the
+// loops); bit 1 = the trailing update on all eight warps BEFORE the factorisation instead of beside it.
+constexpr int DSM_V_MBAR = 1, DSM_V_SERIAL = 2;
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, BaDev D, unsigned long long epoch, int variant) {
     extern __shared__ double sm[];
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int CL = DSM_CL;
@@ -570,6 +610,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
     if (w % D.world != D.rank) return;   // uniform over the cluster
     LmState &st = D.st[w];
     if (st.done) return;
+    const bool use_mbar = variant & DSM_V_MBAR, serial = variant & DSM_V_SERIAL;
     const WinDims dm = D.dims[w];
     const int K = dm.K, NCV = 6 * K + 7, N = 15 * K + 7, NR = N + 1;
     const int ntc = dsm_ntiles(C.N + 1), VL = ntc * 8;   // capacity: tiles per side, vector length
@@ -590,7 +631,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
     double *s_dv = s_Lf + 64;                 // 8: its reciprocal pivots
     double *s_inbox = s_dv + 8;               // [CL][8]
     double *s_xT = s_inbox + 8 * CL;          // 8
-    int *s_fail = (int *) (s_xT + 8);         // (8 doubles reserved)
+    int *s_fail = (int *) (s_xT + 8);         // [0] breakdown, [1] a bounded wait ran out; then the mbarriers (8 doubles reserved)
+    unsigned long long *s_bar = (unsigned long long *) (s_xT + 12);  // [0], [1]: panel column by parity; [2]: back-substitution inbox
     double *s_dg = s_xT + 16;                 // [ntc][64] replicated diagonal tiles
     double *s_P = s_dg + (size_t) ntc * 64;   // [2][ntc][64] panel column, by panel parity
     double *s_tiles = s_P + (size_t) 2 * ntc * 64;
@@ -612,7 +654,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
         s_y[a] = 0, s_contrib[a] = 0, s_x[a] = 0, s_dinv[a] = 0;
     }
     if (tid < 8 * CL) s_inbox[tid] = 0;
-    if (tid == 0) *s_fail = 0;
+    if (tid == 0) {
+        s_fail[0] = 0, s_fail[1] = 0;
+        dsm_mbar_init(smem_u32(s_bar), CL), dsm_mbar_init(smem_u32(s_bar + 1), CL), dsm_mbar_init(smem_u32(s_bar + 2), CL - 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     double gmax_now = gmax_old, x_cost = xcost_old;
     if (f_fresh) {
@@ -626,7 +672,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
     if (f_iter >= f_maxit) term = 1;                               // NO_CONVERGENCE
     else if (f_last && gmax_now <= 1e-10) term = 2;                // gradient tolerance
     else if (f_last && radius <= 1e-32) term = 2;                  // min trust region radius
-    cluster.sync();  // every CTA has read the state it needs (and is running: its shared memory may be written from now on)
+    cluster.sync();  // every CTA has read the state it needs (and is running: its shared memory and barriers may be used from now on)
     if (cr == 0 && tid == 0) {
         st.x_cost = x_cost, st.gmax = gmax_now;
         if (f_first) st.initial_cost = x_cost;
@@ -652,28 +698,31 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
 #ifdef ICG_BA_PHASE_CLOCKS
 #define DSM_CLK(k, t0)                                                                                             \
     if (D.clk && w == 0 && cr == 0 && tid == 0) atomicAdd(&D.clk[k], clock64() - (t0)), atomicAdd(&D.clk[8 + (k)], 1ull);
+#define DSM_CLK2(k, t0)                                                                                            \
+    if (D.clk && w == 0 && cr == 0 && tid == 0) atomicAdd(&D.clk[32 + (k)], clock64() - (t0)), atomicAdd(&D.clk[40 + (k)], 1ull);
 #define DSM_NOW() clock64()
 #else
 #define DSM_CLK(k, t0)
+#define DSM_CLK2(k, t0)
 #define DSM_NOW() 0ull
 #endif
     const unsigned long long tq0 = DSM_NOW();
     (void) tq0;
-    // ---- assembly of S' = s H s + D^2 into the tiles: warp r takes row r of every local tile row (coalesced row reads, 4 loads in flight)
+    // ---- assembly of S' = s H s + D^2 into the tiles: warp r takes row r of every local tile row (coalesced row reads, 8 loads in flight)
     for (int m = 0, T = cr; T < nt; m++, T += CL) {
         double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + warp * 8;
         const int i = 8 * T + warp, ncol = 8 * T;
         const double *src = (i < NCV ? Hs : Hc) + (size_t) (i < N ? i : 0) * C.NS;
         const double si = i < N ? s_scale[i] : 0.0;
-        for (int j0 = 0; j0 < ncol; j0 += 128) {
-            double v[4];
+        for (int j0 = 0; j0 < ncol; j0 += 256) {
+            double v[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int j = j0 + 32 * u + lane;
-                v[u] = (j < ncol && i < N) ? src[j] : 0.0;
+                v[u] = (j < ncol && i < N) ? __ldcg(src + j) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const int j = j0 + 32 * u + lane;
                 if (j < ncol) trow[(j >> 3) * 64 + (j & 7)] = i < N ? si * s_scale[j] * v[u] : (i == N ? s_rhs[j] : 0.0);
             }
@@ -684,7 +733,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
         double v = 0;
         if (c <= r) {
             if (i < N) {
-                v = s_scale[i] * s_scale[j] * ((i < NCV ? Hs : Hc)[(size_t) i * C.NS + j]);
+                v = s_scale[i] * s_scale[j] * __ldcg((i < NCV ? Hs : Hc) + (size_t) i * C.NS + j);
                 if (i == j) v += s_d2[i];
             } else if (i == N && j < N)
                 v = s_rhs[j];
@@ -692,20 +741,78 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
         s_dg[e] = v;
     }
     double *rP[CL];
+    unsigned aP[CL], aBar[CL];   // cluster-window addresses of every CTA's panel buffer and panel barriers (statically indexed: registers)
 #pragma unroll
-    for (int q = 0; q < CL; q++) rP[q] = cluster.map_shared_rank(s_P, q);
+    for (int q = 0; q < CL; q++) {
+        rP[q] = cluster.map_shared_rank(s_P, q);
+        aP[q] = mapa_u32(smem_u32(s_P), q), aBar[q] = mapa_u32(smem_u32(s_bar), q);
+    }
+    volatile int *s_dead = s_fail + 1;
     __syncthreads();
     DSM_CLK(0, tq0)  // assembly
-    const int wi = warp < 4 ? warp - 1 : warp - 2;   // worker index 0 .. 5 of warps 1,2,3,5,6,7
+    const int nwork = serial ? 8 : 6;
+    const int wi = serial ? warp : (warp < 4 ? warp - 1 : warp - 2);   // worker index: all warps, or warps 1,2,3,5,6,7 beside warp 0's factorisation
+    const bool worker = serial || (warp != 0 && warp != 4);
     int fail = 0;
     const unsigned long long tc_all = DSM_NOW();
     (void) tc_all;
     for (int J = 0; J < npan; J++) {
         const int nb = min(8, N - 8 * J);
         const double *PJ = s_P + (size_t) ((J - 1) & 1) * ntc * 64;   // panel J - 1's solved rows (J > 0)
+        const unsigned long long tc0 = DSM_NOW();
+        (void) tc0;
+        if (J > 0) {
+            if (use_mbar) dsm_mbar_wait(smem_u32(s_bar + ((J - 1) & 1)), ((J - 1) >> 1) & 1, s_dead, D.S.err);   // panel J - 1's column has landed
+            if (tid < 8 && Tn > J - 1) s_y[8 * (J - 1) + tid] = PJ[(size_t) Tn * 64 + rn * 8 + tid];         // its right-hand-side entries: y
+        }
+        DSM_CLK2(0, tc0)  // wait for the panel column
         const unsigned long long tc1 = DSM_NOW();
         (void) tc1;
+        if (J > 0 && worker) {
+            const int Jp = J - 1;
+            // local tiles (T, tc), Jp < tc < T
+            int m = (Jp + 2 - cr + CL - 1) / CL;
+            for (int T = cr + CL * m; T < nt; m++, T += CL) {
+                const double2 pa = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
+                const double a0 = -pa.x, a1 = -pa.y;
+                double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + 2 * lane;
+                const double *pb = PJ + 2 * lane;
+                int tc = Jp + 1 + (wi + m) % nwork;
+                for (; tc + 3 * nwork < T; tc += 4 * nwork) {
+                    double2 b[4], c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) b[u] = *(const double2 *) (pb + (size_t) (tc + nwork * u) * 64), c[u] = *(double2 *) (trow + (size_t) (tc + nwork * u) * 64);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a0, b[u].x);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a1, b[u].y);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) *(double2 *) (trow + (size_t) (tc + nwork * u) * 64) = c[u];
+                }
+                for (; tc < T; tc += nwork) {
+                    const double2 b = *(const double2 *) (pb + (size_t) tc * 64);
+                    double2 c = *(double2 *) (trow + (size_t) tc * 64);
+                    dmma884(c.x, c.y, a0, b.x);
+                    dmma884(c.x, c.y, a1, b.y);
+                    *(double2 *) (trow + (size_t) tc * 64) = c;
+                }
+            }
+            // the other diagonal replicas (every tile row, on every CTA)
+            for (int T = Jp + 2 + wi; T < nt; T += nwork) {
+                const double2 p = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
+                double2 c = *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane);
+                dmma884(c.x, c.y, -p.x, p.x);
+                dmma884(c.x, c.y, -p.y, p.y);
+                *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane) = c;
+            }
+        }
+        if (serial) {
+            __syncthreads();
+            DSM_CLK2(1, tc1)  // trailing update on all warps
+        }
         if (warp == 0) {
+            const unsigned long long tf0 = DSM_NOW();
+            (void) tf0;
             double *dg = s_dg + (size_t) J * 64;
             if (J > 0) {   // the previous panel's update of the tile about to be factored
                 const double2 p = *(const double2 *) (PJ + (size_t) J * 64 + 2 * lane);
@@ -715,6 +822,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                 *(double2 *) (dg + 2 * lane) = c;
                 __syncwarp();
             }
+            DSM_CLK2(2, tf0)  // warp 0: update of the diagonal tile
+            const unsigned long long tf1 = DSM_NOW();
+            (void) tf1;
             double Ld[8][8], dinv[8];
             bool bad = false;
 #pragma unroll
@@ -738,6 +848,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     Ld[a][j] = sum * di;
                 }
             }
+#ifdef ICG_BA_PHASE_CLOCKS
+            if (Ld[7][7] == 12345.678) bad = true;  // the clock below is read after the arithmetic
+#endif
+            DSM_CLK2(3, tf1)  // warp 0: block loads + 8 x 8 factorisation in registers
+            const unsigned long long tf2 = DSM_NOW();
+            (void) tf2;
             __syncwarp();  // every lane has read the unfactored block
 #pragma unroll
             for (int a2 = 0; a2 < 8; a2++) {  // static indexing keeps Ld in registers: lane a writes row a
@@ -751,54 +867,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     s_dinv[8 * J + a2] = dinv[a2];
                 }
             }
-            if (lane == 0 && bad) *s_fail = 1;
-            DSM_CLK(1, tc1)  // warp 0: diagonal-tile update + factorisation
-        } else if (J > 0 && warp != 4) {
-            const int Jp = J - 1;
-            // local tiles (T, tc), Jp < tc < T
-            int m = (Jp + 2 - cr + CL - 1) / CL;
-            for (int T = cr + CL * m; T < nt; m++, T += CL) {
-                const double2 pa = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
-                const double a0 = -pa.x, a1 = -pa.y;
-                double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + 2 * lane;
-                const double *pb = PJ + 2 * lane;
-                int tc = Jp + 1 + (wi + m) % 6;
-                for (; tc + 18 < T; tc += 24) {
-                    double2 b[4], c[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) b[u] = *(const double2 *) (pb + (size_t) (tc + 6 * u) * 64), c[u] = *(double2 *) (trow + (size_t) (tc + 6 * u) * 64);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a0, b[u].x);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a1, b[u].y);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) *(double2 *) (trow + (size_t) (tc + 6 * u) * 64) = c[u];
-                }
-                for (; tc < T; tc += 6) {
-                    const double2 b = *(const double2 *) (pb + (size_t) tc * 64);
-                    double2 c = *(double2 *) (trow + (size_t) tc * 64);
-                    dmma884(c.x, c.y, a0, b.x);
-                    dmma884(c.x, c.y, a1, b.y);
-                    *(double2 *) (trow + (size_t) tc * 64) = c;
-                }
-            }
-            // the other diagonal replicas (every tile row, on every CTA)
-            for (int T = Jp + 2 + wi; T < nt; T += 6) {
-                const double2 p = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
-                double2 c = *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane);
-                dmma884(c.x, c.y, -p.x, p.x);
-                dmma884(c.x, c.y, -p.y, p.y);
-                *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane) = c;
-            }
+            if (lane == 0 && bad) s_fail[0] = 1;
+            DSM_CLK2(4, tf2)  // warp 0: write-back
+            DSM_CLK(1, tf0)   // warp 0: diagonal-tile update + factorisation
         }
         __syncthreads();
         DSM_CLK(2, tc1)  // ... until the slower of factorisation and trailing update is through
         const unsigned long long tc2 = DSM_NOW();
         (void) tc2;
-        fail = *s_fail;  // identical on every CTA of the cluster (redundant bit-identical factorisations)
+        fail = s_fail[0];  // identical on every CTA of the cluster (redundant bit-identical factorisations)
         if (fail) break;
         {   // rows below the panel: one thread per row of the local tile rows T > J
-            const int m = (J + 1 - cr + CL - 1) / CL + (tid >> 3), r = tid & 7, T = cr + CL * m;
+            const int m0 = (J + 1 - cr + CL - 1) / CL;
+            const int m = m0 + (tid >> 3), r = tid & 7, T = cr + CL * m;
             if (T < nt) {
                 double *tp = s_tiles + ((size_t) dsm_tile_off(cr, m) + J) * 64 + r * 8;
                 double x[8];
@@ -814,25 +895,43 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     for (int k = 0; k < c; k++) sum -= x[k] * s_Lf[c * 8 + k];
                     x[c] = sum * s_dv[c];
                 }
-                const size_t po = (size_t) (J & 1) * ntc * 64 + (size_t) T * 64 + r * 8;
+                const unsigned po = (unsigned) ((size_t) (J & 1) * ntc * 64 + (size_t) T * 64 + r * 8);
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
                     const double2 t2 = make_double2(x[c], x[c + 1]);
                     *(double2 *) (tp + c) = t2;
+                    if (use_mbar) {
 #pragma unroll
-                    for (int q = 0; q < CL; q++) *(double2 *) (rP[q] + po + c) = t2;
+                        for (int q = 0; q < CL; q++) st_async_v2(aP[q] + 8u * (po + c), x[c], x[c + 1], aBar[q] + 8u * (J & 1));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < CL; q++) *(double2 *) (rP[q] + po + c) = t2;
+                    }
                 }
             }
+            if (use_mbar) {
+                // every CTA arrives on every CTA's barrier of this panel (also with nothing sent: the arrival says "I am done reading the
+                // buffer of panel J - 1", which the receiver's next-but-one panel overwrites) and announces its bytes
+                if (tid < CL) {
+                    const int nloc = cr + CL * m0 < nt ? (nt - 1 - (cr + CL * m0)) / CL + 1 : 0;   // local tile rows below the panel
+                    dsm_mbar_arrive_expect_tx_remote(mapa_u32(smem_u32(s_bar + (J & 1)), tid), 512u * nloc);
+                }
+            } else {
+                cluster.sync();
+            }
         }
-        cluster.sync();
-        if (tid < 8 && Tn > J) s_y[8 * J + tid] = s_P[(size_t) (J & 1) * ntc * 64 + (size_t) Tn * 64 + rn * 8 + tid];
-        DSM_CLK(3, tc2)  // row solves + cluster barrier
+        DSM_CLK(3, tc2)  // row solves + hand-over
     }
     DSM_CLK(4, tc_all)   // whole factorisation
     const bool valid = !fail;
     const unsigned long long tb0 = DSM_NOW();
     (void) tb0;
     if (valid) {
+        {   // the last panel's column (only the right-hand-side row can be below it)
+            const int J = npan - 1;
+            if (use_mbar) dsm_mbar_wait(smem_u32(s_bar + (J & 1)), (J >> 1) & 1, s_dead, D.S.err);
+            if (tid < 8 && Tn > J) s_y[8 * J + tid] = s_P[(size_t) (J & 1) * ntc * 64 + (size_t) Tn * 64 + rn * 8 + tid];
+        }
         if (rn > 0 && tid == 0) {   // the right-hand-side row shares the last diagonal tile with the last rn columns
             double x[8];
             for (int c = 0; c < rn; c++) {
@@ -849,6 +948,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             if (cr == T % CL) {
                 const int nbT = min(8, N - 8 * T), m = T / CL;
                 const double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64;
+                if (use_mbar) {
+                    // three partial-sum messages per tile row (from the owners of T + 1 .. T + 3); the ones that do not exist are arrived here
+                    const int nmiss = max(0, 3 - (npan - 1 - T));
+                    if (tid < nmiss) dsm_mbar_arrive_local(smem_u32(s_bar + 2));
+                    dsm_mbar_wait(smem_u32(s_bar + 2), ((npan - 1 - T) / CL) & 1, s_dead, D.S.err);
+                }
                 if (warp == 0) {
                     const int c = lane & 7;
                     double v = 0, lcol[8];
@@ -869,7 +974,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     if (lane < 8) s_xT[lane] = v, rX0[8 * T + lane] = v;
                 }
                 __syncthreads();
-                for (int col = tid; col < 8 * T; col += SOLVE_THREADS) {
+                // partial sums of the next three tile rows first: they are final on this CTA (its next own tile row is T - 4) and travel now
+                const int c0 = max(0, 8 * (T - 3));
+                if (tid < 8 * T - c0) {
+                    const int col = c0 + tid;
+                    const double *tp = trow + (col >> 3) * 64 + (col & 7);
+                    double acc = s_contrib[col];
+#pragma unroll
+                    for (int r = 0; r < 8; r++) acc += tp[r * 8] * s_xT[r];
+                    s_contrib[col] = acc;
+                    const int Tt = col >> 3, q = Tt % CL;
+                    if (use_mbar) {
+                        const unsigned abar = mapa_u32(smem_u32(s_bar + 2), q);
+                        st_async_f64(mapa_u32(smem_u32(s_inbox + cr * 8 + (col & 7)), q), acc, abar);
+                        if ((col & 7) == 0) dsm_mbar_arrive_expect_tx_remote(abar, 64u);
+                    } else {
+                        cluster.map_shared_rank(s_inbox, q)[cr * 8 + (col & 7)] = acc;
+                    }
+                }
+                for (int col = tid; col < c0; col += SOLVE_THREADS) {
                     const double *tp = trow + (col >> 3) * 64 + (col & 7);
                     double acc = s_contrib[col];
 #pragma unroll
@@ -877,14 +1000,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     s_contrib[col] = acc;
                 }
                 __syncthreads();
-                if (tid < 24) {   // partial sums of the next three tile rows: final on this CTA (its next own tile row is T - 4)
-                    const int k = 1 + (tid >> 3), c = tid & 7, Tt = T - k;
-                    if (Tt >= 0) cluster.map_shared_rank(s_inbox, Tt % CL)[cr * 8 + c] = s_contrib[8 * Tt + c];
-                }
             }
-            cluster.sync();
+            if (!use_mbar) cluster.sync();
         }
     }
+    cluster.sync();  // the solution has landed on CTA 0; no CTA leaves while its shared memory may still be written
     DSM_CLK(5, tb0)  // backward substitution
     if (cr != 0) return;
     // ---- camera part of the model cost change, broadcast of [header | delta = step' * scale]
