@@ -2305,7 +2305,7 @@ static void prof_print(icg_ba *h) {
                 fprintf(stderr, "[icg_ba profile] %s phases of window 0 (SM cycles, mean):\n", h->solve_cam_dsm ? "ba_solve_cam_dsm" : "ba_solve_cam");
                 for (int k = 0; k < 6; k++)
                     if (ck[8 + k]) fprintf(stderr, "  %-34s %9.0f cycles\n", sn[k], (double) ck[k] / (double) ck[8 + k]);
-                static const char *sn2[5] = {"per panel: wait for the panel column", "per panel: trailing update, all warps (serial form)", "per panel: warp 0 diagonal-tile update", "per panel: warp 0 loads + 8x8 factorisation", "per panel: warp 0 write-back"};
+                static const char *sn2[5] = {"per panel: wait for the panel column", "(unused)", "per panel: warp 0 diagonal-tile update", "per panel: warp 0 loads + 8x8 factorisation", "per panel: warp 0 write-back"};
                 for (int k = 0; k < 5 && h->solve_cam_dsm; k++)
                     if (ck[40 + k]) fprintf(stderr, "  %-50s %9.0f cycles\n", sn2[k], (double) ck[32 + k] / (double) ck[40 + k]);
             }
@@ -2447,9 +2447,10 @@ static int split_setup(icg_ba *h, int rank, int world) {
     S.split = 1;
     h->D.rank = rank, h->D.world = world;
     h->x_world = world;
-    // landmark shards: the owner's camera-only kernels are on the attempt's critical path (the vision kernels shrink with the shard, the
-    // per-window IMU chain does not): all 10 warps, two rounds of IMU factors at K = 20 instead of four
-    if (!getenv("ICG_BA_CAM_THREADS")) h->cam_threads = world > 1 ? CAM_THREADS : 160;
+    // four or more landmark shards: the owner's camera-only kernels are on the attempt's critical path (the vision kernels shrink with the
+    // shard -- 410 us at one rank, ~100 at four --, the per-window IMU chain of ~118 us does not): all 10 warps, two rounds of IMU factors at
+    // K = 20 instead of four
+    if (!getenv("ICG_BA_CAM_THREADS")) h->cam_threads = world >= 4 ? CAM_THREADS : 160;
     h->epoch = 0;
     {   // ba_solve_cam: vectors + the larger of the back-substitution staging and [B rows | 8 x 8 hand-over | one A strip per warp]; the A strips are
         // dropped when they do not fit (max_K > 20)
@@ -2460,9 +2461,9 @@ static int split_setup(icg_ba *h, int rank, int world) {
     }
     h->smem_step_lm = sizeof(double) * (40 + (size_t) C.NS);
     h->smem_solve_cam_dsm = sizeof(double) * dsm_smem_doubles(C);
-    h->solve_cam_dsm = h->smem_solve_cam_dsm <= 227 * 1024 && !getenv("ICG_BA_SOLVE_CAM_L2");
+    h->solve_cam_dsm = h->smem_solve_cam_dsm <= 227 * 1024 && C.N <= 32 * 11 && !getenv("ICG_BA_SOLVE_CAM_L2");  // (the assembly stages <= 11 chunks of 32 columns per row)
     if (h->solve_cam_dsm) ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam_dsm, h->smem_solve_cam_dsm));
-    h->dsm_variant = getenv("ICG_BA_DSM_VARIANT") ? atoi(getenv("ICG_BA_DSM_VARIANT")) : 0;
+    h->dsm_variant = getenv("ICG_BA_DSM_VARIANT") ? atoi(getenv("ICG_BA_DSM_VARIANT")) : DSM_V_MBAR_BSUB;
     ICG_CUDA(raise_dynamic_smem((const void *) ba_solve_cam, (size_t) (h->smem_solve_cam)));
     ICG_CUDA(cudaFuncSetAttribute(ba_solve_cam, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     ICG_CUDA(raise_dynamic_smem((const void *) ba_step_lm, (size_t) (h->smem_step_lm)));

@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
 constexpr int DSM_CL = 4;
 static_assert(SOLVE_THREADS == 256 && DSM_CL == SPLIT_CLUSTER, "ba_solve_cam_dsm: warp r assembles row r of a tile row; one launch geometry for both forms");
 __host__ __device__ inline int dsm_tile_off(int cr, int m) { return m * cr + 2 * m * (m - 1); }  // tiles ahead of local tile row m (T = cr + 4 m)
-__host__ __device__ inline int dsm_ntiles(int NR) { return (NR + 7) / 8; }
+__host__ __device__ constexpr int dsm_ntiles(int NR) { return (NR + 7) / 8; }
 __host__ inline size_t dsm_smem_doubles(const BaCaps &C) {
     const int nt = dsm_ntiles(C.N + 1);
     int mx = 0;
@@ -598,9 +598,10 @@ __device__ __forceinline__ void dsm_mbar_wait(unsigned bar, unsigned parity, vol
     }
 }
 
-// variant: bit 0 = hand-over of the panel column / the back-substitution sums with asynchronous stores + mbarriers (no cluster barrier in the
-// loops); bit 1 = the trailing update on all eight warps BEFORE the factorisation instead of beside it.
-constexpr int DSM_V_MBAR = 1, DSM_V_SERIAL = 2;
+// variant: hand-over with asynchronous stores (st.async) + mbarriers carrying transaction counts instead of a cluster barrier -- bit 0: of the
+// panel column, bit 1: of the back-substitution's partial sums.  Measured (profiles/r2_ba_solve_cam_dsm.md): the panel hand-over is bound by the
+// SM-to-SM bandwidth either way and the cluster barrier is the cheaper form there; the back-substitution chain gains 15 % from the point-to-point form.
+constexpr int DSM_V_MBAR_PANEL = 1, DSM_V_MBAR_BSUB = 2;
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, BaDev D, unsigned long long epoch, int variant) {
     extern __shared__ double sm[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
     if (w % D.world != D.rank) return;   // uniform over the cluster
     LmState &st = D.st[w];
     if (st.done) return;
-    const bool use_mbar = variant & DSM_V_MBAR, serial = variant & DSM_V_SERIAL;
+    const bool use_mbar = variant & DSM_V_MBAR_PANEL, bsub_mbar = variant & DSM_V_MBAR_BSUB;
     const WinDims dm = D.dims[w];
     const int K = dm.K, NCV = 6 * K + 7, N = 15 * K + 7, NR = N + 1;
     const int ntc = dsm_ntiles(C.N + 1), VL = ntc * 8;   // capacity: tiles per side, vector length
@@ -708,37 +709,53 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
 #endif
     const unsigned long long tq0 = DSM_NOW();
     (void) tq0;
-    // ---- assembly of S' = s H s + D^2 into the tiles: warp r takes row r of every local tile row (coalesced row reads, 8 loads in flight)
-    for (int m = 0, T = cr; T < nt; m++, T += CL) {
-        double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + warp * 8;
-        const int i = 8 * T + warp, ncol = 8 * T;
-        const double *src = (i < NCV ? Hs : Hc) + (size_t) (i < N ? i : 0) * C.NS;
-        const double si = i < N ? s_scale[i] : 0.0;
-        for (int j0 = 0; j0 < ncol; j0 += 256) {
-            double v[8];
+    // ---- assembly of S' = s H s + D^2 into the tiles: warp r takes row r of every local tile row (coalesced row reads; the loads of two tile
+    //      rows -- up to 20 per lane -- are in flight together: the phase is L2 latency, 24 k cycles with one row at a time)
+    for (int m = 0, T = cr; T < nt; m += 2, T += 2 * CL) {
+        constexpr int NCH = (15 * 22 + 7 + 31) / 32;   // 32-column chunks of the longest row the shared-memory form admits (max_K = 22)
+        double v[2][NCH];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int j = j0 + 32 * u + lane;
-                v[u] = (j < ncol && i < N) ? __ldcg(src + j) : 0.0;
+        for (int h = 0; h < 2; h++) {
+            const int Th = T + h * CL, i = 8 * Th + warp, ncol = 8 * Th;
+            const double *src = (i < NCV ? Hs : Hc) + (size_t) (i < N ? i : 0) * C.NS;
+#pragma unroll
+            for (int u = 0; u < NCH; u++) {
+                const int j = 32 * u + lane;
+                v[h][u] = (Th < nt && j < ncol && i < N) ? __ldcg(src + j) : 0.0;
             }
+        }
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int j = j0 + 32 * u + lane;
-                if (j < ncol) trow[(j >> 3) * 64 + (j & 7)] = i < N ? si * s_scale[j] * v[u] : (i == N ? s_rhs[j] : 0.0);
+        for (int h = 0; h < 2; h++) {
+            const int Th = T + h * CL, i = 8 * Th + warp, ncol = 8 * Th;
+            if (Th >= nt) continue;
+            double *trow = s_tiles + (size_t) dsm_tile_off(cr, m + h) * 64 + warp * 8;
+            const double si = i < N ? s_scale[i] : 0.0;
+#pragma unroll
+            for (int u = 0; u < NCH; u++) {
+                const int j = 32 * u + lane;
+                if (j < ncol) trow[(j >> 3) * 64 + (j & 7)] = i < N ? si * s_scale[j] * v[h][u] : (i == N ? s_rhs[j] : 0.0);
             }
         }
     }
-    for (int e = tid; e < nt * 64; e += SOLVE_THREADS) {   // every diagonal tile, on every CTA
-        const int T = e >> 6, r = (e >> 3) & 7, c = e & 7, i = 8 * T + r, j = 8 * T + c;
-        double v = 0;
-        if (c <= r) {
-            if (i < N) {
-                v = s_scale[i] * s_scale[j] * __ldcg((i < NCV ? Hs : Hc) + (size_t) i * C.NS + j);
-                if (i == j) v += s_d2[i];
-            } else if (i == N && j < N)
-                v = s_rhs[j];
+    {   // every diagonal tile, on every CTA: all of a thread's loads in flight (one dependent L2 round trip instead of one per element)
+        constexpr int NDG = (dsm_ntiles(15 * 22 + 8) * 64 + SOLVE_THREADS - 1) / SOLVE_THREADS;
+        double v[NDG];
+#pragma unroll
+        for (int u = 0; u < NDG; u++) {
+            const int e = tid + u * SOLVE_THREADS, T = e >> 6, r = (e >> 3) & 7, c = e & 7, i = 8 * T + r, j = 8 * T + c;
+            v[u] = (e < nt * 64 && c <= r && i < N) ? __ldcg((i < NCV ? Hs : Hc) + (size_t) i * C.NS + j) : 0.0;
         }
-        s_dg[e] = v;
+#pragma unroll
+        for (int u = 0; u < NDG; u++) {
+            const int e = tid + u * SOLVE_THREADS, T = e >> 6, r = (e >> 3) & 7, c = e & 7, i = 8 * T + r, j = 8 * T + c;
+            if (e >= nt * 64) continue;
+            double x = 0;
+            if (c <= r) {
+                if (i < N) x = s_scale[i] * s_scale[j] * v[u] + (i == j ? s_d2[i] : 0.0);
+                else if (i == N && j < N) x = s_rhs[j];
+            }
+            s_dg[e] = x;
+        }
     }
     double *rP[CL];
     unsigned aP[CL], aBar[CL];   // cluster-window addresses of every CTA's panel buffer and panel barriers (statically indexed: registers)
@@ -750,9 +767,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
     volatile int *s_dead = s_fail + 1;
     __syncthreads();
     DSM_CLK(0, tq0)  // assembly
-    const int nwork = serial ? 8 : 6;
-    const int wi = serial ? warp : (warp < 4 ? warp - 1 : warp - 2);   // worker index: all warps, or warps 1,2,3,5,6,7 beside warp 0's factorisation
-    const bool worker = serial || (warp != 0 && warp != 4);
+    const int wi = warp < 4 ? warp - 1 : warp - 2;   // worker index 0 .. 5 of warps 1,2,3,5,6,7 (warp 4 shares warp 0's scheduler and FP64 pipe: it sits out)
+    const bool worker = warp != 0 && warp != 4;
     int fail = 0;
     const unsigned long long tc_all = DSM_NOW();
     (void) tc_all;
@@ -769,46 +785,45 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
         const unsigned long long tc1 = DSM_NOW();
         (void) tc1;
         if (J > 0 && worker) {
+            // Trailing update of panel Jp = J - 1: the CTA's tiles (T, tc), Jp < tc < T, and the diagonal replicas T >= Jp + 2 (every tile row).
+            // Workers 0 .. 4 take PAIRS of local tile rows -- the i-th shortest with the i-th longest: equal work per pair --, worker 5 the
+            // diagonal replicas (about as many tiles as a pair).  A row is a unit-stride walk (A fragment loaded once, pointers advance by a
+            // tile), four tiles in flight: 8 operand loads, 8 DMMAs in four independent chains, 4 stores.  (A flattened work list with per-item
+            // row look-up cost ~250 cycles per tile on these one-or-two-warp schedulers: the bookkeeping, not the arithmetic.)
             const int Jp = J - 1;
-            // local tiles (T, tc), Jp < tc < T
-            int m = (Jp + 2 - cr + CL - 1) / CL;
-            for (int T = cr + CL * m; T < nt; m++, T += CL) {
-                const double2 pa = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
-                const double a0 = -pa.x, a1 = -pa.y;
-                double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64 + 2 * lane;
-                const double *pb = PJ + 2 * lane;
-                int tc = Jp + 1 + (wi + m) % nwork;
-                for (; tc + 3 * nwork < T; tc += 4 * nwork) {
-                    double2 b[4], c[4];
+            auto run = [&](double a0, double a1, bool diag, const double *pb, double *pc, int n) {
+                // n tiles from pb (B fragments) / pc (C tiles); diag: the A fragment is the tile's own B fragment
+                for (; n > 0; n -= 4, pb += 256, pc += 256) {
+                    double2 bq[4], cq[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) b[u] = *(const double2 *) (pb + (size_t) (tc + nwork * u) * 64), c[u] = *(double2 *) (trow + (size_t) (tc + nwork * u) * 64);
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) bq[u] = *(const double2 *) (pb + 64 * u), cq[u] = *(double2 *) (pc + 64 * u);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a0, b[u].x);
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) dmma884(cq[u].x, cq[u].y, diag ? -bq[u].x : a0, bq[u].x);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) dmma884(c[u].x, c[u].y, a1, b[u].y);
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) dmma884(cq[u].x, cq[u].y, diag ? -bq[u].y : a1, bq[u].y);
 #pragma unroll
-                    for (int u = 0; u < 4; u++) *(double2 *) (trow + (size_t) (tc + nwork * u) * 64) = c[u];
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) *(double2 *) (pc + 64 * u) = cq[u];
                 }
-                for (; tc < T; tc += nwork) {
-                    const double2 b = *(const double2 *) (pb + (size_t) tc * 64);
-                    double2 c = *(double2 *) (trow + (size_t) tc * 64);
-                    dmma884(c.x, c.y, a0, b.x);
-                    dmma884(c.x, c.y, a1, b.y);
-                    *(double2 *) (trow + (size_t) tc * 64) = c;
+            };
+            if (wi < 5) {
+                const int m_lo = (Jp + 2 - cr + CL - 1) / CL, m_hi = cr < nt ? (nt - 1 - cr) / CL : -1;   // local tile rows T = cr + 4 m with Jp + 2 <= T < nt
+                for (int i = wi; m_lo + i <= m_hi - i; i += 5) {
+#pragma unroll 1
+                    for (int h = 0; h < 2; h++) {
+                        const int m = h ? m_hi - i : m_lo + i;
+                        if (h && m == m_lo + i) break;
+                        const int T = cr + CL * m;
+                        const double2 pa = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
+                        run(-pa.x, -pa.y, false, PJ + (size_t) (Jp + 1) * 64 + 2 * lane, s_tiles + ((size_t) dsm_tile_off(cr, m) + Jp + 1) * 64 + 2 * lane, T - (Jp + 1));
+                    }
                 }
+            } else {
+                run(0.0, 0.0, true, PJ + (size_t) (Jp + 2) * 64 + 2 * lane, s_dg + (size_t) (Jp + 2) * 64 + 2 * lane, nt - (Jp + 2));
             }
-            // the other diagonal replicas (every tile row, on every CTA)
-            for (int T = Jp + 2 + wi; T < nt; T += nwork) {
-                const double2 p = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
-                double2 c = *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane);
-                dmma884(c.x, c.y, -p.x, p.x);
-                dmma884(c.x, c.y, -p.y, p.y);
-                *(double2 *) (s_dg + (size_t) T * 64 + 2 * lane) = c;
-            }
-        }
-        if (serial) {
-            __syncthreads();
-            DSM_CLK2(1, tc1)  // trailing update on all warps
         }
         if (warp == 0) {
             const unsigned long long tf0 = DSM_NOW();
@@ -855,17 +870,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             const unsigned long long tf2 = DSM_NOW();
             (void) tf2;
             __syncwarp();  // every lane has read the unfactored block
+            // write-back: every lane holds the whole factor; entry e is stored by lane e mod 32 under a predicate -- statically indexed registers,
+            // no divergent code.  (A switch on the lane, one path per row, cost 1 640 cycles; pairs of entries as 128-bit stores 1 010 -- the
+            // register pairs have to be assembled first; scalar predicated stores 480.)
 #pragma unroll
-            for (int a2 = 0; a2 < 8; a2++) {  // static indexing keeps Ld in registers: lane a writes row a
-                if (a2 != lane) continue;
+            for (int a2 = 0; a2 < 8; a2++) {
 #pragma unroll
-                for (int b = 0; b < 8; b++) s_Lf[a2 * 8 + b] = b <= a2 ? Ld[a2][b] : 0.0;
-                s_dv[a2] = dinv[a2];
-                if (a2 < nb) {
-#pragma unroll
-                    for (int b = 0; b <= a2; b++) dg[a2 * 8 + b] = Ld[a2][b];   // kept for the backward substitution
-                    s_dinv[8 * J + a2] = dinv[a2];
-                }
+                for (int b = 0; b <= a2; b++)
+                    if (lane == ((a2 * 8 + b) & 31) && a2 < nb) dg[a2 * 8 + b] = Ld[a2][b];
+                if (lane == 8 + a2) s_dv[a2] = dinv[a2];
+                if (lane == 16 + a2 && a2 < nb) s_dinv[8 * J + a2] = dinv[a2];
             }
             if (lane == 0 && bad) s_fail[0] = 1;
             DSM_CLK2(4, tf2)  // warp 0: write-back
@@ -882,6 +896,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             const int m = m0 + (tid >> 3), r = tid & 7, T = cr + CL * m;
             if (T < nt) {
                 double *tp = s_tiles + ((size_t) dsm_tile_off(cr, m) + J) * 64 + r * 8;
+                const double *s_Ljj = s_dg + (size_t) J * 64;   // the factored block (nb = 8 whenever there are rows below)
                 double x[8];
 #pragma unroll
                 for (int c = 0; c < 8; c += 2) {
@@ -892,7 +907,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                 for (int c = 0; c < 8; c++) {
                     double sum = x[c];
 #pragma unroll
-                    for (int k = 0; k < c; k++) sum -= x[k] * s_Lf[c * 8 + k];
+                    for (int k = 0; k < c; k++) sum -= x[k] * s_Ljj[c * 8 + k];
                     x[c] = sum * s_dv[c];
                 }
                 const unsigned po = (unsigned) ((size_t) (J & 1) * ntc * 64 + (size_t) T * 64 + r * 8);
@@ -936,7 +951,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             double x[8];
             for (int c = 0; c < rn; c++) {
                 double sum = s_dg[(size_t) Tn * 64 + rn * 8 + c];
-                for (int k = 0; k < c; k++) sum -= x[k] * s_Lf[c * 8 + k];
+                for (int k = 0; k < c; k++) sum -= x[k] * s_dg[(size_t) Tn * 64 + c * 8 + k];
                 x[c] = sum * s_dv[c];
                 s_y[8 * Tn + c] = x[c];
             }
@@ -948,7 +963,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             if (cr == T % CL) {
                 const int nbT = min(8, N - 8 * T), m = T / CL;
                 const double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64;
-                if (use_mbar) {
+                if (bsub_mbar) {
                     // three partial-sum messages per tile row (from the owners of T + 1 .. T + 3); the ones that do not exist are arrived here
                     const int nmiss = max(0, 3 - (npan - 1 - T));
                     if (tid < nmiss) dsm_mbar_arrive_local(smem_u32(s_bar + 2));
@@ -984,7 +999,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     for (int r = 0; r < 8; r++) acc += tp[r * 8] * s_xT[r];
                     s_contrib[col] = acc;
                     const int Tt = col >> 3, q = Tt % CL;
-                    if (use_mbar) {
+                    if (bsub_mbar) {
                         const unsigned abar = mapa_u32(smem_u32(s_bar + 2), q);
                         st_async_f64(mapa_u32(smem_u32(s_inbox + cr * 8 + (col & 7)), q), acc, abar);
                         if ((col & 7) == 0) dsm_mbar_arrive_expect_tx_remote(abar, 64u);
@@ -1001,7 +1016,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                 }
                 __syncthreads();
             }
-            if (!use_mbar) cluster.sync();
+            if (!bsub_mbar) cluster.sync();
         }
     }
     cluster.sync();  // the solution has landed on CTA 0; no CTA leaves while its shared memory may still be written
