@@ -71,6 +71,8 @@ struct ShardDev {
     size_t off_inbox, off_bcast, off_scal, off_flagA, off_flagB, off_flagC;  // offsets in doubles, identical on every rank
     double *redv;              // [NW][RV] owner-side reduced vectors: diag H_vis | g_vis | W phi g_l | cost, sum rho^2, max |g_l|
     int *err;                  // device error word (flag wait timed out)
+    double *slm;               // [NW][STEP_SLICES][8] partial sums of ba_step_lm's landmark slices
+    int *slm_cnt;              // [NW] slices arrived (resets itself)
 };
 
 struct BaDev {  // device pointers (flat, capacity-strided by window)
@@ -2403,6 +2405,8 @@ static void split_release(icg_ba *h) {
     if (h->xbuf) cudaFree(h->xbuf), h->xbuf = nullptr;
     if (h->D.S.redv) cudaFree(h->D.S.redv), h->D.S.redv = nullptr;
     if (h->D.S.err) cudaFree(h->D.S.err), h->D.S.err = nullptr;
+    if (h->D.S.slm) cudaFree(h->D.S.slm), h->D.S.slm = nullptr;
+    if (h->D.S.slm_cnt) cudaFree(h->D.S.slm_cnt), h->D.S.slm_cnt = nullptr;
     if (h->D.Sglobal) cudaFree(h->D.Sglobal), h->D.Sglobal = nullptr;
     h->D.S.split = 0;
 }
@@ -2434,7 +2438,8 @@ static int split_setup(icg_ba *h, int rank, int world) {
     S.off_flagC = off, off += (NW * G + 3) & ~(size_t) 3;
     h->xbuf_doubles = off;
     if (cudaMalloc(&h->xbuf, sizeof(double) * off) != cudaSuccess || cudaMalloc(&S.redv, sizeof(double) * NW * S.RV) != cudaSuccess ||
-        cudaMalloc(&S.err, sizeof(int) * 4) != cudaSuccess ||
+        cudaMalloc(&S.err, sizeof(int) * 4) != cudaSuccess || cudaMalloc(&S.slm, sizeof(double) * NW * STEP_SLICES * 8) != cudaSuccess ||
+        cudaMalloc(&S.slm_cnt, sizeof(int) * NW) != cudaSuccess ||
         cudaMalloc(&h->D.Sglobal, sizeof(double) * NWo * split_S_stride(C)) != cudaSuccess) {
         set_error("split pipeline: allocation of the exchange buffers failed (%zu doubles)", off);
         return ICG_ENOMEM;
@@ -2442,6 +2447,8 @@ static int split_setup(icg_ba *h, int rank, int world) {
     ICG_CUDA(cudaMemset(h->xbuf, 0, sizeof(double) * off));
     ICG_CUDA(cudaMemset(S.redv, 0, sizeof(double) * NW * S.RV));
     ICG_CUDA(cudaMemset(S.err, 0, sizeof(int) * 4));
+    ICG_CUDA(cudaMemset(S.slm, 0, sizeof(double) * NW * STEP_SLICES * 8));
+    ICG_CUDA(cudaMemset(S.slm_cnt, 0, sizeof(int) * NW));
     for (int r = 0; r < 8; r++) S.peer[r] = nullptr;
     S.peer[rank] = h->xbuf;
     S.split = 1;
@@ -2520,7 +2527,7 @@ static int enqueue_lm_split(icg_ba *h, int max_num_iterations) {
         int rc = launch_solve_cam(h, n, epoch);
         if (rc != ICG_OK) return rc;
         prof_mark(h, 8);
-        ba_step_lm<<<n, SOLVE_THREADS, h->smem_step_lm, s>>>(C, D, epoch);
+        ba_step_lm<<<dim3(n, STEP_SLICES), SOLVE_THREADS, h->smem_step_lm, s>>>(C, D, epoch);
         prof_mark(h, 14);
         count_launch(9);
         if (it == max_num_iterations) break;

@@ -1046,22 +1046,31 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
     for (int q = tid; q < D.world; q += SOLVE_THREADS) st_release_sys(x_flagB(D, q, w), epoch);
 }
 
-// ------------------------------------------------------------------------------------------------ step_lm (every rank, CTA per window)
+// ------------------------------------------------------------------------------------------------ step_lm (every rank, STEP_SLICES CTAs per window)
+// Landmark back-substitution (a 2 MB matrix-vector product per cfg-4 window: latency-bound on one CTA, 190 us at 2000 landmarks) is cut into
+// STEP_SLICES contiguous landmark slices, one CTA each; slice 0 also forms the candidate camera blocks.  The slices' partial sums meet in
+// slot order in the CTA that finishes last (a per-window counter that resets itself): the same bits whatever the arrival order and whatever
+// the batch size.
+constexpr int STEP_SLICES = 4;
 __global__ void __launch_bounds__(SOLVE_THREADS) ba_step_lm(BaCaps C, BaDev D, unsigned long long epoch) {
     extern __shared__ double sm[];
-    const int w = blockIdx.x, tid = threadIdx.x;
+    __shared__ int s_last;
+    const int w = blockIdx.x, sl_id = blockIdx.y, tid = threadIdx.x;
     LmState &st = D.st[w];
-    if (st.done) return;
     const WinDims dm = D.dims[w];
     const int K = dm.K, L = dm.L, NCV = 6 * K + 7, N = 15 * K + 7;
     const bool owner = (w % D.world) == D.rank;
     double *s_red = sm, *s_dl = s_red + 40;  // delta (N)
+    // st.done: set in an earlier attempt (the owner's solve then returns without a broadcast: nothing to wait for), or in THIS attempt -- by the
+    // owner's solve earlier in the stream, or by slice 0 of a non-owner mirroring the header while the other slices are still starting; in every
+    // case all slices of the window leave without touching the slice counter
+    if (st.done) return;
+    const double *BC = x_bcast(D, D.rank, w);
     if (tid == 0) wait_flag(x_flagB(D, D.rank, w), epoch, D.S.err);
     __syncthreads();
-    const double *BC = x_bcast(D, D.rank, w);
     const int term = (int) __ldcg(BC + 0), valid = (int) __ldcg(BC + 1);
     double *R3 = D.red2 + (size_t) w * 4;
-    if (!owner && tid == 0) {  // mirror what the owner's solve did to the LM state
+    if (!owner && tid == 0 && sl_id == 0) {  // mirror what the owner's solve did to the LM state
         st.x_cost = __ldcg(BC + 2), st.gmax = __ldcg(BC + 3), st.initial_cost = __ldcg(BC + 4);
         st.fresh_lin = 0, st.first = 0, st.need_lin = 0;
         if (term) st.done = term, st.step_valid = 0;
@@ -1069,7 +1078,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_step_lm(BaCaps C, BaDev D, u
     }
     if (term) return;
     if (!valid) {
-        if (tid == 0) {
+        if (tid == 0 && sl_id == 0) {
             st.chol_ok = 0, st.step_valid = 0;
             R3[0] = 0, R3[1] = 0, R3[2] = 1, R3[3] = 0;
         }
@@ -1081,19 +1090,23 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_step_lm(BaCaps C, BaDev D, u
     const double *hl = D.hl + (size_t) w * C.L, *gl = D.gl + (size_t) w * C.L, *scale_l = D.scale_l + (size_t) w * C.L;
     double *step_l = D.step_l + (size_t) w * C.L;
     const double *AW = D.AW + (size_t) w * C.LP * C.NCA;
-    double part = 0;
+    const double *rho = D.rho + (size_t) w * C.L;
+    double *rho_c = D.rho_c + (size_t) w * C.L;
+    constexpr int LB = 4;
+    const int per = ((L + STEP_SLICES - 1) / STEP_SLICES + LB - 1) / LB * LB;   // landmarks per slice (groups of LB stay whole)
+    const int lbeg = min(L, sl_id * per), lend = min(L, lbeg + per);
+    double part = 0, sn_l = 0, rho2 = 0;
     bool finite = true;
     {
         const int lane = tid & 31, warp = tid >> 5;
-        constexpr int LB = 4;
-        for (int l0 = LB * warp; l0 < L; l0 += LB * (SOLVE_THREADS / 32)) {
+        for (int l0 = lbeg + LB * warp; l0 < lend; l0 += LB * (SOLVE_THREADS / 32)) {
             double d[LB];
 #pragma unroll
             for (int u = 0; u < LB; u++) d[u] = 0;
             for (int c = lane; c < NCV; c += 32) {
                 const double sx = s_dl[c];
 #pragma unroll
-                for (int u = 0; u < LB; u++) d[u] += (l0 + u < L ? AW[(size_t) (l0 + u) * C.NCA + c] : 0.0) * sx;
+                for (int u = 0; u < LB; u++) d[u] += (l0 + u < lend ? AW[(size_t) (l0 + u) * C.NCA + c] : 0.0) * sx;
             }
             double mine = 0;
 #pragma unroll
@@ -1102,66 +1115,78 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_step_lm(BaCaps C, BaDev D, u
                 for (int o = 16; o > 0; o >>= 1) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
                 if (lane == u) mine = d[u];
             }
-            if (lane < LB && l0 + lane < L) {
+            if (lane < LB && l0 + lane < lend) {
                 const int l = l0 + lane;
                 const double sl = scale_l[l], hs = sl * sl * hl[l], d2 = fmin(fmax(hs, 1e-6), 1e32) / radius;
                 const double sp = (-sl * gl[l] - sl * mine) / (hs + d2);
                 finite = finite && isfinite(sp);
                 step_l[l] = sp;
                 part += -0.5 * sp * (sl * gl[l]) + 0.5 * d2 * sp * sp;
+                // candidate inverse depth, |step|^2 and |rho|^2 (x_norm of the parameter tolerance test) of this landmark
+                const double r0 = rho[l], v = r0 + sp * sl;
+                rho_c[l] = v;
+                sn_l += (r0 - v) * (r0 - v);
+                rho2 += r0 * r0;
             }
         }
     }
     __syncthreads();
     const double mcc_l = block_sum(part, s_red);
     const double nfin = block_sum(finite ? 0.0 : 1.0, s_red);
-    // candidate point: camera blocks on every rank (bit-identical), the rank's own landmarks
-    const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8, *rho = D.rho + (size_t) w * C.L;
-    double *pose_c = D.pose_c + (size_t) w * C.K * 7, *mix_c = D.mix_c + (size_t) w * C.K * 9, *ext_c = D.ext_c + (size_t) w * 8, *rho_c = D.rho_c + (size_t) w * C.L;
-    double sn_cam = 0, sn_l = 0;
-    for (int k = tid; k <= K; k += SOLVE_THREADS) {
-        const bool is_ext = (k == K);
-        const double *x = is_ext ? ext : pose + k * 7;
-        double *xc = is_ext ? ext_c : pose_c + k * 7;
-        if (is_ext && dm.ext_const) {
-            for (int e = 0; e < 7; e++) xc[e] = x[e];
-        } else {
-            const int c0 = is_ext ? col_ext(K) : col_pose(k);
-            double d[6];
-            for (int e = 0; e < 6; e++) d[e] = s_dl[c0 + e];
-            pose_plus(x, d, xc);
-            for (int e = 0; e < 7; e++) sn_cam += (x[e] - xc[e]) * (x[e] - xc[e]);
-        }
-    }
-    for (int e = tid; e < K * 9; e += SOLVE_THREADS) {
-        const int k = e / 9, q = e - 9 * k;
-        const double v = mix[e] + s_dl[col_mix(K, k) + q];
-        mix_c[e] = v;
-        sn_cam += (mix[e] - v) * (mix[e] - v);
-    }
-    if (tid == 0) {
-        if (dm.td_const) {
-            ext_c[7] = ext[7];
-        } else {
-            const double v = ext[7] + s_dl[col_td(K)];
-            ext_c[7] = v;
-            sn_cam += (ext[7] - v) * (ext[7] - v);
-        }
-    }
-    for (int l = tid; l < L; l += SOLVE_THREADS) {
-        const double v = rho[l] + step_l[l] * scale_l[l];
-        rho_c[l] = v;
-        sn_l += (rho[l] - v) * (rho[l] - v);
-    }
-    double rho2 = 0;  // |rho|^2 of the CURRENT point (x_norm of the parameter tolerance test)
-    for (int l = tid; l < L; l += SOLVE_THREADS) rho2 += rho[l] * rho[l];
-    sn_cam = block_sum(sn_cam, s_red);
     sn_l = block_sum(sn_l, s_red);
     rho2 = block_sum(rho2, s_red);
-    if (tid == 0) {
-        st.chol_ok = 1, st.step_valid = 1;
-        R3[0] = mcc_l + (owner ? __ldcg(BC + 5) : 0.0), R3[1] = sn_l + (owner ? sn_cam : 0.0), R3[2] = nfin, R3[3] = rho2;
+    // candidate point: camera blocks on every rank (bit-identical), by slice 0
+    double sn_cam = 0;
+    if (sl_id == 0) {
+        const double *pose = D.pose + (size_t) w * C.K * 7, *mix = D.mix + (size_t) w * C.K * 9, *ext = D.ext + (size_t) w * 8;
+        double *pose_c = D.pose_c + (size_t) w * C.K * 7, *mix_c = D.mix_c + (size_t) w * C.K * 9, *ext_c = D.ext_c + (size_t) w * 8;
+        for (int k = tid; k <= K; k += SOLVE_THREADS) {
+            const bool is_ext = (k == K);
+            const double *x = is_ext ? ext : pose + k * 7;
+            double *xc = is_ext ? ext_c : pose_c + k * 7;
+            if (is_ext && dm.ext_const) {
+                for (int e = 0; e < 7; e++) xc[e] = x[e];
+            } else {
+                const int c0 = is_ext ? col_ext(K) : col_pose(k);
+                double d[6];
+                for (int e = 0; e < 6; e++) d[e] = s_dl[c0 + e];
+                pose_plus(x, d, xc);
+                for (int e = 0; e < 7; e++) sn_cam += (x[e] - xc[e]) * (x[e] - xc[e]);
+            }
+        }
+        for (int e = tid; e < K * 9; e += SOLVE_THREADS) {
+            const int k = e / 9, q = e - 9 * k;
+            const double v = mix[e] + s_dl[col_mix(K, k) + q];
+            mix_c[e] = v;
+            sn_cam += (mix[e] - v) * (mix[e] - v);
+        }
+        if (tid == 0) {
+            if (dm.td_const) {
+                ext_c[7] = ext[7];
+            } else {
+                const double v = ext[7] + s_dl[col_td(K)];
+                ext_c[7] = v;
+                sn_cam += (ext[7] - v) * (ext[7] - v);
+            }
+        }
     }
+    sn_cam = block_sum(sn_cam, s_red);
+    // the slices meet: slot [w][slice] = {model cost change, |step_l|^2, non-finite count, |rho|^2, |step_cam|^2}
+    double *slot = D.S.slm + ((size_t) w * STEP_SLICES + sl_id) * 8;
+    if (tid == 0) {
+        slot[0] = mcc_l, slot[1] = sn_l, slot[2] = nfin, slot[3] = rho2, slot[4] = sn_cam;
+        __threadfence();
+        s_last = atomicAdd(D.S.slm_cnt + w, 1) == STEP_SLICES - 1;
+    }
+    __syncthreads();
+    if (!s_last || tid != 0) return;
+    __threadfence();
+    D.S.slm_cnt[w] = 0;
+    double m = 0, sl2 = 0, nf = 0, r2 = 0, sc2 = 0;
+    const double *s0 = D.S.slm + (size_t) w * STEP_SLICES * 8;
+    for (int q = 0; q < STEP_SLICES; q++) m += __ldcg(s0 + q * 8), sl2 += __ldcg(s0 + q * 8 + 1), nf += __ldcg(s0 + q * 8 + 2), r2 += __ldcg(s0 + q * 8 + 3), sc2 += __ldcg(s0 + q * 8 + 4);
+    st.chol_ok = 1, st.step_valid = 1;
+    R3[0] = m + (owner ? __ldcg(BC + 5) : 0.0), R3[1] = sl2 + (owner ? sc2 : 0.0), R3[2] = nf, R3[3] = r2;
 }
 
 // ------------------------------------------------------------------------------------------------ exchange + accept (every rank)
