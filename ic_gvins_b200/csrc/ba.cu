@@ -1159,12 +1159,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 2) ba_solve(BaCaps C, BaDev D) 
             __syncwarp();  // every lane has read the unfactored block
             if (bad && lane == 0) s_fail = 1;
 #pragma unroll
-            for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers
-                if (a2 != lane || a2 >= nb) continue;
+            for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {
+                // every lane holds the whole factor: entry (a2, b) is stored by ONE lane under a predicate -- statically indexed registers and no
+                // divergent code.  ("lane a writes row a" was compiled into a switch on the lane, eight serial paths: 1 640 cycles per panel in
+                // ba_solve_cam_dsm's phase clocks against 480 for this form, profiles/r2_ba_solve_cam_dsm.md.)
                 double *ri = S + (J0 + a2) * (J0 + a2 + 1) / 2 + J0;
 #pragma unroll
-                for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
-                s_diag[J0 + a2] = dinv[a2];
+                for (int b = 0; b <= a2; b++)
+                    if (lane == ((a2 * 8 + b) & 31) && a2 < nb) ri[b] = Ld[a2][b];
+                if (lane == 8 + a2 && a2 < nb) s_diag[J0 + a2] = dinv[a2];
             }
             SOLVE_CLK_ADD(6, pc0)
         } else if (J0 > 0 && warp != 4) {

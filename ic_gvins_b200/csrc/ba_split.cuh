@@ -421,12 +421,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) ba_solve_cam(BaCaps C, BaDev D,
             }
             __syncwarp();  // every lane has read the unfactored block
 #pragma unroll
-            for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // static indexing keeps Ld in registers: lane a writes row a
-                if (a2 != lane || a2 >= nb) continue;
+            for (int a2 = 0; a2 < BA_CHOL_NB; a2++) {  // statically indexed registers, one lane per store under a predicate (no switch on the lane)
                 double *ri = S + (size_t) (J0 + a2) * (J0 + a2 + 1) / 2 + J0;
 #pragma unroll
-                for (int b = 0; b <= a2; b++) ri[b] = Ld[a2][b];
-                dinvg[J0 + a2] = bad ? -1.0 : dinv[a2];
+                for (int b = 0; b <= a2; b++)
+                    if (lane == ((a2 * 8 + b) & 31) && a2 < nb) ri[b] = Ld[a2][b];
+                if (lane == 8 + a2 && a2 < nb) dinvg[J0 + a2] = bad ? -1.0 : dinv[a2];
             }
             CAMS_CLK(1, tc1)  // cluster warp 0: diagonal tile + factorisation
         } else if (J0 > 0) {
