@@ -757,13 +757,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             s_dg[e] = x;
         }
     }
-    double *rP[CL];
-    unsigned aP[CL], aBar[CL];   // cluster-window addresses of every CTA's panel buffer and panel barriers (statically indexed: registers)
-#pragma unroll
-    for (int q = 0; q < CL; q++) {
-        rP[q] = cluster.map_shared_rank(s_P, q);
-        aP[q] = mapa_u32(smem_u32(s_P), q), aBar[q] = mapa_u32(smem_u32(s_bar), q);
-    }
     volatile int *s_dead = s_fail + 1;
     __syncthreads();
     DSM_CLK(0, tq0)  // assembly
@@ -809,16 +802,39 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                         if (u < n) *(double2 *) (pc + 64 * u) = cq[u];
                 }
             };
+            // both rows of a pair over their common columns: ONE B fragment per tile column feeds both rows (a third less shared-memory traffic
+            // -- the update is bound by the shared-memory pipe as much as by the FP64 pipe) and eight DMMA chains are in flight
+            auto run2 = [&](double a10, double a11, double a20, double a21, const double *pb, double *pc1, double *pc2, int n) {
+                for (; n > 0; n -= 4, pb += 256, pc1 += 256, pc2 += 256) {
+                    double2 bq[4], c1[4], c2[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) bq[u] = *(const double2 *) (pb + 64 * u), c1[u] = *(double2 *) (pc1 + 64 * u), c2[u] = *(double2 *) (pc2 + 64 * u);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) dmma884(c1[u].x, c1[u].y, a10, bq[u].x), dmma884(c2[u].x, c2[u].y, a20, bq[u].x);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) dmma884(c1[u].x, c1[u].y, a11, bq[u].y), dmma884(c2[u].x, c2[u].y, a21, bq[u].y);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) *(double2 *) (pc1 + 64 * u) = c1[u], *(double2 *) (pc2 + 64 * u) = c2[u];
+                }
+            };
             if (wi < 5) {
                 const int m_lo = (Jp + 2 - cr + CL - 1) / CL, m_hi = cr < nt ? (nt - 1 - cr) / CL : -1;   // local tile rows T = cr + 4 m with Jp + 2 <= T < nt
                 for (int i = wi; m_lo + i <= m_hi - i; i += 5) {
-#pragma unroll 1
-                    for (int h = 0; h < 2; h++) {
-                        const int m = h ? m_hi - i : m_lo + i;
-                        if (h && m == m_lo + i) break;
-                        const int T = cr + CL * m;
-                        const double2 pa = *(const double2 *) (PJ + (size_t) T * 64 + 2 * lane);
-                        run(-pa.x, -pa.y, false, PJ + (size_t) (Jp + 1) * 64 + 2 * lane, s_tiles + ((size_t) dsm_tile_off(cr, m) + Jp + 1) * 64 + 2 * lane, T - (Jp + 1));
+                    const int m1 = m_lo + i, m2 = m_hi - i, T1 = cr + CL * m1, T2 = cr + CL * m2;
+                    const double2 pa1 = *(const double2 *) (PJ + (size_t) T1 * 64 + 2 * lane);
+                    double *t1 = s_tiles + (size_t) dsm_tile_off(cr, m1) * 64 + 2 * lane;
+                    const double *pb0 = PJ + (size_t) (Jp + 1) * 64 + 2 * lane;
+                    if (m1 == m2) {
+                        run(-pa1.x, -pa1.y, false, pb0, t1 + (size_t) (Jp + 1) * 64, T1 - (Jp + 1));
+                    } else {
+                        const double2 pa2 = *(const double2 *) (PJ + (size_t) T2 * 64 + 2 * lane);
+                        double *t2 = s_tiles + (size_t) dsm_tile_off(cr, m2) * 64 + 2 * lane;
+                        run2(-pa1.x, -pa1.y, -pa2.x, -pa2.y, pb0, t1 + (size_t) (Jp + 1) * 64, t2 + (size_t) (Jp + 1) * 64, T1 - (Jp + 1));
+                        run(-pa2.x, -pa2.y, false, PJ + (size_t) T1 * 64 + 2 * lane, t2 + (size_t) T1 * 64, T2 - T1);   // the longer row's own columns
                     }
                 }
             } else {
@@ -910,17 +926,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                     for (int k = 0; k < c; k++) sum -= x[k] * s_Ljj[c * 8 + k];
                     x[c] = sum * s_dv[c];
                 }
-                const unsigned po = (unsigned) ((size_t) (J & 1) * ntc * 64 + (size_t) T * 64 + r * 8);
+                // the solved row goes into the panel-column buffer of all four CTAs (addresses of the cluster window formed here: nothing of
+                // this is live across the factorisation, whose 8 x 8 block fills the register file)
+                double *dstP = s_P + (size_t) (J & 1) * ntc * 64 + (size_t) T * 64 + r * 8;
 #pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    const double2 t2 = make_double2(x[c], x[c + 1]);
-                    *(double2 *) (tp + c) = t2;
-                    if (use_mbar) {
+                for (int c = 0; c < 8; c += 2) *(double2 *) (tp + c) = make_double2(x[c], x[c + 1]);
+                if (use_mbar) {
+                    const unsigned a0 = smem_u32(dstP), b0 = smem_u32(s_bar + (J & 1));
 #pragma unroll
-                        for (int q = 0; q < CL; q++) st_async_v2(aP[q] + 8u * (po + c), x[c], x[c + 1], aBar[q] + 8u * (J & 1));
-                    } else {
+                    for (int q = 0; q < CL; q++) {
+                        const unsigned ap = mapa_u32(a0, q), ab = mapa_u32(b0, q);
 #pragma unroll
-                        for (int q = 0; q < CL; q++) *(double2 *) (rP[q] + po + c) = t2;
+                        for (int c = 0; c < 8; c += 2) st_async_v2(ap + 8u * c, x[c], x[c + 1], ab);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < CL; q++) {
+                        double *rp = cluster.map_shared_rank(dstP, q);
+#pragma unroll
+                        for (int c = 0; c < 8; c += 2) *(double2 *) (rp + c) = make_double2(x[c], x[c + 1]);
                     }
                 }
             }
@@ -963,17 +987,31 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
             if (cr == T % CL) {
                 const int nbT = min(8, N - 8 * T), m = T / CL;
                 const double *trow = s_tiles + (size_t) dsm_tile_off(cr, m) * 64;
-                if (bsub_mbar) {
-                    // three partial-sum messages per tile row (from the owners of T + 1 .. T + 3); the ones that do not exist are arrived here
-                    const int nmiss = max(0, 3 - (npan - 1 - T));
-                    if (tid < nmiss) dsm_mbar_arrive_local(smem_u32(s_bar + 2));
-                    dsm_mbar_wait(smem_u32(s_bar + 2), ((npan - 1 - T) / CL) & 1, s_dead, D.S.err);
-                }
+                // The chain of the substitution stays inside warp 0: wait for the three partial-sum messages, 8 x 8 triangle, the row's
+                // contribution to the next three tile rows (their columns of the row's tiles are loaded before the wait; x travels by shuffle),
+                // send.  The other warps join at the block barrier and add the row's contribution to the columns further left.
+                const int c0 = max(0, 8 * (T - 3)), ncrit = 8 * T - c0;
                 if (warp == 0) {
-                    const int c = lane & 7;
-                    double v = 0, lcol[8];
+                    const int c = lane & 7, col = c0 + lane;
+                    double lcol[8], tcr[8], acc = 0;
 #pragma unroll
                     for (int r = 0; r < 8; r++) lcol[r] = s_dg[(size_t) T * 64 + r * 8 + c];
+                    if (lane < ncrit) {
+                        const double *tp = trow + (col >> 3) * 64 + (col & 7);
+#pragma unroll
+                        for (int r = 0; r < 8; r++) tcr[r] = tp[r * 8];
+                        acc = s_contrib[col];
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < 8; r++) tcr[r] = 0;
+                    }
+                    if (bsub_mbar) {
+                        // three messages per tile row (from the owners of T + 1 .. T + 3); the ones that do not exist are arrived here
+                        const int nmiss = max(0, 3 - (npan - 1 - T));
+                        if (lane < nmiss) dsm_mbar_arrive_local(smem_u32(s_bar + 2));
+                        dsm_mbar_wait(smem_u32(s_bar + 2), ((npan - 1 - T) / CL) & 1, s_dead, D.S.err);
+                    }
+                    double v = 0;
                     if (lane < nbT) {
                         v = s_y[8 * T + c] - s_contrib[8 * T + c];
 #pragma unroll
@@ -987,26 +1025,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) ba_solve_cam_dsm(BaCaps C, B
                         else if (lane < r) v -= lcol[r] * xr;
                     }
                     if (lane < 8) s_xT[lane] = v, rX0[8 * T + lane] = v;
-                }
-                __syncthreads();
-                // partial sums of the next three tile rows first: they are final on this CTA (its next own tile row is T - 4) and travel now
-                const int c0 = max(0, 8 * (T - 3));
-                if (tid < 8 * T - c0) {
-                    const int col = c0 + tid;
-                    const double *tp = trow + (col >> 3) * 64 + (col & 7);
-                    double acc = s_contrib[col];
 #pragma unroll
-                    for (int r = 0; r < 8; r++) acc += tp[r * 8] * s_xT[r];
-                    s_contrib[col] = acc;
-                    const int Tt = col >> 3, q = Tt % CL;
-                    if (bsub_mbar) {
-                        const unsigned abar = mapa_u32(smem_u32(s_bar + 2), q);
-                        st_async_f64(mapa_u32(smem_u32(s_inbox + cr * 8 + (col & 7)), q), acc, abar);
-                        if ((col & 7) == 0) dsm_mbar_arrive_expect_tx_remote(abar, 64u);
-                    } else {
-                        cluster.map_shared_rank(s_inbox, q)[cr * 8 + (col & 7)] = acc;
+                    for (int r = 0; r < 8; r++) acc += tcr[r] * __shfl_sync(0xffffffffu, v, r);
+                    if (lane < ncrit) {
+                        s_contrib[col] = acc;
+                        const int q = (col >> 3) % CL;
+                        if (bsub_mbar) {
+                            const unsigned abar = mapa_u32(smem_u32(s_bar + 2), q);
+                            st_async_f64(mapa_u32(smem_u32(s_inbox + cr * 8 + (col & 7)), q), acc, abar);
+                            if ((col & 7) == 0) dsm_mbar_arrive_expect_tx_remote(abar, 64u);
+                        } else {
+                            cluster.map_shared_rank(s_inbox, q)[cr * 8 + (col & 7)] = acc;
+                        }
                     }
                 }
+                __syncthreads();
                 for (int col = tid; col < c0; col += SOLVE_THREADS) {
                     const double *tp = trow + (col >> 3) * 64 + (col & 7);
                     double acc = s_contrib[col];
